@@ -1,0 +1,181 @@
+/*
+ * sclens_b200.h - C ABI of libsclens_b200.so, the B200-native drop-in for the
+ * signal-detection hot path of Mathbiomed/scLENS:  scLENS.sclens(pre_df; device_="gpu")
+ * (reference: src/scLENS.jl:649-832 and the helpers it calls, :239-608).
+ *
+ * The reference has no FFI: its only backend seam is the `device_` string keyword that
+ * branches into CUDA.jl library calls at src/scLENS.jl:335-343 (_wishart_matrix),
+ * :365-369 (corr_mat), :377 (_get_eigen), :505 / :558 / :561 (back-projection) and
+ * :814-816 (gene_basis).  A per-function shim would inherit the reference's seven PCIe
+ * crossings per get_eigvec call, so the boundary sits one level up: a handle owns all
+ * device state of one sclens() call; counts go in once (CSC), results come out once.
+ * Function-level entry points (scl_op_*) expose the individual stages for unit parity.
+ *
+ * Conventions: every function returns 0 on success, <0 on error (no exceptions cross the
+ * boundary, no CPU fallback exists); scl_last_error() gives the message.  All pointers are
+ * HOST pointers owned by the caller and are never retained after the call returns.
+ * Matrices are column-major (Julia layout) unless stated.  Indices passed in are
+ * `index_base`-based (1 from Julia, 0 from C/Python); indices returned are 0-based.
+ * A handle is not thread-safe; distinct handles are independent.
+ */
+#ifndef SCLENS_B200_H
+#define SCLENS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SCL_API __attribute__((visibility("default")))
+#else
+#define SCL_API
+#endif
+
+typedef struct scl_handle scl_handle;
+
+enum {
+  SCL_OK = 0,
+  SCL_ERR_INVALID = -1,   /* bad argument / call order */
+  SCL_ERR_CUDA = -2,      /* CUDA runtime / driver error */
+  SCL_ERR_CUSOLVER = -3,  /* cuSOLVER error or non-convergence (reference NaN fallback :379-381 is an error here) */
+  SCL_ERR_NOGPU = -4,     /* no sm_100 device: there is no CPU fallback */
+  SCL_ERR_NCCL = -5,
+  SCL_ERR_NOSIGNAL = -6   /* scl_run_robustness called with zero signals (:780-784) */
+};
+
+/* Gram operand precision. FP16: one tcgen05 kind::f16 pass. FP16X3: hi/lo split, three
+ * passes into the same TMEM accumulator (~fp32 accuracy; reference is FP32 SGEMM :337). */
+enum { SCL_GRAM_FP16 = 0, SCL_GRAM_FP16X3 = 1 };
+
+typedef struct {
+  int32_t device;        /* CUDA device ordinal */
+  int32_t gram_mode;     /* SCL_GRAM_* */
+  int32_t cta_group;     /* 0 = library default, 1 or 2 = force tcgen05 cta_group */
+  int32_t verbose;       /* 1: print the reference's progress lines (:539, :713, :762, :807) */
+  uint64_t seed;         /* seed of the device-side draws when none are injected */
+  int32_t subspace_extra;/* oversampling columns of the block subspace iteration (0 = default) */
+  int32_t subspace_degree;/* Chebyshev degree per sweep (0 = default) */
+  int32_t exact_perturb; /* 1: full syevd per replicate exactly as :775 (parity studies) */
+  int32_t reserved[7];
+} scl_config;
+
+typedef struct {
+  int32_t N, M, nm;          /* cells, genes, min(N,M) */
+  int32_t n_signal;          /* sum(L .> lambda_c)                     (:539/:578) */
+  int32_t n_Lmp;             /* length(L_mp)                           (:458) */
+  int32_t mp_iters;          /* fixed-point iterations of _mp_calculation (:436-455) */
+  int32_t pass;              /* mp_check :pass                         (:486) */
+  int32_t gram_mode_used;    /* SCL_GRAM_* actually used (guard band may escalate) */
+  double lambda_c, b_plus, b_minus, ks_static;
+  double t_ingest_ms, t_normalize_ms, t_null_ms, t_gram_ms, t_syevd_ms, t_fit_ms, t_backproject_ms;
+} scl_signal_info;
+
+typedef struct {
+  int32_t n_search;          /* sparsity-search iterations executed    (:725-761) */
+  int32_t n_perturb;         /* replicates run                         (:771-778) */
+  int32_t min_pc;            /* ceil(1.5 * n_signal)                   (:770) */
+  int32_t n_robust;          /* length(sig_id)                         (:806) */
+  int64_t n_add;             /* round((1-p_)*M*N) at the selected p_   (:772) */
+  double p_sel;              /* "Selected perturb sparisty"            (:762) */
+  double p_th;               /* noise baseline                         (:712) */
+  double t_baseline_ms, t_search_ms, t_search_syevd_ms, t_perturb_ms, t_score_ms, t_outputs_ms;
+} scl_robust_info;
+
+/* ---- lifecycle --------------------------------------------------------------------- */
+SCL_API int32_t scl_version(void);
+SCL_API int32_t scl_create(scl_handle** out, const scl_config* cfg);
+SCL_API int32_t scl_destroy(scl_handle* h);
+SCL_API const char* scl_last_error(scl_handle* h);   /* h may be NULL: last scl_create error */
+
+/* ---- multi-GPU plumbing (one process per GPU) ------------------------- */
+/* 128-byte NCCL unique id, created on rank 0 and distributed by the host language. */
+SCL_API int32_t scl_nccl_unique_id(uint8_t out_id[128]);
+SCL_API int32_t scl_comm_init(scl_handle* h, const uint8_t id[128], int32_t rank, int32_t world);
+/* Pure host logic (testable without a GPU): which replicates / search steps a rank owns. */
+SCL_API int32_t scl_plan_replicates(int32_t n_perturb, int32_t world, int32_t rank, int32_t* out_ids, int32_t* out_n);
+SCL_API int32_t scl_plan_search_wave(int32_t wave, int32_t world, int32_t rank, int32_t* out_step);
+
+/* ---- inputs ------------------------------------------------------------------------ */
+/* df2sparr output (:90-120): SparseMatrixCSC{Float32,UInt32}, N cells x M genes, canonical
+ * order, strictly positive values. */
+SCL_API int32_t scl_set_counts_csc(scl_handle* h, int32_t N, int32_t M, int64_t nnz,
+                           const uint32_t* colptr, const uint32_t* rowval, const float* nzval,
+                           int32_t index_base);
+
+/* ---- injected draws (optional; SURVEY.md 8c "draw injection") ------------------------ */
+/* z_idx1/z_idx2 of :668-673. */
+SCL_API int32_t scl_set_zero_candidates(scl_handle* h, int64_t n, const uint32_t* z_idx1, const uint32_t* z_idx2, int32_t index_base);
+/* shuffle(nz_val) as a gather permutation (:275) and row_i (:247), both of length nnz. */
+SCL_API int32_t scl_set_null_draws(scl_handle* h, int64_t n, const uint32_t* perm, const uint32_t* rows, int32_t index_base);
+SCL_API int32_t scl_set_noise_baseline(scl_handle* h, double p_th);                       /* :709-712 */
+SCL_API int32_t scl_push_search_sample(scl_handle* h, int64_t n, const uint32_t* sple_idx, int32_t index_base);  /* :731 */
+SCL_API int32_t scl_push_perturb_sample(scl_handle* h, int64_t n, const uint32_t* sple_idx, int32_t index_base); /* :772 */
+SCL_API int32_t scl_clear_draws(scl_handle* h);
+
+/* ---- the path ---------------------------------------------------------------------- */
+/* :664-706: normalise, null matrix, get_sigev, mp_check. */
+SCL_API int32_t scl_run_signal(scl_handle* h, scl_signal_info* out);
+/* :709-819: noise baseline, sparsity search, perturbations, robustness scores, outputs. */
+SCL_API int32_t scl_run_robustness(scl_handle* h, double th, double p_step, int32_t n_perturb, scl_robust_info* out);
+
+/* ---- results (caller-allocated; sizes from the info structs) ------------------------- */
+SCL_API int32_t scl_get_L(scl_handle* h, float* L /* nm, ascending, unfiltered (:378) */);
+SCL_API int32_t scl_get_Lmp(scl_handle* h, float* L_mp /* n_Lmp */);
+SCL_API int32_t scl_get_signal_ev(scl_handle* h, float* nL /* n_signal, descending */);
+SCL_API int32_t scl_get_signal_evec(scl_handle* h, float* nV /* N x n_signal col-major, unit columns */);
+SCL_API int32_t scl_get_gene_basis(scl_handle* h, float* g /* n_signal x M col-major (:813-819) */);
+SCL_API int32_t scl_get_rec_vals(scl_handle* h, double* TGC /*N*/, double* mat2_mean /*M*/, double* mat2_std /*M*/,
+                         double* norm_tgc /*N*/, double* cent /*M*/);                 /* :676-695 */
+SCL_API int32_t scl_get_scores(scl_handle* h, float* b_ /* n_signal x C(n_perturb,2) col-major */,
+                       double* m_scores /*n_signal*/, double* sd_scores /*n_signal*/); /* :795-803 */
+SCL_API int32_t scl_get_sig_id(scl_handle* h, int32_t* sig_id /* n_robust, 0-based */);
+SCL_API int32_t scl_get_null_csc(scl_handle* h, int64_t* nnz, uint32_t* colptr /*M+1*/, uint32_t* rowval, float* nzval);
+SCL_API int32_t scl_get_search_trace(scl_handle* h, double* p /*n_search*/, double* second_smallest /*n_search*/);
+SCL_API int32_t scl_get_perturbed_evec(scl_handle* h, int32_t replicate, float* nV /* N x min_pc */, float* nL /* min_pc */);
+
+/* ---- function-level operators (host in / host out; unit parity) ---------------------- */
+/* logn_scale(pre_scale(X)) (:650-652, :677-696).  layout 0: gene-major = column-major N x M
+ * (Julia), 1: cell-major.  out_hi/out_lo are IEEE binary16 bit patterns (lo may be NULL);
+ * ld = leading dimension in elements (multiple of 8). Statistic outputs may be NULL. */
+SCL_API int32_t scl_op_normalize(scl_handle* h, int32_t N, int32_t M, int64_t nnz, const uint32_t* colptr,
+                         const uint32_t* rowval, const float* nzval, int32_t layout, int64_t ld,
+                         uint16_t* out_hi, uint16_t* out_lo,
+                         double* TGC, double* mat2_mean, double* mat2_std, double* norm_tgc, double* cent);
+/* _wishart_matrix (:332-344): G = A * A^T * scale, A = rows x K row-major binary16 (hi [+ lo]). */
+SCL_API int32_t scl_op_gram(scl_handle* h, int32_t rows, int64_t K, int64_t ld, const uint16_t* a_hi, const uint16_t* a_lo,
+                    float scale, float* G /* rows x rows, full symmetric */);
+/* C[m,n] = alpha * sum_k A[m,k] B[n,k]; A m x K, B n x K row-major binary16; C col-major m x n
+ * when c_colmajor else row-major. */
+SCL_API int32_t scl_op_gemm_tn(scl_handle* h, int32_t m, int32_t n, int64_t K, int64_t lda, int64_t ldb,
+                       const uint16_t* a_hi, const uint16_t* a_lo, const uint16_t* b_hi, const uint16_t* b_lo,
+                       float alpha, int32_t c_colmajor, float* C);
+/* _get_eigen (:375-382): cuSOLVER syevd('V','U'), ascending. V may be NULL (values only). */
+SCL_API int32_t scl_op_syevd(scl_handle* h, int32_t n, const float* A, float* L, float* V, double* ms);
+/* _mp_calculation + _tw + mp_check (:424-487) on host doubles. out: [lambda_c,b_plus,b_minus,
+ * ks_static, n_Lmp, mp_iters, pass, n_signal]. */
+SCL_API int32_t scl_op_mp_fit(const float* L, int32_t nL, const float* Lr, int32_t nLr, double out[8]);
+/* random_nz (:261-289) with injected draws -> canonical CSC (duplicates summed). */
+SCL_API int32_t scl_op_permute_null(scl_handle* h, int32_t N, int32_t M, int64_t nnz, const uint32_t* colptr,
+                            const uint32_t* rowval, const float* nzval, const uint32_t* perm, const uint32_t* rows,
+                            int64_t* out_nnz, uint32_t* out_colptr, uint32_t* out_rowval, float* out_val);
+/* sparse(vcat(...)) of :735 (binarise=1) / :774 (binarise=0) -> canonical CSC. */
+SCL_API int32_t scl_op_perturb_merge(scl_handle* h, int32_t N, int32_t M, int64_t nnz, const uint32_t* colptr,
+                             const uint32_t* rowval, const float* nzval, int64_t n_add, const uint32_t* add_row,
+                             const uint32_t* add_col, int32_t binarise,
+                             uint32_t* out_colptr, uint32_t* out_rowval, float* out_val);
+/* d_arr of :742: for each column j of W (n x nw), max_i |<V[:,i], W[:,j]>| over the nv columns of V. */
+SCL_API int32_t scl_op_corr_colabsmax(scl_handle* h, int32_t n, int32_t nv, int32_t nw, const float* V, const float* W, float* d);
+/* Leading k eigenpairs of a symmetric n x n matrix by block Chebyshev subspace iteration. */
+SCL_API int32_t scl_op_topk_subspace(scl_handle* h, int32_t n, const float* G, int32_t k, float* L /*k*/, float* V /* n x k */,
+                             int32_t* iters);
+/* robustness scoring (:786-806) on host-provided vectors: nV N x k, sets n_perturb x (N x min_pc). */
+SCL_API int32_t scl_op_scores(scl_handle* h, int32_t N, int32_t k, int32_t min_pc, int32_t n_perturb, const float* nV,
+                      const float* nV_sets, double th, float* b_, double* m_scores, double* sd_scores,
+                      int32_t* sig_id, int32_t* n_robust);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCLENS_B200_H */

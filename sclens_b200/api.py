@@ -1,0 +1,287 @@
+"""Host-side mirror of the reference interface for the hot path:
+
+    scLENS.sclens(inp_df; device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="mean")
+    (/root/reference/src/scLENS.jl:649) -> Dict with the keys of :826-830.
+
+Everything numeric happens behind the C ABI (libsclens_b200.so); this module only converts
+the DataFrame to CSC (df2sparr, :90-120), calls the library and assembles the result
+dictionary.  The Julia binding a maintainer would add does exactly the same through
+``ccall`` (see INTEGRATION.md and julia/sclens_b200.jl).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from ._lib import Config, RobustInfo, SclError, SignalInfo, as_f32, as_u32, ptr
+
+
+def df2sparr(inp_df):
+    """df2sparr (:90-120): DataFrame (col 0 = 'cell', then genes) -> canonical CSC Float32 with
+    UInt32 indices, plus cell and gene ids.  scipy sparse / ndarray inputs are accepted too."""
+    try:
+        import pandas as pd
+    except ImportError:  # pragma: no cover
+        pd = None
+    if pd is not None and isinstance(inp_df, pd.DataFrame):
+        cell_id = inp_df.iloc[:, 0].astype(str).to_numpy()
+        genes = inp_df.columns[1:]
+        body = inp_df.iloc[:, 1:]
+        if all(isinstance(t, pd.SparseDtype) for t in body.dtypes):
+            X = sp.csc_matrix(body.sparse.to_coo(), dtype=np.float32)
+        else:
+            X = sp.csc_matrix(body.to_numpy(dtype=np.float32))
+        gene_id = np.asarray(genes, dtype=object)
+    else:
+        X = sp.csc_matrix(inp_df, dtype=np.float32)
+        cell_id = np.array([f"c{i}" for i in range(X.shape[0])], dtype=object)
+        gene_id = np.array([f"g{j}" for j in range(X.shape[1])], dtype=object)
+    X.sum_duplicates()
+    X.eliminate_zeros()   # the C ABI requires strictly positive stored values
+    X.sort_indices()
+    return X, cell_id, gene_id
+
+
+class Handle:
+    """Owns one scl_handle (all device state of one sclens() call)."""
+
+    def __init__(self, device: int = 0, gram_mode: int = _lib.SCL_GRAM_FP16, cta_group: int = 0, verbose: bool = False,
+                 seed: int = 0, exact_perturb: bool = False, subspace_extra: int = 0, subspace_degree: int = 0):
+        self.lib = _lib.load()
+        cfg = Config(device=device, gram_mode=gram_mode, cta_group=cta_group, verbose=int(verbose), seed=seed,
+                     subspace_extra=subspace_extra, subspace_degree=subspace_degree, exact_perturb=int(exact_perturb))
+        self.h = C.c_void_p()
+        rc = self.lib.scl_create(C.byref(self.h), C.byref(cfg))
+        if rc != 0:
+            raise SclError(rc, (self.lib.scl_last_error(None) or b"").decode())
+        self.sinfo: Optional[SignalInfo] = None
+        self.rinfo: Optional[RobustInfo] = None
+        self.N = self.M = 0
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.scl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SclError(rc, (self.lib.scl_last_error(self.h) or b"").decode())
+
+    # ---- inputs / draws
+    def set_counts(self, X: sp.csc_matrix):
+        X = sp.csc_matrix(X, dtype=np.float32)
+        X.sort_indices()
+        self.N, self.M = X.shape
+        colptr, rowval, val = as_u32(X.indptr), as_u32(X.indices), as_f32(X.data)
+        self._ck(self.lib.scl_set_counts_csc(self.h, self.N, self.M, X.nnz, ptr(colptr, C.c_uint32),
+                                             ptr(rowval, C.c_uint32), ptr(val, C.c_float), 0))
+
+    def set_zero_candidates(self, z1, z2):
+        z1, z2 = as_u32(z1), as_u32(z2)
+        self._ck(self.lib.scl_set_zero_candidates(self.h, len(z1), ptr(z1, C.c_uint32), ptr(z2, C.c_uint32), 0))
+
+    def set_null_draws(self, perm, rows):
+        perm, rows = as_u32(perm), as_u32(rows)
+        self._ck(self.lib.scl_set_null_draws(self.h, len(perm), ptr(perm, C.c_uint32), ptr(rows, C.c_uint32), 0))
+
+    def set_noise_baseline(self, p_th: float):
+        self._ck(self.lib.scl_set_noise_baseline(self.h, float(p_th)))
+
+    def push_search_sample(self, s):
+        s = as_u32(s)
+        self._ck(self.lib.scl_push_search_sample(self.h, len(s), ptr(s, C.c_uint32), 0))
+
+    def push_perturb_sample(self, s):
+        s = as_u32(s)
+        self._ck(self.lib.scl_push_perturb_sample(self.h, len(s), ptr(s, C.c_uint32), 0))
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._ck(self.lib.scl_comm_init(self.h, buf, rank, world))
+
+    # ---- the path
+    def run_signal(self) -> SignalInfo:
+        info = SignalInfo()
+        self._ck(self.lib.scl_run_signal(self.h, C.byref(info)))
+        self.sinfo = info
+        return info
+
+    def run_robustness(self, th=60.0, p_step=0.001, n_perturb=20) -> RobustInfo:
+        info = RobustInfo()
+        self._ck(self.lib.scl_run_robustness(self.h, float(th), float(p_step), int(n_perturb), C.byref(info)))
+        self.rinfo = info
+        return info
+
+    # ---- results
+    def _getf(self, fn, n, dtype=np.float32, ctype=C.c_float):
+        out = np.empty(n, dtype=dtype)
+        self._ck(fn(self.h, ptr(out, ctype)))
+        return out
+
+    def L(self):
+        return self._getf(self.lib.scl_get_L, self.sinfo.nm)
+
+    def L_mp(self):
+        return self._getf(self.lib.scl_get_Lmp, self.sinfo.n_Lmp)
+
+    def signal_ev(self):
+        return self._getf(self.lib.scl_get_signal_ev, self.sinfo.n_signal)
+
+    def signal_evec(self):
+        """N x n_signal (unit columns)."""
+        k = self.sinfo.n_signal
+        out = np.empty((k, self.N), dtype=np.float32)
+        if k:
+            self._ck(self.lib.scl_get_signal_evec(self.h, ptr(out, C.c_float)))
+        return out.T
+
+    def gene_basis(self):
+        """n_signal x M."""
+        k = self.sinfo.n_signal
+        out = np.empty((self.M, k), dtype=np.float32)
+        self._ck(self.lib.scl_get_gene_basis(self.h, ptr(out, C.c_float)))
+        return out.T
+
+    def rec_vals(self):
+        N, M = self.N, self.M
+        tgc, l2 = np.empty(N), np.empty(N)
+        mean, sd, cent = np.empty(M), np.empty(M), np.empty(M)
+        self._ck(self.lib.scl_get_rec_vals(self.h, ptr(tgc, C.c_double), ptr(mean, C.c_double), ptr(sd, C.c_double),
+                                           ptr(l2, C.c_double), ptr(cent, C.c_double)))
+        return {"TGC": tgc, "mat2_mean": mean.reshape(1, M), "mat2_std": sd.reshape(1, M), "norm_tgc": l2,
+                "cent_": cent.reshape(1, M)}
+
+    def scores(self):
+        k, P = self.sinfo.n_signal, self.rinfo.n_perturb
+        npairs = P * (P - 1) // 2
+        b = np.empty((npairs, k), dtype=np.float32)
+        m, sd = np.empty(k), np.empty(k)
+        self._ck(self.lib.scl_get_scores(self.h, ptr(b, C.c_float), ptr(m, C.c_double), ptr(sd, C.c_double)))
+        return b.T, m, sd
+
+    def sig_id(self):
+        out = np.empty(self.rinfo.n_robust, dtype=np.int32)
+        if len(out):
+            self._ck(self.lib.scl_get_sig_id(self.h, ptr(out, C.c_int32)))
+        return out
+
+    def null_csc(self) -> sp.csc_matrix:
+        nnz = C.c_int64()
+        self._ck(self.lib.scl_get_null_csc(self.h, C.byref(nnz), None, None, None))
+        colptr = np.empty(self.M + 1, np.uint32)
+        rowval = np.empty(max(1, nnz.value), np.uint32)
+        val = np.empty(max(1, nnz.value), np.float32)
+        self._ck(self.lib.scl_get_null_csc(self.h, C.byref(nnz), ptr(colptr, C.c_uint32), ptr(rowval, C.c_uint32),
+                                           ptr(val, C.c_float)))
+        return sp.csc_matrix((val[:nnz.value], rowval[:nnz.value].astype(np.int64), colptr.astype(np.int64)),
+                             shape=(self.N, self.M))
+
+    def search_trace(self):
+        n = self.rinfo.n_search
+        p, d = np.empty(n), np.empty(n)
+        self._ck(self.lib.scl_get_search_trace(self.h, ptr(p, C.c_double), ptr(d, C.c_double)))
+        return p, d
+
+    def perturbed_evec(self, r):
+        mp = self.rinfo.min_pc
+        V = np.empty((mp, self.N), dtype=np.float32)
+        L = np.empty(mp, dtype=np.float32)
+        self._ck(self.lib.scl_get_perturbed_evec(self.h, r, ptr(V, C.c_float), ptr(L, C.c_float)))
+        return V.T, L
+
+
+def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="mean", *, draws=None, seed=0,
+           gram_mode=_lib.SCL_GRAM_FP16, exact_perturb=False, verbose=True, device=0, return_handle=False):
+    """Drop-in for scLENS.sclens (:649-832).  Returns the reference's result dictionary with
+    string keys (":pca" -> "pca", ...; "λ" is also available as "lambda").  ``sig_id`` is
+    0-based here (the Julia shim adds 1).  ``draws`` optionally injects the random draws
+    (an object with the fields of oracle Draws) for parity runs."""
+    if device_ != "gpu":
+        raise ValueError('sclens_b200 implements device_="gpu" only (no CPU fallback exists)')
+    if centering != "mean":
+        raise NotImplementedError('only centering="mean" (the default path) is implemented')
+    try:
+        import pandas as pd
+    except ImportError:  # pragma: no cover
+        pd = None
+    if verbose:
+        print("Extracting matrices")                                    # :661
+    X, cell_id, gene_id = df2sparr(inp_df)
+    N, M = X.shape
+    h = Handle(device=device, gram_mode=gram_mode, verbose=verbose, seed=seed, exact_perturb=exact_perturb)
+    try:
+        h.set_counts(X)
+        if draws is not None:
+            if getattr(draws, "z_idx1", None) is not None:
+                h.set_zero_candidates(draws.z_idx1, draws.z_idx2)
+            if getattr(draws, "null_perm", None) is not None:
+                h.set_null_draws(draws.null_perm, draws.null_rows)
+            if getattr(draws, "p_th", None) is not None:
+                h.set_noise_baseline(draws.p_th)
+            for s in getattr(draws, "search_sple", []) or []:
+                h.push_search_sample(s)
+            for s in getattr(draws, "perturb_sple", []) or []:
+                h.push_perturb_sample(s)
+        if verbose:
+            print("Extracting Signals...")                              # :702
+        si = h.run_signal()
+        L, L_mp = h.L(), h.L_mp()
+        results = {"L": L, "L_mp": L_mp, "λ": si.lambda_c, "lambda": si.lambda_c, "cell_id": cell_id}
+        if si.n_signal == 0:                                            # :780-784
+            if verbose:
+                print("warning: There is no signal")
+            return (results, h) if return_handle else results
+        if verbose:
+            print("Calculating noise baseline...")                      # :707
+            print("Calculating sparsity level for the perturbation...")  # :716
+        ri = h.run_robustness(th=th, p_step=p_step, n_perturb=n_perturb)
+        nV, nL = h.signal_evec(), h.signal_ev()
+        b_, m_scores, sd_scores = h.scores()
+        sig_id = h.sig_id()
+        if verbose:
+            print("Reconstructing reduced data...")                     # :809
+        sq = np.sqrt(nL.astype(np.float32))
+        Xout0 = nV * sq[None, :]                                        # :810
+        Xout1 = nV[:, sig_id] * sq[sig_id][None, :]                     # :811
+
+        def frame(mat):
+            if pd is None:
+                return mat
+            df = pd.DataFrame(mat, columns=[f"x{i + 1}" for i in range(mat.shape[1])])
+            df.insert(0, "cell", cell_id)
+            return df
+
+        results.update({
+            "pca": frame(Xout0), "pca_n1": frame(Xout1), "sig_id": sig_id,
+            "robustness_scores": {"b_": b_, "rob_score": m_scores, "m_scores": m_scores, "sd_scores": sd_scores},
+            "signal_evec": nV, "signal_ev": nL, "gene_id": gene_id, "gene_basis": h.gene_basis(),
+            "pass": bool(si.pass_), "rec_vals": h.rec_vals(),
+            "info": {"p_sel": ri.p_sel, "n_search": ri.n_search, "p_th": ri.p_th, "min_pc": ri.min_pc,
+                     "n_add": ri.n_add, "ks_static": si.ks_static, "b_plus": si.b_plus, "b_minus": si.b_minus,
+                     "timings_ms": {"gram": si.t_gram_ms, "syevd_signal": si.t_syevd_ms, "null": si.t_null_ms,
+                                    "fit": si.t_fit_ms, "backproject": si.t_backproject_ms,
+                                    "baseline": ri.t_baseline_ms, "search": ri.t_search_ms,
+                                    "search_syevd": ri.t_search_syevd_ms, "perturb": ri.t_perturb_ms,
+                                    "score": ri.t_score_ms, "outputs": ri.t_outputs_ms}},
+        })
+        return (results, h) if return_handle else results
+    finally:
+        if not return_handle:
+            h.close()

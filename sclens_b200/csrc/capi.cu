@@ -1,0 +1,512 @@
+// extern "C" surface of libsclens_b200.so (see include/sclens_b200.h).
+#include <nccl.h>
+#include <cstring>
+#include "handle.h"
+#include "tmp.cuh"
+
+using namespace scl;
+
+namespace {
+thread_local std::string g_create_error;
+
+template <typename F>
+int32_t guard(scl_handle* h, F&& f) {
+  try {
+    f();
+    return SCL_OK;
+  } catch (const scl::Error& e) {
+    if (h) h->err = e.what(); else g_create_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    if (h) h->err = e.what(); else g_create_error = e.what();
+    return SCL_ERR_INVALID;
+  }
+}
+
+void upload_u32(DBuf<uint32_t>& dst, const uint32_t* src, size_t n, int base, cudaStream_t st) {
+  dst.ensure(n ? n : 1);
+  if (!n) return;
+  if (base == 0) {
+    SCL_CUDA(cudaMemcpyAsync(dst.p, src, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  } else {
+    std::vector<uint32_t> tmp(src, src + n);
+    for (auto& v : tmp) v -= (uint32_t)base;
+    SCL_CUDA(cudaMemcpyAsync(dst.p, tmp.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+  }
+}
+
+void download_csc(const SpMat& A, uint32_t* colptr, uint32_t* rowval, float* val, cudaStream_t st) {
+  SCL_CUDA(cudaMemcpyAsync(colptr, A.colptr.p, (A.M + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (A.nnz) {
+    SCL_CUDA(cudaMemcpyAsync(rowval, A.rowval.p, A.nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaMemcpyAsync(val, A.val.p, A.nnz * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  SCL_CUDA(cudaStreamSynchronize(st));
+}
+}  // namespace
+
+extern "C" {
+
+int32_t scl_version(void) { return 100; }
+
+int32_t scl_create(scl_handle** out, const scl_config* cfg) {
+  if (!out) return SCL_ERR_INVALID;
+  *out = nullptr;
+  scl_handle* h = nullptr;
+  int32_t rc = guard(nullptr, [&] {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) throw Error(SCL_ERR_NOGPU, "no CUDA device: libsclens_b200 has no CPU fallback");
+    scl_config c{};
+    if (cfg) c = *cfg;
+    SCL_REQUIRE(c.device >= 0 && c.device < ndev, "bad device ordinal");
+    SCL_CUDA(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    SCL_CUDA(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major != 10) throw Error(SCL_ERR_NOGPU, std::string("sm_100 (B200) required, found sm_") + std::to_string(prop.major * 10 + prop.minor));
+    h = new scl_handle;
+    h->cfg = c;
+    SCL_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    SCL_CUDA(cudaDeviceGetDefaultMemPool(&pool, c.device));
+    uint64_t thr = UINT64_MAX;
+    SCL_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    h->solver.reset(new Solver(h->st));
+  });
+  if (rc != SCL_OK) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return SCL_OK;
+}
+
+int32_t scl_destroy(scl_handle* h) {
+  if (!h) return SCL_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->st) cudaStreamSynchronize(h->st);
+  if (h->nccl) ncclCommDestroy((ncclComm_t)h->nccl);
+  h->solver.reset();
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+  return SCL_OK;
+}
+
+const char* scl_last_error(scl_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+// ---- multi-GPU plumbing -----------------------------------------------------------------
+int32_t scl_nccl_unique_id(uint8_t out_id[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return SCL_ERR_NCCL;
+  std::memcpy(out_id, &id, 128);
+  return SCL_OK;
+}
+
+int32_t scl_comm_init(scl_handle* h, const uint8_t id[128], int32_t rank, int32_t world) {
+  if (!h) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+    h->world = world;
+    h->rank = rank;
+    if (world == 1) return;
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, 128);
+    ncclComm_t comm;
+    ncclResult_t r = ncclCommInitRank(&comm, world, uid, rank);
+    if (r != ncclSuccess) throw Error(SCL_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+    h->nccl = comm;
+  });
+}
+
+int32_t scl_plan_replicates(int32_t n_perturb, int32_t world, int32_t rank, int32_t* out_ids, int32_t* out_n) {
+  if (n_perturb < 0 || world < 1 || rank < 0 || rank >= world || !out_n) return SCL_ERR_INVALID;
+  int n = 0;
+  for (int r = rank; r < n_perturb; r += world) {
+    if (out_ids) out_ids[n] = r;
+    ++n;
+  }
+  *out_n = n;
+  return SCL_OK;
+}
+
+int32_t scl_plan_search_wave(int32_t wave, int32_t world, int32_t rank, int32_t* out_step) {
+  if (wave < 0 || world < 1 || rank < 0 || rank >= world || !out_step) return SCL_ERR_INVALID;
+  *out_step = wave * world + rank;
+  return SCL_OK;
+}
+
+// ---- inputs -------------------------------------------------------------------------------
+int32_t scl_set_counts_csc(scl_handle* h, int32_t N, int32_t M, int64_t nnz, const uint32_t* colptr,
+                           const uint32_t* rowval, const float* nzval, int32_t index_base) {
+  if (!h) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_REQUIRE(N > 1 && M > 1 && nnz > 0 && colptr && rowval && nzval, "bad CSC input");
+    SCL_REQUIRE(index_base == 0 || index_base == 1, "index_base must be 0 or 1");
+    SCL_REQUIRE((int64_t)colptr[M] - index_base == nnz, "colptr[M] does not match nnz");
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    upload_csc(h->X, N, M, (size_t)nnz, colptr, rowval, nzval, index_base, h->st);
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+    h->have_X = true;
+    h->signal_done = h->robust_done = false;
+    h->have_zc = h->have_null_draws = h->have_pth = false;
+    h->search_sples.clear();
+    h->perturb_sples.clear();
+  });
+}
+
+int32_t scl_set_zero_candidates(scl_handle* h, int64_t n, const uint32_t* z1, const uint32_t* z2, int32_t index_base) {
+  if (!h) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_REQUIRE(h->have_X && n >= 0 && (n == 0 || (z1 && z2)), "bad zero candidates");
+    upload_u32(h->z1, z1, (size_t)n, index_base, h->st);
+    upload_u32(h->z2, z2, (size_t)n, index_base, h->st);
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+    h->n_cand = (size_t)n;
+    h->have_zc = true;
+  });
+}
+
+int32_t scl_set_null_draws(scl_handle* h, int64_t n, const uint32_t* perm, const uint32_t* rows, int32_t index_base) {
+  if (!h) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_REQUIRE(h->have_X && (size_t)n == h->X.nnz && perm && rows, "null draws must have length nnz");
+    upload_u32(h->null_perm, perm, (size_t)n, index_base, h->st);
+    upload_u32(h->null_rows, rows, (size_t)n, index_base, h->st);
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+    h->have_null_draws = true;
+  });
+}
+
+int32_t scl_set_noise_baseline(scl_handle* h, double p_th) {
+  if (!h || !(p_th > 0)) return SCL_ERR_INVALID;
+  h->p_th = p_th;
+  h->have_pth = true;
+  return SCL_OK;
+}
+
+static int32_t push_sample(scl_handle* h, std::deque<std::vector<uint32_t>>& q, int64_t n, const uint32_t* s, int32_t base) {
+  if (!h || n < 0 || (n > 0 && !s)) return SCL_ERR_INVALID;
+  std::vector<uint32_t> v(s, s + n);
+  if (base)
+    for (auto& x : v) x -= (uint32_t)base;
+  q.push_back(std::move(v));
+  return SCL_OK;
+}
+int32_t scl_push_search_sample(scl_handle* h, int64_t n, const uint32_t* s, int32_t base) {
+  return push_sample(h, h->search_sples, n, s, base);
+}
+int32_t scl_push_perturb_sample(scl_handle* h, int64_t n, const uint32_t* s, int32_t base) {
+  return push_sample(h, h->perturb_sples, n, s, base);
+}
+int32_t scl_clear_draws(scl_handle* h) {
+  if (!h) return SCL_ERR_INVALID;
+  h->have_zc = h->have_null_draws = h->have_pth = false;
+  h->search_sples.clear();
+  h->perturb_sples.clear();
+  return SCL_OK;
+}
+
+// ---- the path -----------------------------------------------------------------------------
+int32_t scl_run_signal(scl_handle* h, scl_signal_info* out) {
+  if (!h) return SCL_ERR_INVALID;
+  int32_t rc = guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    run_signal(h);
+  });
+  if (rc == SCL_OK && out) *out = h->sinfo;
+  return rc;
+}
+
+int32_t scl_run_robustness(scl_handle* h, double th, double p_step, int32_t n_perturb, scl_robust_info* out) {
+  if (!h) return SCL_ERR_INVALID;
+  int32_t rc = guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    run_robustness(h, th, p_step, n_perturb);
+  });
+  if (rc == SCL_OK && out) *out = h->rinfo;
+  return rc;
+}
+
+// ---- results ------------------------------------------------------------------------------
+#define NEED_SIGNAL() SCL_REQUIRE(h->signal_done, "scl_run_signal has not completed")
+#define NEED_ROBUST() SCL_REQUIRE(h->robust_done, "scl_run_robustness has not completed")
+
+int32_t scl_get_L(scl_handle* h, float* L) {
+  if (!h || !L) return SCL_ERR_INVALID;
+  return guard(h, [&] { NEED_SIGNAL(); std::memcpy(L, h->L.data(), h->L.size() * sizeof(float)); });
+}
+int32_t scl_get_Lmp(scl_handle* h, float* L) {
+  if (!h || !L) return SCL_ERR_INVALID;
+  return guard(h, [&] { NEED_SIGNAL(); std::memcpy(L, h->Lmp.data(), h->Lmp.size() * sizeof(float)); });
+}
+int32_t scl_get_signal_ev(scl_handle* h, float* nL) {
+  if (!h || !nL) return SCL_ERR_INVALID;
+  return guard(h, [&] { NEED_SIGNAL(); std::memcpy(nL, h->nL.data(), h->nL.size() * sizeof(float)); });
+}
+int32_t scl_get_signal_evec(scl_handle* h, float* nV) {
+  if (!h || !nV) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    NEED_SIGNAL();
+    size_t n = (size_t)h->sinfo.n_signal * h->sinfo.N;
+    if (n) SCL_CUDA(cudaMemcpy(nV, h->d_nV.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  });
+}
+int32_t scl_get_gene_basis(scl_handle* h, float* g) {
+  if (!h || !g) return SCL_ERR_INVALID;
+  return guard(h, [&] { NEED_ROBUST(); std::memcpy(g, h->gene_basis.data(), h->gene_basis.size() * sizeof(float)); });
+}
+int32_t scl_get_rec_vals(scl_handle* h, double* TGC, double* mean, double* sd, double* norm_tgc, double* cent) {
+  if (!h) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    NEED_SIGNAL();
+    if (TGC) std::memcpy(TGC, h->rec_tgc.data(), h->rec_tgc.size() * sizeof(double));
+    if (mean) std::memcpy(mean, h->rec_mean.data(), h->rec_mean.size() * sizeof(double));
+    if (sd) std::memcpy(sd, h->rec_std.data(), h->rec_std.size() * sizeof(double));
+    if (norm_tgc) std::memcpy(norm_tgc, h->rec_l2.data(), h->rec_l2.size() * sizeof(double));
+    if (cent) std::memcpy(cent, h->rec_cent.data(), h->rec_cent.size() * sizeof(double));
+  });
+}
+int32_t scl_get_scores(scl_handle* h, float* b_, double* m, double* sd) {
+  if (!h) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    NEED_ROBUST();
+    if (b_) std::memcpy(b_, h->b_.data(), h->b_.size() * sizeof(float));
+    if (m) std::memcpy(m, h->m_scores.data(), h->m_scores.size() * sizeof(double));
+    if (sd) std::memcpy(sd, h->sd_scores.data(), h->sd_scores.size() * sizeof(double));
+  });
+}
+int32_t scl_get_sig_id(scl_handle* h, int32_t* sig) {
+  if (!h || !sig) return SCL_ERR_INVALID;
+  return guard(h, [&] { NEED_ROBUST(); std::memcpy(sig, h->sig_id.data(), h->sig_id.size() * sizeof(int32_t)); });
+}
+int32_t scl_get_null_csc(scl_handle* h, int64_t* nnz, uint32_t* colptr, uint32_t* rowval, float* nzval) {
+  if (!h || !nnz) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    NEED_SIGNAL();
+    *nnz = (int64_t)h->Xnull.nnz;
+    if (colptr && rowval && nzval) download_csc(h->Xnull, colptr, rowval, nzval, h->st);
+  });
+}
+int32_t scl_get_search_trace(scl_handle* h, double* p, double* d) {
+  if (!h) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    NEED_ROBUST();
+    if (p) std::memcpy(p, h->trace_p.data(), h->trace_p.size() * sizeof(double));
+    if (d) std::memcpy(d, h->trace_d.data(), h->trace_d.size() * sizeof(double));
+  });
+}
+int32_t scl_get_perturbed_evec(scl_handle* h, int32_t r, float* nV, float* nL) {
+  if (!h) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    NEED_ROBUST();
+    SCL_REQUIRE(r >= 0 && r < h->rinfo.n_perturb, "replicate out of range");
+    const size_t per = (size_t)h->rinfo.min_pc * h->sinfo.N;
+    if (nV) SCL_CUDA(cudaMemcpy(nV, h->d_sets.p + (size_t)r * per, per * sizeof(float), cudaMemcpyDeviceToHost));
+    if (nL) std::memcpy(nL, &h->set_L[(size_t)r * h->rinfo.min_pc], h->rinfo.min_pc * sizeof(float));
+  });
+}
+
+// ---- function-level operators ---------------------------------------------------------------
+int32_t scl_op_normalize(scl_handle* h, int32_t N, int32_t M, int64_t nnz, const uint32_t* colptr,
+                         const uint32_t* rowval, const float* nzval, int32_t layout, int64_t ld, uint16_t* out_hi,
+                         uint16_t* out_lo, double* TGC, double* mean, double* sd, double* norm_tgc, double* cent) {
+  if (!h) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    SpMat A;
+    NormStats S;
+    upload_csc(A, N, M, (size_t)nnz, colptr, rowval, nzval, 0, h->st);
+    compute_norm_stats(A, S, h->st);
+    if (out_hi) {
+      const size_t lines = layout == 1 ? N : M;
+      Tmp<__half> hi(lines * (size_t)ld, h->st), lo(lines * (size_t)ld, h->st);
+      densify(A, S, layout, (size_t)ld, hi.p, out_lo ? lo.p : nullptr, h->st);
+      SCL_CUDA(cudaMemcpyAsync(out_hi, hi.p, lines * (size_t)ld * 2, cudaMemcpyDeviceToHost, h->st));
+      if (out_lo) SCL_CUDA(cudaMemcpyAsync(out_lo, lo.p, lines * (size_t)ld * 2, cudaMemcpyDeviceToHost, h->st));
+      SCL_CUDA(cudaStreamSynchronize(h->st));
+    }
+    auto dl = [&](double* dst, const double* src, size_t n) {
+      if (dst) SCL_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    };
+    dl(TGC, S.tgc.p, N); dl(norm_tgc, S.l2.p, N); dl(mean, S.ybar.p, M); dl(sd, S.sigma.p, M); dl(cent, S.cent.p, M);
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+  });
+}
+
+int32_t scl_op_gram(scl_handle* h, int32_t rows, int64_t K, int64_t ld, const uint16_t* a_hi, const uint16_t* a_lo,
+                    float scale, float* G) {
+  if (!h || !a_hi || !G) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)rows * (size_t)ld;
+    Tmp<__half> hi(n, h->st), lo(n, h->st);
+    Tmp<float> g((size_t)rows * rows, h->st);
+    SCL_CUDA(cudaMemcpyAsync(hi.p, a_hi, n * 2, cudaMemcpyHostToDevice, h->st));
+    if (a_lo) SCL_CUDA(cudaMemcpyAsync(lo.p, a_lo, n * 2, cudaMemcpyHostToDevice, h->st));
+    GemmArgs a;
+    a.A.hi = hi.p; a.A.lo = a_lo ? lo.p : nullptr; a.A.rows = rows; a.A.K = K; a.A.ld = ld;
+    a.B = a.A;
+    a.syrk = true; a.alpha = scale; a.C = g.p; a.ldc = rows;
+    a.cta_group = h->cfg.cta_group == 1 ? 1 : 2;
+    gemm_umma(a, h->st);
+    SCL_CUDA(cudaMemcpyAsync(G, g.p, (size_t)rows * rows * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+  });
+}
+
+int32_t scl_op_gemm_tn(scl_handle* h, int32_t m, int32_t n, int64_t K, int64_t lda, int64_t ldb, const uint16_t* a_hi,
+                       const uint16_t* a_lo, const uint16_t* b_hi, const uint16_t* b_lo, float alpha,
+                       int32_t c_colmajor, float* C) {
+  if (!h || !a_hi || !b_hi || !C) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    const size_t na = (size_t)m * lda, nb = (size_t)n * ldb;
+    const bool split = a_lo && b_lo;
+    Tmp<__half> ah(na, h->st), al(na, h->st), bh(nb, h->st), bl(nb, h->st);
+    Tmp<float> c((size_t)m * n, h->st);
+    SCL_CUDA(cudaMemcpyAsync(ah.p, a_hi, na * 2, cudaMemcpyHostToDevice, h->st));
+    SCL_CUDA(cudaMemcpyAsync(bh.p, b_hi, nb * 2, cudaMemcpyHostToDevice, h->st));
+    if (split) {
+      SCL_CUDA(cudaMemcpyAsync(al.p, a_lo, na * 2, cudaMemcpyHostToDevice, h->st));
+      SCL_CUDA(cudaMemcpyAsync(bl.p, b_lo, nb * 2, cudaMemcpyHostToDevice, h->st));
+    }
+    SCL_CUDA(cudaMemsetAsync(c.p, 0, (size_t)m * n * sizeof(float), h->st));
+    GemmArgs a;
+    a.A.hi = ah.p; a.A.lo = split ? al.p : nullptr; a.A.rows = m; a.A.K = K; a.A.ld = lda;
+    a.B.hi = bh.p; a.B.lo = split ? bl.p : nullptr; a.B.rows = n; a.B.K = K; a.B.ld = ldb;
+    a.alpha = alpha;
+    a.epi = c_colmajor ? Epilogue::StoreTransposed : Epilogue::Store;
+    a.C = c.p;
+    a.ldc = c_colmajor ? m : n;
+    a.cta_group = h->cfg.cta_group == 1 ? 1 : 2;
+    gemm_umma(a, h->st);
+    SCL_CUDA(cudaMemcpyAsync(C, c.p, (size_t)m * n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+  });
+}
+
+int32_t scl_op_syevd(scl_handle* h, int32_t n, const float* A, float* L, float* V, double* ms) {
+  if (!h || !A || !L) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    Tmp<float> a((size_t)n * n, h->st), w(n, h->st);
+    SCL_CUDA(cudaMemcpyAsync(a.p, A, (size_t)n * n * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, h->st);
+    h->solver->syevd(a.p, n, w.p, V != nullptr, h->st);
+    cudaEventRecord(e1, h->st);
+    cudaEventSynchronize(e1);
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms) *ms = t;
+    SCL_CUDA(cudaMemcpyAsync(L, w.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    if (V) SCL_CUDA(cudaMemcpyAsync(V, a.p, (size_t)n * n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+  });
+}
+
+int32_t scl_op_mp_fit(const float* L, int32_t nL, const float* Lr, int32_t nLr, double out[8]) {
+  if (!L || !Lr || !out) return SCL_ERR_INVALID;
+  return guard(nullptr, [&] {
+    MpFit f = mp_fit(L, nL, Lr, nLr);
+    out[0] = f.lambda_c; out[1] = f.b_plus; out[2] = f.b_minus; out[3] = f.ks_static;
+    out[4] = (double)f.L_mp.size(); out[5] = f.iters; out[6] = f.pass ? 1 : 0; out[7] = f.n_signal;
+  });
+}
+
+int32_t scl_op_permute_null(scl_handle* h, int32_t N, int32_t M, int64_t nnz, const uint32_t* colptr,
+                            const uint32_t* rowval, const float* nzval, const uint32_t* perm, const uint32_t* rows,
+                            int64_t* out_nnz, uint32_t* out_colptr, uint32_t* out_rowval, float* out_val) {
+  if (!h || !out_nnz) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    SpMat A, R;
+    upload_csc(A, N, M, (size_t)nnz, colptr, rowval, nzval, 0, h->st);
+    if (perm && rows) {
+      DBuf<uint32_t> dp, dr;
+      upload_u32(dp, perm, (size_t)nnz, 0, h->st);
+      upload_u32(dr, rows, (size_t)nnz, 0, h->st);
+      permute_null(A, dp.p, dr.p, R, h->st);
+      SCL_CUDA(cudaStreamSynchronize(h->st));
+    } else {
+      draw_null_device(A, h->cfg.seed, R, h->st);
+    }
+    *out_nnz = (int64_t)R.nnz;
+    if (out_colptr && out_rowval && out_val) download_csc(R, out_colptr, out_rowval, out_val, h->st);
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+  });
+}
+
+int32_t scl_op_perturb_merge(scl_handle* h, int32_t N, int32_t M, int64_t nnz, const uint32_t* colptr,
+                             const uint32_t* rowval, const float* nzval, int64_t n_add, const uint32_t* add_row,
+                             const uint32_t* add_col, int32_t binarise, uint32_t* out_colptr, uint32_t* out_rowval,
+                             float* out_val) {
+  if (!h || !out_colptr) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    SpMat A, R;
+    upload_csc(A, N, M, (size_t)nnz, colptr, rowval, nzval, 0, h->st);
+    DBuf<uint32_t> dr, dc;
+    upload_u32(dr, add_row, (size_t)n_add, 0, h->st);
+    upload_u32(dc, add_col, (size_t)n_add, 0, h->st);
+    perturb_merge(A, dr.p, dc.p, (size_t)n_add, binarise != 0, R, h->st);
+    download_csc(R, out_colptr, out_rowval, out_val, h->st);
+  });
+}
+
+int32_t scl_op_corr_colabsmax(scl_handle* h, int32_t n, int32_t nv, int32_t nw, const float* V, const float* W, float* d) {
+  if (!h || !V || !W || !d) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    Tmp<float> dv((size_t)nv * n, h->st), dw((size_t)nw * n, h->st), dd(nw, h->st);
+    SCL_CUDA(cudaMemcpyAsync(dv.p, V, (size_t)nv * n * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    SCL_CUDA(cudaMemcpyAsync(dw.p, W, (size_t)nw * n * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    corr_colabsmax(h, dv.p, nv, dw.p, nw, n, dd.p);
+    SCL_CUDA(cudaMemcpyAsync(d, dd.p, nw * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+  });
+}
+
+int32_t scl_op_topk_subspace(scl_handle* h, int32_t n, const float* G, int32_t k, float* L, float* V, int32_t* iters) {
+  if (!h || !G || !L || !V) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    Tmp<float> g((size_t)n * n, h->st), l(k, h->st), v((size_t)k * n, h->st);
+    SCL_CUDA(cudaMemcpyAsync(g.p, G, (size_t)n * n * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    int it = 0;
+    topk_subspace(h, g.p, n, k, l.p, v.p, &it);
+    if (iters) *iters = it;
+    SCL_CUDA(cudaMemcpyAsync(L, l.p, k * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    SCL_CUDA(cudaMemcpyAsync(V, v.p, (size_t)k * n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+  });
+}
+
+int32_t scl_op_scores(scl_handle* h, int32_t N, int32_t k, int32_t min_pc, int32_t n_perturb, const float* nV,
+                      const float* nV_sets, double th, float* b_, double* m_scores, double* sd_scores, int32_t* sig_id,
+                      int32_t* n_robust) {
+  if (!h || !nV || !nV_sets) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    const size_t ns = (size_t)n_perturb * min_pc * N;
+    Tmp<float> dv((size_t)k * N, h->st), ds(ns, h->st);
+    SCL_CUDA(cudaMemcpyAsync(dv.p, nV, (size_t)k * N * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    SCL_CUDA(cudaMemcpyAsync(ds.p, nV_sets, ns * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    std::vector<float> b;
+    std::vector<double> m, sd;
+    std::vector<int32_t> sig;
+    score_sets(h, N, k, min_pc, n_perturb, dv.p, ds.p, th, b, m, sd, sig);
+    if (b_) std::memcpy(b_, b.data(), b.size() * sizeof(float));
+    if (m_scores) std::memcpy(m_scores, m.data(), m.size() * sizeof(double));
+    if (sd_scores) std::memcpy(sd_scores, sd.data(), sd.size() * sizeof(double));
+    if (sig_id) std::memcpy(sig_id, sig.data(), sig.size() * sizeof(int32_t));
+    if (n_robust) *n_robust = (int32_t)sig.size();
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+// Shared declarations of libsclens_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace scl {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define SCL_CUDA(x)                                                                        \
+  do {                                                                                     \
+    cudaError_t e_ = (x);                                                                  \
+    if (e_ != cudaSuccess)                                                                 \
+      throw scl::Error(-2, std::string(#x) + ": " + cudaGetErrorString(e_) + " @" +        \
+                               __FILE__ + ":" + std::to_string(__LINE__));                 \
+  } while (0)
+
+#define SCL_REQUIRE(cond, msg)                                                             \
+  do {                                                                                     \
+    if (!(cond)) throw scl::Error(-1, std::string(msg) + " (" #cond ")");                  \
+  } while (0)
+
+// Device buffer, grows on demand, freed with the handle.
+template <typename T>
+struct DBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  T* ensure(size_t n) {
+    if (n > cap) {
+      release();
+      size_t want = n + n / 16 + 64;
+      SCL_CUDA(cudaMalloc(&p, want * sizeof(T)));
+      cap = want;
+    }
+    return p;
+  }
+  void swap(DBuf& o) {
+    std::swap(p, o.p);
+    std::swap(cap, o.cap);
+  }
+};
+
+// Canonical device sparse matrix: CSC (gene lines) plus its CSR mirror (cell lines).
+// 0-based; both orientations sorted inside a line.
+struct SpMat {
+  int N = 0, M = 0;
+  size_t nnz = 0;
+  DBuf<uint32_t> colptr, rowval, rowptr, colidx;
+  DBuf<float> val, rval;
+  void swap(SpMat& o) {
+    std::swap(N, o.N); std::swap(M, o.M); std::swap(nnz, o.nnz);
+    colptr.swap(o.colptr); rowval.swap(o.rowval); rowptr.swap(o.rowptr); colidx.swap(o.colidx);
+    val.swap(o.val); rval.swap(o.rval);
+  }
+};
+
+// Per-matrix normalisation statistics, all Float64 on device.
+struct NormStats {
+  DBuf<double> tgc, l2, inv_s;      // per cell: r_i, l_i, 1/s_i
+  DBuf<float> inv_s_f;              // float copy streamed by the densify kernels
+  DBuf<double> ybar, sigma, mu, cent;  // per gene
+  DBuf<float> mu_f, cent_f, inv_sigma_f;
+  DBuf<double> scalars;             // [0]=|mu|^2 [1]=mean(l) [2]=sum(1/s)
+};
+
+struct Workspace;  // sparse scratch, defined in sparse.cu
+
+// ---- sparse.cu ----
+void build_csr_mirror(SpMat& A, cudaStream_t st);
+void upload_csc(SpMat& A, int N, int M, size_t nnz, const uint32_t* colptr, const uint32_t* rowval,
+                const float* val, int index_base, cudaStream_t st);
+// out = canonical( base (+ optional value override) + COO additions with value 1 )
+void perturb_merge(const SpMat& base, const uint32_t* d_add_row, const uint32_t* d_add_col, size_t n_add,
+                   bool binarise, SpMat& out, cudaStream_t st);
+// out = canonical( (rows[t], col(t), val[perm[t]]) ) : duplicates summed
+void permute_null(const SpMat& base, const uint32_t* d_perm, const uint32_t* d_rows, SpMat& out, cudaStream_t st);
+// device-side draws (Feistel bijections; see draws.cu)
+void draw_null_device(const SpMat& base, uint64_t seed, SpMat& out, cudaStream_t st);
+size_t draw_zero_candidates_device(const SpMat& base, uint64_t seed, DBuf<uint32_t>& z1, DBuf<uint32_t>& z2,
+                                   cudaStream_t st);
+void draw_subset_device(const uint32_t* z1, const uint32_t* z2, size_t n_cand, size_t n_take, uint64_t seed,
+                        uint32_t* out_row, uint32_t* out_col, cudaStream_t st);
+void gather_pairs(const uint32_t* z1, const uint32_t* z2, const uint32_t* d_idx, size_t n, uint32_t* out_row,
+                  uint32_t* out_col, cudaStream_t st);
+double noise_baseline_device(int nm, int n_rep, uint64_t seed, cudaStream_t st);
+
+// ---- normalize.cu ----
+void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st);
+// layout 0: gene-major out[M][ld] (column-major N x M); 1: cell-major out[N][ld]
+void densify(const SpMat& A, const NormStats& S, int layout, size_t ld, __half* out_hi, __half* out_lo,
+             cudaStream_t st);
+
+// ---- gemm_umma.cu ----
+struct GemmOperand {
+  const __half* hi = nullptr;
+  const __half* lo = nullptr;  // optional low-order part (split mode)
+  int rows = 0;                // logical rows
+  int64_t K = 0;               // contraction length
+  int64_t ld = 0;              // elements between rows (multiple of 8)
+};
+enum class Epilogue : int { Store = 0, StoreTransposed = 1, ColAbsMax = 2 };
+struct GemmArgs {
+  GemmOperand A, B;
+  bool syrk = false;        // B == A, lower-triangular tile schedule, mirrored store
+  float alpha = 1.f;
+  Epilogue epi = Epilogue::Store;
+  float* C = nullptr;       // Store: C[m*ldc+n]; StoreTransposed: C[n*ldc+m]; ColAbsMax: C[n] (pre-zeroed)
+  int64_t ldc = 0;
+  int splits = 1;           // split-K: partial s written at C + s*split_stride (caller reduces)
+  int64_t split_stride = 0;
+  int cta_group = 2;        // 1 or 2
+};
+void gemm_umma(const GemmArgs& a, cudaStream_t st);
+void split_f32_to_f16(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st);
+void strided_split_f32_to_f16(const float* in, int rows, int64_t cols, int64_t ld_in, int64_t ld_out, __half* hi,
+                              __half* lo, cudaStream_t st);
+void reduce_splits(const float* part, int splits, int64_t stride, size_t n, float scale, float* out, cudaStream_t st);
+int sm_count();
+
+}  // namespace scl

@@ -1,0 +1,171 @@
+// Full-spectrum symmetric eigensolve (the one declared library dependency: cuSOLVER syevd,
+// as src/scLENS.jl:377) and the scalar Marchenko-Pastur / Tracy-Widom fit (:390-487).
+#include <cusolverDn.h>
+#include <algorithm>
+#include <cmath>
+#include "common.cuh"
+#include "eigen.h"
+#include "tmp.cuh"
+
+namespace scl {
+
+#define SCL_SOLVER(x)                                                                         \
+  do {                                                                                        \
+    cusolverStatus_t s_ = (x);                                                                \
+    if (s_ != CUSOLVER_STATUS_SUCCESS)                                                        \
+      throw scl::Error(-3, std::string(#x) + ": cusolver status " + std::to_string((int)s_)); \
+  } while (0)
+
+struct Solver::Impl {
+  cusolverDnHandle_t h = nullptr;
+  DBuf<float> work;
+  DBuf<double> dwork;
+  DBuf<int> info;
+};
+
+Solver::Solver(cudaStream_t st) : impl(new Impl) {
+  SCL_SOLVER(cusolverDnCreate(&impl->h));
+  SCL_SOLVER(cusolverDnSetStream(impl->h, st));
+  impl->info.ensure(1);
+}
+Solver::~Solver() {
+  if (impl->h) cusolverDnDestroy(impl->h);
+  delete impl;
+}
+
+// A (n x n, symmetric, full) is overwritten by the eigenvectors when vectors=true.
+void Solver::syevd(float* dA, int n, float* dW, bool vectors, cudaStream_t st) {
+  int lwork = 0;
+  cusolverEigMode_t jobz = vectors ? CUSOLVER_EIG_MODE_VECTOR : CUSOLVER_EIG_MODE_NOVECTOR;
+  SCL_SOLVER(cusolverDnSsyevd_bufferSize(impl->h, jobz, CUBLAS_FILL_MODE_UPPER, n, dA, n, dW, &lwork));
+  impl->work.ensure((size_t)lwork);
+  SCL_SOLVER(cusolverDnSsyevd(impl->h, jobz, CUBLAS_FILL_MODE_UPPER, n, dA, n, dW, impl->work.p, lwork, impl->info.p));
+  int info = 0;
+  SCL_CUDA(cudaMemcpyAsync(&info, impl->info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  if (info != 0) throw Error(-3, "cusolverDnSsyevd did not converge, info=" + std::to_string(info));
+}
+
+void Solver::dsyevd_small(double* dA, int n, double* dW, cudaStream_t st) {
+  int lwork = 0;
+  SCL_SOLVER(cusolverDnDsyevd_bufferSize(impl->h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, dA, n, dW, &lwork));
+  impl->dwork.ensure((size_t)lwork);
+  SCL_SOLVER(cusolverDnDsyevd(impl->h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, dA, n, dW, impl->dwork.p,
+                              lwork, impl->info.p));
+  int info = 0;
+  SCL_CUDA(cudaMemcpyAsync(&info, impl->info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  if (info != 0) throw Error(-3, "cusolverDnDsyevd did not converge, info=" + std::to_string(info));
+}
+
+// ---- Marchenko-Pastur / Tracy-Widom (host, Float64 on the Float32 eigenvalues) ------------
+namespace {
+struct MpParams {
+  double m1, m2, gamma, b_plus, b_minus;
+};
+MpParams mp_parameters(const std::vector<double>& L) {   // _mp_parameters :390-408
+  MpParams p{};
+  double s1 = 0, s2 = 0;
+  for (double v : L) { s1 += v; s2 += v * v; }
+  const double n = (double)L.size();
+  p.m1 = s1 / n;
+  p.m2 = s2 / n;
+  p.gamma = p.m2 / (p.m1 * p.m1) - 1.0;
+  const double sg = std::sqrt(p.gamma);
+  p.b_plus = p.m1 * (1 + sg) * (1 + sg);
+  p.b_minus = p.m1 * (1 - sg) * (1 - sg);
+  return p;
+}
+std::vector<double> window(const std::vector<double>& L, double lo, double hi) {
+  std::vector<double> out;
+  for (double v : L)
+    if (lo < v && v < hi) out.push_back(v);   // strict both sides (:431)
+  return out;
+}
+}  // namespace
+
+MpFit mp_fit(const float* L, int nL, const float* Lr, int nLr) {
+  SCL_REQUIRE(nL > 1 && nLr > 1, "too few eigenvalues for the MP fit");
+  std::vector<double> Ld(L, L + nL), Lrd(Lr, Lr + nLr);
+  MpFit out{};
+  // _mp_calculation :424-459
+  MpParams pr = mp_parameters(Lrd);
+  double b_plus = pr.b_plus, b_minus = pr.b_minus;
+  std::vector<double> Lu = window(Ld, b_minus, b_plus);
+  SCL_REQUIRE(!Lu.empty(), "no eigenvalue inside the null-matrix MP window");
+  MpParams q = mp_parameters(Lu);
+  double new_b_plus = q.b_plus, new_b_minus = q.b_minus;
+  int iter = 0;
+  const double eps = 1e-6, eta = 1.0;
+  const int max_iter = 10000;
+  while (true) {
+    double loss = (1 - new_b_plus / b_plus) * (1 - new_b_plus / b_plus);
+    ++iter;
+    if (loss <= eps || iter == max_iter) break;
+    double gradient = new_b_plus - b_plus;
+    new_b_plus = b_plus + eta * gradient;
+    Lu = window(Ld, new_b_minus, new_b_plus);
+    b_plus = new_b_plus;
+    b_minus = new_b_minus;
+    SCL_REQUIRE(!Lu.empty(), "MP window became empty");
+    q = mp_parameters(Lu);
+    new_b_plus = q.b_plus;
+    new_b_minus = q.b_minus;
+  }
+  out.b_plus = new_b_plus;
+  out.b_minus = new_b_minus;
+  out.iters = iter;
+  for (int i = 0; i < nL; ++i)
+    if (new_b_minus < (double)L[i] && (double)L[i] < new_b_plus) out.L_mp.push_back(L[i]);
+  SCL_REQUIRE(out.L_mp.size() > 1, "MP fit selected fewer than two eigenvalues");
+  // _tw :461-467
+  std::vector<double> Lmpd(out.L_mp.begin(), out.L_mp.end());
+  MpParams pm = mp_parameters(Lmpd);
+  const double gamma = pm.gamma;
+  const double p = (double)nL / gamma;
+  const double sigma = 1.0 / std::pow(p, 2.0 / 3.0) * std::pow(gamma, 5.0 / 6.0) * std::pow(1 + std::sqrt(gamma), 4.0 / 3.0);
+  out.lambda_c = pm.m1 * (1 + std::sqrt(gamma)) * (1 + std::sqrt(gamma)) + sigma;
+  out.gamma = gamma;
+  out.n_signal = 0;
+  for (int i = 0; i < nL; ++i)
+    if ((double)L[i] > out.lambda_c) ++out.n_signal;   // strict (:541)
+  // mp_check :469-487
+  {
+    double mn = *std::min_element(Lmpd.begin(), Lmpd.end()) - 1, mx = *std::max_element(Lmpd.begin(), Lmpd.end()) + 1;
+    const int nb = 99;
+    std::vector<double> edges(nb + 1), cnt(nb, 0.0);
+    for (int i = 0; i <= nb; ++i) edges[i] = mn + (mx - mn) * (double)i / (double)nb;
+    for (double v : Lmpd) {
+      int b = (int)std::floor((v - mn) / (mx - mn) * nb);
+      b = std::max(0, std::min(nb - 1, b));
+      // guard the floating-point edge: bin i is [e_i, e_i+1)
+      while (b > 0 && v < edges[b]) --b;
+      while (b < nb - 1 && v >= edges[b + 1]) ++b;
+      cnt[b] += 1;
+    }
+    const double tot = (double)Lmpd.size();
+    double acc = 0, acc2 = 0, D = 0;
+    std::vector<double> c2(nb);
+    const double sg = std::sqrt(pm.gamma);
+    (void)sg;
+    for (int i = 0; i < nb; ++i) {
+      double x = 0.5 * (edges[i] + edges[i + 1]);
+      double pdf = 0;
+      if (pm.b_minus < x && x < pm.b_plus)
+        pdf = std::sqrt((pm.b_plus - x) * (x - pm.b_minus)) / (2 * pm.m1 * M_PI * pm.gamma * x);
+      acc2 += pdf;
+      c2[i] = acc2;
+    }
+    const double mxc = *std::max_element(c2.begin(), c2.end());
+    for (int i = 0; i < nb; ++i) {
+      acc += cnt[i] / tot;
+      D = std::max(D, std::fabs(acc - c2[i] / mxc));
+    }
+    const double c_alpha = std::sqrt(-0.5 * std::log(0.05));
+    out.ks_static = D;
+    out.pass = D <= c_alpha * std::sqrt((double)(nb + nb) / nb / nb);
+  }
+  return out;
+}
+
+}  // namespace scl

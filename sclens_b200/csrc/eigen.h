@@ -1,0 +1,28 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <vector>
+
+namespace scl {
+
+struct Solver {
+  struct Impl;
+  Impl* impl;
+  explicit Solver(cudaStream_t st);
+  ~Solver();
+  Solver(const Solver&) = delete;
+  Solver& operator=(const Solver&) = delete;
+  // cusolverDnSsyevd('V'|'N','U'): eigenvalues ascending in dW, eigenvectors overwrite dA (col-major)
+  void syevd(float* dA, int n, float* dW, bool vectors, cudaStream_t st);
+  void dsyevd_small(double* dA, int n, double* dW, cudaStream_t st);
+};
+
+struct MpFit {
+  std::vector<float> L_mp;
+  double lambda_c, b_plus, b_minus, gamma, ks_static;
+  int iters, n_signal;
+  bool pass;
+};
+// _mp_calculation(L, Lr) + _tw + mp_check; caller passes Lr already without its largest value (:537)
+MpFit mp_fit(const float* L, int nL, const float* Lr, int nLr);
+
+}  // namespace scl

@@ -1,0 +1,589 @@
+// Orchestration of the sclens() path on one GPU (src/scLENS.jl:649-832): everything between
+// "counts in" and "results out" stays device-resident.  Stage boundaries follow the
+// reference: run_signal == :664-706, run_robustness == :709-819.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include "handle.h"
+#include "tmp.cuh"
+
+namespace scl {
+
+namespace {
+
+inline size_t round8(size_t x) { return (x + 7) / 8 * 8; }
+
+struct Timer {
+  cudaEvent_t a, b;
+  cudaStream_t st;
+  explicit Timer(cudaStream_t s) : st(s) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+  }
+  ~Timer() {
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+  double stop() {
+    cudaEventRecord(b, st);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventRecord(a, st);
+    return ms;
+  }
+};
+
+// rows of `src` (stride ld_src, may be negative to walk backwards) -> dst rows (stride ld_dst)
+__global__ void k_copy_rows(const float* __restrict__ src, long long ld_src, float* __restrict__ dst, long long ld_dst,
+                            int rows, int cols) {
+  for (int r = blockIdx.y; r < rows; r += gridDim.y)
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x)
+      dst[(long long)r * ld_dst + c] = src[(long long)r * ld_src + c];
+}
+
+__global__ void k_gather_rows(const float* __restrict__ src, const int* __restrict__ row_idx, float* __restrict__ dst,
+                              int rows, long long cols) {
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    const float* s = src + (long long)row_idx[r] * cols;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < cols; c += (long long)gridDim.x * blockDim.x)
+      dst[(long long)r * cols + c] = s[c];
+  }
+}
+
+// unit-normalise every row (one block per row), Float64 accumulation  (mapslices(s -> s/norm(s)) :505, :558)
+__global__ void __launch_bounds__(256) k_normalize_rows(float* __restrict__ a, int rows, long long cols) {
+  __shared__ double red[8];
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    float* p = a + (long long)r * cols;
+    double s = 0;
+    for (long long c = threadIdx.x; c < cols; c += blockDim.x) s += (double)p[c] * (double)p[c];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    const float inv = (float)(1.0 / sqrt(t));
+    for (long long c = threadIdx.x; c < cols; c += blockDim.x) p[c] *= inv;
+  }
+}
+
+void copy_rows(const float* src, long long ld_src, float* dst, long long ld_dst, int rows, int cols, cudaStream_t st) {
+  if (!rows) return;
+  dim3 grid((unsigned)std::min((cols + 255) / 256, 64), (unsigned)std::min(rows, 65535));
+  k_copy_rows<<<grid, 256, 0, st>>>(src, ld_src, dst, ld_dst, rows, cols);
+  SCL_CUDA(cudaGetLastError());
+}
+
+void normalize_rows(float* a, int rows, long long cols, cudaStream_t st) {
+  if (!rows) return;
+  k_normalize_rows<<<std::min(rows, 148 * 8), 256, 0, st>>>(a, rows, cols);
+  SCL_CUDA(cudaGetLastError());
+}
+
+int cta_group_of(const scl_handle* h) { return h->cfg.cta_group == 1 ? 1 : 2; }
+
+// number of split-K partitions that fills the machine for a GEMM with `tiles` output tiles
+int pick_splits(int tiles, int64_t K, int cta_group) {
+  int units = sm_count() / cta_group;
+  int kblocks = (int)((K + 63) / 64);
+  int s = std::max(1, units / std::max(1, tiles));
+  return std::max(1, std::min(s, std::max(1, kblocks / 4)));
+}
+
+// C (fp32, host-visible layout given by epi) = alpha * A * B^T through split-K partials.
+void gemm_splitk(scl_handle* h, const GemmOperand& A, const GemmOperand& B, bool syrk, float alpha, Epilogue epi,
+                 float* dC, int64_t ldc, size_t c_elems) {
+  const int cg = cta_group_of(h);
+  const int tile_m = 128 * cg;
+  const int tiles = ((A.rows + tile_m - 1) / tile_m) * ((B.rows + 255) / 256);
+  const int splits = pick_splits(tiles, A.K, cg);
+  GemmArgs g;
+  g.A = A; g.B = B; g.syrk = syrk; g.epi = epi; g.ldc = ldc; g.cta_group = cg;
+  if (splits == 1) {
+    g.alpha = alpha; g.C = dC; g.splits = 1;
+    gemm_umma(g, h->st);
+    return;
+  }
+  Tmp<float> part((size_t)splits * c_elems, h->st);
+  SCL_CUDA(cudaMemsetAsync(part.p, 0, (size_t)splits * c_elems * sizeof(float), h->st));
+  g.alpha = 1.f; g.C = part.p; g.splits = splits; g.split_stride = (int64_t)c_elems;
+  gemm_umma(g, h->st);
+  reduce_splits(part.p, splits, (int64_t)c_elems, c_elems, alpha, dC, h->st);
+}
+
+double quantile7(const std::vector<double>& sorted, double p) {
+  const size_t n = sorted.size();
+  if (n == 1) return sorted[0];
+  double hh = (double)(n - 1) * p;
+  size_t lo = (size_t)std::floor(hh);
+  if (lo >= n - 1) return sorted[n - 1];
+  return sorted[lo] + (hh - (double)lo) * (sorted[lo + 1] - sorted[lo]);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// normalise A and form its Wishart matrix on the smaller side:  dG = operand * operand^T * scale
+void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf<__half>& lo, float* dG, int nm,
+             float scale, bool split) {
+  compute_norm_stats(A, S, h->st);
+  const bool gene_side = A.N > A.M;                 // contract over cells (N > M) or over genes
+  const int rows = gene_side ? A.M : A.N;
+  const int64_t K = gene_side ? A.N : A.M;
+  const size_t ld = round8((size_t)K);
+  SCL_REQUIRE(rows == nm, "Gram size mismatch");
+  hi.ensure((size_t)rows * ld);
+  if (split) lo.ensure((size_t)rows * ld);
+  densify(A, S, gene_side ? 0 : 1, ld, hi.p, split ? lo.p : nullptr, h->st);
+  GemmArgs g;
+  g.A.hi = hi.p; g.A.lo = split ? lo.p : nullptr; g.A.rows = rows; g.A.K = K; g.A.ld = (int64_t)ld;
+  g.B = g.A;
+  g.syrk = true;
+  g.alpha = scale;
+  g.C = dG;
+  g.ldc = nm;
+  g.cta_group = cta_group_of(h);
+  gemm_umma(g, h->st);
+}
+
+// d[j] = max_i |<V_i, W_j>|  (:742) with V pre-converted to binary16 hi/lo rows
+static void corr_colabsmax_pre(scl_handle* h, const GemmOperand& V, const float* dW, int nw, int n, float* d_out) {
+  const size_t ld = (size_t)V.ld;
+  Tmp<__half> w_hi((size_t)nw * ld, h->st), w_lo((size_t)nw * ld, h->st);
+  strided_split_f32_to_f16(dW, nw, n, n, (int64_t)ld, w_hi.p, w_lo.p, h->st);
+  SCL_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nw * sizeof(float), h->st));
+  GemmArgs g;
+  g.A = V;
+  g.B.hi = w_hi.p; g.B.lo = w_lo.p; g.B.rows = nw; g.B.K = n; g.B.ld = (int64_t)ld;
+  g.epi = Epilogue::ColAbsMax;
+  g.C = d_out;
+  g.ldc = 0;
+  g.cta_group = cta_group_of(h);
+  gemm_umma(g, h->st);
+}
+
+void corr_colabsmax(scl_handle* h, const float* dV, int nv, const float* dW, int nw, int n, float* d_out) {
+  const size_t ld = round8((size_t)n);
+  Tmp<__half> v_hi((size_t)nv * ld, h->st), v_lo((size_t)nv * ld, h->st);
+  strided_split_f32_to_f16(dV, nv, n, n, (int64_t)ld, v_hi.p, v_lo.p, h->st);
+  GemmOperand V;
+  V.hi = v_hi.p; V.lo = v_lo.p; V.rows = nv; V.K = n; V.ld = (int64_t)ld;
+  corr_colabsmax_pre(h, V, dW, nw, n, d_out);
+}
+
+// out[k][N] = normalise_rows( Vk[k][M] * Xtilde^T )  i.e. columns X*v / |X*v|  (:503-505, :556-558)
+// dVrows: pointer to the first wanted eigenvector, ld_v elements between consecutive wanted ones
+static void back_project(scl_handle* h, const SpMat& A, const NormStats& S, const float* dVrows, long long ld_v, int k,
+                         float* d_out) {
+  const int N = A.N, M = A.M;
+  const size_t ldm = round8((size_t)M);
+  Tmp<__half> x_hi((size_t)N * ldm, h->st), x_lo((size_t)N * ldm, h->st);
+  densify(A, S, 1, ldm, x_hi.p, x_lo.p, h->st);
+  Tmp<__half> v_hi((size_t)k * ldm, h->st), v_lo((size_t)k * ldm, h->st);
+  strided_split_f32_to_f16(dVrows, k, M, ld_v, (int64_t)ldm, v_hi.p, v_lo.p, h->st);
+  GemmArgs g;
+  g.A.hi = x_hi.p; g.A.lo = x_lo.p; g.A.rows = N; g.A.K = M; g.A.ld = (int64_t)ldm;
+  g.B.hi = v_hi.p; g.B.lo = v_lo.p; g.B.rows = k; g.B.K = M; g.B.ld = (int64_t)ldm;
+  g.epi = Epilogue::StoreTransposed;
+  g.C = d_out;
+  g.ldc = N;
+  g.cta_group = cta_group_of(h);
+  gemm_umma(g, h->st);
+  normalize_rows(d_out, k, N, h->st);
+}
+
+// ---------------------------------------------------------------------------------------
+void run_signal(scl_handle* h) {
+  SCL_REQUIRE(h->have_X, "scl_set_counts_csc must be called first");
+  cudaStream_t st = h->st;
+  const SpMat& X = h->X;
+  const int N = X.N, M = X.M, nm = std::min(N, M);
+  const bool split = h->cfg.gram_mode == SCL_GRAM_FP16X3;
+  scl_signal_info& info = h->sinfo;
+  info = scl_signal_info{};
+  info.N = N; info.M = M; info.nm = nm;
+  info.gram_mode_used = h->cfg.gram_mode;
+  h->signal_done = false;
+  h->robust_done = false;
+
+  DBuf<__half> op_hi, op_lo;
+  DBuf<float> G, W;
+  G.ensure((size_t)nm * nm);
+  W.ensure(nm);
+  Timer tm(st);
+  // --- data matrix: normalise (:677-696), Gram (:529/:569), eigen (:530/:570)
+  gram_of(h, X, h->S_main, op_hi, op_lo, G.p, nm, 1.0f / (float)M, split);
+  info.t_normalize_ms = 0;  // fused into the Gram timing below (one stream); see bench for per-kernel times
+  info.t_gram_ms += tm.stop();
+  h->solver->syevd(G.p, nm, W.p, true, st);
+  info.t_syevd_ms += tm.stop();
+  h->L.resize(nm);
+  SCL_CUDA(cudaMemcpyAsync(h->L.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
+  // rec_vals (:676-695)
+  h->rec_tgc.resize(N); h->rec_l2.resize(N); h->rec_mean.resize(M); h->rec_std.resize(M); h->rec_cent.resize(M);
+  SCL_CUDA(cudaMemcpyAsync(h->rec_tgc.data(), h->S_main.tgc.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaMemcpyAsync(h->rec_l2.data(), h->S_main.l2.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaMemcpyAsync(h->rec_mean.data(), h->S_main.ybar.p, M * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaMemcpyAsync(h->rec_std.data(), h->S_main.sigma.p, M * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaMemcpyAsync(h->rec_cent.data(), h->S_main.cent.p, M * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  for (float v : h->L)
+    if (!std::isfinite(v)) throw Error(SCL_ERR_CUSOLVER, "non-finite eigenvalue (the reference's CPU fallback :379-381 is an error here)");
+  tm.stop();
+
+  // --- null matrix (:701) and its spectrum (:531-532/:571-572)
+  if (h->have_null_draws)
+    permute_null(X, h->null_perm.p, h->null_rows.p, h->Xnull, st);
+  else
+    draw_null_device(X, h->cfg.seed, h->Xnull, st);
+  SCL_REQUIRE(h->Xnull.N == N && h->Xnull.M == M, "null matrix shape");
+  info.t_null_ms += tm.stop();
+  {
+    NormStats Sn;
+    DBuf<float> G2, W2;
+    G2.ensure((size_t)nm * nm);
+    W2.ensure(nm);
+    gram_of(h, h->Xnull, Sn, op_hi, op_lo, G2.p, nm, 1.0f / (float)M, split);
+    info.t_gram_ms += tm.stop();
+    h->solver->syevd(G2.p, nm, W2.p, false, st);
+    info.t_syevd_ms += tm.stop();
+    std::vector<float> Lr(nm);
+    SCL_CUDA(cudaMemcpyAsync(Lr.data(), W2.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+    // --- MP / TW fit (:537-538/:576-577); Lr[1:end-1] drops the largest null eigenvalue
+    auto c0 = std::chrono::steady_clock::now();
+    MpFit fit = mp_fit(h->L.data(), nm, Lr.data(), nm - 1);
+    info.t_fit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count();
+    h->Lmp = fit.L_mp;
+    info.n_signal = fit.n_signal;
+    info.n_Lmp = (int)fit.L_mp.size();
+    info.mp_iters = fit.iters;
+    info.pass = fit.pass ? 1 : 0;
+    info.lambda_c = fit.lambda_c;
+    info.b_plus = fit.b_plus;
+    info.b_minus = fit.b_minus;
+    info.ks_static = fit.ks_static;
+  }
+  if (h->cfg.verbose) printf("(Using gpu) number of signal ev: %d\n", info.n_signal);
+  tm.stop();
+
+  // --- signal eigenpairs, descending (:541-551), cell-space vectors (:556-558)
+  const int k = info.n_signal;
+  h->nL.resize(k);
+  for (int i = 0; i < k; ++i) h->nL[i] = h->L[nm - 1 - i];
+  h->d_nV.ensure((size_t)std::max(1, k) * N);
+  if (k > 0) {
+    const float* top = G.p + (size_t)(nm - 1) * nm;   // eigenvector of the largest eigenvalue; walk backwards
+    if (N > M)
+      back_project(h, X, h->S_main, top, -(long long)nm, k, h->d_nV.p);
+    else
+      copy_rows(top, -(long long)nm, h->d_nV.p, N, k, N, st);
+  }
+  SCL_CUDA(cudaStreamSynchronize(st));
+  info.t_backproject_ms = tm.stop();
+  h->signal_done = true;
+}
+
+// ---------------------------------------------------------------------------------------
+// Robustness scoring (:786-806).  d_nV: [k][N]; d_sets: [n_perturb][min_pc][N].
+void score_sets(scl_handle* h, int N, int k, int min_pc, int n_perturb, const float* d_nV, const float* d_sets,
+                double th, std::vector<float>& b_, std::vector<double>& m_scores, std::vector<double>& sd_scores,
+                std::vector<int32_t>& sig) {
+  cudaStream_t st = h->st;
+  const size_t ld = round8((size_t)N);
+  const int P = n_perturb, tot = P * min_pc;
+  // |nV' * nV_set[r]| for all r at once (:788)
+  Tmp<__half> a_hi((size_t)k * ld, st), a_lo((size_t)k * ld, st), s_hi((size_t)tot * ld, st), s_lo((size_t)tot * ld, st);
+  strided_split_f32_to_f16(d_nV, k, N, N, (int64_t)ld, a_hi.p, a_lo.p, st);
+  strided_split_f32_to_f16(d_sets, tot, N, N, (int64_t)ld, s_hi.p, s_lo.p, st);
+  GemmOperand A, B;
+  A.hi = a_hi.p; A.lo = a_lo.p; A.rows = k; A.K = N; A.ld = (int64_t)ld;
+  B.hi = s_hi.p; B.lo = s_lo.p; B.rows = tot; B.K = N; B.ld = (int64_t)ld;
+  Tmp<float> c1((size_t)k * tot, st);
+  gemm_splitk(h, A, B, false, 1.f, Epilogue::Store, c1.p, tot, (size_t)k * tot);
+  std::vector<float> hc1((size_t)k * tot);
+  SCL_CUDA(cudaMemcpyAsync(hc1.data(), c1.p, hc1.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> rows((size_t)P * k);   // row (r*k + i) of the gathered stack = sets[r][a_b[i,r]]
+  for (int r = 0; r < P; ++r)
+    for (int i = 0; i < k; ++i) {
+      int best = 0;
+      float bv = -1.f;
+      for (int j = 0; j < min_pc; ++j) {
+        float v = std::fabs(hc1[(size_t)i * tot + (size_t)r * min_pc + j]);
+        if (v > bv) { bv = v; best = j; }   // first maximum (argmax, Appendix A14)
+      }
+      rows[(size_t)r * k + i] = r * min_pc + best;
+    }
+  // sub_nVset stack and all pairwise |sub_i' sub_j| (:790-795)
+  const int R = P * k;
+  Tmp<int> d_rows(R, st);
+  SCL_CUDA(cudaMemcpyAsync(d_rows.p, rows.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+  Tmp<float> sub((size_t)R * N, st);
+  {
+    dim3 grid((unsigned)std::min((N + 255) / 256, 64), (unsigned)std::min(R, 65535));
+    k_gather_rows<<<grid, 256, 0, st>>>(d_sets, d_rows.p, sub.p, R, N);
+    SCL_CUDA(cudaGetLastError());
+  }
+  Tmp<__half> u_hi((size_t)R * ld, st), u_lo((size_t)R * ld, st);
+  strided_split_f32_to_f16(sub.p, R, N, N, (int64_t)ld, u_hi.p, u_lo.p, st);
+  GemmOperand U;
+  U.hi = u_hi.p; U.lo = u_lo.p; U.rows = R; U.K = N; U.ld = (int64_t)ld;
+  Tmp<float> c2((size_t)R * R, st);
+  gemm_splitk(h, U, U, true, 1.f, Epilogue::Store, c2.p, R, (size_t)R * R);
+  std::vector<float> hc2((size_t)R * R);
+  SCL_CUDA(cudaMemcpyAsync(hc2.data(), c2.p, hc2.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  const int n_pairs = P * (P - 1) / 2;
+  b_.assign((size_t)k * n_pairs, 0.f);
+  int pair = 0;
+  for (int a = 0; a < P; ++a)
+    for (int b = a + 1; b < P; ++b, ++pair)
+      for (int i = 0; i < k; ++i) {
+        float mx = 0.f;
+        for (int j = 0; j < k; ++j) mx = std::max(mx, std::fabs(hc2[(size_t)(a * k + i) * R + (size_t)(b * k + j)]));
+        b_[(size_t)pair * k + i] = mx;   // column-major k x n_pairs
+      }
+  // Tukey fence, median, corrected std (:797-803)
+  const double th_ = std::cos(th * M_PI / 180.0);
+  m_scores.assign(k, 0.0);
+  sd_scores.assign(k, 0.0);
+  sig.clear();
+  for (int i = 0; i < k; ++i) {
+    std::vector<double> row(n_pairs);
+    for (int q = 0; q < n_pairs; ++q) row[q] = (double)b_[(size_t)q * k + i];
+    std::vector<double> srt = row;
+    std::sort(srt.begin(), srt.end());
+    const double q1 = quantile7(srt, 0.25), q3 = quantile7(srt, 0.75), iqr = q3 - q1;
+    std::vector<double> f;
+    for (double v : srt)
+      if (q1 - 1.5 * iqr <= v && v <= q3 + 1.5 * iqr) f.push_back(v);
+    const size_t n = f.size();
+    double med = n ? ((n & 1) ? f[n / 2] : 0.5 * (f[n / 2 - 1] + f[n / 2])) : NAN;
+    double mean = 0;
+    for (double v : f) mean += v;
+    mean /= (double)std::max<size_t>(1, n);
+    double ss = 0;
+    for (double v : f) ss += (v - mean) * (v - mean);
+    m_scores[i] = med;
+    sd_scores[i] = n > 1 ? std::sqrt(ss / (double)(n - 1)) : NAN;
+    if (med > th_) sig.push_back(i);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+namespace {
+
+// additions (row, col) for one perturbation: injected sample indices or a device draw
+void make_additions(scl_handle* h, std::deque<std::vector<uint32_t>>& injected, size_t n_add, uint64_t draw_seed,
+                    uint32_t* d_row, uint32_t* d_col) {
+  if (!injected.empty()) {
+    std::vector<uint32_t> s = std::move(injected.front());
+    injected.pop_front();
+    SCL_REQUIRE(s.size() == n_add, "injected sample has the wrong length for this sparsity step");
+    Tmp<uint32_t> d_idx(n_add, h->st);
+    SCL_CUDA(cudaMemcpyAsync(d_idx.p, s.data(), n_add * sizeof(uint32_t), cudaMemcpyHostToDevice, h->st));
+    gather_pairs(h->z1.p, h->z2.p, d_idx.p, n_add, d_row, d_col, h->st);
+    SCL_CUDA(cudaStreamSynchronize(h->st));   // `s` is released on return
+  } else {
+    draw_subset_device(h->z1.p, h->z2.p, h->n_cand, n_add, draw_seed, d_row, d_col, h->st);
+  }
+}
+
+int first_positive(const std::vector<float>& L) {
+  int i = 0;
+  while (i < (int)L.size() && !(L[i] > 0.f)) ++i;   // L .> 0 (:495)
+  return i;
+}
+
+}  // namespace
+
+void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
+  SCL_REQUIRE(h->signal_done, "scl_run_signal must succeed first");
+  if (h->sinfo.n_signal == 0) throw Error(SCL_ERR_NOSIGNAL, "warning: There is no signal");
+  SCL_REQUIRE(n_perturb >= 2, "n_perturb must be >= 2");
+  cudaStream_t st = h->st;
+  const SpMat& X = h->X;
+  const int N = X.N, M = X.M, nm = std::min(N, M);
+  const bool split = h->cfg.gram_mode == SCL_GRAM_FP16X3;
+  scl_robust_info& info = h->rinfo;
+  info = scl_robust_info{};
+  h->robust_done = false;
+  Timer tm(st);
+
+  // --- noise baseline (:709-713)
+  const double p_th = h->have_pth ? h->p_th : noise_baseline_device(nm, 5000, h->cfg.seed, st);
+  info.p_th = p_th;
+  if (h->cfg.verbose) printf("spth_: %.17g\n", p_th);
+  if (!h->have_zc) {
+    h->n_cand = draw_zero_candidates_device(X, h->cfg.seed, h->z1, h->z2, st);
+  }
+  info.t_baseline_ms = tm.stop();
+
+  DBuf<__half> op_hi, op_lo;
+  DBuf<float> G, W;
+  G.ensure((size_t)nm * nm);
+  W.ensure(nm);
+  SpMat Xp;
+  NormStats Sp;
+  std::vector<float> Lh(nm);
+  const float bin_scale = 1.0f / (float)(N > M ? N : M);   // transposed call when N > M (Appendix A9)
+
+  // --- reference basis of the binarised matrix (:717-721)
+  perturb_merge(X, nullptr, nullptr, 0, true, Xp, st);
+  gram_of(h, Xp, Sp, op_hi, op_lo, G.p, nm, bin_scale, split);
+  double t_gram = tm.stop();
+  h->solver->syevd(G.p, nm, W.p, true, st);
+  info.t_search_syevd_ms += tm.stop();
+  SCL_CUDA(cudaMemcpyAsync(Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  const int i0r = first_positive(Lh);
+  const int npos_ref = nm - i0r;
+  SCL_REQUIRE(npos_ref >= 10, "binarised matrix has too few positive eigenvalues");
+  const int n_2 = (int)std::nearbyint((double)npos_ref / 2.0);   // round(Int, .) ties-to-even (:722)
+  const size_t ldv = round8((size_t)nm);
+  DBuf<__half> vr_hi, vr_lo;
+  vr_hi.ensure((size_t)npos_ref * ldv);
+  vr_lo.ensure((size_t)npos_ref * ldv);
+  strided_split_f32_to_f16(G.p + (size_t)i0r * nm, npos_ref, nm, nm, (int64_t)ldv, vr_hi.p, vr_lo.p, st);
+  GemmOperand Vr;
+  Vr.hi = vr_hi.p; Vr.lo = vr_lo.p; Vr.rows = npos_ref; Vr.K = nm; Vr.ld = (int64_t)ldv;
+
+  // --- sparsity search (:715-762)
+  double p_ = 0.999;
+  const int tank_n = 5;
+  std::vector<double> tank2;   // row 2 of tank_ (second smallest of d_arr per step)
+  h->trace_p.clear();
+  h->trace_d.clear();
+  int step = 0;
+  Tmp<float> d_d(nm, st);
+  std::vector<float> d_host;
+  while (true) {
+    const long long nnzidx = (long long)std::nearbyint((1.0 - p_) * (double)M * (double)N);   // :726
+    if ((long long)h->n_cand < nnzidx) {
+      p_ += p_step;
+      break;
+    }
+    Tmp<uint32_t> a_row((size_t)std::max<long long>(1, nnzidx), st), a_col((size_t)std::max<long long>(1, nnzidx), st);
+    make_additions(h, h->search_sples, (size_t)nnzidx, h->cfg.seed + 0x5eed0000ull + (uint64_t)step, a_row.p, a_col.p);
+    perturb_merge(X, a_row.p, a_col.p, (size_t)nnzidx, true, Xp, st);
+    gram_of(h, Xp, Sp, op_hi, op_lo, G.p, nm, bin_scale, split);
+    t_gram += tm.stop();
+    h->solver->syevd(G.p, nm, W.p, true, st);
+    info.t_search_syevd_ms += tm.stop();
+    SCL_CUDA(cudaMemcpyAsync(Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+    const int i0 = first_positive(Lh);
+    const int npos = nm - i0;
+    SCL_REQUIRE(npos >= n_2 + 1, "perturbed matrix has too few positive eigenvalues");
+    const int nw = n_2 + 1;                                  // nV_2[:, end-n_2:end] (Appendix A13)
+    corr_colabsmax_pre(h, Vr, G.p + (size_t)i0 * nm, nw, nm, d_d.p);
+    d_host.resize(nw);
+    SCL_CUDA(cudaMemcpyAsync(d_host.data(), d_d.p, nw * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+    SCL_REQUIRE(nw >= 5, "too few noise vectors");
+    std::partial_sort(d_host.begin(), d_host.begin() + 5, d_host.end());
+    tank2.push_back((double)d_host[1]);
+    h->trace_p.push_back(p_);
+    h->trace_d.push_back((double)d_host[1]);
+    if (h->cfg.verbose) printf("%.9g\n", (double)d_host[1]);
+    ++step;
+    int below = 0;
+    const int cnt = (int)tank2.size() < tank_n ? (int)tank2.size() : tank_n;
+    for (int q = 0; q < cnt; ++q)
+      if (tank2[tank2.size() - 1 - q] < p_th) ++below;
+    if (below > tank_n - 1 || p_ < 0.9) {                    // :756
+      p_ += (double)(tank_n - 1) * p_step;
+      break;
+    }
+    p_ -= p_step;
+  }
+  info.n_search = step;
+  info.p_sel = p_;
+  info.t_search_ms = t_gram + tm.stop();
+  if (h->cfg.verbose) printf("Selected perturb sparisty: %.17g\n", p_);
+  vr_hi.release();
+  vr_lo.release();
+
+  // --- perturbations (:767-778)
+  const int k = h->sinfo.n_signal;
+  const int min_pc = (int)std::ceil((double)k * 1.5);
+  SCL_REQUIRE(min_pc <= nm / 2, "too many signals for the perturbation stage");
+  const long long n_add = (long long)std::nearbyint((1.0 - p_) * (double)M * (double)N);     // :772
+  SCL_REQUIRE((long long)h->n_cand >= n_add, "zero-candidate pool smaller than the perturbation size");
+  info.min_pc = min_pc;
+  info.n_add = n_add;
+  info.n_perturb = n_perturb;
+  h->d_sets.ensure((size_t)n_perturb * min_pc * N);
+  h->set_L.assign((size_t)n_perturb * min_pc, 0.f);
+  const bool exact = h->cfg.exact_perturb != 0;
+  Tmp<float> topL(min_pc, st), topV((size_t)min_pc * nm, st);
+  for (int r = 0; r < n_perturb; ++r) {
+    Tmp<uint32_t> a_row((size_t)std::max<long long>(1, n_add), st), a_col((size_t)std::max<long long>(1, n_add), st);
+    make_additions(h, h->perturb_sples, (size_t)n_add, h->cfg.seed + 0xbeef0000ull + (uint64_t)r, a_row.p, a_col.p);
+    perturb_merge(X, a_row.p, a_col.p, (size_t)n_add, false, Xp, st);                          // :774
+    gram_of(h, Xp, Sp, op_hi, op_lo, G.p, nm, 1.0f / (float)M, split);                         // :775 -> :492/:512
+    float* set_r = h->d_sets.p + (size_t)r * min_pc * N;
+    const float* vec0;
+    long long ldvec;
+    if (exact) {
+      h->solver->syevd(G.p, nm, W.p, true, st);
+      SCL_CUDA(cudaMemcpyAsync(Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
+      SCL_CUDA(cudaStreamSynchronize(st));
+      SCL_REQUIRE(nm - first_positive(Lh) >= min_pc, "too few positive eigenvalues in a replicate");
+      for (int i = 0; i < min_pc; ++i) h->set_L[(size_t)r * min_pc + i] = Lh[nm - 1 - i];
+      vec0 = G.p + (size_t)(nm - 1) * nm;
+      ldvec = -(long long)nm;
+    } else {
+      int iters = 0;
+      topk_subspace(h, G.p, nm, min_pc, topL.p, topV.p, &iters);
+      SCL_CUDA(cudaMemcpyAsync(&h->set_L[(size_t)r * min_pc], topL.p, min_pc * sizeof(float), cudaMemcpyDeviceToHost, st));
+      vec0 = topV.p;
+      ldvec = nm;
+    }
+    if (N > M)
+      back_project(h, Xp, Sp, vec0, ldvec, min_pc, set_r);
+    else
+      copy_rows(vec0, ldvec, set_r, N, min_pc, N, st);
+  }
+  SCL_CUDA(cudaStreamSynchronize(st));
+  info.t_perturb_ms = tm.stop();
+
+  // --- robustness scores (:786-807)
+  score_sets(h, N, k, min_pc, n_perturb, h->d_nV.p, h->d_sets.p, th, h->b_, h->m_scores, h->sd_scores, h->sig_id);
+  info.n_robust = (int)h->sig_id.size();
+  if (h->cfg.verbose) printf("Number of filtered signal: %d\n", info.n_robust);
+  info.t_score_ms = tm.stop();
+
+  // --- gene_basis = diag(1/sqrt(nL)) * nV' * scaled_X / sqrt(M)   (:813-819)
+  {
+    const size_t ldn = round8((size_t)N);
+    Tmp<__half> x_hi((size_t)M * ldn, st), x_lo((size_t)M * ldn, st), v_hi((size_t)k * ldn, st), v_lo((size_t)k * ldn, st);
+    densify(X, h->S_main, 0, ldn, x_hi.p, x_lo.p, st);
+    strided_split_f32_to_f16(h->d_nV.p, k, N, N, (int64_t)ldn, v_hi.p, v_lo.p, st);
+    Tmp<float> gb((size_t)M * k, st);
+    GemmArgs g;
+    g.A.hi = x_hi.p; g.A.lo = x_lo.p; g.A.rows = M; g.A.K = N; g.A.ld = (int64_t)ldn;
+    g.B.hi = v_hi.p; g.B.lo = v_lo.p; g.B.rows = k; g.B.K = N; g.B.ld = (int64_t)ldn;
+    g.epi = Epilogue::Store;
+    g.alpha = 1.0f / std::sqrt((float)M);
+    g.C = gb.p;
+    g.ldc = k;
+    g.cta_group = cta_group_of(h);
+    gemm_umma(g, st);
+    h->gene_basis.resize((size_t)M * k);
+    SCL_CUDA(cudaMemcpyAsync(h->gene_basis.data(), gb.p, h->gene_basis.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+    for (int j = 0; j < M; ++j)
+      for (int i = 0; i < k; ++i) h->gene_basis[(size_t)j * k + i] /= std::sqrt(h->nL[i]);
+  }
+  info.t_outputs_ms = tm.stop();
+  h->robust_done = true;
+}
+
+}  // namespace scl

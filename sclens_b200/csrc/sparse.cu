@@ -1,0 +1,585 @@
+// Integer-exact sparse plumbing on device: CSR mirror, line canonicalisation (sort + sum
+// duplicates), the perturbation merge of src/scLENS.jl:735/:774 and the null-matrix
+// permutation of :239-289.  All HBM-bound; no sorting library is used - a line (one gene
+// column or one cell row) is scattered into a dense shared-memory strip and compacted in
+// index order, which is exactly the semantics of Julia's sparse(I,J,V) (duplicates summed,
+// (col,row) order).
+#include "common.cuh"
+#include "tmp.cuh"
+
+namespace scl {
+
+static constexpr int kCanonChunk = 8192;  // positions per shared-memory strip (32 KB)
+static constexpr int kCanonThreads = 256;
+
+// ---------------------------------------------------------------------------------------
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+// out[0..n] = exclusive scan of in[0..n-1]; out[n] = total.  One block.
+__global__ void __launch_bounds__(1024) k_exclusive_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n) {
+  __shared__ uint32_t part[1024];
+  int tid = threadIdx.x;
+  int chunk = (n + 1023) / 1024;
+  int b = tid * chunk, e = min(n, b + chunk);
+  uint32_t s = 0;
+  for (int i = b; i < e; ++i) s += in[i];
+  part[tid] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    uint32_t v = tid >= off ? part[tid - off] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  uint32_t run = tid ? part[tid - 1] : 0;
+  for (int i = b; i < e; ++i) {
+    uint32_t v = in[i];
+    out[i] = run;
+    run += v;
+  }
+  if (tid == 1023) out[n] = part[1023];
+}
+
+__global__ void k_count_index(const uint32_t* __restrict__ idx, size_t n, uint32_t* __restrict__ cnt) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) atomicAdd(&cnt[idx[i]], 1u);
+}
+
+// One block per CSC column (grid-stride): scatter entries into row buckets.
+__global__ void k_scatter_to_rows(const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ rowval,
+                                  const float* __restrict__ val, int M, const uint32_t* __restrict__ rowptr,
+                                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ out_col,
+                                  float* __restrict__ out_val) {
+  for (int j = blockIdx.x; j < M; j += gridDim.x) {
+    uint32_t b = colptr[j], e = colptr[j + 1];
+    for (uint32_t t = b + threadIdx.x; t < e; t += blockDim.x) {
+      uint32_t r = rowval[t];
+      uint32_t slot = atomicAdd(&cursor[r], 1u);
+      uint32_t dst = rowptr[r] + slot;
+      out_col[dst] = (uint32_t)j;
+      out_val[dst] = val[t];
+    }
+  }
+}
+
+// Canonicalise lines: every line l owns the input segment [in_ptr[l], in_ptr[l+1]) of
+// (pos,val) pairs in arbitrary order, possibly with duplicate pos.  Output is sorted by pos
+// with duplicates summed.  COUNT_ONLY writes the distinct count per line to out_cnt.
+template <bool COUNT_ONLY>
+__global__ void __launch_bounds__(kCanonThreads) k_canon(const uint32_t* __restrict__ in_ptr,
+                                                        const uint32_t* __restrict__ in_pos,
+                                                        const float* __restrict__ in_val,
+                                                        const uint32_t* __restrict__ out_ptr,
+                                                        uint32_t* __restrict__ out_pos, float* __restrict__ out_val,
+                                                        uint32_t* __restrict__ out_cnt, int n_lines, int line_len) {
+  __shared__ float acc[kCanonChunk];
+  __shared__ uint32_t warp_cnt[kCanonThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kCanonThreads / 32;
+  constexpr int kPerWarp = kCanonChunk / kWarps;  // 1024 positions per warp
+  for (int l = blockIdx.x; l < n_lines; l += gridDim.x) {
+    const uint32_t sb = in_ptr[l], se = in_ptr[l + 1];
+    uint32_t written = 0;  // uniform across the block
+    if (sb == se) {
+      if (COUNT_ONLY && tid == 0) out_cnt[l] = 0;
+      continue;
+    }
+    const uint32_t ob = COUNT_ONLY ? 0u : out_ptr[l];
+    for (int base = 0; base < line_len; base += kCanonChunk) {
+      const int len = min(kCanonChunk, line_len - base);
+      for (int i = tid; i < kCanonChunk; i += kCanonThreads) acc[i] = 0.f;
+      __syncthreads();
+      for (uint32_t t = sb + tid; t < se; t += kCanonThreads) {
+        uint32_t p = in_pos[t];
+        if (p >= (uint32_t)base && p < (uint32_t)(base + len)) atomicAdd(&acc[p - base], in_val[t]);
+      }
+      __syncthreads();
+      // pass 1: per-warp distinct counts over its 1024-position strip
+      uint32_t c = 0;
+      const int w0 = warp * kPerWarp;
+      for (int i = 0; i < kPerWarp; i += 32) c += __popc(__ballot_sync(0xffffffffu, acc[w0 + i + lane] != 0.f));
+      if (lane == 0) warp_cnt[warp] = c;
+      __syncthreads();
+      uint32_t wbase = 0, total = 0;
+      for (int w = 0; w < kWarps; ++w) {
+        uint32_t v = warp_cnt[w];
+        if (w < warp) wbase += v;
+        total += v;
+      }
+      if (!COUNT_ONLY) {
+        uint32_t run = ob + written + wbase;
+        for (int i = 0; i < kPerWarp; i += 32) {
+          float v = acc[w0 + i + lane];
+          uint32_t m = __ballot_sync(0xffffffffu, v != 0.f);
+          if (v != 0.f) {
+            uint32_t dst = run + __popc(m & ((1u << lane) - 1u));
+            out_pos[dst] = (uint32_t)(base + w0 + i + lane);
+            out_val[dst] = v;
+          }
+          run += __popc(m);
+        }
+      }
+      written += total;
+      __syncthreads();
+    }
+    if (COUNT_ONLY && tid == 0) out_cnt[l] = written;
+  }
+}
+
+static inline int grid_for(size_t n, int threads, int cap = 148 * 16) {
+  size_t g = (n + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > (size_t)cap) g = cap;
+  return (int)g;
+}
+
+static void exclusive_scan(const uint32_t* in, uint32_t* out, int n, cudaStream_t st) {
+  k_exclusive_scan<<<1, 1024, 0, st>>>(in, out, n);
+  SCL_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------
+void build_csr_mirror(SpMat& A, cudaStream_t st) {
+  const int N = A.N, M = A.M;
+  const size_t nnz = A.nnz;
+  A.rowptr.ensure(N + 1);
+  A.colidx.ensure(nnz ? nnz : 1);
+  A.rval.ensure(nnz ? nnz : 1);
+  Tmp<uint32_t> cnt(N + 1, st), cursor(N + 1, st), tcol(nnz ? nnz : 1, st);
+  Tmp<float> tval(nnz ? nnz : 1, st);
+  SCL_CUDA(cudaMemsetAsync(cnt.p, 0, (N + 1) * sizeof(uint32_t), st));
+  SCL_CUDA(cudaMemsetAsync(cursor.p, 0, (N + 1) * sizeof(uint32_t), st));
+  if (nnz) k_count_index<<<grid_for(nnz, 256), 256, 0, st>>>(A.rowval.p, nnz, cnt.p);
+  exclusive_scan(cnt.p, A.rowptr.p, N, st);
+  if (nnz) {
+    k_scatter_to_rows<<<min(M, 148 * 8), 128, 0, st>>>(A.colptr.p, A.rowval.p, A.val.p, M, A.rowptr.p, cursor.p,
+                                                        tcol.p, tval.p);
+    k_canon<false><<<min(N, 148 * 8), kCanonThreads, 0, st>>>(A.rowptr.p, tcol.p, tval.p, A.rowptr.p, A.colidx.p,
+                                                              A.rval.p, nullptr, N, M);
+  }
+  SCL_CUDA(cudaGetLastError());
+}
+
+__global__ void k_rebase(uint32_t* p, size_t n, uint32_t base) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] -= base;
+}
+
+void upload_csc(SpMat& A, int N, int M, size_t nnz, const uint32_t* colptr, const uint32_t* rowval, const float* val,
+                int index_base, cudaStream_t st) {
+  A.N = N; A.M = M; A.nnz = nnz;
+  A.colptr.ensure(M + 1);
+  A.rowval.ensure(nnz ? nnz : 1);
+  A.val.ensure(nnz ? nnz : 1);
+  SCL_CUDA(cudaMemcpyAsync(A.colptr.p, colptr, (M + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  if (nnz) {
+    SCL_CUDA(cudaMemcpyAsync(A.rowval.p, rowval, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    SCL_CUDA(cudaMemcpyAsync(A.val.p, val, nnz * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  if (index_base) {
+    k_rebase<<<grid_for(M + 1, 256), 256, 0, st>>>(A.colptr.p, M + 1, (uint32_t)index_base);
+    if (nnz) k_rebase<<<grid_for(nnz, 256), 256, 0, st>>>(A.rowval.p, nnz, (uint32_t)index_base);
+  }
+  SCL_CUDA(cudaGetLastError());
+  build_csr_mirror(A, st);
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void k_merged_counts(const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ addcnt, int M,
+                                uint32_t* __restrict__ cnt) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < M) cnt[j] = (colptr[j + 1] - colptr[j]) + addcnt[j];
+}
+
+__global__ void k_copy_base(const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ rowval,
+                            const float* __restrict__ val, int M, const uint32_t* __restrict__ newptr, bool binarise,
+                            uint32_t* __restrict__ out_row, float* __restrict__ out_val) {
+  for (int j = blockIdx.x; j < M; j += gridDim.x) {
+    uint32_t b = colptr[j], e = colptr[j + 1], nb = newptr[j];
+    for (uint32_t t = b + threadIdx.x; t < e; t += blockDim.x) {
+      out_row[nb + (t - b)] = rowval[t];
+      out_val[nb + (t - b)] = binarise ? 1.f : val[t];
+    }
+  }
+}
+
+__global__ void k_scatter_additions(const uint32_t* __restrict__ add_row, const uint32_t* __restrict__ add_col,
+                                    size_t n_add, const uint32_t* __restrict__ colptr,
+                                    const uint32_t* __restrict__ newptr, uint32_t* __restrict__ cursor,
+                                    uint32_t* __restrict__ out_row, float* __restrict__ out_val) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n_add; i += stride) {
+    uint32_t j = add_col[i];
+    uint32_t slot = atomicAdd(&cursor[j], 1u);
+    uint32_t dst = newptr[j] + (colptr[j + 1] - colptr[j]) + slot;
+    out_row[dst] = add_row[i];
+    out_val[dst] = 1.f;
+  }
+}
+
+void perturb_merge(const SpMat& base, const uint32_t* d_add_row, const uint32_t* d_add_col, size_t n_add,
+                   bool binarise, SpMat& out, cudaStream_t st) {
+  const int N = base.N, M = base.M;
+  const size_t nnz = base.nnz + n_add;
+  out.N = N; out.M = M; out.nnz = nnz;
+  out.colptr.ensure(M + 1);
+  out.rowval.ensure(nnz ? nnz : 1);
+  out.val.ensure(nnz ? nnz : 1);
+  Tmp<uint32_t> addcnt(M + 1, st), cnt(M + 1, st), cursor(M + 1, st), trow(nnz ? nnz : 1, st);
+  Tmp<float> tval(nnz ? nnz : 1, st);
+  SCL_CUDA(cudaMemsetAsync(addcnt.p, 0, (M + 1) * sizeof(uint32_t), st));
+  SCL_CUDA(cudaMemsetAsync(cursor.p, 0, (M + 1) * sizeof(uint32_t), st));
+  if (n_add) k_count_index<<<grid_for(n_add, 256), 256, 0, st>>>(d_add_col, n_add, addcnt.p);
+  k_merged_counts<<<(M + 255) / 256, 256, 0, st>>>(base.colptr.p, addcnt.p, M, cnt.p);
+  exclusive_scan(cnt.p, out.colptr.p, M, st);
+  k_copy_base<<<min(M, 148 * 8), 128, 0, st>>>(base.colptr.p, base.rowval.p, base.val.p, M, out.colptr.p, binarise,
+                                               trow.p, tval.p);
+  if (n_add)
+    k_scatter_additions<<<grid_for(n_add, 256), 256, 0, st>>>(d_add_row, d_add_col, n_add, base.colptr.p,
+                                                              out.colptr.p, cursor.p, trow.p, tval.p);
+  k_canon<false><<<min(M, 148 * 8), kCanonThreads, 0, st>>>(out.colptr.p, trow.p, tval.p, out.colptr.p, out.rowval.p,
+                                                            out.val.p, nullptr, M, N);
+  SCL_CUDA(cudaGetLastError());
+  build_csr_mirror(out, st);
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void k_gather_f32(const float* __restrict__ src, const uint32_t* __restrict__ perm, size_t n,
+                             float* __restrict__ dst) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = src[perm[i]];
+}
+
+// Shared tail of the null-matrix builders: (trow, tval) hold, per base column segment, the
+// new rows and shuffled values; canonicalise with duplicate summation.
+static void finish_null(const SpMat& base, const uint32_t* trow, const float* tval, SpMat& out, cudaStream_t st) {
+  const int N = base.N, M = base.M;
+  out.N = N; out.M = M;
+  out.colptr.ensure(M + 1);
+  Tmp<uint32_t> cnt(M + 1, st);
+  k_canon<true><<<min(M, 148 * 8), kCanonThreads, 0, st>>>(base.colptr.p, trow, tval, nullptr, nullptr, nullptr, cnt.p,
+                                                           M, N);
+  exclusive_scan(cnt.p, out.colptr.p, M, st);
+  uint32_t total = 0;
+  SCL_CUDA(cudaMemcpyAsync(&total, out.colptr.p + M, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  out.nnz = total;
+  out.rowval.ensure(total ? total : 1);
+  out.val.ensure(total ? total : 1);
+  k_canon<false><<<min(M, 148 * 8), kCanonThreads, 0, st>>>(base.colptr.p, trow, tval, out.colptr.p, out.rowval.p,
+                                                            out.val.p, nullptr, M, N);
+  SCL_CUDA(cudaGetLastError());
+  build_csr_mirror(out, st);
+}
+
+void permute_null(const SpMat& base, const uint32_t* d_perm, const uint32_t* d_rows, SpMat& out, cudaStream_t st) {
+  const size_t nnz = base.nnz;
+  Tmp<float> tval(nnz ? nnz : 1, st);
+  if (nnz) k_gather_f32<<<grid_for(nnz, 256), 256, 0, st>>>(base.val.p, d_perm, nnz, tval.p);
+  finish_null(base, d_rows, tval.p, out, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// Device-side draws.  A keyed Feistel network on ceil(log2 n) bits with cycle walking is a
+// bijection of [0,n): perm(t) is computed independently per element, so a random
+// permutation / a without-replacement sample costs one pass and no sort.
+__host__ __device__ inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+
+struct Feistel {
+  uint64_t n;
+  uint32_t half_bits;   // bits per half
+  uint64_t keys[8];
+  __host__ static Feistel make(uint64_t n, uint64_t seed) {
+    Feistel f;
+    f.n = n;
+    uint32_t bits = 2;
+    while (bits < 64 && (1ull << bits) < n) ++bits;
+    if (bits & 1) ++bits;
+    f.half_bits = bits / 2;
+    for (int r = 0; r < 8; ++r) f.keys[r] = mix64(seed + 0x9e3779b97f4a7c15ull * (uint64_t)(r + 1));
+    return f;
+  }
+  __host__ __device__ inline uint64_t encrypt(uint64_t x) const {
+    const uint64_t mask = (1ull << half_bits) - 1ull;
+    uint64_t L = x >> half_bits, R = x & mask;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      uint64_t F = mix64(R ^ keys[r]) & mask;
+      uint64_t nl = R;
+      R = L ^ F;
+      L = nl;
+    }
+    return (L << half_bits) | R;
+  }
+  __host__ __device__ inline uint64_t operator()(uint64_t t) const {
+    uint64_t x = encrypt(t);
+    while (x >= n) x = encrypt(x);
+    return x;
+  }
+};
+
+// Null matrix, aligned semantics: gene j receives count_j distinct uniformly random rows
+// (:247) and globally shuffled values (:275).  One block per gene; rows are drawn by
+// rejection against a shared-memory bitmap (the complement is drawn for dense genes).
+__global__ void __launch_bounds__(256) k_null_rows(const uint32_t* __restrict__ colptr, int N, int M, uint64_t seed,
+                                                   uint32_t* __restrict__ out_row) {
+  extern __shared__ uint32_t bitmap[];  // ceil(N/32) words
+  __shared__ uint32_t accepted;
+  __shared__ uint32_t warp_cnt[8];
+  const int words = (N + 31) / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int j = blockIdx.x; j < M; j += gridDim.x) {
+    const uint32_t b = colptr[j], cnt = colptr[j + 1] - b;
+    if (cnt == 0) continue;
+    const bool complement = cnt > (uint32_t)N / 2;
+    const uint32_t target = complement ? (uint32_t)N - cnt : cnt;
+    for (int w = tid; w < words; w += blockDim.x) bitmap[w] = 0;
+    if (tid == 0) accepted = 0;
+    __syncthreads();
+    uint64_t ctr = 0;
+    // rounds of proposals: at most `remaining` threads propose, so the count never overshoots
+    while (true) {
+      __syncthreads();
+      const uint32_t have = accepted;
+      __syncthreads();
+      if (have >= target) break;
+      if ((uint32_t)tid < target - have) {
+        uint64_t h = mix64(seed ^ mix64(((uint64_t)j << 32) ^ (ctr * blockDim.x + tid)));
+        uint32_t r = (uint32_t)(((h >> 32) * (uint64_t)N) >> 32);
+        uint32_t bit = 1u << (r & 31);
+        uint32_t prev = atomicOr(&bitmap[r >> 5], bit);
+        if (!(prev & bit)) atomicAdd(&accepted, 1u);
+      }
+      ++ctr;
+    }
+    // emit rows in ascending order (set bits, or clear bits when the complement was drawn)
+    uint32_t run = 0;
+    for (int w0 = 0; w0 < words; w0 += blockDim.x) {
+      int w = w0 + tid;
+      uint32_t bits = 0;
+      if (w < words) {
+        bits = bitmap[w];
+        if (complement) bits = ~bits;
+        int valid = N - w * 32;
+        if (valid < 32) bits &= (valid <= 0) ? 0u : ((1u << valid) - 1u);
+      }
+      uint32_t c = __popc(bits);
+      // block exclusive prefix of c
+      uint32_t incl = c;
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) warp_cnt[warp] = incl;
+      __syncthreads();
+      uint32_t wb = 0, tot = 0;
+      for (int q = 0; q < 8; ++q) {
+        uint32_t v = warp_cnt[q];
+        if (q < warp) wb += v;
+        tot += v;
+      }
+      uint32_t dst = b + run + wb + incl - c;
+      while (bits) {
+        int k = __ffs(bits) - 1;
+        bits &= bits - 1;
+        out_row[dst++] = (uint32_t)(w * 32 + k);
+      }
+      run += tot;
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void k_feistel_gather_f32(const float* __restrict__ src, Feistel f, float* __restrict__ dst) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < f.n; i += stride) dst[i] = src[f(i)];
+}
+
+void draw_null_device(const SpMat& base, uint64_t seed, SpMat& out, cudaStream_t st) {
+  const size_t nnz = base.nnz;
+  SCL_REQUIRE(nnz > 0, "empty matrix");
+  Tmp<uint32_t> trow(nnz, st);
+  Tmp<float> tval(nnz, st);
+  size_t smem = ((size_t)base.N + 31) / 32 * sizeof(uint32_t);
+  SCL_REQUIRE(smem <= 200 * 1024, "N too large for the shared-memory row bitmap");
+  SCL_CUDA(cudaFuncSetAttribute(k_null_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_null_rows<<<min(base.M, 148 * 4), 256, smem, st>>>(base.colptr.p, base.N, base.M, mix64(seed ^ 0x6e756c6cull),
+                                                      trow.p);
+  Feistel f = Feistel::make(nnz, mix64(seed ^ 0x73687566ull));
+  k_feistel_gather_f32<<<grid_for(nnz, 256), 256, 0, st>>>(base.val.p, f, tval.p);
+  SCL_CUDA(cudaGetLastError());
+  // rows are distinct inside a gene, so no duplicates arise; the shared tail still applies
+  finish_null(base, trow.p, tval.p, out, st);
+}
+
+// Zero candidates (:668-673): T distinct grid positions from a Feistel bijection of [0,N*M),
+// minus the non-zero set (binary search in the gene's sorted row list), compacted in order.
+__global__ void k_zero_cand_flags(const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ rowval, int N,
+                                  Feistel f, size_t T, uint32_t* __restrict__ cand_row, uint32_t* __restrict__ cand_col,
+                                  uint32_t* __restrict__ block_cnt) {
+  __shared__ uint32_t wc[8];
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  bool keep = false;
+  uint32_t r = 0, c = 0;
+  if (i < T) {
+    uint64_t g = f(i);
+    c = (uint32_t)(g / (uint64_t)N);
+    r = (uint32_t)(g % (uint64_t)N);
+    uint32_t lo = colptr[c], hi = colptr[c + 1];
+    while (lo < hi) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (rowval[mid] < r) lo = mid + 1; else hi = mid;
+    }
+    keep = !(lo < colptr[c + 1] && rowval[lo] == r);
+    cand_row[i] = keep ? r : 0xffffffffu;
+    cand_col[i] = c;
+  }
+  uint32_t m = __ballot_sync(0xffffffffu, keep);
+  if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = 0;
+    for (int q = 0; q < 8; ++q) s += wc[q];
+    block_cnt[blockIdx.x] = s;
+  }
+}
+
+__global__ void k_zero_cand_compact(const uint32_t* __restrict__ cand_row, const uint32_t* __restrict__ cand_col,
+                                    size_t T, const uint32_t* __restrict__ block_off, uint32_t* __restrict__ z1,
+                                    uint32_t* __restrict__ z2) {
+  __shared__ uint32_t wc[8];
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  uint32_t r = i < T ? cand_row[i] : 0xffffffffu;
+  bool keep = r != 0xffffffffu;
+  uint32_t m = __ballot_sync(0xffffffffu, keep);
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) wc[warp] = __popc(m);
+  __syncthreads();
+  uint32_t wb = 0;
+  for (int q = 0; q < warp; ++q) wb += wc[q];
+  if (keep) {
+    uint32_t dst = block_off[blockIdx.x] + wb + __popc(m & ((1u << lane) - 1u));
+    z1[dst] = r;
+    z2[dst] = cand_col[i];
+  }
+}
+
+// Large exclusive scan (block counts can exceed 1024*chunk comfortably handled by k_exclusive_scan).
+size_t draw_zero_candidates_device(const SpMat& base, uint64_t seed, DBuf<uint32_t>& z1, DBuf<uint32_t>& z2,
+                                   cudaStream_t st) {
+  const uint64_t grid = (uint64_t)base.N * (uint64_t)base.M;
+  // expected number of distinct positions among nnz uniform draws (the reference draws nnz pairs)
+  double d = (double)base.nnz / (double)grid;
+  size_t T = (size_t)llround((double)grid * (1.0 - exp(-d)));
+  if (T > grid) T = grid;
+  SCL_REQUIRE(T > 0, "empty matrix");
+  Feistel f = Feistel::make(grid, mix64(seed ^ 0x7a65726full));
+  const int threads = 256;
+  const size_t blocks = (T + threads - 1) / threads;
+  SCL_REQUIRE(blocks < (1ull << 31), "too many candidate blocks");
+  Tmp<uint32_t> crow(T, st), ccol(T, st), bcnt(blocks + 1, st), boff(blocks + 1, st);
+  k_zero_cand_flags<<<(unsigned)blocks, threads, 0, st>>>(base.colptr.p, base.rowval.p, base.N, f, T, crow.p, ccol.p,
+                                                          bcnt.p);
+  exclusive_scan(bcnt.p, boff.p, (int)blocks, st);
+  uint32_t total = 0;
+  SCL_CUDA(cudaMemcpyAsync(&total, boff.p + blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  z1.ensure(total ? total : 1);
+  z2.ensure(total ? total : 1);
+  k_zero_cand_compact<<<(unsigned)blocks, threads, 0, st>>>(crow.p, ccol.p, T, boff.p, z1.p, z2.p);
+  SCL_CUDA(cudaGetLastError());
+  return total;
+}
+
+// sample(1:n_cand, n_take, replace=false) (:731, :772) as the first n_take images of a keyed
+// bijection of [0,n_cand); gathers the (row,col) pairs directly.
+__global__ void k_subset_pairs(const uint32_t* __restrict__ z1, const uint32_t* __restrict__ z2, Feistel f,
+                               size_t n_take, uint32_t* __restrict__ out_row, uint32_t* __restrict__ out_col) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n_take; i += stride) {
+    uint64_t s = f(i);
+    out_row[i] = z1[s];
+    out_col[i] = z2[s];
+  }
+}
+
+void draw_subset_device(const uint32_t* z1, const uint32_t* z2, size_t n_cand, size_t n_take, uint64_t seed,
+                        uint32_t* out_row, uint32_t* out_col, cudaStream_t st) {
+  SCL_REQUIRE(n_take <= n_cand, "sample larger than the candidate pool");
+  if (!n_take) return;
+  Feistel f = Feistel::make(n_cand, seed);
+  k_subset_pairs<<<grid_for(n_take, 256), 256, 0, st>>>(z1, z2, f, n_take, out_row, out_col);
+  SCL_CUDA(cudaGetLastError());
+}
+
+__global__ void k_gather_pairs(const uint32_t* __restrict__ z1, const uint32_t* __restrict__ z2,
+                               const uint32_t* __restrict__ idx, size_t n, uint32_t* __restrict__ out_row,
+                               uint32_t* __restrict__ out_col) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    uint32_t s = idx[i];
+    out_row[i] = z1[s];
+    out_col[i] = z2[s];
+  }
+}
+
+void gather_pairs(const uint32_t* z1, const uint32_t* z2, const uint32_t* d_idx, size_t n, uint32_t* out_row,
+                  uint32_t* out_col, cudaStream_t st) {
+  if (!n) return;
+  k_gather_pairs<<<grid_for(n, 256), 256, 0, st>>>(z1, z2, d_idx, n, out_row, out_col);
+  SCL_CUDA(cudaGetLastError());
+}
+
+// Noise baseline (:709-712): mean over n_rep blocks of max_{nm} |N(0,1/nm)|.
+__global__ void __launch_bounds__(256) k_noise_baseline(int nm, uint64_t seed, double* __restrict__ out_max) {
+  __shared__ float red[8];
+  const uint64_t rep = blockIdx.x;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < (nm + 1) / 2; i += blockDim.x) {
+    uint64_t h = mix64(seed ^ mix64((rep << 32) ^ (uint64_t)i));
+    float u1 = ((uint32_t)(h >> 40) + 1u) * (1.0f / 16777217.0f);   // (0,1]
+    float u2 = (uint32_t)(h & 0xffffffu) * (1.0f / 16777216.0f);
+    float rad = sqrtf(-2.f * logf(u1));
+    float s, c;
+    sincospif(2.f * u2, &s, &c);
+    m = fmaxf(m, fabsf(rad * c));
+    if (2 * i + 1 < nm) m = fmaxf(m, fabsf(rad * s));
+  }
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; ++q) m = fmaxf(m, red[q]);
+    out_max[rep] = (double)m;
+  }
+}
+
+double noise_baseline_device(int nm, int n_rep, uint64_t seed, cudaStream_t st) {
+  Tmp<double> mx(n_rep, st);
+  k_noise_baseline<<<n_rep, 256, 0, st>>>(nm, mix64(seed ^ 0x70746821ull), mx.p);
+  SCL_CUDA(cudaGetLastError());
+  std::vector<double> h(n_rep);
+  SCL_CUDA(cudaMemcpyAsync(h.data(), mx.p, n_rep * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  double s = 0;
+  for (double v : h) s += v;
+  return s / n_rep * sqrt(1.0 / nm);
+}
+
+}  // namespace scl

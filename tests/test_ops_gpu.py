@@ -1,0 +1,283 @@
+"""-m gpu parity tests of the function-level operators, called through the C ABI and checked
+against the CPU oracle (oracle/sclens_oracle.py) on the same seeded inputs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import sclens_oracle as orc
+from sclens_b200 import Handle, _lib
+from sclens_b200._lib import ptr
+from sclens_b200.synth import make_counts
+
+pytestmark = pytest.mark.gpu
+
+
+def f16_split(a):
+    hi = a.astype(np.float16)
+    lo = (a - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
+def pad_rows(a, ld):
+    out = np.zeros((a.shape[0], ld), dtype=a.dtype)
+    out[:, :a.shape[1]] = a
+    return out
+
+
+@pytest.fixture(scope="module")
+def h():
+    with Handle() as hh:
+        yield hh
+
+
+@pytest.fixture(scope="module")
+def h1():
+    with Handle(cta_group=1) as hh:
+        yield hh
+
+
+def run_gemm(hh, A, B, split, colmajor=False, alpha=1.0):
+    m, K = A.shape
+    n = B.shape[0]
+    ld = (K + 7) // 8 * 8
+    a_hi, a_lo = f16_split(A)
+    b_hi, b_lo = f16_split(B)
+    a_hi, a_lo, b_hi, b_lo = [np.ascontiguousarray(pad_rows(x, ld)).view(np.uint16) for x in (a_hi, a_lo, b_hi, b_lo)]
+    Cm = np.empty((n, m) if colmajor else (m, n), dtype=np.float32)
+    rc = hh.lib.scl_op_gemm_tn(hh.h, m, n, K, ld, ld, ptr(a_hi, C.c_uint16), ptr(a_lo, C.c_uint16) if split else None,
+                               ptr(b_hi, C.c_uint16), ptr(b_lo, C.c_uint16) if split else None, alpha, int(colmajor),
+                               ptr(Cm, C.c_float))
+    hh._ck(rc)
+    return Cm.T if colmajor else Cm
+
+
+@pytest.mark.parametrize("shape", [(128, 256, 64), (300, 200, 1000), (1000, 37, 4100), (257, 513, 72), (64, 16, 8)])
+@pytest.mark.parametrize("cg", [2, 1])
+def test_gemm_tn_fp16(h, h1, shape, cg):
+    hh = h if cg == 2 else h1
+    m, n, K = shape
+    rng = np.random.default_rng(m * 7 + n)
+    A = rng.standard_normal((m, K)).astype(np.float32)
+    B = rng.standard_normal((n, K)).astype(np.float32)
+    ref = A.astype(np.float16).astype(np.float64) @ B.astype(np.float16).astype(np.float64).T
+    got = run_gemm(hh, A, B, split=False)
+    scale = np.sqrt(K)
+    assert np.max(np.abs(got - ref)) / scale < 2e-5     # fp32 accumulation of exact fp16 products
+    got_t = run_gemm(hh, A, B, split=False, colmajor=True, alpha=0.5)
+    assert np.max(np.abs(got_t - 0.5 * ref)) / scale < 2e-5
+
+
+@pytest.mark.parametrize("cg", [2, 1])
+def test_gemm_tn_split_is_fp32_accurate(h, h1, cg):
+    hh = h if cg == 2 else h1
+    rng = np.random.default_rng(5)
+    m, n, K = 384, 96, 3000
+    A = rng.standard_normal((m, K)).astype(np.float32)
+    B = rng.standard_normal((n, K)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    got = run_gemm(hh, A, B, split=True)
+    err = np.max(np.abs(got - ref)) / np.sqrt(K)
+    assert err < 5e-6, err
+
+
+@pytest.mark.parametrize("rows,K", [(256, 512), (700, 1300), (1030, 333), (90, 4000)])
+@pytest.mark.parametrize("cg", [2, 1])
+@pytest.mark.parametrize("split", [False, True])
+def test_gram_syrk(h, h1, rows, K, cg, split):
+    hh = h if cg == 2 else h1
+    rng = np.random.default_rng(rows + K)
+    A = rng.standard_normal((rows, K)).astype(np.float32)
+    ld = (K + 7) // 8 * 8
+    hi, lo = f16_split(A)
+    hi_p = np.ascontiguousarray(pad_rows(hi, ld)).view(np.uint16)
+    lo_p = np.ascontiguousarray(pad_rows(lo, ld)).view(np.uint16)
+    G = np.empty((rows, rows), dtype=np.float32)
+    hh._ck(hh.lib.scl_op_gram(hh.h, rows, K, ld, ptr(hi_p, C.c_uint16), ptr(lo_p, C.c_uint16) if split else None,
+                              1.0 / K, ptr(G, C.c_float)))
+    src = A.astype(np.float64) if split else hi.astype(np.float64)
+    ref = src @ src.T / K
+    tol = 5e-6 if split else 2e-5
+    assert np.max(np.abs(G - ref)) * np.sqrt(K) < tol * K / np.sqrt(K) + 1e-5
+    assert np.array_equal(G, G.T)       # mirrored store: exactly symmetric
+
+
+@pytest.mark.parametrize("N,M", [(500, 800), (900, 400)])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_normalize_matches_oracle(h, N, M, layout):
+    X = make_counts(N, M, seed=11, K=4, de_prob=0.3, lfc_sd=1.5)
+    ref, rec = orc.normalize_main(X)
+    lines, length = (M, N) if layout == 0 else (N, M)
+    ld = (length + 7) // 8 * 8
+    hi = np.empty((lines, ld), dtype=np.uint16)
+    lo = np.empty((lines, ld), dtype=np.uint16)
+    tgc, l2 = np.empty(N), np.empty(N)
+    mean, sd, cent = np.empty(M), np.empty(M), np.empty(M)
+    colptr, rowval, val = _lib.as_u32(X.indptr), _lib.as_u32(X.indices), _lib.as_f32(X.data)
+    h._ck(h.lib.scl_op_normalize(h.h, N, M, X.nnz, ptr(colptr, C.c_uint32), ptr(rowval, C.c_uint32),
+                                 ptr(val, C.c_float), layout, ld, ptr(hi, C.c_uint16), ptr(lo, C.c_uint16),
+                                 ptr(tgc, C.c_double), ptr(mean, C.c_double), ptr(sd, C.c_double),
+                                 ptr(l2, C.c_double), ptr(cent, C.c_double)))
+    np.testing.assert_array_equal(tgc, rec["TGC"])
+    np.testing.assert_allclose(mean, rec["mat2_mean"].ravel(), rtol=1e-12)
+    np.testing.assert_allclose(sd, rec["mat2_std"].ravel(), rtol=1e-11)
+    np.testing.assert_allclose(l2, rec["norm_tgc"], rtol=1e-11)
+    np.testing.assert_allclose(cent, rec["cent_"].ravel(), rtol=1e-9, atol=1e-15)
+    want = ref.T if layout == 0 else ref
+    got_hi = hi.view(np.float16)[:, :length].astype(np.float64)
+    got = got_hi + lo.view(np.float16)[:, :length].astype(np.float64)
+    # hi alone is the correctly rounded binary16 value (up to float32 background arithmetic)
+    assert np.max(np.abs(got_hi - want) / (np.abs(want) + 1e-3)) < 6e-4
+    assert np.max(np.abs(got - want) / (np.abs(want) + 1e-3)) < 2e-6
+    assert not hi.view(np.float16)[:, length:].any()
+
+
+def csc_arrays(X):
+    return _lib.as_u32(X.indptr), _lib.as_u32(X.indices), _lib.as_f32(X.data)
+
+
+@pytest.mark.parametrize("N,M", [(300, 500), (9000, 60), (70, 9000)])
+@pytest.mark.parametrize("binarise", [0, 1])
+def test_perturb_merge_bit_exact(h, N, M, binarise):
+    X = make_counts(N, M, seed=3, K=3)
+    rng = np.random.default_rng(4)
+    z1, z2 = orc.draw_zero_candidates(X, rng)
+    sple = rng.choice(len(z1), size=len(z1) // 3, replace=False)
+    want = orc.perturbed_matrix(X, z1, z2, sple, bool(binarise))
+    colptr, rowval, val = csc_arrays(X)
+    ar, ac = _lib.as_u32(z1[sple]), _lib.as_u32(z2[sple])
+    nnz_out = X.nnz + len(sple)
+    oc, orow, ov = np.empty(M + 1, np.uint32), np.empty(nnz_out, np.uint32), np.empty(nnz_out, np.float32)
+    h._ck(h.lib.scl_op_perturb_merge(h.h, N, M, X.nnz, ptr(colptr, C.c_uint32), ptr(rowval, C.c_uint32),
+                                     ptr(val, C.c_float), len(sple), ptr(ar, C.c_uint32), ptr(ac, C.c_uint32),
+                                     binarise, ptr(oc, C.c_uint32), ptr(orow, C.c_uint32), ptr(ov, C.c_float)))
+    np.testing.assert_array_equal(oc, want.indptr)
+    np.testing.assert_array_equal(orow, want.indices)
+    np.testing.assert_array_equal(ov, want.data)
+
+
+@pytest.mark.parametrize("N,M", [(300, 500), (9000, 60)])
+@pytest.mark.parametrize("aligned", [True, False])
+def test_permute_null_bit_exact(h, N, M, aligned):
+    X = make_counts(N, M, seed=5, K=3)
+    rng = np.random.default_rng(6)
+    order = None if aligned else rng.permutation(M)   # emulates Julia's Dict order (duplicates summed)
+    perm, rows = orc.draw_null(X, rng, order)
+    if not aligned:
+        rows[-1] = N - 1                              # keep the reference's implied shape == (N, M)
+    want = orc.build_null(X, perm, rows)
+    colptr, rowval, val = csc_arrays(X)
+    nnz = C.c_int64()
+    oc, orow, ov = np.empty(M + 1, np.uint32), np.empty(X.nnz, np.uint32), np.empty(X.nnz, np.float32)
+    h._ck(h.lib.scl_op_permute_null(h.h, N, M, X.nnz, ptr(colptr, C.c_uint32), ptr(rowval, C.c_uint32),
+                                    ptr(val, C.c_float), ptr(perm, C.c_uint32), ptr(rows, C.c_uint32), C.byref(nnz),
+                                    ptr(oc, C.c_uint32), ptr(orow, C.c_uint32), ptr(ov, C.c_float)))
+    assert nnz.value == want.nnz
+    if not aligned:
+        assert want.nnz < X.nnz                       # duplicates really were merged
+    np.testing.assert_array_equal(oc[:want.shape[1] + 1], want.indptr)
+    np.testing.assert_array_equal(orow[:want.nnz], want.indices)
+    np.testing.assert_array_equal(ov[:want.nnz], want.data)
+
+
+def test_device_null_draw_properties(h):
+    """Device-drawn null matrix: same per-gene counts, same value multiset, rows distinct."""
+    N, M = 2000, 300
+    X = make_counts(N, M, seed=8, K=3)
+    colptr, rowval, val = csc_arrays(X)
+    nnz = C.c_int64()
+    oc, orow, ov = np.empty(M + 1, np.uint32), np.empty(X.nnz, np.uint32), np.empty(X.nnz, np.float32)
+    h._ck(h.lib.scl_op_permute_null(h.h, N, M, X.nnz, ptr(colptr, C.c_uint32), ptr(rowval, C.c_uint32),
+                                    ptr(val, C.c_float), None, None, C.byref(nnz), ptr(oc, C.c_uint32),
+                                    ptr(orow, C.c_uint32), ptr(ov, C.c_float)))
+    assert nnz.value == X.nnz
+    np.testing.assert_array_equal(oc, X.indptr)
+    np.testing.assert_array_equal(np.sort(ov), np.sort(X.data))
+    for j in range(M):
+        seg = orow[oc[j]:oc[j + 1]]
+        assert np.all(np.diff(seg.astype(np.int64)) > 0) and (len(seg) == 0 or seg[-1] < N)
+    assert not np.array_equal(orow, X.indices)
+
+
+def test_syevd_and_mp_fit(h):
+    rng = np.random.default_rng(2)
+    n = 600
+    A = rng.standard_normal((n, 900)).astype(np.float32)
+    G = (A @ A.T / 900).astype(np.float32)
+    L, V, ms = np.empty(n, np.float32), np.empty((n, n), np.float32), C.c_double()
+    h._ck(h.lib.scl_op_syevd(h.h, n, ptr(G, C.c_float), ptr(L, C.c_float), ptr(V, C.c_float), C.byref(ms)))
+    Lref = np.linalg.eigvalsh(G.astype(np.float64))
+    np.testing.assert_allclose(L, Lref, rtol=2e-5, atol=2e-6)
+    Vc = V.T  # column-major eigenvectors
+    assert np.max(np.abs(G.astype(np.float64) @ Vc - Vc * L[None, :])) < 5e-5
+    # mp fit against the oracle
+    B = rng.standard_normal((n, 900)).astype(np.float32)
+    Lr = np.linalg.eigvalsh((B @ B.T / 900).astype(np.float64)).astype(np.float32)
+    Lsig = L.copy()
+    Lsig[-3:] *= 1.6
+    out = np.empty(8)
+    assert h.lib.scl_op_mp_fit(ptr(Lsig, C.c_float), n, ptr(Lr[:-1].copy(), C.c_float), n - 1, ptr(out, C.c_double)) == 0
+    L_mp, b_plus, b_min, it = orc.mp_calculation(Lsig.astype(np.float64), Lr[:-1].astype(np.float64))
+    lam = orc.tw(Lsig.astype(np.float64), L_mp)[0]
+    assert abs(out[0] - lam) < 1e-12 * lam and abs(out[1] - b_plus) < 1e-12 and abs(out[2] - b_min) < 1e-12
+    assert int(out[4]) == len(L_mp) and int(out[5]) == it and int(out[7]) == int((Lsig > lam).sum())
+    chk = orc.mp_check(L_mp)
+    assert abs(out[3] - chk["ks_static"]) < 1e-9 and bool(out[6]) == chk["pass"]
+
+
+def test_corr_colabsmax(h):
+    rng = np.random.default_rng(9)
+    n, nv, nw = 700, 650, 331
+    V = np.linalg.qr(rng.standard_normal((n, nv)))[0].T.astype(np.float32).copy()
+    W = np.linalg.qr(rng.standard_normal((n, nw)))[0].T.astype(np.float32).copy()
+    d = np.empty(nw, np.float32)
+    h._ck(h.lib.scl_op_corr_colabsmax(h.h, n, nv, nw, ptr(V, C.c_float), ptr(W, C.c_float), ptr(d, C.c_float)))
+    ref = np.max(np.abs(V.astype(np.float64) @ W.astype(np.float64).T), axis=0)
+    np.testing.assert_allclose(d, ref, rtol=0, atol=3e-6)
+
+
+def test_topk_subspace(h):
+    rng = np.random.default_rng(12)
+    n, K = 1500, 2500
+    A = rng.standard_normal((n, K))
+    U = np.linalg.qr(rng.standard_normal((n, 6)))[0]
+    A += U @ (np.array([9, 6, 4, 3, 2.2, 1.9])[:, None] * rng.standard_normal((6, K)))
+    G = (A @ A.T / K).astype(np.float32)
+    k = 9
+    L, V, it = np.empty(k, np.float32), np.empty((k, n), np.float32), C.c_int32()
+    h._ck(h.lib.scl_op_topk_subspace(h.h, n, ptr(G, C.c_float), k, ptr(L, C.c_float), ptr(V, C.c_float), C.byref(it)))
+    Lr, Vr = np.linalg.eigh(G.astype(np.float64))
+    Lr, Vr = Lr[::-1][:k], Vr[:, ::-1][:, :k]
+    np.testing.assert_allclose(L, Lr, rtol=2e-5)
+    cosines = np.abs(np.sum(V.T.astype(np.float64) * Vr, axis=0))
+    gaps = np.minimum(np.abs(np.diff(np.concatenate([[np.inf], Lr]))), np.abs(np.diff(np.concatenate([Lr, [np.linalg.eigvalsh(G.astype(np.float64))[-k - 1]]]))))
+    ang = np.arccos(np.clip(cosines, 0, 1))
+    assert np.all(ang < 2e-4 * Lr / gaps + 1e-3), (ang, gaps)
+
+
+def test_scores_match_oracle(h):
+    rng = np.random.default_rng(13)
+    N, k, min_pc, P = 900, 4, 6, 7
+    nV = np.linalg.qr(rng.standard_normal((N, k)))[0]
+    sets = []
+    for r in range(P):
+        noise = np.concatenate([np.full(k // 2, 0.15), np.full(k - k // 2, 1.2)])
+        base = np.concatenate([nV + noise[None, :] * rng.standard_normal((N, k)) / np.sqrt(N) * 3,
+                               rng.standard_normal((N, min_pc - k))], axis=1)
+        Q = np.linalg.qr(base)[0][:, rng.permutation(min_pc)]
+        sets.append(Q)
+    rob, sig = orc.robustness_scores(nV, sets, 60)
+    nV32 = np.ascontiguousarray(nV.T, dtype=np.float32)
+    sets32 = np.ascontiguousarray(np.stack([s.T for s in sets]), dtype=np.float32)
+    npairs = P * (P - 1) // 2
+    b = np.empty((npairs, k), np.float32)
+    m, sd = np.empty(k), np.empty(k)
+    sid, nrob = np.empty(k, np.int32), C.c_int32()
+    h._ck(h.lib.scl_op_scores(h.h, N, k, min_pc, P, ptr(nV32, C.c_float), ptr(sets32, C.c_float), 60.0,
+                              ptr(b, C.c_float), ptr(m, C.c_double), ptr(sd, C.c_double), ptr(sid, C.c_int32),
+                              C.byref(nrob)))
+    np.testing.assert_allclose(b.T, rob["b_"], atol=5e-6)
+    np.testing.assert_allclose(m, rob["m_scores"], atol=5e-6)
+    np.testing.assert_allclose(sd, rob["sd_scores"], atol=5e-6)
+    np.testing.assert_array_equal(sid[:nrob.value], sig)

@@ -1,0 +1,88 @@
+"""-m gpu end-to-end parity: sclens() through the C ABI vs the CPU oracle with identical draws."""
+import numpy as np
+import pytest
+
+from oracle import sclens_oracle as orc
+from sclens_b200 import SCL_GRAM_FP16, SCL_GRAM_FP16X3, sclens
+from sclens_b200.synth import make_counts
+
+pytestmark = pytest.mark.gpu
+
+CASES = {"wide": (450, 800), "tall": (900, 420)}   # N < M (cell Gram) and N > M (gene Gram + back-projection)
+_cache = {}
+
+
+def oracle_run(name):
+    if name not in _cache:
+        N, M = CASES[name]
+        X = make_counts(N, M, seed=21, K=5, de_prob=0.3, lfc_sd=1.5)
+        res, draws, info = orc.sclens(X, rng=np.random.default_rng(7), mode="gpu-ref", n_perturb=6, n_baseline=300)
+        _cache[name] = (X, res, draws, info)
+    return _cache[name]
+
+
+def col_angles(A, B):
+    c = np.abs(np.sum(A.astype(np.float64) * B.astype(np.float64), axis=0))
+    c /= np.linalg.norm(A, axis=0) * np.linalg.norm(B, axis=0)
+    return np.arccos(np.clip(c, 0, 1))
+
+
+@pytest.mark.parametrize("name", ["wide", "tall"])
+@pytest.mark.parametrize("gram_mode", [SCL_GRAM_FP16, SCL_GRAM_FP16X3])
+@pytest.mark.parametrize("exact", [True, False])
+def test_sclens_matches_oracle(name, gram_mode, exact):
+    X, ref, draws, info = oracle_run(name)
+    N, M = X.shape
+    out, h = sclens(X, draws=draws, n_perturb=6, gram_mode=gram_mode, exact_perturb=exact, verbose=False,
+                    return_handle=True)
+    try:
+        # bit-exact: signal count, null-matrix CSC (permutation indices)
+        assert len(out["signal_ev"]) == len(ref["signal_ev"])
+        null = h.null_csc()
+        want = info["null"]
+        np.testing.assert_array_equal(null.indptr, want.indptr)
+        np.testing.assert_array_equal(null.indices, want.indices)
+        np.testing.assert_array_equal(null.data, want.data)
+        # eigenvalues within 1e-4 relative (north star); the bottom of the spectrum (|L| << 1) absolute
+        tol = 1e-4 if gram_mode == SCL_GRAM_FP16 else 2e-5
+        L, Lr = out["L"].astype(np.float64), np.asarray(ref["L"], np.float64)
+        big = Lr > 1e-2 * Lr.max()
+        assert np.max(np.abs(L[big] - Lr[big]) / Lr[big]) < tol
+        assert abs(out["lambda"] - float(ref["lambda"])) / float(ref["lambda"]) < tol
+        assert len(out["L_mp"]) == len(ref["L_mp"])
+        np.testing.assert_allclose(out["signal_ev"], ref["signal_ev"], rtol=tol)
+        # signal eigenvectors up to sign: max angle 5e-3 rad (fp16 operands) / 5e-4 (split)
+        ang = col_angles(out["signal_evec"], np.asarray(ref["signal_evec"]))
+        assert ang.max() < (5e-3 if gram_mode == SCL_GRAM_FP16 else 1e-3), ang
+        # rec_vals
+        for key in ("TGC", "mat2_mean", "mat2_std", "norm_tgc", "cent_"):
+            np.testing.assert_allclose(np.ravel(out["rec_vals"][key]), np.ravel(ref["rec_vals"][key]), rtol=1e-9, atol=1e-14)
+        # sparsity search: the trace the oracle walked must be reproduced while both walk the same p_
+        p_tr, d_tr = h.search_trace()
+        ref_tr = info["search_trace"]
+        n_common = min(len(p_tr), len(ref_tr))
+        for i in range(n_common):
+            assert p_tr[i] == ref_tr[i][0]
+            assert abs(d_tr[i] - ref_tr[i][2]) < 0.05 * ref_tr[i][2] + 2e-3
+        if gram_mode == SCL_GRAM_FP16X3:
+            assert out["info"]["n_search"] == info["n_search"] and out["info"]["p_sel"] == info["p_sel"]
+            # robustness scores
+            np.testing.assert_allclose(out["robustness_scores"]["m_scores"], ref["robustness_scores"]["m_scores"], atol=2e-2)
+            np.testing.assert_array_equal(out["sig_id"], ref["sig_id"])
+            sgn = np.sign(np.sum(out["signal_evec"] * np.asarray(ref["signal_evec"]), axis=0))
+            np.testing.assert_allclose(out["pca"].iloc[:, 1:].to_numpy() * sgn[None, :], ref["pca"], atol=2e-3)
+            gb = out["gene_basis"] * sgn[:, None]
+            assert np.max(np.abs(gb - ref["gene_basis"])) < 2e-3 * np.max(np.abs(ref["gene_basis"]))
+        assert set(["pca", "pca_n1", "sig_id", "L", "L_mp", "λ", "robustness_scores", "signal_evec", "signal_ev",
+                    "cell_id", "gene_id", "gene_basis", "pass", "rec_vals"]) <= set(out)
+    finally:
+        h.close()
+
+
+def test_production_draws_run():
+    """No injected draws: the library draws on the device; same signal count as the oracle."""
+    X, ref, draws, info = oracle_run("wide")
+    out = sclens(X, n_perturb=4, verbose=False, seed=5)
+    assert len(out["signal_ev"]) == len(ref["signal_ev"])
+    assert 0.9 <= out["info"]["p_sel"] <= 0.999
+    assert np.all(out["robustness_scores"]["m_scores"] <= 1.0 + 1e-5)
