@@ -83,11 +83,28 @@ typedef struct {
   double t_baseline_ms, t_search_ms, t_search_syevd_ms, t_perturb_ms, t_score_ms, t_outputs_ms;
 } scl_robust_info;
 
+/* Kernel-class timings (CUDA events on the library's stream) and algorithmic work counters,
+ * accumulated since scl_reset_profile; what bench.py's roofline figures are computed from. */
+typedef struct {
+  double gram_gemm_ms, other_gemm_ms, densify_ms, stats_ms, sparse_ms, syevd_ms;
+  int64_t gram_gemm_launches, other_gemm_launches, densify_launches, sparse_calls, syevd_calls;
+  double gram_alg_flops;      /* sum of n(n+1)K over Gram launches (SYRK-minimal) */
+  double other_gemm_flops;    /* sum of 2mnk */
+  double densify_alg_bytes;   /* sum of 8 nnz + 4(M+1) + N*M*s_out */
+  double sparse_alg_bytes;    /* 20 nnz per null permutation, 8 nnz + 12 n_add per merge */
+  int64_t kernel_launches;    /* kernels of this library launched by the process since load */
+} scl_profile;
+
 /* ---- lifecycle --------------------------------------------------------------------- */
 SCL_API int32_t scl_version(void);
 SCL_API int32_t scl_create(scl_handle** out, const scl_config* cfg);
 SCL_API int32_t scl_destroy(scl_handle* h);
 SCL_API const char* scl_last_error(scl_handle* h);   /* h may be NULL: last scl_create error */
+SCL_API int32_t scl_get_profile(scl_handle* h, scl_profile* out);
+SCL_API int32_t scl_reset_profile(scl_handle* h);
+/* CUDA-event stopwatch on the handle's stream (the stream every kernel of the path is launched on). */
+SCL_API int32_t scl_timer_start(scl_handle* h);
+SCL_API int32_t scl_timer_stop(scl_handle* h, double* ms);
 
 /* ---- multi-GPU plumbing (one process per GPU) ------------------------- */
 /* 128-byte NCCL unique id, created on rank 0 and distributed by the host language. */

@@ -292,13 +292,38 @@ def _colnorm(A: np.ndarray) -> np.ndarray:
     return A / np.linalg.norm(A, axis=0, keepdims=True)
 
 
-def get_eigvec(X: np.ndarray, mode: str):
-    """get_eigvec (:489-524): keep L>0, sort descending (stable), back-project if N>M."""
+def positive_mask(L: np.ndarray) -> np.ndarray:
+    """``L .> 0`` (:495, :515) read in exact arithmetic.  A column-centred N x M matrix with
+    N <= M has rank <= N-1, so its cell Gram has one eigenvalue that is exactly zero; in floating
+    point it comes out as +-1e-16 (Float64) or +-1e-7 (Float32) and the reference keeps or drops
+    that vector by the sign of rounding noise.  Oracle and CUDA path both use the exact-arithmetic
+    answer: an eigenvalue below eps_rel * max(L) is not positive (deviations)."""
+    L = np.asarray(L)
+    eps_rel = 1e-5 if L.dtype == np.float32 else 1e-10
+    return L > eps_rel * L.max()
+
+
+def get_eigvec(X: np.ndarray, mode: str, keep_null: bool = False):
+    """get_eigvec (:489-524): keep L>0, sort descending (stable), back-project if N>M.
+
+    ``keep_null=True`` keeps the complete eigenbasis.  It is used for the reference basis Vr2 of the
+    sparsity search only (:717-721): there the reference's ``L .> 0`` keeps each exactly-null
+    direction (real data has several: z_data_785's binarised matrix has rank N-5) by the sign of
+    rounding noise, and every dropped one makes the matching small-eigenvalue vectors of the
+    perturbed matrices look maximally delocalised (d ~ 0.01), which stops the search after five
+    steps.  Keeping them all is the outcome the reference produces when those eigenvalues round
+    positive, and is the only one under which d_arr measures what it is meant to measure."""
     N, M = X.shape
+    if keep_null:
+        assert N <= M, "the search passes the transposed matrix when N > M (:718)"
+        Y = wishart_matrix(X, 1, mode)
+        L, V = get_eigen(Y, mode)
+        idx = np.argsort(-L, kind="stable")
+        return L[idx], V[:, idx]
     if N > M:
         Y = wishart_matrix(X, 2, mode)
         L, V = get_eigen(Y, mode)
-        pos = L > 0
+        pos = positive_mask(L)
         L, V = L[pos], V[:, pos]
         idx = np.argsort(-L, kind="stable")
         nL, nVs = L[idx], V[:, idx]
@@ -310,7 +335,7 @@ def get_eigvec(X: np.ndarray, mode: str):
         return nL, _colnorm(prod)
     Y = wishart_matrix(X, 1, mode)
     L, V = get_eigen(Y, mode)
-    pos = L > 0
+    pos = positive_mask(L)
     L, V = L[pos], V[:, pos]
     idx = np.argsort(-L, kind="stable")
     return L[idx], V[:, idx]
@@ -432,7 +457,7 @@ def sclens(X, draws: Optional[Draws] = None, rng: Optional[np.random.Generator] 
     Xb = X.copy()
     Xb.data = np.ones_like(Xb.data)
     nb = logn_scale_pre_scale(Xb)
-    Vr2 = get_eigvec(nb.T if N > M else nb, mode)[1]                                  # :717-721
+    Vr2 = get_eigvec(nb.T if N > M else nb, mode, keep_null=True)[1]                  # :717-721
     n_2 = julia_round(Vr2.shape[1] / 2)                                               # :722
     tank = np.zeros((5, 0))
     tank_n = 5
@@ -498,3 +523,47 @@ def sclens(X, draws: Optional[Draws] = None, rng: Optional[np.random.Generator] 
                signal_evec=nV, signal_ev=nL, gene_basis=gene_basis,
                **{"pass": mpc["pass"]}, ks_static=mpc["ks_static"], rec_vals=rec_vals)
     return res, draws, info
+
+
+# --------------------------------------------------------------------------------------
+# QC (parity row P0; host work in the reference too)
+# --------------------------------------------------------------------------------------
+def preprocess(X, gene_name, min_tp_c=0, min_tp_g=0, max_tp_c=np.inf, max_tp_g=np.inf, min_genes_per_cell=200,
+               max_genes_per_cell=0, min_cells_per_gene=15, mito_percent=5.0, ribo_percent=0.0):
+    """preprocess (:160-236) restated literally on a dense Float32 matrix.  Returns
+    (fc_idx, gene_idx) where gene_idx = positions of the surviving genes in output order
+    (fg_idx -> nn_idx -> stable sortperm of the Float32 per-gene mean, :218-225), or None."""
+    import re
+    A = np.asarray(X.todense() if sp.issparse(X) else X, dtype=np.float32)
+    n_cell_counts = (A != 0).sum(axis=0)                                             # :184
+    n_cell_counts_sum = A.sum(axis=0, dtype=np.float32)                              # :185
+    fg_idx = (n_cell_counts_sum > min_tp_g) & (n_cell_counts_sum < max_tp_g) & (n_cell_counts >= min_cells_per_gene)
+    n_gene_counts = (A != 0).sum(axis=1)                                             # :191
+    n_gene_counts_sum = A.sum(axis=1, dtype=np.float32)                              # :192
+    b1 = n_gene_counts_sum > min_tp_c
+    b2 = n_gene_counts_sum < max_tp_c
+    b3 = n_gene_counts >= min_genes_per_cell
+    mito = np.array([re.match(r"^mt-.", g, flags=re.I) is not None for g in gene_name])   # :196
+    ribo = np.array([re.match(r"^RP[SL].", g, flags=re.I) is not None for g in gene_name])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if mito_percent == 0:
+            b4 = np.ones_like(b1)
+        else:
+            ratio = A[:, mito].sum(axis=1, dtype=np.float32) / n_gene_counts_sum      # Float32 ratio
+            b4 = ratio.astype(np.float64) < mito_percent / 100                        # :201 strict
+        if ribo_percent == 0:
+            b5 = np.ones_like(b1)
+        else:
+            ratio = A[:, ribo].sum(axis=1, dtype=np.float32) / n_gene_counts_sum
+            b5 = ratio.astype(np.float64) < ribo_percent / 100
+    b6 = np.ones_like(b1) if max_genes_per_cell == 0 else n_gene_counts < max_genes_per_cell
+    fc_idx = b1 & b2 & b3 & b4 & b5 & b6                                             # :216
+    if not (fc_idx.any() and fg_idx.any()):
+        return None
+    oo = A[fc_idx][:, fg_idx]
+    nn_idx = oo.sum(axis=0, dtype=np.float32) != 0                                   # :220
+    oo = oo[:, nn_idx]
+    mean_ = (oo.sum(axis=0, dtype=np.float32) / np.float32(oo.shape[0])).astype(np.float32)
+    s_idx = np.argsort(mean_, kind="stable")                                         # :224
+    gene_idx = np.nonzero(fg_idx)[0][nn_idx][s_idx]
+    return fc_idx, gene_idx

@@ -42,6 +42,15 @@ class RobustInfo(C.Structure):
                 ("t_score_ms", C.c_double), ("t_outputs_ms", C.c_double)]
 
 
+class Profile(C.Structure):
+    _fields_ = [("gram_gemm_ms", C.c_double), ("other_gemm_ms", C.c_double), ("densify_ms", C.c_double),
+                ("stats_ms", C.c_double), ("sparse_ms", C.c_double), ("syevd_ms", C.c_double),
+                ("gram_gemm_launches", C.c_int64), ("other_gemm_launches", C.c_int64), ("densify_launches", C.c_int64),
+                ("sparse_calls", C.c_int64), ("syevd_calls", C.c_int64), ("gram_alg_flops", C.c_double),
+                ("other_gemm_flops", C.c_double), ("densify_alg_bytes", C.c_double), ("sparse_alg_bytes", C.c_double),
+                ("kernel_launches", C.c_int64)]
+
+
 _u32p = C.POINTER(C.c_uint32)
 _f32p = C.POINTER(C.c_float)
 _f64p = C.POINTER(C.c_double)
@@ -56,6 +65,10 @@ SIGNATURES = {
     "scl_create": [C.POINTER(_hp), C.POINTER(Config)],
     "scl_destroy": [_hp],
     "scl_last_error": [_hp],
+    "scl_get_profile": [_hp, C.POINTER(Profile)],
+    "scl_reset_profile": [_hp],
+    "scl_timer_start": [_hp],
+    "scl_timer_stop": [_hp, _f64p],
     "scl_nccl_unique_id": [C.POINTER(C.c_uint8)],
     "scl_comm_init": [_hp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32],
     "scl_plan_replicates": [C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p],

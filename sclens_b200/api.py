@@ -18,7 +18,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from . import _lib
-from ._lib import Config, RobustInfo, SclError, SignalInfo, as_f32, as_u32, ptr
+from ._lib import Config, Profile, RobustInfo, SclError, SignalInfo, as_f32, as_u32, ptr
 
 
 def df2sparr(inp_df):
@@ -45,6 +45,20 @@ def df2sparr(inp_df):
     X.eliminate_zeros()   # the C ABI requires strictly positive stored values
     X.sort_indices()
     return X, cell_id, gene_id
+
+
+def speculative_search_merge(d2_in_step_order, p_th, p_step=0.001, tank_n=5):
+    """Stop rule of the sparsity search (:748-760) applied in step order to second-smallest values that
+    ranks evaluated speculatively (step s used p_ = 0.999 - s*p_step).  Returns (n_steps, p_selected)
+    once the rule fires, else None - identical to running the loop sequentially.  Mirrors the C++ logic
+    of run_robustness for the multi-rank search; pure host code."""
+    p_ = 0.999
+    for step in range(len(d2_in_step_order)):
+        last = d2_in_step_order[max(0, step + 1 - tank_n): step + 1]
+        if (sum(x < p_th for x in last) > tank_n - 1) or p_ < 0.9:
+            return step + 1, p_ + (tank_n - 1) * p_step
+        p_ -= p_step
+    return None
 
 
 class Handle:
@@ -115,6 +129,22 @@ class Handle:
     def comm_init(self, uid: bytes, rank: int, world: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         self._ck(self.lib.scl_comm_init(self.h, buf, rank, world))
+
+    def profile(self) -> Profile:
+        p = Profile()
+        self._ck(self.lib.scl_get_profile(self.h, C.byref(p)))
+        return p
+
+    def timer_start(self):
+        self._ck(self.lib.scl_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._ck(self.lib.scl_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def reset_profile(self):
+        self._ck(self.lib.scl_reset_profile(self.h))
 
     # ---- the path
     def run_signal(self) -> SignalInfo:

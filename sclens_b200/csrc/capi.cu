@@ -87,6 +87,8 @@ int32_t scl_destroy(scl_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->nccl) ncclCommDestroy((ncclComm_t)h->nccl);
+  h->prof.resolve();
+  if (h->t0) { cudaEventDestroy(h->t0); cudaEventDestroy(h->t1); }
   h->solver.reset();
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
@@ -94,6 +96,46 @@ int32_t scl_destroy(scl_handle* h) {
 }
 
 const char* scl_last_error(scl_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int32_t scl_get_profile(scl_handle* h, scl_profile* out) {
+  if (!h || !out) return SCL_ERR_INVALID;
+  h->prof.resolve();
+  const Prof& p = h->prof;
+  out->gram_gemm_ms = p.ms[PK_GRAM_GEMM]; out->other_gemm_ms = p.ms[PK_OTHER_GEMM]; out->densify_ms = p.ms[PK_DENSIFY];
+  out->stats_ms = p.ms[PK_STATS]; out->sparse_ms = p.ms[PK_SPARSE]; out->syevd_ms = p.ms[PK_SYEVD];
+  out->gram_gemm_launches = p.calls[PK_GRAM_GEMM]; out->other_gemm_launches = p.calls[PK_OTHER_GEMM];
+  out->densify_launches = p.calls[PK_DENSIFY]; out->sparse_calls = p.calls[PK_SPARSE]; out->syevd_calls = p.calls[PK_SYEVD];
+  out->gram_alg_flops = p.gram_alg_flops; out->other_gemm_flops = p.other_gemm_flops;
+  out->densify_alg_bytes = p.densify_alg_bytes; out->sparse_alg_bytes = p.sparse_alg_bytes;
+  out->kernel_launches = g_kernel_launches.load();
+  return SCL_OK;
+}
+
+int32_t scl_reset_profile(scl_handle* h) {
+  if (!h) return SCL_ERR_INVALID;
+  h->prof.reset();
+  return SCL_OK;
+}
+
+int32_t scl_timer_start(scl_handle* h) {
+  if (!h) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    if (!h->t0) { SCL_CUDA(cudaEventCreate(&h->t0)); SCL_CUDA(cudaEventCreate(&h->t1)); }
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+    SCL_CUDA(cudaEventRecord(h->t0, h->st));
+  });
+}
+
+int32_t scl_timer_stop(scl_handle* h, double* ms) {
+  if (!h || !ms || !h->t0) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaEventRecord(h->t1, h->st));
+    SCL_CUDA(cudaEventSynchronize(h->t1));
+    float t = 0;
+    SCL_CUDA(cudaEventElapsedTime(&t, h->t0, h->t1));
+    *ms = t;
+  });
+}
 
 // ---- multi-GPU plumbing -----------------------------------------------------------------
 int32_t scl_nccl_unique_id(uint8_t out_id[128]) {

@@ -7,6 +7,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include "prof.h"
 
 namespace scl {
 
@@ -126,6 +127,7 @@ struct GemmArgs {
   int splits = 1;           // split-K: partial s written at C + s*split_stride (caller reduces)
   int64_t split_stride = 0;
   int cta_group = 2;        // 1 or 2
+  int chunk_kb = 0;         // k-blocks (of 64) per TMEM accumulation chunk; 0 = default (32, or 8 in split mode)
 };
 void gemm_umma(const GemmArgs& a, cudaStream_t st);
 void split_f32_to_f16(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st);

@@ -42,6 +42,7 @@ struct KParams {
   int k_blocks_total;   // ceil(K / 64)
   int splits;
   int block_n;          // UMMA N (multiple of 16, <= 256)
+  int chunk_kb;         // k-blocks accumulated in TMEM before the FP32 sum is promoted to global memory
   int syrk;
   int epi;
   float alpha;
@@ -297,34 +298,41 @@ k_gemm_umma(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__
       const Tile t = p.tiles[it];
       const int kb0 = t.split * kb_per_split;
       const int kb1 = min(p.k_blocks_total, kb0 + kb_per_split);
-      mbar_wait(&tmem_empty[accum], accum_phase ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(accum * kMaxBlockN);
-      uint32_t first = 1;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      // The tensor core accumulates in FP32 with truncation, so a long same-sign sum (a Gram
+      // diagonal) drifts low by ~1e-7 per MMA.  Accumulate at most chunk_kb k-blocks in TMEM,
+      // then let the epilogue add the chunk into the FP32 result with round-to-nearest.
+      int kb = kb0;
+      do {
+        const int kend = min(kb1, kb + p.chunk_kb);
+        mbar_wait(&tmem_empty[accum], accum_phase ^ 1);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-        const uint64_t a_hi = make_smem_desc(sa);
-        const uint64_t b_hi = make_smem_desc(sa + C::kBytesA);
-        const uint64_t a_lo = make_smem_desc(sa + C::kBytesA + C::kBytesB);
-        const uint64_t b_lo = make_smem_desc(sa + 2 * C::kBytesA + C::kBytesB);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(accum * kMaxBlockN);
+        uint32_t first = 1;
+        for (; kb < kend; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint64_t a_hi = make_smem_desc(sa);
+          const uint64_t b_hi = make_smem_desc(sa + C::kBytesA);
+          const uint64_t a_lo = make_smem_desc(sa + C::kBytesA + C::kBytesB);
+          const uint64_t b_lo = make_smem_desc(sa + 2 * C::kBytesA + C::kBytesB);
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 16 elements = 32 bytes along K inside the swizzle atom
-          umma_f16<CG>(tmem_d, a_hi + adv, b_hi + adv, idesc, first ? 0u : 1u);
-          first = 0;
-          if (SPLIT) {
-            umma_f16<CG>(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_f16<CG>(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 16 elements = 32 bytes along K inside the swizzle atom
+            umma_f16<CG>(tmem_d, a_hi + adv, b_hi + adv, idesc, first ? 0u : 1u);
+            first = 0;
+            if (SPLIT) {
+              umma_f16<CG>(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_f16<CG>(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
           }
+          umma_commit<CG>(&empty_bar[stage]);     // frees the smem slot in every CTA of the group
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit<CG>(&empty_bar[stage]);     // frees the smem slot in every CTA of the group
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
-      }
-      if (kb1 > kb0) umma_commit<CG>(&tmem_full[accum]);
-      accum ^= 1;
-      if (accum == 0) accum_phase ^= 1;
+        if (kb1 > kb0) umma_commit<CG>(&tmem_full[accum]);
+        accum ^= 1;
+        if (accum == 0) accum_phase ^= 1;
+      } while (kb < kb1);
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
@@ -338,75 +346,97 @@ k_gemm_umma(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__
       const int r = t.tm * (kTileRowsA * CG) + (int)rank * kTileRowsA + q * 32 + lane;   // global row of this thread
       const int col0 = t.tn * block_n;
       float* Cs = p.C + (long long)t.split * p.split_stride;
-      if (kb1 > kb0) {
-        mbar_wait(&tmem_full[accum], accum_phase);
-        tc_fence_after();
-      }
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(accum * kMaxBlockN);
       const int warp_row_lo = r - lane, warp_row_hi = warp_row_lo + 31;
-      for (int c0 = 0; c0 < block_n; c0 += 32) {
-        const int gc0 = col0 + c0;
-        if (gc0 >= p.n_rows || warp_row_lo >= p.m_rows) break;              // warp-uniform
-        if (p.syrk && gc0 > warp_row_hi) break;                              // strictly above the diagonal
-        uint32_t v[32];
+      const bool row_ok = r < p.m_rows;
+      int kb = kb0;
+      do {   // one pass per accumulation chunk; chunk > 0 adds into what chunk 0 stored
+        const bool first_chunk = kb == kb0;
+        kb = min(kb1, kb + p.chunk_kb);
+        const bool last_chunk = kb >= kb1;
         if (kb1 > kb0) {
-          tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
+          mbar_wait(&tmem_full[accum], accum_phase);
+          tc_fence_after();
         }
-        const bool row_ok = r < p.m_rows;
-        if (p.epi == (int)Epilogue::ColAbsMax) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(accum * kMaxBlockN);
+        for (int c0 = 0; c0 < block_n; c0 += 32) {
+          const int gc0 = col0 + c0;
+          if (gc0 >= p.n_rows || warp_row_lo >= p.m_rows) break;              // warp-uniform
+          if (p.syrk && gc0 > warp_row_hi) break;                              // strictly above the diagonal
+          uint32_t v[32];
+          if (kb1 > kb0) {
+            tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float a = row_ok ? fabsf(__uint_as_float(v[i]) * p.alpha) : 0.f;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
-            if (lane == 0 && gc0 + i < p.n_rows) atomicMax(reinterpret_cast<int*>(Cs) + gc0 + i, __float_as_int(a));
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
           }
-        } else if (p.syrk) {
-          const bool interior = gc0 + 31 <= warp_row_lo;                     // whole 32x32 block below the diagonal
+          if (p.epi == (int)Epilogue::ColAbsMax) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c = gc0 + i;
-            const float x = __uint_as_float(v[i]) * p.alpha;
-            if (row_ok && c < p.n_rows && (interior || c <= r)) {
-              Cs[(long long)r * p.ldc + c] = x;
-              if (c != r) Cs[(long long)c * p.ldc + r] = x;
-            }
-          }
-        } else if (p.epi == (int)Epilogue::Store) {
-          float* dst = Cs + (long long)r * p.ldc + gc0;
-          const bool vec = row_ok && gc0 + 32 <= p.n_rows && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-          if (vec) {
+            for (int i = 0; i < 32; ++i) {
+              float a = row_ok ? fabsf(__uint_as_float(v[i]) * p.alpha) : 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 o = make_float4(__uint_as_float(v[i]) * p.alpha, __uint_as_float(v[i + 1]) * p.alpha,
-                                     __uint_as_float(v[i + 2]) * p.alpha, __uint_as_float(v[i + 3]) * p.alpha);
-              *reinterpret_cast<float4*>(dst + i) = o;
+              for (int o = 16; o; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+              if (lane == 0 && gc0 + i < p.n_rows) atomicMax(reinterpret_cast<int*>(Cs) + gc0 + i, __float_as_int(a));
             }
-          } else if (row_ok) {
+          } else if (p.syrk) {
+            const bool interior = gc0 + 31 <= warp_row_lo;                     // whole 32x32 block below the diagonal
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = gc0 + i;
+              if (row_ok && c < p.n_rows && (interior || c <= r)) {
+                float* d0 = Cs + (long long)r * p.ldc + c;
+                float x = __uint_as_float(v[i]) * p.alpha;
+                if (!first_chunk) x += *d0;
+                *d0 = x;
+                if (last_chunk && c != r) Cs[(long long)c * p.ldc + r] = x;    // mirror once, from one value
+              }
+            }
+          } else if (p.epi == (int)Epilogue::Store) {
+            float* dst = Cs + (long long)r * p.ldc + gc0;
+            const bool vec = row_ok && gc0 + 32 <= p.n_rows && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+            if (vec) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 o = make_float4(__uint_as_float(v[i]) * p.alpha, __uint_as_float(v[i + 1]) * p.alpha,
+                                       __uint_as_float(v[i + 2]) * p.alpha, __uint_as_float(v[i + 3]) * p.alpha);
+                if (!first_chunk) {
+                  const float4 prev = *reinterpret_cast<const float4*>(dst + i);
+                  o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+                }
+                *reinterpret_cast<float4*>(dst + i) = o;
+              }
+            } else if (row_ok) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (gc0 + i < p.n_rows) {
+                  float x = __uint_as_float(v[i]) * p.alpha;
+                  if (!first_chunk) x += dst[i];
+                  dst[i] = x;
+                }
+            }
+          } else {  // StoreTransposed: C[n * ldc + m], coalesced across the warp's rows
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (gc0 + i < p.n_rows) dst[i] = __uint_as_float(v[i]) * p.alpha;
+              if (row_ok && gc0 + i < p.n_rows) {
+                float* d0 = Cs + (long long)(gc0 + i) * p.ldc + r;
+                float x = __uint_as_float(v[i]) * p.alpha;
+                if (!first_chunk) x += *d0;
+                *d0 = x;
+              }
           }
-        } else {  // StoreTransposed: C[n * ldc + m], coalesced across the warp's rows
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (row_ok && gc0 + i < p.n_rows) Cs[(long long)(gc0 + i) * p.ldc + r] = __uint_as_float(v[i]) * p.alpha;
         }
-      }
-      // release the accumulator stage to the MMA issuer (leader CTA's barrier)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 2) mbar_arrive_cluster(&tmem_empty[accum], 0); else mbar_arrive_local(&tmem_empty[accum]);
-      }
-      accum ^= 1;
-      if (accum == 0) accum_phase ^= 1;
+        // release the accumulator stage to the MMA issuer (leader CTA's barrier)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(&tmem_empty[accum], 0); else mbar_arrive_local(&tmem_empty[accum]);
+        }
+        accum ^= 1;
+        if (accum == 0) accum_phase ^= 1;
+      } while (kb < kb1);
     }
   }
 
+  __syncwarp();
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) tmem_dealloc<CG>(tmem_base, kTmemCols);
@@ -496,6 +526,8 @@ void launch(const GemmArgs& a, cudaStream_t st) {
   p.k_blocks_total = kblocks;
   p.splits = splits;
   p.block_n = block_n;
+  // ColAbsMax needs the complete sum before |.|; its operands are unit vectors with random-sign products
+  p.chunk_kb = a.epi == Epilogue::ColAbsMax ? (1 << 30) : (a.chunk_kb > 0 ? a.chunk_kb : (SPLIT ? 8 : 32));
   p.syrk = a.syrk ? 1 : 0;
   p.epi = (int)a.epi;
   p.alpha = a.alpha;
@@ -521,6 +553,7 @@ void launch(const GemmArgs& a, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   SCL_CUDA(cudaLaunchKernelEx(&cfg, kern, mA_hi, mA_lo, mB_hi, mB_lo, p));
+  count_launches(1);
 }
 
 // ---- small elementwise helpers ----------------------------------------------------------
@@ -583,6 +616,7 @@ void gemm_umma(const GemmArgs& a, cudaStream_t st) {
 
 void split_f32_to_f16(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st) {
   if (!n) return;
+  count_launches(1);
   int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
   k_split_f32<<<grid, 256, 0, st>>>(in, n, hi, lo);
   SCL_CUDA(cudaGetLastError());
@@ -591,6 +625,7 @@ void split_f32_to_f16(const float* in, size_t n, __half* hi, __half* lo, cudaStr
 void strided_split_f32_to_f16(const float* in, int rows, int64_t cols, int64_t ld_in, int64_t ld_out, __half* hi,
                               __half* lo, cudaStream_t st) {
   if (!rows) return;
+  count_launches(1);
   dim3 grid((unsigned)std::min<int64_t>((ld_out + 255) / 256, 64), (unsigned)std::min(rows, 65535));
   k_strided_split_f32<<<grid, 256, 0, st>>>(in, rows, cols, ld_in, ld_out, hi, lo);
   SCL_CUDA(cudaGetLastError());
@@ -598,6 +633,7 @@ void strided_split_f32_to_f16(const float* in, int rows, int64_t cols, int64_t l
 
 void reduce_splits(const float* part, int splits, int64_t stride, size_t n, float scale, float* out, cudaStream_t st) {
   if (!n) return;
+  count_launches(1);
   int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
   k_reduce_splits<<<grid, 256, 0, st>>>(part, splits, stride, n, scale, out);
   SCL_CUDA(cudaGetLastError());

@@ -7,6 +7,7 @@
 #include "../../include/sclens_b200.h"
 #include "common.cuh"
 #include "eigen.h"
+#include "prof.h"
 
 struct scl_handle {
   scl_config cfg{};
@@ -15,6 +16,8 @@ struct scl_handle {
   std::unique_ptr<scl::Solver> solver;
   int world = 1, rank = 0;
   void* nccl = nullptr;   // ncclComm_t
+  scl::Prof prof;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
 
   // inputs
   scl::SpMat X;

@@ -164,6 +164,7 @@ void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st) {
   S.ybar.ensure(M); S.sigma.ensure(M); S.mu.ensure(M); S.cent.ensure(M);
   S.mu_f.ensure(M); S.cent_f.ensure(M); S.inv_sigma_f.ensure(M);
   S.scalars.ensure(4);
+  count_launches(8);
   const int wgrid = min((N + 7) / 8, 148 * 8);
   k_row_sum<<<wgrid, 256, 0, st>>>(A.rowptr.p, A.rval.p, N, S.tgc.p);
   k_gene_stats<<<min(M, 148 * 16), 128, 0, st>>>(A.colptr.p, A.rowval.p, A.val.p, S.tgc.p, N, M, S.ybar.p, S.sigma.p,
@@ -257,6 +258,7 @@ k_densify(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx, co
 
 void densify(const SpMat& A, const NormStats& S, int layout, size_t ld, __half* out_hi, __half* out_lo,
              cudaStream_t st) {
+  count_launches(1);
   const bool cell_major = layout == 1;
   const int n_lines = cell_major ? A.N : A.M;
   const int line_len = cell_major ? A.M : A.N;

@@ -145,6 +145,7 @@ static void exclusive_scan(const uint32_t* in, uint32_t* out, int n, cudaStream_
 
 // ---------------------------------------------------------------------------------------
 void build_csr_mirror(SpMat& A, cudaStream_t st) {
+  count_launches(4);
   const int N = A.N, M = A.M;
   const size_t nnz = A.nnz;
   A.rowptr.ensure(N + 1);
@@ -187,6 +188,7 @@ void upload_csc(SpMat& A, int N, int M, size_t nnz, const uint32_t* colptr, cons
     if (nnz) k_rebase<<<grid_for(nnz, 256), 256, 0, st>>>(A.rowval.p, nnz, (uint32_t)index_base);
   }
   SCL_CUDA(cudaGetLastError());
+  count_launches(index_base ? 2 : 0);
   build_csr_mirror(A, st);
 }
 
@@ -226,6 +228,7 @@ __global__ void k_scatter_additions(const uint32_t* __restrict__ add_row, const 
 
 void perturb_merge(const SpMat& base, const uint32_t* d_add_row, const uint32_t* d_add_col, size_t n_add,
                    bool binarise, SpMat& out, cudaStream_t st) {
+  count_launches(n_add ? 6 : 4);
   const int N = base.N, M = base.M;
   const size_t nnz = base.nnz + n_add;
   out.N = N; out.M = M; out.nnz = nnz;
@@ -261,6 +264,7 @@ __global__ void k_gather_f32(const float* __restrict__ src, const uint32_t* __re
 // Shared tail of the null-matrix builders: (trow, tval) hold, per base column segment, the
 // new rows and shuffled values; canonicalise with duplicate summation.
 static void finish_null(const SpMat& base, const uint32_t* trow, const float* tval, SpMat& out, cudaStream_t st) {
+  count_launches(3);
   const int N = base.N, M = base.M;
   out.N = N; out.M = M;
   out.colptr.ensure(M + 1);
@@ -281,6 +285,7 @@ static void finish_null(const SpMat& base, const uint32_t* trow, const float* tv
 }
 
 void permute_null(const SpMat& base, const uint32_t* d_perm, const uint32_t* d_rows, SpMat& out, cudaStream_t st) {
+  count_launches(1);
   const size_t nnz = base.nnz;
   Tmp<float> tval(nnz ? nnz : 1, st);
   if (nnz) k_gather_f32<<<grid_for(nnz, 256), 256, 0, st>>>(base.val.p, d_perm, nnz, tval.p);
@@ -410,6 +415,7 @@ __global__ void k_feistel_gather_f32(const float* __restrict__ src, Feistel f, f
 }
 
 void draw_null_device(const SpMat& base, uint64_t seed, SpMat& out, cudaStream_t st) {
+  count_launches(2);
   const size_t nnz = base.nnz;
   SCL_REQUIRE(nnz > 0, "empty matrix");
   Tmp<uint32_t> trow(nnz, st);
@@ -481,6 +487,7 @@ __global__ void k_zero_cand_compact(const uint32_t* __restrict__ cand_row, const
 // Large exclusive scan (block counts can exceed 1024*chunk comfortably handled by k_exclusive_scan).
 size_t draw_zero_candidates_device(const SpMat& base, uint64_t seed, DBuf<uint32_t>& z1, DBuf<uint32_t>& z2,
                                    cudaStream_t st) {
+  count_launches(3);
   const uint64_t grid = (uint64_t)base.N * (uint64_t)base.M;
   // expected number of distinct positions among nnz uniform draws (the reference draws nnz pairs)
   double d = (double)base.nnz / (double)grid;
@@ -522,6 +529,7 @@ void draw_subset_device(const uint32_t* z1, const uint32_t* z2, size_t n_cand, s
                         uint32_t* out_row, uint32_t* out_col, cudaStream_t st) {
   SCL_REQUIRE(n_take <= n_cand, "sample larger than the candidate pool");
   if (!n_take) return;
+  count_launches(1);
   Feistel f = Feistel::make(n_cand, seed);
   k_subset_pairs<<<grid_for(n_take, 256), 256, 0, st>>>(z1, z2, f, n_take, out_row, out_col);
   SCL_CUDA(cudaGetLastError());
@@ -542,6 +550,7 @@ __global__ void k_gather_pairs(const uint32_t* __restrict__ z1, const uint32_t* 
 void gather_pairs(const uint32_t* z1, const uint32_t* z2, const uint32_t* d_idx, size_t n, uint32_t* out_row,
                   uint32_t* out_col, cudaStream_t st) {
   if (!n) return;
+  count_launches(1);
   k_gather_pairs<<<grid_for(n, 256), 256, 0, st>>>(z1, z2, d_idx, n, out_row, out_col);
   SCL_CUDA(cudaGetLastError());
 }
@@ -571,6 +580,7 @@ __global__ void __launch_bounds__(256) k_noise_baseline(int nm, uint64_t seed, d
 }
 
 double noise_baseline_device(int nm, int n_rep, uint64_t seed, cudaStream_t st) {
+  count_launches(1);
   Tmp<double> mx(n_rep, st);
   k_noise_baseline<<<n_rep, 256, 0, st>>>(nm, mix64(seed ^ 0x70746821ull), mx.p);
   SCL_CUDA(cudaGetLastError());

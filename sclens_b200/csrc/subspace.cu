@@ -166,6 +166,7 @@ void gram_ts(const Ctx& c, const float* A, int ra, const float* B, int rb, doubl
   size_t smem = (size_t)kSlab * (A == B ? pa : pa + pb) * sizeof(float);
   SCL_CUDA(cudaFuncSetAttribute(k_gram_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   k_gram_ts<<<(c.n + kSlab - 1) / kSlab, 256, smem, c.st>>>(A, ra, B, rb, c.n, dS);
+  count_launches(1);
   SCL_CUDA(cudaGetLastError());
 }
 
@@ -174,6 +175,7 @@ void combine_rows(const Ctx& c, const float* In, int rin, const double* dTt, int
   size_t smem = (size_t)rin * kSlab * sizeof(float);
   SCL_CUDA(cudaFuncSetAttribute(k_combine_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   k_combine_rows<<<(c.n + kSlab - 1) / kSlab, 256, smem, c.st>>>(In, rin, dTt, rout, c.n, alpha, base, beta, out);
+  count_launches(1);
   SCL_CUDA(cudaGetLastError());
 }
 
@@ -198,6 +200,8 @@ void apply_G(const Ctx& c, const float* Q, int rows, float* Z) {
     double cost = std::ceil((double)tiles * s / units) / s + 0.02 * s;
     if (cost < best_cost) { best_cost = cost; best = s; }
   }
+  ProfScope ps(&c.h->prof, c.st, PK_OTHER_GEMM);
+  c.h->prof.other_gemm_flops += 2.0 * (double)c.n * c.n * rows;
   if (best == 1) {
     g.C = Z; g.alpha = 1.f;
     gemm_umma(g, c.st);
@@ -308,6 +312,7 @@ void topk_subspace(scl_handle* h, const float* dG, int n, int k, float* dL, floa
       const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
       apply_G(c, Qa, ba, Z.p); ++gemms;
       k_cheb_step<<<grid, 256, 0, st>>>(Z.p, Qa, nullptr, (float)cc, (float)(sigma / e), 0.f, total, Y1.p);
+      count_launches(d);
       SCL_CUDA(cudaMemcpyAsync(Y0.p, Qa, total * sizeof(float), cudaMemcpyDeviceToDevice, st));
       float *xp = Y0.p, *y = Y1.p, *yn = Y2.p;
       for (int i = 2; i <= d; ++i) {
@@ -354,6 +359,7 @@ void topk_subspace(scl_handle* h, const float* dG, int n, int k, float* dL, floa
     combine_rows(c, Qa, ba, dTt.p, ba, 1.0, nullptr, 0.0, Y0.p);    // Q <- Ritz vectors
     combine_rows(c, Z.p, ba, dTt.p, ba, 1.0, nullptr, 0.0, Y1.p);   // Z <- G * Ritz vectors
     k_residuals<<<std::min(ba, 148 * 4), 256, 0, st>>>(Y1.p, Y0.p, dTheta.p, ba, n, dRes.p);
+    count_launches(1);
     SCL_CUDA(cudaGetLastError());
     SCL_CUDA(cudaMemcpyAsync(res.data(), dRes.p, ba * sizeof(double), cudaMemcpyDeviceToHost, st));
     SCL_CUDA(cudaMemcpyAsync(Qa, Y0.p, (size_t)ba * n * sizeof(float), cudaMemcpyDeviceToDevice, st));

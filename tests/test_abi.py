@@ -1,0 +1,106 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every symbol the header declares,
+binds with the signatures the Python mirror uses, and fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "sclens_b200.h")).read()
+    return sorted(set(re.findall(r"SCL_API\s+[\w\s\*]+?\b(scl_\w+)\s*\(", txt)))
+
+
+def test_header_and_binding_agree(lib_built):
+    from sclens_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 40
+    assert sorted(_lib.SIGNATURES) == syms
+    lib = C.CDLL(lib_built)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/sclens_b200.h but not exported"
+
+
+def test_no_torch_types_in_the_abi():
+    txt = open(os.path.join(ROOT, "include", "sclens_b200.h")).read()
+    assert "torch" not in txt.lower() and "at::" not in txt and "std::" not in txt
+    assert 'extern "C"' in txt
+
+
+def test_struct_layouts_match_header(lib_built, tmp_path):
+    """sizeof of every struct as gcc sees the header == the ctypes mirror (plain C, no C++ needed)."""
+    import subprocess
+    from sclens_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "sclens_b200.h"\nint main(void){printf("%zu %zu %zu %zu\\n",'
+                   'sizeof(scl_config),sizeof(scl_signal_info),sizeof(scl_robust_info),sizeof(scl_profile));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [C.sizeof(_lib.Config), C.sizeof(_lib.SignalInfo), C.sizeof(_lib.RobustInfo), C.sizeof(_lib.Profile)]
+
+
+def test_fails_loudly_without_gpu(lib_built):
+    import torch
+    from sclens_b200 import Handle, SclError, sclens
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(SclError) as e:
+        Handle()
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+    with pytest.raises(ValueError):
+        sclens(np.eye(4), device_="cpu")
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: no product source imports it, and importing the package does
+    not pull it in."""
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "sclens_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f"{f} imports the oracle"
+    code = "import sys; sys.path.insert(0, %r); import sclens_b200, sclens_b200.preprocess, sclens_b200.synth; " \
+           "assert not [m for m in sys.modules if m.split('.')[0] == 'oracle']" % ROOT
+    subprocess.check_call([sys.executable, "-c", code])
+
+
+def test_host_only_entry_points(lib_built):
+    """scl_op_mp_fit and the work-partition helpers are pure host code: callable without a GPU."""
+    from oracle import sclens_oracle as orc
+    from sclens_b200 import _lib
+    from sclens_b200._lib import ptr
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    n, K = 300, 700
+    L = np.linalg.eigvalsh(np.cov(rng.standard_normal((n, K)), bias=True)).astype(np.float32)
+    Lr = np.linalg.eigvalsh(np.cov(rng.standard_normal((n, K)), bias=True)).astype(np.float32)
+    L[-3:] = [3.5, 4.5, 7.0]
+    out = np.empty(8)
+    Lr1 = np.ascontiguousarray(Lr[:-1])
+    assert lib.scl_op_mp_fit(ptr(L, C.c_float), n, ptr(Lr1, C.c_float), n - 1, ptr(out, C.c_double)) == 0
+    L_mp, b_plus, b_min, it = orc.mp_calculation(L.astype(np.float64), Lr1.astype(np.float64))
+    lam = orc.tw(L.astype(np.float64), L_mp)[0]
+    assert abs(out[0] - lam) < 1e-12 * lam and abs(out[1] - b_plus) < 1e-12 and abs(out[2] - b_min) < 1e-12
+    assert int(out[4]) == len(L_mp) and int(out[5]) == it and int(out[7]) == 3
+    chk = orc.mp_check(L_mp)
+    assert abs(out[3] - chk["ks_static"]) < 1e-9 and bool(out[6]) == chk["pass"]
+    # degenerate input -> error code, not a crash
+    assert lib.scl_op_mp_fit(ptr(L, C.c_float), 1, ptr(Lr1, C.c_float), 1, ptr(out, C.c_double)) < 0
+    ids = np.empty(32, np.int32)
+    cnt = C.c_int32()
+    seen = []
+    for r in range(3):
+        assert lib.scl_plan_replicates(20, 3, r, ptr(ids, C.c_int32), C.byref(cnt)) == 0
+        seen += ids[:cnt.value].tolist()
+    assert sorted(seen) == list(range(20))
+    step = C.c_int32()
+    assert lib.scl_plan_search_wave(2, 8, 5, C.byref(step)) == 0 and step.value == 21
+    assert lib.scl_plan_replicates(20, 0, 0, None, C.byref(cnt)) < 0

@@ -1,0 +1,67 @@
+"""-m gpu checks at BASELINE.json's full single-GPU shape (configs[1]: 10k cells x 20k genes): the
+north-star numerics contract (eigenvalues within 1e-4 relative, exact signal count) against a
+Float64 evaluation of the same normalised matrix, plus size-independent properties."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from sclens_b200 import Handle, SCL_GRAM_FP16, _lib
+from sclens_b200._lib import ptr
+from sclens_b200.synth import make_counts, qc_is_identity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big():
+    X = make_counts(10000, 20000, seed=0)
+    assert qc_is_identity(X)          # QC is the identity on the benchmark input
+    assert abs((1 - X.nnz / (X.shape[0] * X.shape[1])) - 0.92) < 0.003
+    return X
+
+
+def test_signal_stage_full_size(big):
+    import torch
+    X = big
+    N, M = X.shape
+    with Handle(gram_mode=SCL_GRAM_FP16, seed=0) as h:
+        h.set_counts(X)
+        si = h.run_signal()
+        L = h.L().astype(np.float64)
+        # Float64 reference spectrum of the same matrix: dense normalised operand (hi+lo = Float32 value) from
+        # the normalisation operator, Gram and eigvalsh in Float64 on the GPU with torch (test infrastructure)
+        ld = M
+        hi = np.empty((N, ld), np.uint16)
+        lo = np.empty((N, ld), np.uint16)
+        colptr, rowval, val = _lib.as_u32(X.indptr), _lib.as_u32(X.indices), _lib.as_f32(X.data)
+        h._ck(h.lib.scl_op_normalize(h.h, N, M, X.nnz, ptr(colptr, C.c_uint32), ptr(rowval, C.c_uint32),
+                                     ptr(val, C.c_float), 1, ld, ptr(hi, C.c_uint16), ptr(lo, C.c_uint16),
+                                     None, None, None, None, None))
+        A = torch.from_numpy(hi.view(np.float16)).cuda().double() + torch.from_numpy(lo.view(np.float16)).cuda().double()
+        G = A @ A.T / M
+        Lref = torch.linalg.eigvalsh(G).cpu().numpy()
+        keep = Lref >= si.b_minus
+        rel = np.abs(L[keep] - Lref[keep]) / Lref[keep]
+        assert rel.max() < 1e-4, rel.max()                    # north star: eigenvalues within 1e-4 relative
+        assert si.n_signal == int((Lref > si.lambda_c).sum())  # bit-exact signal count
+        assert si.n_signal == 7                                # K-1 planted cell-type contrasts
+        # columns of the operand are centred: the cell Gram annihilates the ones vector
+        assert abs(L[0]) < 1e-4 * L[-1]
+        # trace identity: sum of eigenvalues == |Xtilde|_F^2 / M
+        tr = float((A * A).sum().item()) / M
+        assert abs(L.sum() - tr) / tr < 2e-5
+
+
+def test_moderate_size_matches_oracle_eigenvalues():
+    from oracle import sclens_oracle as orc
+    X = make_counts(2500, 5000, seed=4)
+    dense, _ = orc.normalize_main(X)
+    Lref = np.linalg.eigvalsh(dense @ dense.T / X.shape[1])
+    with Handle(seed=1) as h:
+        h.set_counts(X)
+        si = h.run_signal()
+        L = h.L().astype(np.float64)
+    keep = Lref >= si.b_minus
+    assert np.max(np.abs(L[keep] - Lref[keep]) / Lref[keep]) < 1e-4
+    assert si.n_signal == int((Lref > si.lambda_c).sum())

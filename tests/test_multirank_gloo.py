@@ -1,0 +1,75 @@
+"""World-size-2 gloo test (CPU) of the N>1 host logic: every replicate and every speculative search
+step is owned by exactly one rank, and applying the stop rule in step order to gathered results gives
+the sequential answer."""
+import os
+import sys
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sequential_stop(d2, p_th, p_step=0.001, tank_n=5):
+    """The reference's loop (:725-761) on a precomputed sequence of second-smallest values."""
+    p_, tank = 0.999, []
+    for step, d in enumerate(d2):
+        tank.append(d)
+        last = tank[-tank_n:]
+        if (sum(x < p_th for x in last) > tank_n - 1) or p_ < 0.9:
+            return step + 1, p_ + (tank_n - 1) * p_step
+        p_ -= p_step
+    raise AssertionError("sequence too short")
+
+
+def worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import ctypes as C
+    import torch
+    from sclens_b200 import _lib
+    from sclens_b200._lib import ptr
+    from sclens_b200.api import speculative_search_merge
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = _lib.load()
+    ids = np.empty(64, np.int32)
+    cnt = C.c_int32()
+    assert lib.scl_plan_replicates(21, world, rank, ptr(ids, C.c_int32), C.byref(cnt)) == 0
+    mine = torch.zeros(21, dtype=torch.int32)
+    mine[ids[:cnt.value].tolist()] = 1
+    dist.all_reduce(mine)
+    assert bool((mine == 1).all())                      # each replicate owned exactly once
+    # speculative search: rank g evaluates step wave*world+g of a fixed synthetic d2 sequence
+    rng = np.random.default_rng(0)
+    d2_all = np.concatenate([0.3 - 0.01 * np.arange(12), 0.1 + 0.001 * rng.standard_normal(30)])
+    p_th = 0.15
+    gathered, stop = [], None
+    wave = 0
+    while stop is None:
+        step = C.c_int32()
+        assert lib.scl_plan_search_wave(wave, world, rank, C.byref(step)) == 0
+        local = torch.tensor([d2_all[step.value]], dtype=torch.float64)
+        out = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(out, local)
+        gathered += [float(o.item()) for o in out]
+        stop = speculative_search_merge(gathered, p_th)
+        wave += 1
+    want = sequential_stop(d2_all, p_th)
+    assert stop[0] == want[0] and stop[1] == want[1], (stop, want)
+    q.put((rank, stop))
+    dist.destroy_process_group()
+
+
+def test_two_rank_partition_and_speculative_search():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    res = sorted(q.get() for _ in range(2))
+    assert res[0][1] == res[1][1]

@@ -63,8 +63,9 @@ def test_gemm_tn_fp16(h, h1, shape, cg):
     B = rng.standard_normal((n, K)).astype(np.float32)
     ref = A.astype(np.float16).astype(np.float64) @ B.astype(np.float16).astype(np.float64).T
     got = run_gemm(hh, A, B, split=False)
-    scale = np.sqrt(K)
-    assert np.max(np.abs(got - ref)) / scale < 2e-5     # fp32 accumulation of exact fp16 products
+    scale = np.max(np.abs(ref))
+    # exact binary16 products, FP32 tensor-core accumulation (truncating) in chunks of <= 2048 terms
+    assert np.max(np.abs(got - ref)) / scale < 2e-5
     got_t = run_gemm(hh, A, B, split=False, colmajor=True, alpha=0.5)
     assert np.max(np.abs(got_t - 0.5 * ref)) / scale < 2e-5
 
@@ -78,8 +79,8 @@ def test_gemm_tn_split_is_fp32_accurate(h, h1, cg):
     B = rng.standard_normal((n, K)).astype(np.float32)
     ref = A.astype(np.float64) @ B.astype(np.float64).T
     got = run_gemm(hh, A, B, split=True)
-    err = np.max(np.abs(got - ref)) / np.sqrt(K)
-    assert err < 5e-6, err
+    err = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
+    assert err < 1e-5, err
 
 
 @pytest.mark.parametrize("rows,K", [(256, 512), (700, 1300), (1030, 333), (90, 4000)])
@@ -98,8 +99,7 @@ def test_gram_syrk(h, h1, rows, K, cg, split):
                               1.0 / K, ptr(G, C.c_float)))
     src = A.astype(np.float64) if split else hi.astype(np.float64)
     ref = src @ src.T / K
-    tol = 5e-6 if split else 2e-5
-    assert np.max(np.abs(G - ref)) * np.sqrt(K) < tol * K / np.sqrt(K) + 1e-5
+    assert np.max(np.abs(G - ref)) / np.max(np.abs(ref)) < 2e-5
     assert np.array_equal(G, G.T)       # mirrored store: exactly symmetric
 
 
@@ -129,7 +129,8 @@ def test_normalize_matches_oracle(h, N, M, layout):
     got = got_hi + lo.view(np.float16)[:, :length].astype(np.float64)
     # hi alone is the correctly rounded binary16 value (up to float32 background arithmetic)
     assert np.max(np.abs(got_hi - want) / (np.abs(want) + 1e-3)) < 6e-4
-    assert np.max(np.abs(got - want) / (np.abs(want) + 1e-3)) < 2e-6
+    # hi + lo reproduces the Float32 rounding of the Float64 reference value
+    assert np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))) < 4e-7
     assert not hi.view(np.float16)[:, length:].any()
 
 
