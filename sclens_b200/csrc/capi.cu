@@ -229,7 +229,7 @@ int32_t scl_set_noise_baseline(scl_handle* h, double p_th) {
   return SCL_OK;
 }
 
-static int32_t push_sample(scl_handle* h, std::deque<std::vector<uint32_t>>& q, int64_t n, const uint32_t* s, int32_t base) {
+static int32_t push_sample(scl_handle* h, std::vector<std::vector<uint32_t>>& q, int64_t n, const uint32_t* s, int32_t base) {
   if (!h || n < 0 || (n > 0 && !s)) return SCL_ERR_INVALID;
   std::vector<uint32_t> v(s, s + n);
   if (base)

@@ -105,8 +105,12 @@ double noise_baseline_device(int nm, int n_rep, uint64_t seed, cudaStream_t st);
 // ---- normalize.cu ----
 void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st);
 // layout 0: gene-major out[M][ld] (column-major N x M); 1: cell-major out[N][ld]
+// sumsq_partial (optional, [lines][densify_strips(ld)]): exact per-strip sums of squares of the emitted values
+// [pos0,pos1): range of positions of every line to emit (default: the whole padded line) - the cell block of a rank
 void densify(const SpMat& A, const NormStats& S, int layout, size_t ld, __half* out_hi, __half* out_lo,
-             cudaStream_t st);
+             cudaStream_t st, double* sumsq_partial = nullptr, long long pos0 = 0, long long pos1 = -1);
+int densify_strips(size_t n_pos);
+void set_gram_diagonal(float* G, int n, int n_strips, const double* partial, double scale, cudaStream_t st);
 
 // ---- gemm_umma.cu ----
 struct GemmOperand {
@@ -131,8 +135,10 @@ struct GemmArgs {
 };
 void gemm_umma(const GemmArgs& a, cudaStream_t st);
 void split_f32_to_f16(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st);
+// pre_scale (a power of two) is applied before rounding so the low-order part of small entries (unit vectors in
+// high dimension: ~1/sqrt(n)) stays in the normal binary16 range; the caller divides alpha by it
 void strided_split_f32_to_f16(const float* in, int rows, int64_t cols, int64_t ld_in, int64_t ld_out, __half* hi,
-                              __half* lo, cudaStream_t st);
+                              __half* lo, cudaStream_t st, float pre_scale = 1.f);
 void reduce_splits(const float* part, int splits, int64_t stride, size_t n, float scale, float* out, cudaStream_t st);
 int sm_count();
 

@@ -569,10 +569,10 @@ __global__ void k_split_f32(const float* __restrict__ in, size_t n, __half* __re
 }
 
 __global__ void k_strided_split_f32(const float* __restrict__ in, int rows, long long cols, long long ld_in,
-                                    long long ld_out, __half* __restrict__ hi, __half* __restrict__ lo) {
+                                    long long ld_out, __half* __restrict__ hi, __half* __restrict__ lo, float pre_scale) {
   for (int r = blockIdx.y; r < rows; r += gridDim.y) {
     for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ld_out; c += (long long)gridDim.x * blockDim.x) {
-      float x = c < cols ? in[(long long)r * ld_in + c] : 0.f;
+      float x = c < cols ? in[(long long)r * ld_in + c] * pre_scale : 0.f;
       __half h = __float2half_rn(x);
       hi[(long long)r * ld_out + c] = h;
       if (lo) lo[(long long)r * ld_out + c] = __float2half_rn(x - __half2float(h));
@@ -623,11 +623,11 @@ void split_f32_to_f16(const float* in, size_t n, __half* hi, __half* lo, cudaStr
 }
 
 void strided_split_f32_to_f16(const float* in, int rows, int64_t cols, int64_t ld_in, int64_t ld_out, __half* hi,
-                              __half* lo, cudaStream_t st) {
+                              __half* lo, cudaStream_t st, float pre_scale) {
   if (!rows) return;
   count_launches(1);
   dim3 grid((unsigned)std::min<int64_t>((ld_out + 255) / 256, 64), (unsigned)std::min(rows, 65535));
-  k_strided_split_f32<<<grid, 256, 0, st>>>(in, rows, cols, ld_in, ld_out, hi, lo);
+  k_strided_split_f32<<<grid, 256, 0, st>>>(in, rows, cols, ld_in, ld_out, hi, lo, pre_scale);
   SCL_CUDA(cudaGetLastError());
 }
 

@@ -30,7 +30,7 @@ struct scl_handle {
   scl::DBuf<uint32_t> null_perm, null_rows;
   bool have_pth = false;
   double p_th = 0;
-  std::deque<std::vector<uint32_t>> search_sples, perturb_sples;
+  std::vector<std::vector<uint32_t>> search_sples, perturb_sples;   // indexed by search step / replicate
 
   // signal stage results
   bool signal_done = false;
@@ -58,8 +58,10 @@ namespace scl {
 void run_signal(scl_handle* h);
 void run_robustness(scl_handle* h, double th, double p_step, int n_perturb);
 // shared building blocks (also used by the scl_op_* entry points)
+// shard=true (and world > 1): every rank contracts its own slice of the long axis (cells when N > M) and the
+// partial Gram matrices are summed with ncclAllReduce
 void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf<__half>& lo, float* dG, int nm,
-             float scale, bool split);
+             float scale, bool split, bool shard = false);
 void corr_colabsmax(scl_handle* h, const float* dV, int nv, const float* dW, int nw, int n, float* d_out);
 void topk_subspace(scl_handle* h, const float* dG, int n, int k, float* dL, float* dV, int* iters);
 void score_sets(scl_handle* h, int N, int k, int min_pc, int n_perturb, const float* d_nV, const float* d_sets,

@@ -191,15 +191,18 @@ k_densify(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx, co
           const double* __restrict__ tgc, const double* __restrict__ sigma, const double* __restrict__ mu,
           const double* __restrict__ inv_s, const double* __restrict__ cent, const float* __restrict__ inv_s_f,
           const float* __restrict__ mu_f, const float* __restrict__ cent_f, int n_lines, int line_len, size_t ld,
-          __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+          __half* __restrict__ out_hi, __half* __restrict__ out_lo, double* __restrict__ sumsq_partial, int pos0,
+          int pos1) {
   __shared__ __align__(16) float tile[kDenseChunk];
-  const int n_strips = (int)((ld + kDenseChunk - 1) / kDenseChunk);
+  __shared__ double red_sq[kDenseThreads / 32];
+  // positions [pos0, pos1) of every line are emitted (pos0 multiple of 8; the whole padded line by default)
+  const int n_strips = (pos1 - pos0 + kDenseChunk - 1) / kDenseChunk;
   const long long total = (long long)n_lines * n_strips;
   for (long long w = blockIdx.x; w < total; w += gridDim.x) {
     const int line = (int)(w / n_strips);
-    const int base = (int)(w % n_strips) * kDenseChunk;
-    const int span = (int)min((size_t)kDenseChunk, ld - base);       // includes the zero pad up to ld
-    const int len = max(0, min(kDenseChunk, line_len - base));       // real positions
+    const int base = pos0 + (int)(w % n_strips) * kDenseChunk;
+    const int span = min(kDenseChunk, pos1 - base);                  // includes the zero pad up to ld
+    const int len = max(0, min(span, line_len - base));              // real positions
     // background
     if (CELL_MAJOR) {
       const float a = -inv_s_f[line];
@@ -238,6 +241,7 @@ k_densify(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx, co
     // stream out: 8 elements (16 bytes) per store
     __half* dst_hi = out_hi + (size_t)line * ld + base;
     __half* dst_lo = WITH_LO ? out_lo + (size_t)line * ld + base : nullptr;
+    double sq = 0;   // exact sum of squares of the emitted (rounded) values: the Gram diagonal
     for (int i = threadIdx.x * 8; i < span; i += kDenseThreads * 8) {
       float4 v0 = *reinterpret_cast<const float4*>(&tile[i]);
       float4 v1 = *reinterpret_cast<const float4*>(&tile[i + 4]);
@@ -248,22 +252,53 @@ k_densify(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx, co
       for (int q = 0; q < 8; ++q) {
         h[q] = __float2half_rn(f[q]);
         if (WITH_LO) l[q] = __float2half_rn(f[q] - __half2float(h[q]));
+        const double e = WITH_LO ? (double)__half2float(h[q]) + (double)__half2float(l[q]) : (double)__half2float(h[q]);
+        sq += e * e;
       }
       *reinterpret_cast<uint4*>(dst_hi + i) = *reinterpret_cast<const uint4*>(h);
       if (WITH_LO) *reinterpret_cast<uint4*>(dst_lo + i) = *reinterpret_cast<const uint4*>(l);
+    }
+    if (sumsq_partial) {
+      sq = warp_sum(sq);
+      if ((threadIdx.x & 31) == 0) red_sq[threadIdx.x >> 5] = sq;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = 0;
+        for (int q = 0; q < kDenseThreads / 32; ++q) t += red_sq[q];
+        sumsq_partial[w] = t;   // [line][strip]
+      }
     }
     __syncthreads();
   }
 }
 
+// G[i][i] = scale * sum over the line's strips of the exact sums of squares (fixed order: deterministic)
+__global__ void k_set_diagonal(float* __restrict__ G, int n, int n_strips, const double* __restrict__ partial, double scale) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0;
+  for (int q = 0; q < n_strips; ++q) s += partial[(size_t)i * n_strips + q];
+  G[(size_t)i * n + i] = (float)(s * scale);
+}
+
+int densify_strips(size_t n_pos) { return (int)((n_pos + kDenseChunk - 1) / kDenseChunk); }
+
+void set_gram_diagonal(float* G, int n, int n_strips, const double* partial, double scale, cudaStream_t st) {
+  count_launches(1);
+  k_set_diagonal<<<(n + 255) / 256, 256, 0, st>>>(G, n, n_strips, partial, scale);
+  SCL_CUDA(cudaGetLastError());
+}
+
 void densify(const SpMat& A, const NormStats& S, int layout, size_t ld, __half* out_hi, __half* out_lo,
-             cudaStream_t st) {
+             cudaStream_t st, double* sumsq_partial, long long pos0, long long pos1) {
   count_launches(1);
   const bool cell_major = layout == 1;
   const int n_lines = cell_major ? A.N : A.M;
   const int line_len = cell_major ? A.M : A.N;
   SCL_REQUIRE(ld % 8 == 0 && ld >= (size_t)line_len, "leading dimension must be a multiple of 8 and >= line length");
-  const long long total = (long long)n_lines * ((ld + kDenseChunk - 1) / kDenseChunk);
+  if (pos1 < 0) { pos0 = 0; pos1 = (long long)ld; }
+  SCL_REQUIRE(pos0 % 8 == 0 && pos0 >= 0 && pos1 <= (long long)ld && pos1 > pos0 && (pos1 % 8 == 0 || pos1 == (long long)ld), "bad densify range");
+  const long long total = (long long)n_lines * ((pos1 - pos0 + kDenseChunk - 1) / kDenseChunk);
   const int grid = (int)(total < 148LL * 6 ? total : 148LL * 6);
   const uint32_t* ptr = cell_major ? A.rowptr.p : A.colptr.p;
   const uint32_t* idx = cell_major ? A.colidx.p : A.rowval.p;
@@ -271,7 +306,8 @@ void densify(const SpMat& A, const NormStats& S, int layout, size_t ld, __half* 
 #define SCL_LAUNCH_DENSIFY(CM, LO)                                                                              \
   k_densify<CM, LO><<<grid, kDenseThreads, 0, st>>>(ptr, idx, val, S.tgc.p, S.sigma.p, S.mu.p, S.inv_s.p,       \
                                                     S.cent.p, S.inv_s_f.p, S.mu_f.p, S.cent_f.p, n_lines,       \
-                                                    line_len, ld, out_hi, out_lo)
+                                                    line_len, ld, out_hi, out_lo, sumsq_partial, (int)pos0,   \
+                                                    (int)pos1)
   if (cell_major) {
     if (out_lo) SCL_LAUNCH_DENSIFY(true, true); else SCL_LAUNCH_DENSIFY(true, false);
   } else {

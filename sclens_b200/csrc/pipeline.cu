@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <nccl.h>
 #include "handle.h"
 #include "tmp.cuh"
 
@@ -33,6 +34,18 @@ void Prof::reset() {
 namespace {
 
 inline size_t round8(size_t x) { return (x + 7) / 8 * 8; }
+
+// Unit vectors in dimension n have entries ~1/sqrt(n); scaled by 2^10 before the binary16 hi/lo split their
+// low-order parts stay normal numbers (|entry| <= 1 -> <= 1024, far below 65504).  Undone through alpha.
+constexpr float kUnitScale = 1024.f;
+
+#define SCL_NCCL(x)                                                                                   \
+  do {                                                                                                \
+    ncclResult_t r_ = (x);                                                                            \
+    if (r_ != ncclSuccess) throw scl::Error(SCL_ERR_NCCL, std::string(#x) + ": " + ncclGetErrorString(r_)); \
+  } while (0)
+
+inline bool multi(const scl_handle* h) { return h->world > 1 && h->nccl != nullptr; }
 
 struct Timer {
   cudaEvent_t a, b;
@@ -153,7 +166,7 @@ double quantile7(const std::vector<double>& sorted, double p) {
 // ---------------------------------------------------------------------------------------
 // normalise A and form its Wishart matrix on the smaller side:  dG = operand * operand^T * scale
 void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf<__half>& lo, float* dG, int nm,
-             float scale, bool split) {
+             float scale, bool split, bool shard) {
   {
     ProfScope ps(&h->prof, h->st, PK_STATS);
     compute_norm_stats(A, S, h->st);
@@ -165,23 +178,49 @@ void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf
   SCL_REQUIRE(rows == nm, "Gram size mismatch");
   hi.ensure((size_t)rows * ld);
   if (split) lo.ensure((size_t)rows * ld);
-  {
-    ProfScope ps(&h->prof, h->st, PK_DENSIFY);
-    densify(A, S, gene_side ? 0 : 1, ld, hi.p, split ? lo.p : nullptr, h->st);
-    h->prof.densify_alg_bytes += 8.0 * (double)A.nnz + 4.0 * (A.M + 1) + (double)A.N * A.M * (split ? 4.0 : 2.0);
+  // Multi-GPU: rank g owns the g-th block of the contraction axis (a cell block when N > M).  It densifies and
+  // contracts only that block; the partial Gram matrices are summed over NVLink.
+  int64_t k0 = 0, k1 = (int64_t)ld;
+  const bool sharded = shard && multi(h);
+  if (sharded) {
+    const int64_t kblocks = (K + 63) / 64, per = (kblocks + h->world - 1) / h->world;
+    k0 = std::min<int64_t>(K, (int64_t)h->rank * per * 64);
+    k1 = std::min<int64_t>((int64_t)ld, (int64_t)(h->rank + 1) * per * 64);
+    if (h->rank == h->world - 1) k1 = (int64_t)ld;
   }
-  GemmArgs g;
-  g.A.hi = hi.p; g.A.lo = split ? lo.p : nullptr; g.A.rows = rows; g.A.K = K; g.A.ld = (int64_t)ld;
-  g.B = g.A;
-  g.syrk = true;
-  g.alpha = scale;
-  g.C = dG;
-  g.ldc = nm;
-  g.cta_group = cta_group_of(h);
-  {
-    ProfScope ps(&h->prof, h->st, PK_GRAM_GEMM);
-    gemm_umma(g, h->st);
-    h->prof.gram_alg_flops += (double)rows * (rows + 1.0) * (double)K;
+  const bool have_work = k1 > k0;
+  // exact Gram diagonal: the tensor core's truncating FP32 accumulation biases long same-sign sums low; the
+  // diagonal (the only systematically same-sign sum) is taken from the writer's exact Float64 sums of squares
+  const int n_strips = have_work ? densify_strips((size_t)(k1 - k0)) : 1;
+  Tmp<double> sumsq((size_t)rows * n_strips, h->st);
+  if (have_work) {
+    {
+      ProfScope ps(&h->prof, h->st, PK_DENSIFY);
+      densify(A, S, gene_side ? 0 : 1, ld, hi.p, split ? lo.p : nullptr, h->st, sumsq.p, k0, k1);
+      const double frac = (double)(k1 - k0) / (double)ld;
+      h->prof.densify_alg_bytes += frac * (8.0 * (double)A.nnz + (double)A.N * A.M * (split ? 4.0 : 2.0)) + 4.0 * (A.M + 1);
+    }
+    const int64_t Ks = std::min<int64_t>(K, k1) - k0;
+    GemmArgs g;
+    g.A.hi = hi.p + k0; g.A.lo = split ? lo.p + k0 : nullptr; g.A.rows = rows; g.A.K = Ks; g.A.ld = (int64_t)ld;
+    g.B = g.A;
+    g.syrk = true;
+    g.alpha = scale;
+    g.C = dG;
+    g.ldc = nm;
+    g.cta_group = cta_group_of(h);
+    {
+      ProfScope ps(&h->prof, h->st, PK_GRAM_GEMM);
+      gemm_umma(g, h->st);
+      h->prof.gram_alg_flops += (double)rows * (rows + 1.0) * (double)Ks;
+    }
+    set_gram_diagonal(dG, nm, n_strips, sumsq.p, (double)scale, h->st);
+  } else {
+    SCL_CUDA(cudaMemsetAsync(dG, 0, (size_t)nm * nm * sizeof(float), h->st));
+  }
+  if (sharded) {
+    ProfScope ps(&h->prof, h->st, PK_SMALL);
+    SCL_NCCL(ncclAllReduce(dG, dG, (size_t)nm * nm, ncclFloat, ncclSum, (ncclComm_t)h->nccl, h->st));
   }
 }
 
@@ -189,9 +228,10 @@ void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf
 static void corr_colabsmax_pre(scl_handle* h, const GemmOperand& V, const float* dW, int nw, int n, float* d_out) {
   const size_t ld = (size_t)V.ld;
   Tmp<__half> w_hi((size_t)nw * ld, h->st), w_lo((size_t)nw * ld, h->st);
-  strided_split_f32_to_f16(dW, nw, n, n, (int64_t)ld, w_hi.p, w_lo.p, h->st);
+  strided_split_f32_to_f16(dW, nw, n, n, (int64_t)ld, w_hi.p, w_lo.p, h->st, kUnitScale);
   SCL_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nw * sizeof(float), h->st));
   GemmArgs g;
+  g.alpha = 1.f / (kUnitScale * kUnitScale);
   g.A = V;
   g.B.hi = w_hi.p; g.B.lo = w_lo.p; g.B.rows = nw; g.B.K = n; g.B.ld = (int64_t)ld;
   g.epi = Epilogue::ColAbsMax;
@@ -206,7 +246,7 @@ static void corr_colabsmax_pre(scl_handle* h, const GemmOperand& V, const float*
 void corr_colabsmax(scl_handle* h, const float* dV, int nv, const float* dW, int nw, int n, float* d_out) {
   const size_t ld = round8((size_t)n);
   Tmp<__half> v_hi((size_t)nv * ld, h->st), v_lo((size_t)nv * ld, h->st);
-  strided_split_f32_to_f16(dV, nv, n, n, (int64_t)ld, v_hi.p, v_lo.p, h->st);
+  strided_split_f32_to_f16(dV, nv, n, n, (int64_t)ld, v_hi.p, v_lo.p, h->st, kUnitScale);
   GemmOperand V;
   V.hi = v_hi.p; V.lo = v_lo.p; V.rows = nv; V.K = n; V.ld = (int64_t)ld;
   corr_colabsmax_pre(h, V, dW, nw, n, d_out);
@@ -221,7 +261,7 @@ static void back_project(scl_handle* h, const SpMat& A, const NormStats& S, cons
   Tmp<__half> x_hi((size_t)N * ldm, h->st), x_lo((size_t)N * ldm, h->st);
   densify(A, S, 1, ldm, x_hi.p, x_lo.p, h->st);
   Tmp<__half> v_hi((size_t)k * ldm, h->st), v_lo((size_t)k * ldm, h->st);
-  strided_split_f32_to_f16(dVrows, k, M, ld_v, (int64_t)ldm, v_hi.p, v_lo.p, h->st);
+  strided_split_f32_to_f16(dVrows, k, M, ld_v, (int64_t)ldm, v_hi.p, v_lo.p, h->st, kUnitScale);   // rows are normalised afterwards
   GemmArgs g;
   g.A.hi = x_hi.p; g.A.lo = x_lo.p; g.A.rows = N; g.A.K = M; g.A.ld = (int64_t)ldm;
   g.B.hi = v_hi.p; g.B.lo = v_lo.p; g.B.rows = k; g.B.K = M; g.B.ld = (int64_t)ldm;
@@ -257,7 +297,7 @@ void run_signal(scl_handle* h) {
   W.ensure(nm);
   Timer tm(st);
   // --- data matrix: normalise (:677-696), Gram (:529/:569), eigen (:530/:570)
-  gram_of(h, X, h->S_main, op_hi, op_lo, G.p, nm, 1.0f / (float)M, split);
+  gram_of(h, X, h->S_main, op_hi, op_lo, G.p, nm, 1.0f / (float)M, split, /*shard=*/true);
   info.t_normalize_ms = 0;  // fused into the Gram timing below (one stream); see bench for per-kernel times
   info.t_gram_ms += tm.stop();
   { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G.p, nm, W.p, true, st); }
@@ -292,7 +332,7 @@ void run_signal(scl_handle* h) {
     DBuf<float> G2, W2;
     G2.ensure((size_t)nm * nm);
     W2.ensure(nm);
-    gram_of(h, h->Xnull, Sn, op_hi, op_lo, G2.p, nm, 1.0f / (float)M, split);
+    gram_of(h, h->Xnull, Sn, op_hi, op_lo, G2.p, nm, 1.0f / (float)M, split, /*shard=*/true);
     info.t_gram_ms += tm.stop();
     { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G2.p, nm, W2.p, false, st); }
     info.t_syevd_ms += tm.stop();
@@ -344,13 +384,13 @@ void score_sets(scl_handle* h, int N, int k, int min_pc, int n_perturb, const fl
   const int P = n_perturb, tot = P * min_pc;
   // |nV' * nV_set[r]| for all r at once (:788)
   Tmp<__half> a_hi((size_t)k * ld, st), a_lo((size_t)k * ld, st), s_hi((size_t)tot * ld, st), s_lo((size_t)tot * ld, st);
-  strided_split_f32_to_f16(d_nV, k, N, N, (int64_t)ld, a_hi.p, a_lo.p, st);
-  strided_split_f32_to_f16(d_sets, tot, N, N, (int64_t)ld, s_hi.p, s_lo.p, st);
+  strided_split_f32_to_f16(d_nV, k, N, N, (int64_t)ld, a_hi.p, a_lo.p, st, kUnitScale);
+  strided_split_f32_to_f16(d_sets, tot, N, N, (int64_t)ld, s_hi.p, s_lo.p, st, kUnitScale);
   GemmOperand A, B;
   A.hi = a_hi.p; A.lo = a_lo.p; A.rows = k; A.K = N; A.ld = (int64_t)ld;
   B.hi = s_hi.p; B.lo = s_lo.p; B.rows = tot; B.K = N; B.ld = (int64_t)ld;
   Tmp<float> c1((size_t)k * tot, st);
-  gemm_splitk(h, A, B, false, 1.f, Epilogue::Store, c1.p, tot, (size_t)k * tot);
+  gemm_splitk(h, A, B, false, 1.f / (kUnitScale * kUnitScale), Epilogue::Store, c1.p, tot, (size_t)k * tot);
   std::vector<float> hc1((size_t)k * tot);
   SCL_CUDA(cudaMemcpyAsync(hc1.data(), c1.p, hc1.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
   SCL_CUDA(cudaStreamSynchronize(st));
@@ -377,11 +417,11 @@ void score_sets(scl_handle* h, int N, int k, int min_pc, int n_perturb, const fl
     SCL_CUDA(cudaGetLastError());
   }
   Tmp<__half> u_hi((size_t)R * ld, st), u_lo((size_t)R * ld, st);
-  strided_split_f32_to_f16(sub.p, R, N, N, (int64_t)ld, u_hi.p, u_lo.p, st);
+  strided_split_f32_to_f16(sub.p, R, N, N, (int64_t)ld, u_hi.p, u_lo.p, st, kUnitScale);
   GemmOperand U;
   U.hi = u_hi.p; U.lo = u_lo.p; U.rows = R; U.K = N; U.ld = (int64_t)ld;
   Tmp<float> c2((size_t)R * R, st);
-  gemm_splitk(h, U, U, true, 1.f, Epilogue::Store, c2.p, R, (size_t)R * R);
+  gemm_splitk(h, U, U, true, 1.f / (kUnitScale * kUnitScale), Epilogue::Store, c2.p, R, (size_t)R * R);
   std::vector<float> hc2((size_t)R * R);
   SCL_CUDA(cudaMemcpyAsync(hc2.data(), c2.p, hc2.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
   SCL_CUDA(cudaStreamSynchronize(st));
@@ -425,17 +465,17 @@ void score_sets(scl_handle* h, int N, int k, int min_pc, int n_perturb, const fl
 // ---------------------------------------------------------------------------------------
 namespace {
 
-// additions (row, col) for one perturbation: injected sample indices or a device draw
-void make_additions(scl_handle* h, std::deque<std::vector<uint32_t>>& injected, size_t n_add, uint64_t draw_seed,
-                    uint32_t* d_row, uint32_t* d_col) {
-  if (!injected.empty()) {
-    std::vector<uint32_t> s = std::move(injected.front());
-    injected.pop_front();
+// additions (row, col) for one perturbation: injected sample indices (indexed by search step / replicate) or a
+// device draw keyed by the same index, so every rank of a multi-GPU run derives identical draws
+void make_additions(scl_handle* h, const std::vector<std::vector<uint32_t>>& injected, size_t index, size_t n_add,
+                    uint64_t draw_seed, uint32_t* d_row, uint32_t* d_col) {
+  if (index < injected.size()) {
+    const std::vector<uint32_t>& s = injected[index];
     SCL_REQUIRE(s.size() == n_add, "injected sample has the wrong length for this sparsity step");
     Tmp<uint32_t> d_idx(n_add, h->st);
     SCL_CUDA(cudaMemcpyAsync(d_idx.p, s.data(), n_add * sizeof(uint32_t), cudaMemcpyHostToDevice, h->st));
     gather_pairs(h->z1.p, h->z2.p, d_idx.p, n_add, d_row, d_col, h->st);
-    SCL_CUDA(cudaStreamSynchronize(h->st));   // `s` is released on return
+    SCL_CUDA(cudaStreamSynchronize(h->st));
   } else {
     draw_subset_device(h->z1.p, h->z2.p, h->n_cand, n_add, draw_seed, d_row, d_col, h->st);
   }
@@ -503,62 +543,92 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
   DBuf<__half> vr_hi, vr_lo;
   vr_hi.ensure((size_t)npos_ref * ldv);
   vr_lo.ensure((size_t)npos_ref * ldv);
-  strided_split_f32_to_f16(G.p + (size_t)i0r * nm, npos_ref, nm, nm, (int64_t)ldv, vr_hi.p, vr_lo.p, st);
+  strided_split_f32_to_f16(G.p + (size_t)i0r * nm, npos_ref, nm, nm, (int64_t)ldv, vr_hi.p, vr_lo.p, st, kUnitScale);
   GemmOperand Vr;
   Vr.hi = vr_hi.p; Vr.lo = vr_lo.p; Vr.rows = npos_ref; Vr.K = nm; Vr.ld = (int64_t)ldv;
 
   // --- sparsity search (:715-762)
-  double p_ = 0.999;
+  // Steps are independent given their draws; only the stop rule is sequential.  With G ranks, wave w evaluates
+  // steps w*G .. w*G+G-1 speculatively (rank g takes step w*G+g, p_ = 0.999 - step*p_step accumulated exactly as
+  // the reference's repeated `p_ -= p_step`), the second-smallest values are gathered, and the stop rule is applied
+  // in step order - the result is identical to the sequential loop.  G = 1 is the plain loop.
+  const int G_ = multi(h) ? h->world : 1;
   const int tank_n = 5;
   std::vector<double> tank2;   // row 2 of tank_ (second smallest of d_arr per step)
   h->trace_p.clear();
   h->trace_d.clear();
-  int step = 0;
   Tmp<float> d_d(nm, st);
+  Tmp<double> wave_dev(G_, st);
   std::vector<float> d_host;
-  while (true) {
-    const long long nnzidx = (long long)std::nearbyint((1.0 - p_) * (double)M * (double)N);   // :726
-    if ((long long)h->n_cand < nnzidx) {
-      p_ += p_step;
-      break;
+  std::vector<double> p_of_step(1, 0.999);
+  auto p_at = [&](int s_) {
+    while ((int)p_of_step.size() <= s_) p_of_step.push_back(p_of_step.back() - p_step);   // :760, same rounding drift
+    return p_of_step[s_];
+  };
+  double p_ = 0.999;
+  int step = 0;
+  bool stop = false;
+  for (int wave = 0; !stop; ++wave) {
+    const int my_step = wave * G_ + (multi(h) ? h->rank : 0);
+    const double my_p = p_at(my_step);
+    const long long nnzidx = (long long)std::nearbyint((1.0 - my_p) * (double)M * (double)N);   // :726
+    double my_d2 = -1.0;   // sentinel: candidate pool exhausted at this step (:727-730)
+    if ((long long)h->n_cand >= nnzidx && my_p > 0.85) {
+      Tmp<uint32_t> a_row((size_t)std::max<long long>(1, nnzidx), st), a_col((size_t)std::max<long long>(1, nnzidx), st);
+      make_additions(h, h->search_sples, (size_t)my_step, (size_t)nnzidx, h->cfg.seed + 0x5eed0000ull + (uint64_t)my_step,
+                     a_row.p, a_col.p);
+      {
+        ProfScope ps(&h->prof, st, PK_SPARSE);
+        perturb_merge(X, a_row.p, a_col.p, (size_t)nnzidx, true, Xp, st);
+        h->prof.sparse_alg_bytes += 8.0 * (double)X.nnz + 12.0 * (double)nnzidx;
+      }
+      gram_of(h, Xp, Sp, op_hi, op_lo, G.p, nm, bin_scale, split);
+      t_gram += tm.stop();
+      { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G.p, nm, W.p, true, st); }
+      info.t_search_syevd_ms += tm.stop();
+      SCL_CUDA(cudaMemcpyAsync(Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
+      SCL_CUDA(cudaStreamSynchronize(st));
+      const int i0 = first_positive(Lh);
+      const int npos = nm - i0;
+      SCL_REQUIRE(npos >= n_2 + 1, "perturbed matrix has too few positive eigenvalues");
+      const int nw = n_2 + 1;                                  // nV_2[:, end-n_2:end] (Appendix A13)
+      SCL_REQUIRE(nw >= 5, "too few noise vectors");
+      corr_colabsmax_pre(h, Vr, G.p + (size_t)i0 * nm, nw, nm, d_d.p);
+      d_host.resize(nw);
+      SCL_CUDA(cudaMemcpyAsync(d_host.data(), d_d.p, nw * sizeof(float), cudaMemcpyDeviceToHost, st));
+      SCL_CUDA(cudaStreamSynchronize(st));
+      std::partial_sort(d_host.begin(), d_host.begin() + 5, d_host.end());
+      my_d2 = (double)d_host[1];
     }
-    Tmp<uint32_t> a_row((size_t)std::max<long long>(1, nnzidx), st), a_col((size_t)std::max<long long>(1, nnzidx), st);
-    make_additions(h, h->search_sples, (size_t)nnzidx, h->cfg.seed + 0x5eed0000ull + (uint64_t)step, a_row.p, a_col.p);
-    {
-      ProfScope ps(&h->prof, st, PK_SPARSE);
-      perturb_merge(X, a_row.p, a_col.p, (size_t)nnzidx, true, Xp, st);
-      h->prof.sparse_alg_bytes += 8.0 * (double)X.nnz + 12.0 * (double)nnzidx;
+    std::vector<double> wave_d2(G_, my_d2);
+    if (G_ > 1) {
+      SCL_CUDA(cudaMemcpyAsync(wave_dev.p + h->rank, &my_d2, sizeof(double), cudaMemcpyHostToDevice, st));
+      SCL_NCCL(ncclAllGather(wave_dev.p + h->rank, wave_dev.p, 1, ncclDouble, (ncclComm_t)h->nccl, st));
+      SCL_CUDA(cudaMemcpyAsync(wave_d2.data(), wave_dev.p, G_ * sizeof(double), cudaMemcpyDeviceToHost, st));
+      SCL_CUDA(cudaStreamSynchronize(st));
     }
-    gram_of(h, Xp, Sp, op_hi, op_lo, G.p, nm, bin_scale, split);
-    t_gram += tm.stop();
-    { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G.p, nm, W.p, true, st); }
-    info.t_search_syevd_ms += tm.stop();
-    SCL_CUDA(cudaMemcpyAsync(Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
-    SCL_CUDA(cudaStreamSynchronize(st));
-    const int i0 = first_positive(Lh);
-    const int npos = nm - i0;
-    SCL_REQUIRE(npos >= n_2 + 1, "perturbed matrix has too few positive eigenvalues");
-    const int nw = n_2 + 1;                                  // nV_2[:, end-n_2:end] (Appendix A13)
-    corr_colabsmax_pre(h, Vr, G.p + (size_t)i0 * nm, nw, nm, d_d.p);
-    d_host.resize(nw);
-    SCL_CUDA(cudaMemcpyAsync(d_host.data(), d_d.p, nw * sizeof(float), cudaMemcpyDeviceToHost, st));
-    SCL_CUDA(cudaStreamSynchronize(st));
-    SCL_REQUIRE(nw >= 5, "too few noise vectors");
-    std::partial_sort(d_host.begin(), d_host.begin() + 5, d_host.end());
-    tank2.push_back((double)d_host[1]);
-    h->trace_p.push_back(p_);
-    h->trace_d.push_back((double)d_host[1]);
-    if (h->cfg.verbose) printf("%.9g\n", (double)d_host[1]);
-    ++step;
-    int below = 0;
-    const int cnt = (int)tank2.size() < tank_n ? (int)tank2.size() : tank_n;
-    for (int q = 0; q < cnt; ++q)
-      if (tank2[tank2.size() - 1 - q] < p_th) ++below;
-    if (below > tank_n - 1 || p_ < 0.9) {                    // :756
-      p_ += (double)(tank_n - 1) * p_step;
-      break;
+    // the reference's loop body, in step order
+    for (int g = 0; g < G_ && !stop; ++g) {
+      p_ = p_at(wave * G_ + g);
+      if (wave_d2[g] < 0) {            // lastindex(z_idx1) < nnzidx  (:727-730)
+        p_ += p_step;
+        stop = true;
+        break;
+      }
+      tank2.push_back(wave_d2[g]);
+      h->trace_p.push_back(p_);
+      h->trace_d.push_back(wave_d2[g]);
+      if (h->cfg.verbose) printf("%.9g\n", wave_d2[g]);
+      ++step;
+      int below = 0;
+      const int cnt = (int)tank2.size() < tank_n ? (int)tank2.size() : tank_n;
+      for (int q = 0; q < cnt; ++q)
+        if (tank2[tank2.size() - 1 - q] < p_th) ++below;
+      if (below > tank_n - 1 || p_ < 0.9) {                    // :756
+        p_ += (double)(tank_n - 1) * p_step;
+        stop = true;
+      }
     }
-    p_ -= p_step;
   }
   info.n_search = step;
   info.p_sel = p_;
@@ -580,9 +650,11 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
   h->set_L.assign((size_t)n_perturb * min_pc, 0.f);
   const bool exact = h->cfg.exact_perturb != 0;
   Tmp<float> topL(min_pc, st), topV((size_t)min_pc * nm, st);
+  Tmp<float> setL_dev((size_t)n_perturb * min_pc, st);
   for (int r = 0; r < n_perturb; ++r) {
+    if (multi(h) && r % h->world != h->rank) continue;   // replicate r belongs to rank r mod G (scl_plan_replicates)
     Tmp<uint32_t> a_row((size_t)std::max<long long>(1, n_add), st), a_col((size_t)std::max<long long>(1, n_add), st);
-    make_additions(h, h->perturb_sples, (size_t)n_add, h->cfg.seed + 0xbeef0000ull + (uint64_t)r, a_row.p, a_col.p);
+    make_additions(h, h->perturb_sples, (size_t)r, (size_t)n_add, h->cfg.seed + 0xbeef0000ull + (uint64_t)r, a_row.p, a_col.p);
     {
       ProfScope ps(&h->prof, st, PK_SPARSE);
       perturb_merge(X, a_row.p, a_col.p, (size_t)n_add, false, Xp, st);                        // :774
@@ -613,6 +685,20 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
       copy_rows(vec0, ldvec, set_r, N, min_pc, N, st);
   }
   SCL_CUDA(cudaStreamSynchronize(st));
+  if (multi(h)) {
+    // every rank scores all replicates: N x min_pc blocks travel once over NVLink from their owner
+    SCL_CUDA(cudaMemcpyAsync(setL_dev.p, h->set_L.data(), h->set_L.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    SCL_NCCL(ncclGroupStart());
+    for (int r = 0; r < n_perturb; ++r) {
+      float* set_r = h->d_sets.p + (size_t)r * min_pc * N;
+      SCL_NCCL(ncclBroadcast(set_r, set_r, (size_t)min_pc * N, ncclFloat, r % h->world, (ncclComm_t)h->nccl, st));
+      SCL_NCCL(ncclBroadcast(setL_dev.p + (size_t)r * min_pc, setL_dev.p + (size_t)r * min_pc, (size_t)min_pc, ncclFloat,
+                             r % h->world, (ncclComm_t)h->nccl, st));
+    }
+    SCL_NCCL(ncclGroupEnd());
+    SCL_CUDA(cudaMemcpyAsync(h->set_L.data(), setL_dev.p, h->set_L.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+  }
   info.t_perturb_ms = tm.stop();
 
   // --- robustness scores (:786-807)
@@ -626,13 +712,13 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
     const size_t ldn = round8((size_t)N);
     Tmp<__half> x_hi((size_t)M * ldn, st), x_lo((size_t)M * ldn, st), v_hi((size_t)k * ldn, st), v_lo((size_t)k * ldn, st);
     densify(X, h->S_main, 0, ldn, x_hi.p, x_lo.p, st);
-    strided_split_f32_to_f16(h->d_nV.p, k, N, N, (int64_t)ldn, v_hi.p, v_lo.p, st);
+    strided_split_f32_to_f16(h->d_nV.p, k, N, N, (int64_t)ldn, v_hi.p, v_lo.p, st, kUnitScale);
     Tmp<float> gb((size_t)M * k, st);
     GemmArgs g;
     g.A.hi = x_hi.p; g.A.lo = x_lo.p; g.A.rows = M; g.A.K = N; g.A.ld = (int64_t)ldn;
     g.B.hi = v_hi.p; g.B.lo = v_lo.p; g.B.rows = k; g.B.K = N; g.B.ld = (int64_t)ldn;
     g.epi = Epilogue::Store;
-    g.alpha = 1.0f / std::sqrt((float)M);
+    g.alpha = 1.0f / std::sqrt((float)M) / kUnitScale;
     g.C = gb.p;
     g.ldc = k;
     g.cta_group = cta_group_of(h);

@@ -22,6 +22,9 @@ namespace {
 
 constexpr int kSlab = 64;
 constexpr double kAmpLimit = 2.0e3;
+// G's off-diagonal entries are ~1/sqrt(n) of its diagonal: scaled by 2^6 before the binary16 hi/lo split so
+// their low-order parts stay normal numbers (diagonal ~O(1..30) -> <= 2e3, far below 65504)
+constexpr float kGScale = 64.f;
 
 inline size_t round8(size_t x) { return (x + 7) / 8 * 8; }
 
@@ -95,7 +98,8 @@ __global__ void __launch_bounds__(256) k_gram_ts(const float* __restrict__ A, in
 // out[c][t] = beta * base[c][t] + alpha * sum_r Tt[c][r] * In[r][t]   (Float64 accumulation)
 __global__ void __launch_bounds__(256) k_combine_rows(const float* __restrict__ In, int rin, const double* __restrict__ Tt,
                                                       int rout, int n, double alpha, const float* __restrict__ base,
-                                                      double beta, float* __restrict__ out) {
+                                                      double beta, float* __restrict__ out,
+                                                      const double* __restrict__ wgt) {
   extern __shared__ float sIn[];   // [rin][kSlab]
   const int t0 = blockIdx.x * kSlab;
   const int tl = min(kSlab, n - t0);
@@ -109,7 +113,11 @@ __global__ void __launch_bounds__(256) k_combine_rows(const float* __restrict__ 
   for (int c = g; c < rout; c += 4) {
     const double* trow = Tt + (size_t)c * rin;
     double acc = 0;
-    for (int r = 0; r < rin; ++r) acc += trow[r] * (double)sIn[r * kSlab + t];
+    if (wgt) {
+      for (int r = 0; r < rin; ++r) acc += trow[r] * wgt[r] * (double)sIn[r * kSlab + t];
+    } else {
+      for (int r = 0; r < rin; ++r) acc += trow[r] * (double)sIn[r * kSlab + t];
+    }
     double v = alpha * acc;
     if (base) v += beta * (double)base[(size_t)c * n + t0 + t];
     out[(size_t)c * n + t0 + t] = (float)v;
@@ -171,10 +179,10 @@ void gram_ts(const Ctx& c, const float* A, int ra, const float* B, int rb, doubl
 }
 
 void combine_rows(const Ctx& c, const float* In, int rin, const double* dTt, int rout, double alpha, const float* base,
-                  double beta, float* out) {
+                  double beta, float* out, const double* wgt = nullptr) {
   size_t smem = (size_t)rin * kSlab * sizeof(float);
   SCL_CUDA(cudaFuncSetAttribute(k_combine_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  k_combine_rows<<<(c.n + kSlab - 1) / kSlab, 256, smem, c.st>>>(In, rin, dTt, rout, c.n, alpha, base, beta, out);
+  k_combine_rows<<<(c.n + kSlab - 1) / kSlab, 256, smem, c.st>>>(In, rin, dTt, rout, c.n, alpha, base, beta, out, wgt);
   count_launches(1);
   SCL_CUDA(cudaGetLastError());
 }
@@ -190,6 +198,7 @@ void apply_G(const Ctx& c, const float* Q, int rows, float* Z) {
   g.epi = Epilogue::StoreTransposed;
   g.ldc = c.n;
   g.cta_group = cg;
+  const float inv_scale = 1.f / kGScale;
   // split-K so the machine is filled: pick the split count with the fewest waves per unit of work
   const int units = sm_count() / cg;
   const int tiles = (c.n + 128 * cg - 1) / (128 * cg);
@@ -203,14 +212,14 @@ void apply_G(const Ctx& c, const float* Q, int rows, float* Z) {
   ProfScope ps(&c.h->prof, c.st, PK_OTHER_GEMM);
   c.h->prof.other_gemm_flops += 2.0 * (double)c.n * c.n * rows;
   if (best == 1) {
-    g.C = Z; g.alpha = 1.f;
+    g.C = Z; g.alpha = inv_scale;
     gemm_umma(g, c.st);
   } else {
     const size_t elems = (size_t)rows * c.n;
     Tmp<float> part((size_t)best * elems, c.st);
     g.C = part.p; g.splits = best; g.split_stride = (int64_t)elems;
     gemm_umma(g, c.st);
-    reduce_splits(part.p, best, (int64_t)elems, elems, 1.f, Z, c.st);
+    reduce_splits(part.p, best, (int64_t)elems, elems, inv_scale, Z, c.st);
   }
 }
 
@@ -279,12 +288,14 @@ void topk_subspace(scl_handle* h, const float* dG, int n, int k, float* dL, floa
   Ctx c;
   c.h = h; c.st = st; c.n = n; c.ldn = round8((size_t)n);
   Tmp<__half> g_hi((size_t)n * c.ldn, st), g_lo((size_t)n * c.ldn, st);
-  strided_split_f32_to_f16(dG, n, n, n, (int64_t)c.ldn, g_hi.p, g_lo.p, st);
+  strided_split_f32_to_f16(dG, n, n, n, (int64_t)c.ldn, g_hi.p, g_lo.p, st, kGScale);
   c.g_hi = g_hi.p; c.g_lo = g_lo.p;
 
   const size_t bn = (size_t)b * n;
   Tmp<float> Q(bn, st), Z(bn, st), Y0(bn, st), Y1(bn, st), Y2(bn, st), Vlock((size_t)k * n, st);
-  Tmp<double> dH((size_t)b * b, st), dW(b, st), dTt((size_t)b * b, st), dTheta(b, st), dRes(b, st), dC((size_t)k * b, st);
+  Tmp<double> dH((size_t)b * b, st), dW(b, st), dTt((size_t)b * b, st), dTheta(b, st), dRes(b, st), dC((size_t)k * b, st),
+      dShift(k, st);
+  std::vector<double> shift(k);
   std::vector<double> Hh((size_t)b * b), Wh(b), Tt((size_t)b * b), theta(b), res(b), Llock;
   int nlock = 0;
 
@@ -310,14 +321,26 @@ void topk_subspace(scl_handle* h, const float* dG, int n, int k, float* dL, floa
       const double tau = 2.0 / sigma;
       const size_t total = (size_t)ba * n;
       const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-      apply_G(c, Qa, ba, Z.p); ++gemms;
+      // Locked eigenpairs are deflated from the operator, G' = G - sum_l (theta_l - cc) v_l v_l^T, which moves
+      // them to the centre of the damped interval: without this the filter re-amplifies the ~1e-7 component the
+      // FP32 active block keeps along a locked signal direction by T_d(x_l)/T_d(x_top) (1e20 at degree 30).
+      for (int l = 0; l < nlock; ++l) shift[l] = Llock[l] - cc;
+      if (nlock) SCL_CUDA(cudaMemcpyAsync(dShift.p, shift.data(), nlock * sizeof(double), cudaMemcpyHostToDevice, st));
+      auto apply_deflated = [&](const float* y) {
+        apply_G(c, y, ba, Z.p); ++gemms;
+        if (nlock) {
+          gram_ts(c, y, ba, Vlock.p, nlock, dC.p);                                   // C[ba][nlock] = y * Vlock^T
+          combine_rows(c, Vlock.p, nlock, dC.p, ba, -1.0, Z.p, 1.0, Z.p, dShift.p);  // Z -= C diag(shift) Vlock
+        }
+      };
+      apply_deflated(Qa);
       k_cheb_step<<<grid, 256, 0, st>>>(Z.p, Qa, nullptr, (float)cc, (float)(sigma / e), 0.f, total, Y1.p);
       count_launches(d);
       SCL_CUDA(cudaMemcpyAsync(Y0.p, Qa, total * sizeof(float), cudaMemcpyDeviceToDevice, st));
       float *xp = Y0.p, *y = Y1.p, *yn = Y2.p;
       for (int i = 2; i <= d; ++i) {
         const double sigma_new = 1.0 / (tau - sigma);
-        apply_G(c, y, ba, Z.p); ++gemms;
+        apply_deflated(y);
         k_cheb_step<<<grid, 256, 0, st>>>(Z.p, y, xp, (float)cc, (float)(2.0 * sigma_new / e), (float)(sigma * sigma_new),
                                           total, yn);
         float* t = xp; xp = y; y = yn; yn = t;

@@ -1,0 +1,69 @@
+"""torchrun --nproc-per-node G scripts/multi_gpu_check.py : the G-rank cooperative sclens() pass (cell-sharded
+Gram + NCCL all-reduce, speculative search waves, replicate-parallel perturbations) must reproduce the 1-GPU pass."""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from sclens_b200 import Handle  # noqa: E402
+from sclens_b200.synth import make_counts  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+shape = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1200, 900)
+X = make_counts(*shape, seed=21, K=5, de_prob=0.3, lfc_sd=1.5)
+
+
+def run(h):
+    t0 = time.perf_counter()
+    si = h.run_signal()
+    ri = h.run_robustness(n_perturb=8)
+    dt = time.perf_counter() - t0
+    b, m, sd = h.scores()
+    return dict(L=h.L(), nL=h.signal_ev(), nV=h.signal_evec(), n_signal=si.n_signal, lam=si.lambda_c, p_sel=ri.p_sel,
+                n_search=ri.n_search, trace=h.search_trace(), m=m, sig=h.sig_id(), dt=dt)
+
+
+h = Handle(device=local, seed=7)
+uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+if rank == 0:
+    buf = (C.c_uint8 * 128)()
+    assert h.lib.scl_nccl_unique_id(buf) == 0
+    uid = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+dist.broadcast(uid, 0)
+h.comm_init(bytes(uid.cpu().tolist()), rank, world)
+h.set_counts(X)
+multi = run(h)
+multi2 = run(h)
+dist.barrier()
+ok = True
+if rank == 0:
+    with Handle(device=local, seed=7) as h1:
+        h1.set_counts(X)
+        single = run(h1)
+        single = run(h1)
+    print(f"world={world} shape={shape} multi {multi2['dt']:.2f}s single {single['dt']:.2f}s n_signal {multi['n_signal']} "
+          f"p_sel {multi['p_sel']} n_search {multi['n_search']}", flush=True)
+    assert multi["n_signal"] == single["n_signal"] and multi["n_search"] == single["n_search"] and multi["p_sel"] == single["p_sel"]
+    np.testing.assert_allclose(multi["L"][10:], single["L"][10:], rtol=2e-5)
+    np.testing.assert_allclose(multi["trace"][1], single["trace"][1], rtol=2e-2)
+    np.testing.assert_allclose(multi["m"], single["m"], atol=2e-2)
+    np.testing.assert_array_equal(multi["sig"], single["sig"])
+    cos = np.abs(np.sum(multi["nV"] * single["nV"], axis=0))
+    assert cos.min() > 1 - 1e-5
+    print("MULTI_GPU_CHECK_OK", flush=True)
+# every rank must hold identical results
+t = torch.tensor([multi["p_sel"], float(multi["n_search"]), float(len(multi["sig"])), float(multi["m"].sum())], device=dev, dtype=torch.float64)
+ref = t.clone()
+dist.broadcast(ref, 0)
+assert torch.equal(t, ref), (rank, t, ref)
+h.close()
+dist.destroy_process_group()
