@@ -192,6 +192,16 @@ SCL_API int32_t scl_op_scores(scl_handle* h, int32_t N, int32_t k, int32_t min_p
                       const float* nV_sets, double th, float* b_, double* m_scores, double* sd_scores,
                       int32_t* sig_id, int32_t* n_robust);
 
+/* ---- kernel-level timing harness (device-resident synthetic operands; used by bench.py and the ncu captures) ---- */
+/* Gram / GEMM kernel alone: rows x K binary16 operand generated on the device; mode bit0 = split (hi+lo) operands,
+ * bit1 = full GEMM instead of the syrk schedule; chunk_kb = k-blocks per accumulation chunk (0 = default).
+ * ms_avg: CUDA-event time per launch on the handle's stream; checksum: mean diagonal of the result. */
+SCL_API int32_t scl_bench_gram(scl_handle* h, int32_t rows, int64_t K, int32_t mode, int32_t chunk_kb, int32_t reps,
+                       double* ms_avg, double* checksum);
+/* Normalisation kernels on the handle's counts (:677-696): statistics pre-passes and the fused densify writer. */
+SCL_API int32_t scl_bench_normalize(scl_handle* h, int32_t layout, int32_t with_lo, int32_t reps, double* ms_stats,
+                            double* ms_densify, double* alg_bytes_densify);
+
 #ifdef __cplusplus
 }
 #endif

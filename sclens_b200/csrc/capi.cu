@@ -399,6 +399,90 @@ int32_t scl_op_gram(scl_handle* h, int32_t rows, int64_t K, int64_t ld, const ui
   });
 }
 
+/* Kernel-level timing on device-resident synthetic operands (bench / ncu harness; no host data moves).
+ * mode bit0: split (hi+lo) operands; bit1: plain GEMM A*B^T instead of the syrk schedule. */
+int32_t scl_bench_gram(scl_handle* h, int32_t rows, int64_t K, int32_t mode, int32_t chunk_kb, int32_t reps,
+                       double* ms_avg, double* checksum) {
+  if (!h || rows <= 0 || K <= 0 || reps <= 0) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    const int64_t ld = (K + 7) / 8 * 8;
+    const size_t n = (size_t)rows * (size_t)ld;
+    const bool split = mode & 1;
+    Tmp<__half> hi(n, h->st), lo(split ? n : 1, h->st);
+    Tmp<float> g((size_t)rows * rows, h->st);
+    fill_random_f16(hi.p, n, 0x1234u, 1.0f, h->st);
+    if (split) fill_random_f16(lo.p, n, 0x9876u, 1.0f / 2048.f, h->st);
+    GemmArgs a;
+    a.A.hi = hi.p; a.A.lo = split ? lo.p : nullptr; a.A.rows = rows; a.A.K = K; a.A.ld = ld;
+    a.B = a.A;
+    a.syrk = !(mode & 2); a.alpha = 1.0f / (float)K; a.C = g.p; a.ldc = rows;
+    a.cta_group = h->cfg.cta_group == 1 ? 1 : 2;
+    a.chunk_kb = chunk_kb;
+    gemm_umma(a, h->st);   // warm-up
+    cudaEvent_t e0, e1;
+    SCL_CUDA(cudaEventCreate(&e0));
+    SCL_CUDA(cudaEventCreate(&e1));
+    SCL_CUDA(cudaEventRecord(e0, h->st));
+    for (int r = 0; r < reps; ++r) gemm_umma(a, h->st);
+    SCL_CUDA(cudaEventRecord(e1, h->st));
+    SCL_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    SCL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_avg) *ms_avg = ms / reps;
+    if (checksum) {
+      std::vector<float> d(rows);
+      SCL_CUDA(cudaMemcpy2DAsync(d.data(), sizeof(float), g.p, (size_t)(rows + 1) * sizeof(float), sizeof(float), rows,
+                                 cudaMemcpyDeviceToHost, h->st));
+      SCL_CUDA(cudaStreamSynchronize(h->st));
+      double t = 0;
+      for (float v : d) t += v;
+      *checksum = t / rows;   // mean diagonal: ~E[x^2] of the synthetic operand
+    }
+  });
+}
+
+/* Times the normalisation kernels on the handle's counts: the statistics pre-passes and the fused densify writer
+ * (layout 0 gene-major / 1 cell-major, with_lo: also emit the low-order binary16 part). */
+int32_t scl_bench_normalize(scl_handle* h, int32_t layout, int32_t with_lo, int32_t reps, double* ms_stats,
+                            double* ms_densify, double* alg_bytes_densify) {
+  if (!h || reps <= 0) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_REQUIRE(h->have_X, "scl_set_counts_csc must be called first");
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    const SpMat& X = h->X;
+    const size_t line_len = layout == 1 ? X.M : X.N, lines = layout == 1 ? X.N : X.M;
+    const size_t ld = (line_len + 7) / 8 * 8;
+    Tmp<__half> hi(lines * ld, h->st), lo(with_lo ? lines * ld : 1, h->st);
+    NormStats S;
+    const int n_strips = densify_strips(ld);
+    Tmp<double> sumsq(lines * (size_t)n_strips, h->st);
+    cudaEvent_t e0, e1, e2;
+    SCL_CUDA(cudaEventCreate(&e0));
+    SCL_CUDA(cudaEventCreate(&e1));
+    SCL_CUDA(cudaEventCreate(&e2));
+    double ts = 0, td = 0;
+    for (int r = -1; r < reps; ++r) {   // r = -1: warm-up
+      SCL_CUDA(cudaEventRecord(e0, h->st));
+      compute_norm_stats(X, S, h->st);
+      SCL_CUDA(cudaEventRecord(e1, h->st));
+      densify(X, S, layout, ld, hi.p, with_lo ? lo.p : nullptr, h->st, sumsq.p);
+      SCL_CUDA(cudaEventRecord(e2, h->st));
+      SCL_CUDA(cudaEventSynchronize(e2));
+      float a = 0, b = 0;
+      SCL_CUDA(cudaEventElapsedTime(&a, e0, e1));
+      SCL_CUDA(cudaEventElapsedTime(&b, e1, e2));
+      if (r >= 0) { ts += a; td += b; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    if (ms_stats) *ms_stats = ts / reps;
+    if (ms_densify) *ms_densify = td / reps;
+    if (alg_bytes_densify) *alg_bytes_densify = 8.0 * (double)X.nnz + 4.0 * (X.M + 1) + (double)X.N * X.M * (with_lo ? 4.0 : 2.0);
+  });
+}
+
 int32_t scl_op_gemm_tn(scl_handle* h, int32_t m, int32_t n, int64_t K, int64_t lda, int64_t ldb, const uint16_t* a_hi,
                        const uint16_t* a_lo, const uint16_t* b_hi, const uint16_t* b_lo, float alpha,
                        int32_t c_colmajor, float* C) {

@@ -131,7 +131,7 @@ struct GemmArgs {
   int splits = 1;           // split-K: partial s written at C + s*split_stride (caller reduces)
   int64_t split_stride = 0;
   int cta_group = 2;        // 1 or 2
-  int chunk_kb = 0;         // k-blocks (of 64) per TMEM accumulation chunk; 0 = default (32, or 8 in split mode)
+  int chunk_kb = 0;         // k-blocks (of 64) per tensor-core accumulation chunk; 0 = default (64, or 21 in split mode)
 };
 void gemm_umma(const GemmArgs& a, cudaStream_t st);
 void split_f32_to_f16(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st);
@@ -139,6 +139,7 @@ void split_f32_to_f16(const float* in, size_t n, __half* hi, __half* lo, cudaStr
 // high dimension: ~1/sqrt(n)) stays in the normal binary16 range; the caller divides alpha by it
 void strided_split_f32_to_f16(const float* in, int rows, int64_t cols, int64_t ld_in, int64_t ld_out, __half* hi,
                               __half* lo, cudaStream_t st, float pre_scale = 1.f);
+void fill_random_f16(__half* out, size_t n, uint32_t seed, float scale, cudaStream_t st);   // ~N(0, scale^2), bench harness
 void reduce_splits(const float* part, int splits, int64_t stride, size_t n, float scale, float* out, cudaStream_t st);
 int sm_count();
 

@@ -99,7 +99,9 @@ def test_gram_syrk(h, h1, rows, K, cg, split):
                               1.0 / K, ptr(G, C.c_float)))
     src = A.astype(np.float64) if split else hi.astype(np.float64)
     ref = src @ src.T / K
-    assert np.max(np.abs(G - ref)) / np.max(np.abs(ref)) < 2e-5
+    # bound: tensor-core truncation bias on a same-sign sum, <= 256 MMAs per accumulation chunk x ~8e-8;
+    # the pipeline replaces the diagonal (the only such sum) by exact Float64 sums of squares
+    assert np.max(np.abs(G - ref)) / np.max(np.abs(ref)) < 3e-5
     assert np.array_equal(G, G.T)       # mirrored store: exactly symmetric
 
 
