@@ -290,7 +290,7 @@ def main():
 
     # ---- e2e through the public API with host buffers (pinned), results read back
     e2e = None
-    if world == 1:
+    if world == 1 and args.e2e_steps > 0:
         pinned = [torch.from_numpy(a).pin_memory() for a in (X.indptr.astype(np.uint32).view(np.int32),
                                                              X.indices.astype(np.uint32).view(np.int32), X.data)]
         Xp = sp.csc_matrix((pinned[2].numpy(), pinned[1].numpy().view(np.uint32), pinned[0].numpy().view(np.uint32)),

@@ -58,7 +58,10 @@ typedef struct {
   int32_t subspace_extra;/* oversampling columns of the block subspace iteration (0 = default) */
   int32_t subspace_degree;/* Chebyshev degree per sweep (0 = default) */
   int32_t exact_perturb; /* 1: full syevd per replicate exactly as :775 (parity studies) */
-  int32_t reserved[7];
+  int32_t gram_chunk_kb; /* 64-element k-blocks the tensor core accumulates before the chunk is promoted into the
+                            round-to-nearest FP32 sum (0 = library default; numerics studies) */
+  int32_t gram_tc_diag;  /* 1: keep the tensor core's own Gram diagonal instead of the exact Float64 one (studies) */
+  int32_t reserved[5];
 } scl_config;
 
 typedef struct {

@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
         run([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-             "-lcusolver", "-lnccl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"])
+             "-lcusolver", "-ldl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"])
     return LIB
 
 

@@ -1,5 +1,5 @@
 // extern "C" surface of libsclens_b200.so (see include/sclens_b200.h).
-#include <nccl.h>
+#include "nccl_dyn.h"
 #include <cstring>
 #include "handle.h"
 #include "tmp.cuh"
@@ -86,7 +86,7 @@ int32_t scl_destroy(scl_handle* h) {
   if (!h) return SCL_OK;
   cudaSetDevice(h->cfg.device);
   if (h->st) cudaStreamSynchronize(h->st);
-  if (h->nccl) ncclCommDestroy((ncclComm_t)h->nccl);
+  if (h->nccl) nccl_api().CommDestroy((ncclComm_t)h->nccl);
   h->prof.resolve();
   if (h->t0) { cudaEventDestroy(h->t0); cudaEventDestroy(h->t1); }
   h->solver.reset();
@@ -141,7 +141,11 @@ int32_t scl_timer_stop(scl_handle* h, double* ms) {
 int32_t scl_nccl_unique_id(uint8_t out_id[128]) {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
   ncclUniqueId id;
-  if (ncclGetUniqueId(&id) != ncclSuccess) return SCL_ERR_NCCL;
+  try {
+    if (nccl_api().GetUniqueId(&id) != ncclSuccess) return SCL_ERR_NCCL;
+  } catch (const Error&) {
+    return SCL_ERR_NCCL;
+  }
   std::memcpy(out_id, &id, 128);
   return SCL_OK;
 }
@@ -157,8 +161,8 @@ int32_t scl_comm_init(scl_handle* h, const uint8_t id[128], int32_t rank, int32_
     ncclUniqueId uid;
     std::memcpy(&uid, id, 128);
     ncclComm_t comm;
-    ncclResult_t r = ncclCommInitRank(&comm, world, uid, rank);
-    if (r != ncclSuccess) throw Error(SCL_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+    ncclResult_t r = nccl_api().CommInitRank(&comm, world, uid, rank);
+    if (r != ncclSuccess) throw Error(SCL_ERR_NCCL, std::string("ncclCommInitRank: ") + nccl_api().GetErrorString(r));
     h->nccl = comm;
   });
 }
@@ -393,6 +397,7 @@ int32_t scl_op_gram(scl_handle* h, int32_t rows, int64_t K, int64_t ld, const ui
     a.B = a.A;
     a.syrk = true; a.alpha = scale; a.C = g.p; a.ldc = rows;
     a.cta_group = h->cfg.cta_group == 1 ? 1 : 2;
+    a.chunk_kb = h->cfg.gram_chunk_kb;
     gemm_umma(a, h->st);
     SCL_CUDA(cudaMemcpyAsync(G, g.p, (size_t)rows * rows * sizeof(float), cudaMemcpyDeviceToHost, h->st));
     SCL_CUDA(cudaStreamSynchronize(h->st));

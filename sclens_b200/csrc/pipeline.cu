@@ -6,7 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
-#include <nccl.h>
+#include "nccl_dyn.h"
 #include "handle.h"
 #include "tmp.cuh"
 
@@ -42,7 +42,7 @@ constexpr float kUnitScale = 1024.f;
 #define SCL_NCCL(x)                                                                                   \
   do {                                                                                                \
     ncclResult_t r_ = (x);                                                                            \
-    if (r_ != ncclSuccess) throw scl::Error(SCL_ERR_NCCL, std::string(#x) + ": " + ncclGetErrorString(r_)); \
+    if (r_ != ncclSuccess) throw scl::Error(SCL_ERR_NCCL, std::string(#x) + ": " + nccl_api().GetErrorString(r_)); \
   } while (0)
 
 inline bool multi(const scl_handle* h) { return h->world > 1 && h->nccl != nullptr; }
@@ -209,18 +209,19 @@ void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf
     g.C = dG;
     g.ldc = nm;
     g.cta_group = cta_group_of(h);
+    g.chunk_kb = h->cfg.gram_chunk_kb;
     {
       ProfScope ps(&h->prof, h->st, PK_GRAM_GEMM);
       gemm_umma(g, h->st);
       h->prof.gram_alg_flops += (double)rows * (rows + 1.0) * (double)Ks;
     }
-    set_gram_diagonal(dG, nm, n_strips, sumsq.p, (double)scale, h->st);
+    if (!h->cfg.gram_tc_diag) set_gram_diagonal(dG, nm, n_strips, sumsq.p, (double)scale, h->st);
   } else {
     SCL_CUDA(cudaMemsetAsync(dG, 0, (size_t)nm * nm * sizeof(float), h->st));
   }
   if (sharded) {
     ProfScope ps(&h->prof, h->st, PK_SMALL);
-    SCL_NCCL(ncclAllReduce(dG, dG, (size_t)nm * nm, ncclFloat, ncclSum, (ncclComm_t)h->nccl, h->st));
+    SCL_NCCL(nccl_api().AllReduce(dG, dG, (size_t)nm * nm, ncclFloat, ncclSum, (ncclComm_t)h->nccl, h->st));
   }
 }
 
@@ -603,7 +604,7 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
     std::vector<double> wave_d2(G_, my_d2);
     if (G_ > 1) {
       SCL_CUDA(cudaMemcpyAsync(wave_dev.p + h->rank, &my_d2, sizeof(double), cudaMemcpyHostToDevice, st));
-      SCL_NCCL(ncclAllGather(wave_dev.p + h->rank, wave_dev.p, 1, ncclDouble, (ncclComm_t)h->nccl, st));
+      SCL_NCCL(nccl_api().AllGather(wave_dev.p + h->rank, wave_dev.p, 1, ncclDouble, (ncclComm_t)h->nccl, st));
       SCL_CUDA(cudaMemcpyAsync(wave_d2.data(), wave_dev.p, G_ * sizeof(double), cudaMemcpyDeviceToHost, st));
       SCL_CUDA(cudaStreamSynchronize(st));
     }
@@ -688,14 +689,14 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
   if (multi(h)) {
     // every rank scores all replicates: N x min_pc blocks travel once over NVLink from their owner
     SCL_CUDA(cudaMemcpyAsync(setL_dev.p, h->set_L.data(), h->set_L.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-    SCL_NCCL(ncclGroupStart());
+    SCL_NCCL(nccl_api().GroupStart());
     for (int r = 0; r < n_perturb; ++r) {
       float* set_r = h->d_sets.p + (size_t)r * min_pc * N;
-      SCL_NCCL(ncclBroadcast(set_r, set_r, (size_t)min_pc * N, ncclFloat, r % h->world, (ncclComm_t)h->nccl, st));
-      SCL_NCCL(ncclBroadcast(setL_dev.p + (size_t)r * min_pc, setL_dev.p + (size_t)r * min_pc, (size_t)min_pc, ncclFloat,
+      SCL_NCCL(nccl_api().Broadcast(set_r, set_r, (size_t)min_pc * N, ncclFloat, r % h->world, (ncclComm_t)h->nccl, st));
+      SCL_NCCL(nccl_api().Broadcast(setL_dev.p + (size_t)r * min_pc, setL_dev.p + (size_t)r * min_pc, (size_t)min_pc, ncclFloat,
                              r % h->world, (ncclComm_t)h->nccl, st));
     }
-    SCL_NCCL(ncclGroupEnd());
+    SCL_NCCL(nccl_api().GroupEnd());
     SCL_CUDA(cudaMemcpyAsync(h->set_L.data(), setL_dev.p, h->set_L.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
     SCL_CUDA(cudaStreamSynchronize(st));
   }

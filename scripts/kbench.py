@@ -6,6 +6,7 @@ import sys
 
 sys.path.insert(0, ".")
 import numpy as np  # noqa: E402
+import torch  # noqa: E402,F401
 
 from sclens_b200 import Handle  # noqa: E402
 
