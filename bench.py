@@ -333,7 +333,7 @@ def main():
                                "frac": dens_gbs / hbm_peak, "launches": int(prof.densify_launches)}}
     stage_ms = {"gram_gemm": prof.gram_gemm_ms, "other_gemm": prof.other_gemm_ms, "densify": prof.densify_ms,
                 "stats": prof.stats_ms, "sparse": prof.sparse_ms, "syevd_library": prof.syevd_ms,
-                "syevd_calls": int(prof.syevd_calls), "total": ms}
+                "syevd_calls": int(prof.syevd_calls), "refine_f64": prof.refine_ms, "small": prof.small_ms, "total": ms}
     line = {"metric": "sclens_cells_per_s", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (Gram), f32 syevd, f64 statistics",

@@ -60,8 +60,10 @@ typedef struct {
   int32_t exact_perturb; /* 1: full syevd per replicate exactly as :775 (parity studies) */
   int32_t gram_chunk_kb; /* 64-element k-blocks the tensor core accumulates before the chunk is promoted into the
                             round-to-nearest FP32 sum (0 = library default; numerics studies) */
-  int32_t gram_tc_diag;  /* 1: keep the tensor core's own Gram diagonal instead of the exact Float64 one (studies) */
-  int32_t reserved[5];
+  int32_t gram_tc_diag;  /* numerics studies. 0: exact Float64 Gram diagonal + calibration of the tensor core's
+                            accumulation bias (default); 1: the raw tensor-core result; 2: exact diagonal only */
+  int32_t no_refine;     /* 1: return the FP32 eigensolver's eigenvalues as they are (no Float64 Rayleigh-quotient refinement) */
+  int32_t reserved[4];
 } scl_config;
 
 typedef struct {
@@ -96,6 +98,8 @@ typedef struct {
   double densify_alg_bytes;   /* sum of 8 nnz + 4(M+1) + N*M*s_out */
   double sparse_alg_bytes;    /* 20 nnz per null permutation, 8 nnz + 12 n_add per merge */
   int64_t kernel_launches;    /* kernels of this library launched by the process since load */
+  double refine_ms;           /* Float64 Rayleigh-quotient refinement of the data spectrum */
+  double small_ms;            /* calibration, reductions, collectives and other small kernels */
 } scl_profile;
 
 /* ---- lifecycle --------------------------------------------------------------------- */

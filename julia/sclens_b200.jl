@@ -16,8 +16,8 @@ struct SclConfig
     device::Int32; gram_mode::Int32; cta_group::Int32; verbose::Int32
     seed::UInt64
     subspace_extra::Int32; subspace_degree::Int32; exact_perturb::Int32
-    gram_chunk_kb::Int32; gram_tc_diag::Int32
-    reserved::NTuple{5,Int32}
+    gram_chunk_kb::Int32; gram_tc_diag::Int32; no_refine::Int32
+    reserved::NTuple{4,Int32}
 end
 mutable struct SclSignalInfo
     N::Int32; M::Int32; nm::Int32; n_signal::Int32; n_Lmp::Int32; mp_iters::Int32; pass::Int32; gram_mode_used::Int32

@@ -24,7 +24,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("gram_mode", C.c_int32), ("cta_group", C.c_int32), ("verbose", C.c_int32),
                 ("seed", C.c_uint64), ("subspace_extra", C.c_int32), ("subspace_degree", C.c_int32),
                 ("exact_perturb", C.c_int32), ("gram_chunk_kb", C.c_int32), ("gram_tc_diag", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("no_refine", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class SignalInfo(C.Structure):
@@ -49,7 +49,7 @@ class Profile(C.Structure):
                 ("gram_gemm_launches", C.c_int64), ("other_gemm_launches", C.c_int64), ("densify_launches", C.c_int64),
                 ("sparse_calls", C.c_int64), ("syevd_calls", C.c_int64), ("gram_alg_flops", C.c_double),
                 ("other_gemm_flops", C.c_double), ("densify_alg_bytes", C.c_double), ("sparse_alg_bytes", C.c_double),
-                ("kernel_launches", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("refine_ms", C.c_double), ("small_ms", C.c_double)]
 
 
 _u32p = C.POINTER(C.c_uint32)

@@ -66,11 +66,11 @@ class Handle:
 
     def __init__(self, device: int = 0, gram_mode: int = _lib.SCL_GRAM_FP16, cta_group: int = 0, verbose: bool = False,
                  seed: int = 0, exact_perturb: bool = False, subspace_extra: int = 0, subspace_degree: int = 0,
-                 gram_chunk_kb: int = 0, gram_tc_diag: bool = False):
+                 gram_chunk_kb: int = 0, gram_tc_diag: int = 0, no_refine: bool = False):
         self.lib = _lib.load()
         cfg = Config(device=device, gram_mode=gram_mode, cta_group=cta_group, verbose=int(verbose), seed=seed,
                      subspace_extra=subspace_extra, subspace_degree=subspace_degree, exact_perturb=int(exact_perturb),
-                     gram_chunk_kb=int(gram_chunk_kb), gram_tc_diag=int(gram_tc_diag))
+                     gram_chunk_kb=int(gram_chunk_kb), gram_tc_diag=int(gram_tc_diag), no_refine=int(no_refine))
         self.h = C.c_void_p()
         rc = self.lib.scl_create(C.byref(self.h), C.byref(cfg))
         if rc != 0:

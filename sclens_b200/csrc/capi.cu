@@ -108,6 +108,8 @@ int32_t scl_get_profile(scl_handle* h, scl_profile* out) {
   out->gram_alg_flops = p.gram_alg_flops; out->other_gemm_flops = p.other_gemm_flops;
   out->densify_alg_bytes = p.densify_alg_bytes; out->sparse_alg_bytes = p.sparse_alg_bytes;
   out->kernel_launches = g_kernel_launches.load();
+  out->refine_ms = p.ms[PK_REFINE];
+  out->small_ms = p.ms[PK_SMALL];
   return SCL_OK;
 }
 

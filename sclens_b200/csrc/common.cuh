@@ -79,6 +79,10 @@ struct NormStats {
   DBuf<double> ybar, sigma, mu, cent;  // per gene
   DBuf<float> mu_f, cent_f, inv_sigma_f;
   DBuf<double> scalars;             // [0]=|mu|^2 [1]=mean(l) [2]=sum(1/s)
+  // per non-zero intermediates, evaluated once by the statistics passes and reused by the later ones
+  DBuf<double> y_csc;               // log1p(x_ij / r_i), CSC order
+  DBuf<double> z_csr;               // y_ij / sigma_j, CSR order  (cell-major writer: patch = z / s_i)
+  DBuf<float> patch_csc;            // z_ij / s_i, CSC order     (gene-major writer)
 };
 
 struct Workspace;  // sparse scratch, defined in sparse.cu
@@ -105,7 +109,7 @@ double noise_baseline_device(int nm, int n_rep, uint64_t seed, cudaStream_t st);
 // ---- normalize.cu ----
 void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st);
 // layout 0: gene-major out[M][ld] (column-major N x M); 1: cell-major out[N][ld]
-// sumsq_partial (optional, [lines][densify_strips(ld)]): exact per-strip sums of squares of the emitted values
+// sumsq_partial (optional, [lines][densify_strips(pos1 - pos0)]): partial sums of squares of the emitted values
 // [pos0,pos1): range of positions of every line to emit (default: the whole padded line) - the cell block of a rank
 void densify(const SpMat& A, const NormStats& S, int layout, size_t ld, __half* out_hi, __half* out_lo,
              cudaStream_t st, double* sumsq_partial = nullptr, long long pos0 = 0, long long pos1 = -1);

@@ -17,6 +17,7 @@ struct scl_handle {
   int world = 1, rank = 0;
   void* nccl = nullptr;   // ncclComm_t
   scl::Prof prof;
+  scl::DBuf<double> gram_factor;   // common factor (1 - delta) of the Gram matrix gram_of() produced last
   cudaEvent_t t0 = nullptr, t1 = nullptr;
 
   // inputs
@@ -54,6 +55,8 @@ struct scl_handle {
 };
 
 namespace scl {
+// refine.cu
+void refine_eigenvalues(const float* dG, const float* dV, int n, float* dW, cudaStream_t st);
 // pipeline.cu
 void run_signal(scl_handle* h);
 void run_robustness(scl_handle* h, double th, double p_step, int n_perturb);

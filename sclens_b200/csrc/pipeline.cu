@@ -152,6 +152,100 @@ void gemm_splitk(scl_handle* h, const GemmOperand& A, const GemmOperand& B, bool
   reduce_splits(part.p, splits, (int64_t)c_elems, c_elems, alpha, dC, h->st);
 }
 
+// ---- calibration of the tensor core's accumulation bias -----------------------------------
+// tcgen05 accumulates in FP32 with truncation: every partial sum is pulled towards zero, so a Gram matrix
+// comes out as (1 - delta) * G with delta ~ 3e-8 per MMA of the accumulation chain (measured, profiles/
+// r1_diag_eig_error_*.txt), uniformly over the off-diagonal entries.  Together with the exact Float64 diagonal
+// that is a relative diagonal excess delta, which moves an eigenvalue by delta * (mean diagonal - lambda) - ten
+// times delta at the lower Marchenko-Pastur edge.  delta is measured per Gram matrix from kCalibSamples
+// off-diagonal entries evaluated exactly (Float64 dot products of the binary16 operand rows); the diagonal is
+// scaled by (1 - delta) so the whole matrix carries one common factor, which is divided out of the eigenvalues.
+constexpr int kCalibSamples = 2048;
+
+__device__ __forceinline__ void calib_pair(int s, int rows, int& i, int& j) {
+  uint64_t h = (uint64_t)(s + 1) * 0x9E3779B97F4A7C15ull;
+  h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+  i = (int)((h & 0xffffffffull) % (uint64_t)rows);
+  j = (int)((h >> 32) % (uint64_t)(rows - 1));
+  if (j >= i) ++j;   // j != i
+}
+
+// ex[s] = sum_k a_i[k] a_j[k] over [k0, k0 + Ks) exactly as the tensor core would form it without rounding
+// (hi*hi, plus hi*lo + lo*hi in split mode); rows are zero padded up to a multiple of 8 elements
+__global__ void __launch_bounds__(256) k_sample_dots(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                                     long long ld, long long k0, long long Ks, int rows,
+                                                     double* __restrict__ ex) {
+  __shared__ double red[8];
+  int i, j;
+  calib_pair(blockIdx.x, rows, i, j);
+  const __half* ai = hi + (long long)i * ld + k0;
+  const __half* aj = hi + (long long)j * ld + k0;
+  const __half* li = lo ? lo + (long long)i * ld + k0 : nullptr;
+  const __half* lj = lo ? lo + (long long)j * ld + k0 : nullptr;
+  const long long n8 = (Ks + 7) / 8;
+  double acc = 0;
+  for (long long c = threadIdx.x; c < n8; c += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(ai + c * 8), v = *reinterpret_cast<const uint4*>(aj + c * 8);
+    const __half2* x = reinterpret_cast<const __half2*>(&u);
+    const __half2* y = reinterpret_cast<const __half2*>(&v);
+    uint4 ul = make_uint4(0, 0, 0, 0), vl = ul;
+    if (lo) { ul = *reinterpret_cast<const uint4*>(li + c * 8); vl = *reinterpret_cast<const uint4*>(lj + c * 8); }
+    const __half2* xl = reinterpret_cast<const __half2*>(&ul);
+    const __half2* yl = reinterpret_cast<const __half2*>(&vl);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 a = __half22float2(x[q]), b = __half22float2(y[q]);
+      acc += (double)a.x * (double)b.x + (double)a.y * (double)b.y;
+      if (lo) {
+        const float2 al = __half22float2(xl[q]), bl = __half22float2(yl[q]);
+        acc += (double)a.x * (double)bl.x + (double)al.x * (double)b.x + (double)a.y * (double)bl.y + (double)al.y * (double)b.y;
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    ex[blockIdx.x] = t;
+  }
+}
+
+// factor[0] = 1 + least-squares slope of (G_tc - G_exact) on G_exact over the samples  (= 1 - delta)
+__global__ void __launch_bounds__(256) k_fit_shrink(const float* __restrict__ G, int n, double inv_scale,
+                                                    const double* __restrict__ ex, int S, double* __restrict__ factor) {
+  __shared__ double rx[8], ry[8];
+  double sxx = 0, sxy = 0;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    int i, j;
+    calib_pair(s, n, i, j);
+    const double e = ex[s], t = (double)G[(size_t)i * n + j] * inv_scale;
+    sxx += e * e;
+    sxy += (t - e) * e;
+  }
+  for (int o = 16; o; o >>= 1) { sxx += __shfl_xor_sync(0xffffffffu, sxx, o); sxy += __shfl_xor_sync(0xffffffffu, sxy, o); }
+  if ((threadIdx.x & 31) == 0) { rx[threadIdx.x >> 5] = sxx; ry[threadIdx.x >> 5] = sxy; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) { a += rx[w]; b += ry[w]; }
+    double f = a > 0 ? 1.0 + b / a : 1.0;
+    if (!(f > 0.999 && f < 1.001)) f = 1.0;   // a bias this large is not the effect being calibrated
+    factor[0] = f;
+  }
+}
+
+__global__ void k_scale_diagonal(float* __restrict__ G, int n, const double* __restrict__ factor) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) G[(size_t)i * n + i] = (float)((double)G[(size_t)i * n + i] * factor[0]);
+}
+
+__global__ void k_unscale_values(float* __restrict__ w, int n, const double* __restrict__ factor) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) w[i] = (float)((double)w[i] / factor[0]);
+}
+
 double quantile7(const std::vector<double>& sorted, double p) {
   const size_t n = sorted.size();
   if (n == 1) return sorted[0];
@@ -215,14 +309,47 @@ void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf
       gemm_umma(g, h->st);
       h->prof.gram_alg_flops += (double)rows * (rows + 1.0) * (double)Ks;
     }
-    if (!h->cfg.gram_tc_diag) set_gram_diagonal(dG, nm, n_strips, sumsq.p, (double)scale, h->st);
+    if (h->cfg.gram_tc_diag != 1) set_gram_diagonal(dG, nm, n_strips, sumsq.p, (double)scale, h->st);
   } else {
     SCL_CUDA(cudaMemsetAsync(dG, 0, (size_t)nm * nm * sizeof(float), h->st));
+  }
+  // exact values of the calibration samples over this rank's part of the contraction
+  const bool calibrate = h->cfg.gram_tc_diag == 0 && nm >= 64;
+  Tmp<double> ex(kCalibSamples, h->st);
+  h->gram_factor.ensure(1);
+  if (calibrate) {
+    ProfScope ps(&h->prof, h->st, PK_SMALL);
+    count_launches(1);
+    if (have_work)
+      k_sample_dots<<<kCalibSamples, 256, 0, h->st>>>(hi.p, split ? lo.p : nullptr, (long long)ld, (long long)k0,
+                                                      (long long)(std::min<int64_t>(K, k1) - k0), rows, ex.p);
+    else
+      SCL_CUDA(cudaMemsetAsync(ex.p, 0, kCalibSamples * sizeof(double), h->st));
+    SCL_CUDA(cudaGetLastError());
   }
   if (sharded) {
     ProfScope ps(&h->prof, h->st, PK_SMALL);
     SCL_NCCL(nccl_api().AllReduce(dG, dG, (size_t)nm * nm, ncclFloat, ncclSum, (ncclComm_t)h->nccl, h->st));
+    if (calibrate) SCL_NCCL(nccl_api().AllReduce(ex.p, ex.p, kCalibSamples, ncclDouble, ncclSum, (ncclComm_t)h->nccl, h->st));
   }
+  if (calibrate) {
+    ProfScope ps(&h->prof, h->st, PK_SMALL);
+    count_launches(2);
+    k_fit_shrink<<<1, 256, 0, h->st>>>(dG, nm, 1.0 / (double)scale, ex.p, kCalibSamples, h->gram_factor.p);
+    k_scale_diagonal<<<(nm + 255) / 256, 256, 0, h->st>>>(dG, nm, h->gram_factor.p);
+    SCL_CUDA(cudaGetLastError());
+  } else {
+    const double one = 1.0;
+    SCL_CUDA(cudaMemcpyAsync(h->gram_factor.p, &one, sizeof(double), cudaMemcpyHostToDevice, h->st));
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+  }
+}
+
+// eigenvalues of the matrix gram_of() produced last -> eigenvalues of the Gram matrix itself
+void unscale_eigenvalues(scl_handle* h, float* dW, int n) {
+  count_launches(1);
+  k_unscale_values<<<(n + 255) / 256, 256, 0, h->st>>>(dW, n, h->gram_factor.p);
+  SCL_CUDA(cudaGetLastError());
 }
 
 // d[j] = max_i |<V_i, W_j>|  (:742) with V pre-converted to binary16 hi/lo rows
@@ -301,8 +428,21 @@ void run_signal(scl_handle* h) {
   gram_of(h, X, h->S_main, op_hi, op_lo, G.p, nm, 1.0f / (float)M, split, /*shard=*/true);
   info.t_normalize_ms = 0;  // fused into the Gram timing below (one stream); see bench for per-kernel times
   info.t_gram_ms += tm.stop();
+  // the FP32 solver's eigenvalues carry an absolute error ~eps32*|G|; the spectrum of the data matrix is an output
+  // (:L, :L_mp), so it is refined by Float64 Rayleigh quotients of the computed eigenvectors (refine.cu)
+  const bool refine = !h->cfg.no_refine;
+  DBuf<float> Gkeep;
+  if (refine) {
+    Gkeep.ensure((size_t)nm * nm);
+    SCL_CUDA(cudaMemcpyAsync(Gkeep.p, G.p, (size_t)nm * nm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
   { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G.p, nm, W.p, true, st); }
   info.t_syevd_ms += tm.stop();
+  if (refine) {
+    ProfScope ps(&h->prof, st, PK_REFINE);
+    refine_eigenvalues(Gkeep.p, G.p, nm, W.p, st);
+  }
+  unscale_eigenvalues(h, W.p, nm);
   h->L.resize(nm);
   SCL_CUDA(cudaMemcpyAsync(h->L.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
   // rec_vals (:676-695)
@@ -315,6 +455,10 @@ void run_signal(scl_handle* h) {
   SCL_CUDA(cudaStreamSynchronize(st));
   for (float v : h->L)
     if (!std::isfinite(v)) throw Error(SCL_ERR_CUSOLVER, "non-finite eigenvalue (the reference's CPU fallback :379-381 is an error here)");
+  Gkeep.release();
+  // Rayleigh quotients of neighbouring bulk eigenvectors can swap by ~1e-6 relative: :L is ascending (:378); the
+  // signal eigenvalues are far apart, so their pairing with the eigenvectors is untouched
+  if (refine) std::sort(h->L.begin(), h->L.end());
   tm.stop();
 
   // --- null matrix (:701) and its spectrum (:531-532/:571-572)
@@ -336,6 +480,7 @@ void run_signal(scl_handle* h) {
     gram_of(h, h->Xnull, Sn, op_hi, op_lo, G2.p, nm, 1.0f / (float)M, split, /*shard=*/true);
     info.t_gram_ms += tm.stop();
     { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G2.p, nm, W2.p, false, st); }
+    unscale_eigenvalues(h, W2.p, nm);
     info.t_syevd_ms += tm.stop();
     std::vector<float> Lr(nm);
     SCL_CUDA(cudaMemcpyAsync(Lr.data(), W2.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -667,6 +812,7 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
     long long ldvec;
     if (exact) {
       { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G.p, nm, W.p, true, st); }
+      unscale_eigenvalues(h, W.p, nm);
       SCL_CUDA(cudaMemcpyAsync(Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
       SCL_CUDA(cudaStreamSynchronize(st));
       SCL_REQUIRE(nm - first_positive(Lh) >= min_pc, "too few positive eigenvalues in a replicate");
@@ -676,6 +822,7 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
     } else {
       int iters = 0;
       topk_subspace(h, G.p, nm, min_pc, topL.p, topV.p, &iters);
+      unscale_eigenvalues(h, topL.p, min_pc);
       SCL_CUDA(cudaMemcpyAsync(&h->set_L[(size_t)r * min_pc], topL.p, min_pc * sizeof(float), cudaMemcpyDeviceToHost, st));
       vec0 = topV.p;
       ldvec = nm;

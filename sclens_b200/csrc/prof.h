@@ -8,7 +8,7 @@
 
 namespace scl {
 
-enum ProfKind { PK_GRAM_GEMM = 0, PK_OTHER_GEMM, PK_DENSIFY, PK_STATS, PK_SPARSE, PK_SYEVD, PK_SMALL, PK_COUNT };
+enum ProfKind { PK_GRAM_GEMM = 0, PK_OTHER_GEMM, PK_DENSIFY, PK_STATS, PK_SPARSE, PK_SYEVD, PK_SMALL, PK_REFINE, PK_COUNT };
 
 struct ProfEvent {
   cudaEvent_t a, b;

@@ -226,28 +226,196 @@ __global__ void k_scatter_additions(const uint32_t* __restrict__ add_row, const 
   }
 }
 
+// ---- bitmap merge -----------------------------------------------------------------------
+// The perturbed matrices of :735/:774 are the (sorted) base lines plus a set of ones at zero positions.
+// One CTA per line: base and added positions are marked in two shared-memory bitmaps of line_len bits; a
+// block-wide prefix sum over the word popcounts gives every set bit its output slot, so the merged line comes
+// out sorted without sorting anything, and the base values are found by their rank in the base bitmap.
+// Additions that hit a stored position or each other (impossible for draws from the zero candidates) raise
+// `flag`, and the caller falls back to the general canonicalisation.
+static constexpr int kMergeThreads = 256;
+
+__global__ void k_count_adds(const uint32_t* __restrict__ add_row, const uint32_t* __restrict__ add_col, size_t n_add,
+                             uint32_t* __restrict__ cnt_col, uint32_t* __restrict__ cnt_row) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n_add; i += stride) {
+    atomicAdd(&cnt_col[add_col[i]], 1u);
+    atomicAdd(&cnt_row[add_row[i]], 1u);
+  }
+}
+
+// bucket_col[aptr_col[c] + k] = row, bucket_row[aptr_row[r] + k] = col  (unordered inside a bucket)
+__global__ void k_bucket_adds(const uint32_t* __restrict__ add_row, const uint32_t* __restrict__ add_col, size_t n_add,
+                              const uint32_t* __restrict__ aptr_col, const uint32_t* __restrict__ aptr_row,
+                              uint32_t* __restrict__ cur_col, uint32_t* __restrict__ cur_row,
+                              uint32_t* __restrict__ bucket_col, uint32_t* __restrict__ bucket_row) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n_add; i += stride) {
+    const uint32_t r = add_row[i], c = add_col[i];
+    bucket_col[aptr_col[c] + atomicAdd(&cur_col[c], 1u)] = r;
+    bucket_row[aptr_row[r] + atomicAdd(&cur_row[r], 1u)] = c;
+  }
+}
+
+__global__ void k_add_ptrs(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int n, uint32_t* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
+__global__ void __launch_bounds__(kMergeThreads)
+k_merge_lines(const uint32_t* __restrict__ base_ptr, const uint32_t* __restrict__ base_idx,
+              const float* __restrict__ base_val, const uint32_t* __restrict__ add_ptr,
+              const uint32_t* __restrict__ add_pos, const uint32_t* __restrict__ out_ptr, uint32_t* __restrict__ out_idx,
+              float* __restrict__ out_val, int n_lines, int line_len, int binarise, int* __restrict__ flag) {
+  extern __shared__ uint32_t bm[];   // [2][words]: base bits, added bits
+  __shared__ unsigned long long warp_tot[kMergeThreads / 32];
+  const int words = (line_len + 31) >> 5;
+  uint32_t* bmB = bm;
+  uint32_t* bmA = bm + words;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wpt = (words + kMergeThreads - 1) / kMergeThreads;   // contiguous words per thread
+  for (int l = blockIdx.x; l < n_lines; l += gridDim.x) {
+    const uint32_t bb = base_ptr[l], be = base_ptr[l + 1], ab = add_ptr[l], ae = add_ptr[l + 1], ob = out_ptr[l];
+    if (ae == ab) {   // nothing added to this line: copy
+      for (uint32_t t = bb + tid; t < be; t += kMergeThreads) {
+        out_idx[ob + (t - bb)] = base_idx[t];
+        out_val[ob + (t - bb)] = binarise ? 1.f : base_val[t];
+      }
+      continue;
+    }
+    for (int w = tid; w < 2 * words; w += kMergeThreads) bm[w] = 0u;
+    __syncthreads();
+    for (uint32_t t = bb + tid; t < be; t += kMergeThreads) {
+      const uint32_t p = base_idx[t];
+      atomicOr(&bmB[p >> 5], 1u << (p & 31));
+    }
+    bool bad = false;
+    for (uint32_t t = ab + tid; t < ae; t += kMergeThreads) {
+      const uint32_t p = add_pos[t];
+      if (p >= (uint32_t)line_len) { bad = true; continue; }
+      const uint32_t bit = 1u << (p & 31);
+      if (atomicOr(&bmA[p >> 5], bit) & bit) bad = true;       // the same position added twice
+    }
+    __syncthreads();
+    // per-thread counts over its contiguous words: (merged << 32) | base
+    const int w0 = min(words, tid * wpt), w1 = min(words, w0 + wpt);
+    unsigned long long cnt = 0;
+    for (int w = w0; w < w1; ++w) {
+      const uint32_t B = bmB[w], A = bmA[w];
+      if (B & A) bad = true;                                     // an addition on a stored position
+      cnt += ((unsigned long long)__popc(B | A) << 32) | (unsigned long long)__popc(B);
+    }
+    unsigned long long incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned long long wbase = 0;
+    for (int q = 0; q < warp; ++q) wbase += warp_tot[q];
+    const unsigned long long excl = wbase + incl - cnt;
+    uint32_t ru = (uint32_t)(excl >> 32), rb = (uint32_t)(excl & 0xffffffffull);
+    if (bad) atomicOr(flag, 1);
+    for (int w = w0; w < w1; ++w) {
+      const uint32_t B = bmB[w], A = bmA[w];
+      uint32_t u = B | A;
+      while (u) {
+        const int k = __ffs(u) - 1;
+        u &= u - 1;
+        const uint32_t bit = 1u << k;
+        float v = 0.f;
+        if (B & bit) { v = binarise ? 1.f : base_val[bb + rb]; ++rb; }
+        if (A & bit) v += 1.f;
+        out_idx[ob + ru] = (uint32_t)(w * 32 + k);
+        out_val[ob + ru] = v;
+        ++ru;
+      }
+    }
+    __syncthreads();   // bitmaps and warp_tot are reused by the next line
+  }
+}
+
+static void perturb_merge_general(const SpMat& base, const uint32_t* d_add_row, const uint32_t* d_add_col, size_t n_add,
+                                  bool binarise, SpMat& out, cudaStream_t st);
+
 void perturb_merge(const SpMat& base, const uint32_t* d_add_row, const uint32_t* d_add_col, size_t n_add,
                    bool binarise, SpMat& out, cudaStream_t st) {
+  const int N = base.N, M = base.M;
+  const size_t nnz = base.nnz + n_add;
+  const size_t smem_c = (size_t)2 * ((N + 31) / 32) * sizeof(uint32_t), smem_r = (size_t)2 * ((M + 31) / 32) * sizeof(uint32_t);
+  if (smem_c > 200 * 1024 || smem_r > 200 * 1024) {   // a line's bitmaps must fit in shared memory
+    perturb_merge_general(base, d_add_row, d_add_col, n_add, binarise, out, st);
+    return;
+  }
+  count_launches(n_add ? 8 : 4);
+  out.N = N; out.M = M; out.nnz = nnz;
+  out.colptr.ensure(M + 1); out.rowptr.ensure(N + 1);
+  out.rowval.ensure(nnz ? nnz : 1); out.val.ensure(nnz ? nnz : 1);
+  out.colidx.ensure(nnz ? nnz : 1); out.rval.ensure(nnz ? nnz : 1);
+  Tmp<uint32_t> cnt((size_t)M + N + 2, st), aptr((size_t)M + N + 2, st), cur((size_t)M + N + 2, st);
+  Tmp<uint32_t> bucket_col(n_add ? n_add : 1, st), bucket_row(n_add ? n_add : 1, st);
+  Tmp<int> flag(1, st);
+  uint32_t *cnt_col = cnt.p, *cnt_row = cnt.p + M + 1, *aptr_col = aptr.p, *aptr_row = aptr.p + M + 1;
+  uint32_t *cur_col = cur.p, *cur_row = cur.p + M + 1;
+  SCL_CUDA(cudaMemsetAsync(cnt.p, 0, ((size_t)M + N + 2) * sizeof(uint32_t), st));
+  SCL_CUDA(cudaMemsetAsync(cur.p, 0, ((size_t)M + N + 2) * sizeof(uint32_t), st));
+  SCL_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+  if (n_add) k_count_adds<<<grid_for(n_add, 256), 256, 0, st>>>(d_add_row, d_add_col, n_add, cnt_col, cnt_row);
+  exclusive_scan(cnt_col, aptr_col, M, st);
+  exclusive_scan(cnt_row, aptr_row, N, st);
+  if (n_add)
+    k_bucket_adds<<<grid_for(n_add, 256), 256, 0, st>>>(d_add_row, d_add_col, n_add, aptr_col, aptr_row, cur_col, cur_row,
+                                                        bucket_col.p, bucket_row.p);
+  k_add_ptrs<<<(M + 256) / 256, 256, 0, st>>>(base.colptr.p, aptr_col, M + 1, out.colptr.p);
+  k_add_ptrs<<<(N + 256) / 256, 256, 0, st>>>(base.rowptr.p, aptr_row, N + 1, out.rowptr.p);
+  SCL_CUDA(cudaFuncSetAttribute(k_merge_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  k_merge_lines<<<min(M, 148 * 8), kMergeThreads, smem_c, st>>>(base.colptr.p, base.rowval.p, base.val.p, aptr_col,
+                                                                bucket_col.p, out.colptr.p, out.rowval.p, out.val.p, M, N,
+                                                                binarise ? 1 : 0, flag.p);
+  k_merge_lines<<<min(N, 148 * 8), kMergeThreads, smem_r, st>>>(base.rowptr.p, base.colidx.p, base.rval.p, aptr_row,
+                                                                bucket_row.p, out.rowptr.p, out.colidx.p, out.rval.p, N, M,
+                                                                binarise ? 1 : 0, flag.p);
+  SCL_CUDA(cudaGetLastError());
+  int bad = 0;
+  SCL_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  if (bad) perturb_merge_general(base, d_add_row, d_add_col, n_add, binarise, out, st);   // sparse(I,J,V) sums them
+}
+
+// General path: any additions (coinciding with stored entries or with each other); lines are canonicalised.
+static void perturb_merge_general(const SpMat& base, const uint32_t* d_add_row, const uint32_t* d_add_col, size_t n_add,
+                                  bool binarise, SpMat& out, cudaStream_t st) {
   count_launches(n_add ? 6 : 4);
   const int N = base.N, M = base.M;
   const size_t nnz = base.nnz + n_add;
-  out.N = N; out.M = M; out.nnz = nnz;
+  out.N = N; out.M = M;
   out.colptr.ensure(M + 1);
-  out.rowval.ensure(nnz ? nnz : 1);
-  out.val.ensure(nnz ? nnz : 1);
-  Tmp<uint32_t> addcnt(M + 1, st), cnt(M + 1, st), cursor(M + 1, st), trow(nnz ? nnz : 1, st);
+  Tmp<uint32_t> addcnt(M + 1, st), cnt(M + 1, st), tptr(M + 1, st), cursor(M + 1, st), trow(nnz ? nnz : 1, st);
   Tmp<float> tval(nnz ? nnz : 1, st);
   SCL_CUDA(cudaMemsetAsync(addcnt.p, 0, (M + 1) * sizeof(uint32_t), st));
   SCL_CUDA(cudaMemsetAsync(cursor.p, 0, (M + 1) * sizeof(uint32_t), st));
   if (n_add) k_count_index<<<grid_for(n_add, 256), 256, 0, st>>>(d_add_col, n_add, addcnt.p);
   k_merged_counts<<<(M + 255) / 256, 256, 0, st>>>(base.colptr.p, addcnt.p, M, cnt.p);
-  exclusive_scan(cnt.p, out.colptr.p, M, st);
-  k_copy_base<<<min(M, 148 * 8), 128, 0, st>>>(base.colptr.p, base.rowval.p, base.val.p, M, out.colptr.p, binarise,
+  exclusive_scan(cnt.p, tptr.p, M, st);
+  k_copy_base<<<min(M, 148 * 8), 128, 0, st>>>(base.colptr.p, base.rowval.p, base.val.p, M, tptr.p, binarise,
                                                trow.p, tval.p);
   if (n_add)
     k_scatter_additions<<<grid_for(n_add, 256), 256, 0, st>>>(d_add_row, d_add_col, n_add, base.colptr.p,
-                                                              out.colptr.p, cursor.p, trow.p, tval.p);
-  k_canon<false><<<min(M, 148 * 8), kCanonThreads, 0, st>>>(out.colptr.p, trow.p, tval.p, out.colptr.p, out.rowval.p,
+                                                              tptr.p, cursor.p, trow.p, tval.p);
+  // duplicates are summed, so the canonical lines can be shorter than the staged ones: count, scan, emit
+  k_canon<true><<<min(M, 148 * 8), kCanonThreads, 0, st>>>(tptr.p, trow.p, tval.p, nullptr, nullptr, nullptr, cnt.p, M, N);
+  exclusive_scan(cnt.p, out.colptr.p, M, st);
+  uint32_t total = 0;
+  SCL_CUDA(cudaMemcpyAsync(&total, out.colptr.p + M, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  out.nnz = total;
+  out.rowval.ensure(total ? total : 1);
+  out.val.ensure(total ? total : 1);
+  k_canon<false><<<min(M, 148 * 8), kCanonThreads, 0, st>>>(tptr.p, trow.p, tval.p, out.colptr.p, out.rowval.p,
                                                             out.val.p, nullptr, M, N);
   SCL_CUDA(cudaGetLastError());
   build_csr_mirror(out, st);

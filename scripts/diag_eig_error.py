@@ -77,14 +77,12 @@ for chunk in chunks:
         Ge = Go.clone()
         Ge.diagonal().copy_(Ghi64.diagonal())
         rep("exact diagonal, f64 eig", torch.linalg.eigvalsh(Ge).cpu().numpy())
-        Gc = Go / (1.0 + slope_diag)
-        rep("tensor-core diag, all / (1+diag shrink), f64 eig", torch.linalg.eigvalsh(Gc).cpu().numpy())
-        Gc2 = Go / (1.0 + slope_diag)
+        Gc2 = Go / (1.0 + slope_off)
         Gc2.diagonal().copy_(Ghi64.diagonal())
-        rep("exact diag, off-diag / (1+diag shrink), f64 eig", torch.linalg.eigvalsh(Gc2).cpu().numpy())
-        del Go, Ge, Gc, Gc2, d, resid
-    for tcd in (False, True):
+        rep("exact diag, off-diag / (1+off-diag shrink), f64 eig", torch.linalg.eigvalsh(Gc2).cpu().numpy())
+        del Go, Ge, Gc2, d, resid
+    for tcd in (0, 2):
         with Handle(seed=0, gram_chunk_kb=chunk, gram_tc_diag=tcd) as h:
             h.set_counts(X)
             s2 = h.run_signal()
-            rep(f"pipeline L (Ssyevd), tc_diag={int(tcd)}, n_signal={s2.n_signal}", h.L())
+            rep(f"pipeline L, mode={tcd} (0 calibrated, 2 exact diag only), n_signal={s2.n_signal}", h.L())

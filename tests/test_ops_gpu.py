@@ -105,7 +105,7 @@ def test_gram_syrk(h, h1, rows, K, cg, split):
     assert np.array_equal(G, G.T)       # mirrored store: exactly symmetric
 
 
-@pytest.mark.parametrize("N,M", [(500, 800), (900, 400)])
+@pytest.mark.parametrize("N,M", [(500, 800), (900, 400), (2301, 4700)])   # the last spans several writer strips
 @pytest.mark.parametrize("layout", [0, 1])
 def test_normalize_matches_oracle(h, N, M, layout):
     X = make_counts(N, M, seed=11, K=4, de_prob=0.3, lfc_sd=1.5)
@@ -158,6 +158,37 @@ def test_perturb_merge_bit_exact(h, N, M, binarise):
     np.testing.assert_array_equal(oc, want.indptr)
     np.testing.assert_array_equal(orow, want.indices)
     np.testing.assert_array_equal(ov, want.data)
+
+
+def test_perturb_merge_general_semantics(h):
+    """sparse(I,J,V) semantics for additions that hit stored entries or each other (cannot happen for draws from
+    the zero candidates, but the operator must still sum them like Julia's sparse(), src/scLENS.jl:735/:774),
+    and the degenerate cases: no additions at all, additions only in empty lines."""
+    N, M = 400, 300
+    X = make_counts(N, M, seed=9, K=3)
+    colptr, rowval, val = csc_arrays(X)
+    coo = X.tocoo()
+    rng = np.random.default_rng(10)
+    hit = rng.choice(X.nnz, size=50, replace=False)
+    zr, zc = orc.draw_zero_candidates(X, rng)
+    ar = np.concatenate([coo.row[hit], zr[:200], zr[:20]])          # 50 on stored entries, 20 duplicated zeros
+    ac = np.concatenate([coo.col[hit], zc[:200], zc[:20]])
+    for binarise, (rows_, cols_) in [(0, (ar, ac)), (1, (ar, ac)), (0, (ar[:0], ac[:0]))]:
+        base = X.copy()
+        if binarise:
+            base.data[:] = 1.0
+        want = sp.csc_matrix(base + sp.coo_matrix((np.ones(len(rows_), np.float32), (rows_, cols_)), shape=(N, M)))
+        want.sort_indices()
+        n_out = X.nnz + len(rows_)
+        oc, orow, ov = np.empty(M + 1, np.uint32), np.zeros(n_out, np.uint32), np.zeros(n_out, np.float32)
+        a1, a2 = _lib.as_u32(rows_), _lib.as_u32(cols_)
+        h._ck(h.lib.scl_op_perturb_merge(h.h, N, M, X.nnz, ptr(colptr, C.c_uint32), ptr(rowval, C.c_uint32),
+                                         ptr(val, C.c_float), len(rows_), ptr(a1, C.c_uint32) if len(rows_) else None,
+                                         ptr(a2, C.c_uint32) if len(rows_) else None, binarise, ptr(oc, C.c_uint32),
+                                         ptr(orow, C.c_uint32), ptr(ov, C.c_float)))
+        np.testing.assert_array_equal(oc, want.indptr)
+        np.testing.assert_array_equal(orow[:want.nnz], want.indices)
+        np.testing.assert_array_equal(ov[:want.nnz], want.data)
 
 
 @pytest.mark.parametrize("N,M", [(300, 500), (9000, 60)])
