@@ -17,6 +17,11 @@ from typing import Optional
 import numpy as np
 import scipy.sparse as sp
 
+try:   # DataFrames in, DataFrames out (as the reference); imported once here, not inside a call
+    import pandas as pd
+except ImportError:  # pragma: no cover
+    pd = None
+
 from . import _lib
 from ._lib import Config, Profile, RobustInfo, SclError, SignalInfo, as_f32, as_u32, ptr
 
@@ -24,10 +29,6 @@ from ._lib import Config, Profile, RobustInfo, SclError, SignalInfo, as_f32, as_
 def df2sparr(inp_df):
     """df2sparr (:90-120): DataFrame (col 0 = 'cell', then genes) -> canonical CSC Float32 with
     UInt32 indices, plus cell and gene ids.  scipy sparse / ndarray inputs are accepted too."""
-    try:
-        import pandas as pd
-    except ImportError:  # pragma: no cover
-        pd = None
     if pd is not None and isinstance(inp_df, pd.DataFrame):
         cell_id = inp_df.iloc[:, 0].astype(str).to_numpy()
         genes = inp_df.columns[1:]
@@ -38,12 +39,17 @@ def df2sparr(inp_df):
             X = sp.csc_matrix(body.to_numpy(dtype=np.float32))
         gene_id = np.asarray(genes, dtype=object)
     else:
-        X = sp.csc_matrix(inp_df, dtype=np.float32)
+        X = inp_df if (sp.isspmatrix_csc(inp_df) and inp_df.dtype == np.float32) else sp.csc_matrix(inp_df, dtype=np.float32)
         cell_id = np.array([f"c{i}" for i in range(X.shape[0])], dtype=object)
         gene_id = np.array([f"g{j}" for j in range(X.shape[1])], dtype=object)
-    X.sum_duplicates()
-    X.eliminate_zeros()   # the C ABI requires strictly positive stored values
-    X.sort_indices()
+    # canonical CSC with strictly positive stored values is what the C ABI takes; an input that already is
+    # canonical (one O(nnz) check) is passed through without a copy
+    if not X.has_canonical_format:
+        X = X.copy()
+        X.sum_duplicates()
+    if X.nnz and float(X.data.min()) <= 0.0:
+        X = X.copy()
+        X.eliminate_zeros()
     return X, cell_id, gene_id
 
 
@@ -249,10 +255,6 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
         raise ValueError('sclens_b200 implements device_="gpu" only (no CPU fallback exists)')
     if centering != "mean":
         raise NotImplementedError('only centering="mean" (the default path) is implemented')
-    try:
-        import pandas as pd
-    except ImportError:  # pragma: no cover
-        pd = None
     if verbose:
         print("Extracting matrices")                                    # :661
     X, cell_id, gene_id = df2sparr(inp_df)

@@ -464,8 +464,6 @@ int32_t scl_bench_normalize(scl_handle* h, int32_t layout, int32_t with_lo, int3
     const size_t ld = (line_len + 7) / 8 * 8;
     Tmp<__half> hi(lines * ld, h->st), lo(with_lo ? lines * ld : 1, h->st);
     NormStats S;
-    const int n_strips = densify_strips(ld);
-    Tmp<double> sumsq(lines * (size_t)n_strips, h->st);
     cudaEvent_t e0, e1, e2;
     SCL_CUDA(cudaEventCreate(&e0));
     SCL_CUDA(cudaEventCreate(&e1));
@@ -475,7 +473,7 @@ int32_t scl_bench_normalize(scl_handle* h, int32_t layout, int32_t with_lo, int3
       SCL_CUDA(cudaEventRecord(e0, h->st));
       compute_norm_stats(X, S, h->st);
       SCL_CUDA(cudaEventRecord(e1, h->st));
-      densify(X, S, layout, ld, hi.p, with_lo ? lo.p : nullptr, h->st, sumsq.p);
+      densify(X, S, layout, ld, hi.p, with_lo ? lo.p : nullptr, h->st);
       SCL_CUDA(cudaEventRecord(e2, h->st));
       SCL_CUDA(cudaEventSynchronize(e2));
       float a = 0, b = 0;

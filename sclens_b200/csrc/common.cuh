@@ -45,8 +45,11 @@ struct DBuf {
   }
   T* ensure(size_t n) {
     if (n > cap) {
+      // a buffer that has to grow again is growing with the problem (the perturbed matrices of the sparsity
+      // search gain ~1 % of entries per step): cudaFree/cudaMalloc cost ~10 ms per 100 MB, so leave headroom
+      const bool regrow = p != nullptr;
       release();
-      size_t want = n + n / 16 + 64;
+      size_t want = regrow ? n + n / 2 + 64 : n + n / 16 + 64;
       SCL_CUDA(cudaMalloc(&p, want * sizeof(T)));
       cap = want;
     }
@@ -78,11 +81,12 @@ struct NormStats {
   DBuf<float> inv_s_f;              // float copy streamed by the densify kernels
   DBuf<double> ybar, sigma, mu, cent;  // per gene
   DBuf<float> mu_f, cent_f, inv_sigma_f;
-  DBuf<double> scalars;             // [0]=|mu|^2 [1]=mean(l) [2]=sum(1/s)
+  DBuf<double> scalars;             // [0]=|mu|^2 [1]=mean(l) [2]=sum(1/s) [3]=sum(1/s^2) [4]=mu.c [5]=|c|^2
+  DBuf<double> sumsq_gene, sumsq_cell;   // exact sums of squares of the normalised matrix's columns / rows
   // per non-zero intermediates, evaluated once by the statistics passes and reused by the later ones
   DBuf<double> y_csc;               // log1p(x_ij / r_i), CSC order
-  DBuf<double> z_csr;               // y_ij / sigma_j, CSR order  (cell-major writer: patch = z / s_i)
-  DBuf<float> patch_csc;            // z_ij / s_i, CSC order     (gene-major writer)
+  DBuf<double> z_csr;               // y_ij / sigma_j, CSR order  (the cell-major writer finishes it per line)
+  DBuf<float> patch_csc;            // final value (z_ij - mu_j)/s_i - c_j of a stored entry, CSC order (gene-major writer)
 };
 
 struct Workspace;  // sparse scratch, defined in sparse.cu
@@ -109,12 +113,12 @@ double noise_baseline_device(int nm, int n_rep, uint64_t seed, cudaStream_t st);
 // ---- normalize.cu ----
 void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st);
 // layout 0: gene-major out[M][ld] (column-major N x M); 1: cell-major out[N][ld]
-// sumsq_partial (optional, [lines][densify_strips(pos1 - pos0)]): partial sums of squares of the emitted values
 // [pos0,pos1): range of positions of every line to emit (default: the whole padded line) - the cell block of a rank
 void densify(const SpMat& A, const NormStats& S, int layout, size_t ld, __half* out_hi, __half* out_lo,
-             cudaStream_t st, double* sumsq_partial = nullptr, long long pos0 = 0, long long pos1 = -1);
-int densify_strips(size_t n_pos);
-void set_gram_diagonal(float* G, int n, int n_strips, const double* partial, double scale, cudaStream_t st);
+             cudaStream_t st, long long pos0 = 0, long long pos1 = -1);
+// exact Float64 Gram diagonal (unscaled) of the normalised matrix on its gene side / cell side
+const double* gram_diagonal(const SpMat& A, NormStats& S, bool gene_side, cudaStream_t st);
+void set_gram_diagonal(float* G, int n, const double* sumsq, double scale, cudaStream_t st);
 
 // ---- gemm_umma.cu ----
 struct GemmOperand {

@@ -42,6 +42,13 @@ struct scl_handle {
   scl::DBuf<float> d_nV;          // [n_signal][N]  (== column-major N x n_signal)
   std::vector<double> rec_tgc, rec_mean, rec_std, rec_l2, rec_cent;
 
+  // work buffers kept between calls (a second pass over the same handle allocates nothing)
+  scl::DBuf<__half> ws_op_hi, ws_op_lo;     // dense Gram operand (hi, optional lo)
+  scl::DBuf<__half> ws_vr_hi, ws_vr_lo;     // reference eigenbasis of the binarised matrix (search loop)
+  scl::DBuf<float> ws_G, ws_G2, ws_W, ws_W2, ws_Gkeep;
+  scl::SpMat ws_Xp;                         // perturbed matrix of the current search step / replicate
+  scl::NormStats ws_Sp, ws_Sn;              // its statistics; the null matrix's statistics
+
   // robustness stage results
   bool robust_done = false;
   scl_robust_info rinfo{};

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include "nccl_dyn.h"
@@ -284,13 +285,11 @@ void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf
   }
   const bool have_work = k1 > k0;
   // exact Gram diagonal: the tensor core's truncating FP32 accumulation biases long same-sign sums low; the
-  // diagonal (the only systematically same-sign sum) is taken from the writer's exact Float64 sums of squares
-  const int n_strips = have_work ? densify_strips((size_t)(k1 - k0)) : 1;
-  Tmp<double> sumsq((size_t)rows * n_strips, h->st);
+  // diagonal (the only systematically same-sign sum) comes from the statistics passes in Float64 instead
   if (have_work) {
     {
       ProfScope ps(&h->prof, h->st, PK_DENSIFY);
-      densify(A, S, gene_side ? 0 : 1, ld, hi.p, split ? lo.p : nullptr, h->st, sumsq.p, k0, k1);
+      densify(A, S, gene_side ? 0 : 1, ld, hi.p, split ? lo.p : nullptr, h->st, k0, k1);
       const double frac = (double)(k1 - k0) / (double)ld;
       h->prof.densify_alg_bytes += frac * (8.0 * (double)A.nnz + (double)A.N * A.M * (split ? 4.0 : 2.0)) + 4.0 * (A.M + 1);
     }
@@ -309,7 +308,6 @@ void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf
       gemm_umma(g, h->st);
       h->prof.gram_alg_flops += (double)rows * (rows + 1.0) * (double)Ks;
     }
-    if (h->cfg.gram_tc_diag != 1) set_gram_diagonal(dG, nm, n_strips, sumsq.p, (double)scale, h->st);
   } else {
     SCL_CUDA(cudaMemsetAsync(dG, 0, (size_t)nm * nm * sizeof(float), h->st));
   }
@@ -331,6 +329,11 @@ void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf
     ProfScope ps(&h->prof, h->st, PK_SMALL);
     SCL_NCCL(nccl_api().AllReduce(dG, dG, (size_t)nm * nm, ncclFloat, ncclSum, (ncclComm_t)h->nccl, h->st));
     if (calibrate) SCL_NCCL(nccl_api().AllReduce(ex.p, ex.p, kCalibSamples, ncclDouble, ncclSum, (ncclComm_t)h->nccl, h->st));
+  }
+  // every rank holds the complete statistics, so the full-length diagonal is written after the reduction
+  if (h->cfg.gram_tc_diag != 1) {
+    ProfScope ps(&h->prof, h->st, PK_STATS);
+    set_gram_diagonal(dG, nm, gram_diagonal(A, S, gene_side, h->st), (double)scale, h->st);
   }
   if (calibrate) {
     ProfScope ps(&h->prof, h->st, PK_SMALL);
@@ -419,8 +422,8 @@ void run_signal(scl_handle* h) {
   h->signal_done = false;
   h->robust_done = false;
 
-  DBuf<__half> op_hi, op_lo;
-  DBuf<float> G, W;
+  DBuf<__half>&op_hi = h->ws_op_hi, &op_lo = h->ws_op_lo;
+  DBuf<float>&G = h->ws_G, &W = h->ws_W;
   G.ensure((size_t)nm * nm);
   W.ensure(nm);
   Timer tm(st);
@@ -431,7 +434,7 @@ void run_signal(scl_handle* h) {
   // the FP32 solver's eigenvalues carry an absolute error ~eps32*|G|; the spectrum of the data matrix is an output
   // (:L, :L_mp), so it is refined by Float64 Rayleigh quotients of the computed eigenvectors (refine.cu)
   const bool refine = !h->cfg.no_refine;
-  DBuf<float> Gkeep;
+  DBuf<float>& Gkeep = h->ws_Gkeep;
   if (refine) {
     Gkeep.ensure((size_t)nm * nm);
     SCL_CUDA(cudaMemcpyAsync(Gkeep.p, G.p, (size_t)nm * nm * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -455,7 +458,6 @@ void run_signal(scl_handle* h) {
   SCL_CUDA(cudaStreamSynchronize(st));
   for (float v : h->L)
     if (!std::isfinite(v)) throw Error(SCL_ERR_CUSOLVER, "non-finite eigenvalue (the reference's CPU fallback :379-381 is an error here)");
-  Gkeep.release();
   // Rayleigh quotients of neighbouring bulk eigenvectors can swap by ~1e-6 relative: :L is ascending (:378); the
   // signal eigenvalues are far apart, so their pairing with the eigenvectors is untouched
   if (refine) std::sort(h->L.begin(), h->L.end());
@@ -473,8 +475,8 @@ void run_signal(scl_handle* h) {
   SCL_REQUIRE(h->Xnull.N == N && h->Xnull.M == M, "null matrix shape");
   info.t_null_ms += tm.stop();
   {
-    NormStats Sn;
-    DBuf<float> G2, W2;
+    NormStats& Sn = h->ws_Sn;
+    DBuf<float>&G2 = h->ws_G2, &W2 = h->ws_W2;
     G2.ensure((size_t)nm * nm);
     W2.ensure(nm);
     gram_of(h, h->Xnull, Sn, op_hi, op_lo, G2.p, nm, 1.0f / (float)M, split, /*shard=*/true);
@@ -662,12 +664,12 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
   }
   info.t_baseline_ms = tm.stop();
 
-  DBuf<__half> op_hi, op_lo;
-  DBuf<float> G, W;
+  DBuf<__half>&op_hi = h->ws_op_hi, &op_lo = h->ws_op_lo;
+  DBuf<float>&G = h->ws_G, &W = h->ws_W;
   G.ensure((size_t)nm * nm);
   W.ensure(nm);
-  SpMat Xp;
-  NormStats Sp;
+  SpMat& Xp = h->ws_Xp;
+  NormStats& Sp = h->ws_Sp;
   std::vector<float> Lh(nm);
   const float bin_scale = 1.0f / (float)(N > M ? N : M);   // transposed call when N > M (Appendix A9)
 
@@ -686,7 +688,7 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
   const int npos_ref = nm;
   const int n_2 = (int)std::nearbyint((double)npos_ref / 2.0);   // round(Int, .) ties-to-even (:722)
   const size_t ldv = round8((size_t)nm);
-  DBuf<__half> vr_hi, vr_lo;
+  DBuf<__half>&vr_hi = h->ws_vr_hi, &vr_lo = h->ws_vr_lo;
   vr_hi.ensure((size_t)npos_ref * ldv);
   vr_lo.ensure((size_t)npos_ref * ldv);
   strided_split_f32_to_f16(G.p + (size_t)i0r * nm, npos_ref, nm, nm, (int64_t)ldv, vr_hi.p, vr_lo.p, st, kUnitScale);
@@ -739,12 +741,15 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
       SCL_REQUIRE(npos >= n_2 + 1, "perturbed matrix has too few positive eigenvalues");
       const int nw = n_2 + 1;                                  // nV_2[:, end-n_2:end] (Appendix A13)
       SCL_REQUIRE(nw >= 5, "too few noise vectors");
+      const double t_step_syevd = tm.stop();
       corr_colabsmax_pre(h, Vr, G.p + (size_t)i0 * nm, nw, nm, d_d.p);
       d_host.resize(nw);
       SCL_CUDA(cudaMemcpyAsync(d_host.data(), d_d.p, nw * sizeof(float), cudaMemcpyDeviceToHost, st));
       SCL_CUDA(cudaStreamSynchronize(st));
       std::partial_sort(d_host.begin(), d_host.begin() + 5, d_host.end());
       my_d2 = (double)d_host[1];
+      if (getenv("SCL_TRACE"))
+        fprintf(stderr, "[scl] search step %d: n_add %lld, eigenvalue copy+sync %.2f ms, corr %.2f ms\n", my_step, nnzidx, t_step_syevd, tm.stop());
     }
     std::vector<double> wave_d2(G_, my_d2);
     if (G_ > 1) {
@@ -780,8 +785,6 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
   info.p_sel = p_;
   info.t_search_ms = t_gram + tm.stop();
   if (h->cfg.verbose) printf("Selected perturb sparisty: %.17g\n", p_);
-  vr_hi.release();
-  vr_lo.release();
 
   // --- perturbations (:767-778)
   const int k = h->sinfo.n_signal;

@@ -11,6 +11,8 @@
 // Kernel: classic register-tiled GEMM  Z = V * G  (G symmetric, so both operands are read K-major), 128 x 128
 // output tile per CTA, 8 x 8 per thread, FP32 operands staged in shared memory and widened in registers, FP64
 // accumulation; the epilogue contracts the tile of Z with the matching tile of V, so Z is never written.
+#include <algorithm>
+#include <cmath>
 #include "common.cuh"
 #include "tmp.cuh"
 
@@ -21,8 +23,10 @@ namespace {
 constexpr int kTile = 128;
 constexpr int kStepK = 16;
 constexpr int kRqThreads = 256;
+constexpr int kBand = 8;          // H = V G V' is evaluated on its diagonals 0..kBand
+constexpr int kMaxCluster = 96;
 
-// part[i * n_tiles + tc] = sum over c in column tile tc of (V G)[i][c] * V[i][c]
+// part[(i * n_tiles + tc) * (kBand+1) + d] = sum over c in column tile tc of (V G)[i][c] * V[i+d][c]
 __global__ void __launch_bounds__(kRqThreads)
 k_rq_partial(const float* __restrict__ V, const float* __restrict__ G, int n, int n_tiles, double* __restrict__ part) {
   __shared__ __align__(16) float As[2][kStepK][kTile];   // V tile, [k][row]
@@ -98,53 +102,138 @@ k_rq_partial(const float* __restrict__ V, const float* __restrict__ G, int n, in
     if (more) stash(buf ^ 1, va, vb);
     __syncthreads();
   }
-  // epilogue: contract with V[i][c] over this tile's columns, reduce over the 16 threads that share the rows
+  // epilogue: contract the tile of Z = V G with rows r, r+1, ..., r+kBand of V over this tile's columns (a band of
+  // H = V G V'), reducing over the 16 threads that share the rows
+  for (int d = 0; d <= kBand; ++d) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-    double s = 0.0;
-    if (r < n) {
+    for (int i = 0; i < 8; ++i) {
+      const int r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+      const int rr = r + d;
+      double s = 0.0;
+      if (rr < n) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
-        if (c < n) s = fma(acc[i][j], (double)V[(size_t)r * n + c], s);
+        for (int j = 0; j < 8; ++j) {
+          const int c = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+          if (c < n) s = fma(acc[i][j], (double)V[(size_t)rr * n + c], s);
+        }
       }
-    }
 #pragma unroll
-    for (int o = 8; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);   // lanes of one ty: 16 consecutive
-    if (tx == 0 && r < n) part[(size_t)r * n_tiles + tc] = s;
+      for (int o = 8; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);   // lanes of one ty: 16 consecutive
+      if (tx == 0 && r < n) part[((size_t)r * n_tiles + tc) * (kBand + 1) + d] = s;
+    }
   }
 }
 
-// w[i] = sum_t part[i][t] / |v_i|^2   (one warp per eigenvector, fixed order)
-__global__ void __launch_bounds__(256) k_rq_finish(const float* __restrict__ V, const double* __restrict__ part, int n,
-                                                   int n_tiles, float* __restrict__ w) {
+// vv[i] = |v_i|^2  (one warp per eigenvector)
+__global__ void __launch_bounds__(256) k_row_norm2(const float* __restrict__ V, int n, double* __restrict__ vv) {
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= n) return;
-  double vv = 0.0, s = 0.0;
+  double s = 0.0;
   for (int c = lane; c < n; c += 32) {
     const double x = (double)V[(size_t)i * n + c];
-    vv = fma(x, x, vv);
+    s = fma(x, x, s);
   }
-  for (int t = lane; t < n_tiles; t += 32) s += part[(size_t)i * n_tiles + t];
-  for (int o = 16; o; o >>= 1) {
-    vv += __shfl_xor_sync(0xffffffffu, vv, o);
-    s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) vv[i] = s;
+}
+
+// Hb[i][d] = v_i' G v_{i+d} / (|v_i| |v_{i+d}|)   (sum of the tile partials in a fixed order)
+__global__ void __launch_bounds__(256) k_band_finish(const double* __restrict__ part, const double* __restrict__ vv, int n,
+                                                     int n_tiles, double* __restrict__ Hb) {
+  const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (w >= (long long)n * (kBand + 1)) return;
+  const int i = (int)(w / (kBand + 1)), d = (int)(w % (kBand + 1));
+  double s = 0.0;
+  if (i + d < n) {
+    for (int t = 0; t < n_tiles; ++t) s += part[((size_t)i * n_tiles + t) * (kBand + 1) + d];
+    s /= sqrt(vv[i] * vv[i + d]);
   }
-  if (lane == 0) w[i] = (float)(s / vv);
+  Hb[w] = s;
+}
+
+// eigenvalues of a small dense symmetric matrix (row-major m x m, destroyed) by cyclic Jacobi rotations
+void jacobi_eigenvalues(std::vector<double>& a, int m, std::vector<double>& ev) {
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0, diag = 0;
+    for (int p = 0; p < m; ++p) {
+      diag += a[(size_t)p * m + p] * a[(size_t)p * m + p];
+      for (int q = p + 1; q < m; ++q) off += a[(size_t)p * m + q] * a[(size_t)p * m + q];
+    }
+    if (off <= 1e-30 * diag) break;
+    for (int p = 0; p < m; ++p)
+      for (int q = p + 1; q < m; ++q) {
+        const double apq = a[(size_t)p * m + q];
+        if (apq == 0.0) continue;
+        const double theta = (a[(size_t)q * m + q] - a[(size_t)p * m + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < m; ++k) {   // columns p, q
+          const double akp = a[(size_t)k * m + p], akq = a[(size_t)k * m + q];
+          a[(size_t)k * m + p] = c * akp - sn * akq;
+          a[(size_t)k * m + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < m; ++k) {   // rows p, q
+          const double apk = a[(size_t)p * m + k], aqk = a[(size_t)q * m + k];
+          a[(size_t)p * m + k] = c * apk - sn * aqk;
+          a[(size_t)q * m + k] = sn * apk + c * aqk;
+        }
+      }
+  }
+  ev.resize(m);
+  for (int p = 0; p < m; ++p) ev[p] = a[(size_t)p * m + p];
+  std::sort(ev.begin(), ev.end());
 }
 
 }  // namespace
 
-// dV: eigenvectors as rows of memory (cuSOLVER's column-major result), dG: the matrix they belong to (symmetric)
+// dV: eigenvectors as rows of memory (cuSOLVER's column-major result), dG: the matrix they belong to (symmetric).
+// dW (ascending FP32 eigenvalues) is overwritten by the refined eigenvalues, ascending.
 void refine_eigenvalues(const float* dG, const float* dV, int n, float* dW, cudaStream_t st) {
   const int n_tiles = (n + kTile - 1) / kTile;
-  Tmp<double> part((size_t)n * n_tiles, st);
-  count_launches(2);
+  const int nb = kBand + 1;
+  Tmp<double> part((size_t)n * n_tiles * nb, st), vv(n, st), dHb((size_t)n * nb, st);
+  count_launches(3);
   k_rq_partial<<<dim3(n_tiles, n_tiles), kRqThreads, 0, st>>>(dV, dG, n, n_tiles, part.p);
-  k_rq_finish<<<(n * 32 + 255) / 256, 256, 0, st>>>(dV, part.p, n, n_tiles, dW);
+  k_row_norm2<<<(n * 32 + 255) / 256, 256, 0, st>>>(dV, n, vv.p);
+  k_band_finish<<<(unsigned)(((long long)n * nb + 255) / 256), 256, 0, st>>>(part.p, vv.p, n, n_tiles, dHb.p);
   SCL_CUDA(cudaGetLastError());
+  std::vector<double> Hb((size_t)n * nb);
+  SCL_CUDA(cudaMemcpyAsync(Hb.data(), dHb.p, Hb.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  auto H = [&](int i, int j) -> double {   // i <= j <= i + kBand
+    return Hb[(size_t)i * nb + (j - i)];
+  };
+  // Rayleigh quotients H_ii are exact to second order in the eigenvector error - except inside a cluster of
+  // eigenvalues closer than the solver's backward error, where the computed vectors are an arbitrary rotation
+  // of the true ones: there the Rayleigh-Ritz values of the cluster (eigenvalues of H restricted to it) are.
+  // i and j are linked when the rotation angle |H_ij / (H_jj - H_ii)| is not negligible.
+  std::vector<double> out(n);
+  std::vector<double> blk, ev;
+  int i = 0;
+  while (i < n) {
+    int hi = i;                                    // cluster = [i, hi]
+    for (int a = i; a <= hi && hi - i + 1 < kMaxCluster; ++a)
+      for (int b = std::max(a + 1, hi + 1); b <= std::min(n - 1, a + kBand); ++b)
+        if (std::fabs(H(a, b)) > 0.02 * std::fabs(H(b, b) - H(a, a))) hi = std::max(hi, b);
+    hi = std::min(hi, i + kMaxCluster - 1);
+    const int m = hi - i + 1;
+    if (m == 1) {
+      out[i] = H(i, i);
+    } else {
+      blk.assign((size_t)m * m, 0.0);
+      for (int a = 0; a < m; ++a)
+        for (int b = a; b < m && b - a <= kBand; ++b) blk[(size_t)a * m + b] = blk[(size_t)b * m + a] = H(i + a, i + b);
+      jacobi_eigenvalues(blk, m, ev);
+      for (int a = 0; a < m; ++a) out[i + a] = ev[a];
+    }
+    i = hi + 1;
+  }
+  std::sort(out.begin(), out.end());
+  std::vector<float> outf(n);
+  for (int q = 0; q < n; ++q) outf[q] = (float)out[q];
+  SCL_CUDA(cudaMemcpyAsync(dW, outf.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
 }
 
 }  // namespace scl

@@ -4,6 +4,8 @@
 // column or one cell row) is scattered into a dense shared-memory strip and compacted in
 // index order, which is exactly the semantics of Julia's sparse(I,J,V) (duplicates summed,
 // (col,row) order).
+#include <chrono>
+#include <cstdlib>
 #include "common.cuh"
 #include "tmp.cuh"
 
@@ -352,6 +354,10 @@ void perturb_merge(const SpMat& base, const uint32_t* d_add_row, const uint32_t*
     return;
   }
   count_launches(n_add ? 8 : 4);
+  static const bool trace = getenv("SCL_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+  const auto t_begin = now();
   out.N = N; out.M = M; out.nnz = nnz;
   out.colptr.ensure(M + 1); out.rowptr.ensure(N + 1);
   out.rowval.ensure(nnz ? nnz : 1); out.val.ensure(nnz ? nnz : 1);
@@ -361,6 +367,7 @@ void perturb_merge(const SpMat& base, const uint32_t* d_add_row, const uint32_t*
   Tmp<int> flag(1, st);
   uint32_t *cnt_col = cnt.p, *cnt_row = cnt.p + M + 1, *aptr_col = aptr.p, *aptr_row = aptr.p + M + 1;
   uint32_t *cur_col = cur.p, *cur_row = cur.p + M + 1;
+  const double t_alloc = ms_since(t_begin);
   SCL_CUDA(cudaMemsetAsync(cnt.p, 0, ((size_t)M + N + 2) * sizeof(uint32_t), st));
   SCL_CUDA(cudaMemsetAsync(cur.p, 0, ((size_t)M + N + 2) * sizeof(uint32_t), st));
   SCL_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
@@ -381,8 +388,12 @@ void perturb_merge(const SpMat& base, const uint32_t* d_add_row, const uint32_t*
                                                                 binarise ? 1 : 0, flag.p);
   SCL_CUDA(cudaGetLastError());
   int bad = 0;
+  const double t_launch = ms_since(t_begin);
   SCL_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   SCL_CUDA(cudaStreamSynchronize(st));
+  if (trace)
+    fprintf(stderr, "[scl] perturb_merge n_add=%zu: alloc %.3f ms, launched at %.3f ms, done at %.3f ms, fallback=%d\n", n_add,
+            t_alloc, t_launch, ms_since(t_begin), bad);
   if (bad) perturb_merge_general(base, d_add_row, d_add_col, n_add, binarise, out, st);   // sparse(I,J,V) sums them
 }
 
@@ -586,18 +597,22 @@ void draw_null_device(const SpMat& base, uint64_t seed, SpMat& out, cudaStream_t
   count_launches(2);
   const size_t nnz = base.nnz;
   SCL_REQUIRE(nnz > 0, "empty matrix");
-  Tmp<uint32_t> trow(nnz, st);
-  Tmp<float> tval(nnz, st);
+  // k_null_rows emits every gene's rows ascending and distinct, so the canonical CSC of the null matrix is
+  // written in place: same column pointers, new rows, values moved by one keyed bijection of [0, nnz)
+  out.N = base.N; out.M = base.M; out.nnz = nnz;
+  out.colptr.ensure(base.M + 1);
+  out.rowval.ensure(nnz);
+  out.val.ensure(nnz);
+  SCL_CUDA(cudaMemcpyAsync(out.colptr.p, base.colptr.p, (base.M + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   size_t smem = ((size_t)base.N + 31) / 32 * sizeof(uint32_t);
   SCL_REQUIRE(smem <= 200 * 1024, "N too large for the shared-memory row bitmap");
   SCL_CUDA(cudaFuncSetAttribute(k_null_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_null_rows<<<min(base.M, 148 * 4), 256, smem, st>>>(base.colptr.p, base.N, base.M, mix64(seed ^ 0x6e756c6cull),
-                                                      trow.p);
+                                                      out.rowval.p);
   Feistel f = Feistel::make(nnz, mix64(seed ^ 0x73687566ull));
-  k_feistel_gather_f32<<<grid_for(nnz, 256), 256, 0, st>>>(base.val.p, f, tval.p);
+  k_feistel_gather_f32<<<grid_for(nnz, 256), 256, 0, st>>>(base.val.p, f, out.val.p);
   SCL_CUDA(cudaGetLastError());
-  // rows are distinct inside a gene, so no duplicates arise; the shared tail still applies
-  finish_null(base, trow.p, tval.p, out, st);
+  build_csr_mirror(out, st);
 }
 
 // Zero candidates (:668-673): T distinct grid positions from a Feistel bijection of [0,N*M),
