@@ -68,6 +68,10 @@ struct SpMat {
   size_t nnz = 0;
   DBuf<uint32_t> colptr, rowval, rowptr, colidx;
   DBuf<float> val, rval;
+  // capacity for nnz_cap stored entries in both orientations (no-op when already large enough)
+  void reserve(size_t nnz_cap) {
+    rowval.ensure(nnz_cap); val.ensure(nnz_cap); colidx.ensure(nnz_cap); rval.ensure(nnz_cap);
+  }
   void swap(SpMat& o) {
     std::swap(N, o.N); std::swap(M, o.M); std::swap(nnz, o.nnz);
     colptr.swap(o.colptr); rowval.swap(o.rowval); rowptr.swap(o.rowptr); colidx.swap(o.colidx);
@@ -85,8 +89,11 @@ struct NormStats {
   DBuf<double> sumsq_gene, sumsq_cell;   // exact sums of squares of the normalised matrix's columns / rows
   // per non-zero intermediates, evaluated once by the statistics passes and reused by the later ones
   DBuf<double> y_csc;               // log1p(x_ij / r_i), CSC order
-  DBuf<double> z_csr;               // y_ij / sigma_j, CSR order  (the cell-major writer finishes it per line)
-  DBuf<float> patch_csc;            // final value (z_ij - mu_j)/s_i - c_j of a stored entry, CSC order (gene-major writer)
+  DBuf<double> z_csr;               // y_ij / sigma_j, CSR order
+  DBuf<float> patch_csc, patch_csr; // final value (z_ij - mu_j)/s_i - c_j of every stored entry, in CSC / CSR order
+  void reserve(size_t nnz_cap) {
+    y_csc.ensure(nnz_cap); z_csr.ensure(nnz_cap); patch_csc.ensure(nnz_cap); patch_csr.ensure(nnz_cap);
+  }
 };
 
 struct Workspace;  // sparse scratch, defined in sparse.cu

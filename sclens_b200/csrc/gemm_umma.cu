@@ -369,9 +369,12 @@ k_gemm_umma(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__
       const Tile t = p.tiles[it];
       const int kb0 = t.split * kb_per_split;
       const int kb1 = min(p.k_blocks_total, kb0 + kb_per_split);
-      // The tensor core accumulates in FP32 with truncation, so a long same-sign sum drifts low by ~1e-7 per MMA.
-      // At most chunk_kb k-blocks are accumulated by the tensor core; the epilogue warps then add the chunk into
-      // a running FP32 sum (round-to-nearest) that lives in the other half of tensor memory.
+      // The tensor core accumulates in FP32 with truncation towards zero: every partial sum shrinks by ~1e-7 of its
+      // magnitude per MMA (more for coherent same-sign sums than for random-sign ones).  The truncation is symmetric in
+      // sign - accumulating alternate chunks with the operand negated (instruction-descriptor bit 13) and subtracting
+      // them changed the measured bias by < 15 %, so that is not done.  At most chunk_kb k-blocks are accumulated by the
+      // tensor core; the epilogue warps then add the chunk into a running FP32 sum (round-to-nearest) that lives in the
+      // other half of tensor memory; the remaining uniform shrink is calibrated out by the caller (pipeline.cu).
       int kb = kb0;
       do {
         const int kend = min(kb1, kb + p.chunk_kb);

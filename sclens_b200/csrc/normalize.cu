@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(256) k_gene_stats(const uint32_t* __restrict__
   const int lane = threadIdx.x & 31;
   int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int per_grid = (gridDim.x * blockDim.x) >> 5;
-  for (; j < M; j += per_grid) {
+  for (int jj = j; jj < M; jj += per_grid) {
+    const int j = M - 1 - jj;   // genes arrive sorted by mean expression (:224): densest columns first, short tail
     const uint32_t b = colptr[j], e = colptr[j + 1];
     double s1 = 0, s2 = 0;
     for (uint32_t t = b + lane; t < e; t += 32 * kStatUnroll) {
@@ -190,7 +191,8 @@ __global__ void __launch_bounds__(256) k_gene_center(const uint32_t* __restrict_
   int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int per_grid = (gridDim.x * blockDim.x) >> 5;
   const double sum_inv_s = scalars[2], sum_inv_s2 = scalars[3];
-  for (; j < M; j += per_grid) {
+  for (int jj = j; jj < M; jj += per_grid) {
+    const int j = M - 1 - jj;   // densest columns first
     const uint32_t b = colptr[j], e = colptr[j + 1];
     const double sd = sigma[j], m = mu[j];
     double su = 0, suu = 0, sui = 0;    // sum u, sum u^2, sum u/s_i
@@ -248,23 +250,44 @@ __global__ void __launch_bounds__(1024) k_dot(const double* __restrict__ a, cons
   if (threadIdx.x == 0) *out = s;
 }
 
-// ---- exact sum of squares of every cell's normalised row (the Gram diagonal when cells are the Gram side) ----
-// sum_j (is mu_j + c_j)^2 in closed form from |mu|^2, mu.c, |c|^2, plus w^2 - bg^2 at the stored entries.
-__global__ void k_cell_sumsq(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ colidx,
-                             const double* __restrict__ z_csr, const double* __restrict__ mu,
-                             const double* __restrict__ cent, const double* __restrict__ inv_s,
-                             const double* __restrict__ scalars, int N, double* __restrict__ sumsq_cell) {
+// ---- cell-side finishing pass (CSR, one warp per cell) --------------------------------------
+// Emits the cell-major writer's sparse patch - the final value (z_ij - mu_j)/s_i - c_j of every stored entry, Float64
+// rounded once to Float32, CSR order - and the exact sum of squares of every cell's normalised row (the Gram diagonal
+// when cells are the Gram side): sum_j (mu_j/s_i + c_j)^2 in closed form from |mu|^2, mu.c, |c|^2, plus w^2 - bg^2 at
+// the stored entries.
+__global__ void __launch_bounds__(256) k_cell_finish(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ colidx,
+                                                     const double* __restrict__ z_csr, const double* __restrict__ mu,
+                                                     const double* __restrict__ cent, const double* __restrict__ inv_s,
+                                                     const double* __restrict__ scalars, int N,
+                                                     float* __restrict__ patch_csr, double* __restrict__ sumsq_cell) {
   const int lane = threadIdx.x & 31;
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nrows_per_grid = (gridDim.x * blockDim.x) >> 5;
   const double mu2 = scalars[0], muc = scalars[4], c2 = scalars[5];
   for (; row < N; row += nrows_per_grid) {
     const double is = inv_s[row];
+    const uint32_t b = rowptr[row], e = rowptr[row + 1];
     double dq = 0;
-    for (uint32_t t = rowptr[row] + lane; t < rowptr[row + 1]; t += 32) {
-      const uint32_t c = colidx[t];
-      const double bg = is * mu[c] + cent[c], w = z_csr[t] * is - bg;
-      dq += w * w - bg * bg;
+    for (uint32_t t = b + lane; t < e; t += 32 * kStatUnroll) {
+      double z[kStatUnroll], m[kStatUnroll], cc[kStatUnroll];
+#pragma unroll
+      for (int u = 0; u < kStatUnroll; ++u) {
+        const uint32_t tt = t + 32 * u;
+        const bool ok = tt < e;
+        const uint32_t c = ok ? colidx[tt] : 0;
+        z[u] = ok ? z_csr[tt] : 0.0;
+        m[u] = mu[c];
+        cc[u] = cent[c];
+      }
+#pragma unroll
+      for (int u = 0; u < kStatUnroll; ++u) {
+        const uint32_t tt = t + 32 * u;
+        if (tt < e) {
+          const double bg = is * m[u] + cc[u], w = (z[u] - m[u]) * is - cc[u];
+          patch_csr[tt] = (float)w;
+          dq += w * w - bg * bg;
+        }
+      }
     }
     dq = warp_sum(dq);
     if (lane == 0) sumsq_cell[row] = is * is * mu2 + 2.0 * is * muc + c2 + dq;
@@ -279,8 +302,8 @@ void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st) {
   S.mu_f.ensure(M); S.cent_f.ensure(M); S.inv_sigma_f.ensure(M);
   S.scalars.ensure(8);
   S.y_csc.ensure(A.nnz); S.z_csr.ensure(A.nnz); S.patch_csc.ensure(A.nnz);
-  S.sumsq_gene.ensure(M);
-  count_launches(9);
+  S.sumsq_gene.ensure(M); S.sumsq_cell.ensure(N); S.patch_csr.ensure(A.nnz);
+  count_launches(12);
   const int wgrid = min((N + 7) / 8, 148 * 8);
   k_row_sum<<<wgrid, 256, 0, st>>>(A.rowptr.p, A.rval.p, N, S.tgc.p);
   const int ggrid = min((M + 7) / 8, 148 * 8);
@@ -296,6 +319,10 @@ void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st) {
   k_gene_center<<<ggrid, 256, 0, st>>>(A.colptr.p, A.rowval.p, S.y_csc.p, S.sigma.p, S.mu.p, S.inv_s.p,
                                                    S.scalars.p, N, M, S.patch_csc.p, S.cent.p, S.cent_f.p,
                                                    S.sumsq_gene.p);
+  k_dot<<<1, 1024, 0, st>>>(S.mu.p, S.cent.p, M, S.scalars.p + 4);
+  k_reduce<<<1, 1024, 0, st>>>(S.cent.p, M, 0, S.scalars.p + 5);
+  k_cell_finish<<<wgrid, 256, 0, st>>>(A.rowptr.p, A.colidx.p, S.z_csr.p, S.mu.p, S.cent.p, S.inv_s.p, S.scalars.p, N,
+                                       S.patch_csr.p, S.sumsq_cell.p);
   SCL_CUDA(cudaGetLastError());
 }
 
@@ -331,9 +358,8 @@ __global__ void k_strip_offsets(const uint32_t* __restrict__ ptr, const uint32_t
 
 template <bool CELL_MAJOR, bool WITH_LO>
 __global__ void __launch_bounds__(kDenseThreads)
-k_densify(const uint32_t* __restrict__ off, const uint32_t* __restrict__ idx, const double* __restrict__ z_csr,
-          const float* __restrict__ patch_csc, const double* __restrict__ inv_s, const double* __restrict__ mu,
-          const double* __restrict__ cent, const float* __restrict__ inv_s_f, const float* __restrict__ mu_f,
+k_densify(const uint32_t* __restrict__ off, const uint32_t* __restrict__ idx, const float* __restrict__ patch,
+          const float* __restrict__ inv_s_f, const float* __restrict__ mu_f,
           const float* __restrict__ cent_f, int n_lines, int line_len, size_t ld,
           int n_strips, int pos0, int pos1, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
   // two lines per barrier, double buffered: overlay[set][line of the pair][slot]
@@ -377,9 +403,6 @@ k_densify(const uint32_t* __restrict__ off, const uint32_t* __restrict__ idx, co
   }
   __syncthreads();
 
-  auto patch_value = [&](uint32_t t, uint32_t p, int line) -> float {
-    return CELL_MAJOR ? (float)((z_csr[t] - mu[p]) * inv_s[line] - cent[p]) : patch_csc[t];
-  };
   // first stored entry of line l (CTA-relative) this thread carries into the overlay; the rest go the slow way
   auto load_patch = [&](int l, uint32_t& t, uint32_t& t_end, uint32_t& pos, float& v) {
     t = 0; t_end = 0; pos = 0; v = 0.f;
@@ -388,17 +411,14 @@ k_densify(const uint32_t* __restrict__ off, const uint32_t* __restrict__ idx, co
       t_end = seg[l][1];
       if (t < t_end) {
         pos = idx[t];
-        v = patch_value(t, pos, line0 + l);
+        v = patch[t];
       }
     }
   };
-  auto scatter = [&](float* ov, int l, uint32_t t, uint32_t t_end, uint32_t pos, float v) {
+  auto scatter = [&](float* ov, uint32_t t, uint32_t t_end, uint32_t pos, float v) {
     if (t < t_end) {
       ov[slot_of(pos - base)] = v;
-      for (uint32_t u = t + kDenseThreads; u < t_end; u += kDenseThreads) {
-        const uint32_t p = idx[u];
-        ov[slot_of(p - base)] = patch_value(u, p, line0 + l);
-      }
+      for (uint32_t u = t + kDenseThreads; u < t_end; u += kDenseThreads) ov[slot_of(idx[u] - base)] = patch[u];
     }
   };
   auto emit = [&](float* ov, int l, __half* dst_hi, __half* dst_lo) {
@@ -439,8 +459,8 @@ k_densify(const uint32_t* __restrict__ off, const uint32_t* __restrict__ idx, co
   int set = 0;
   for (int l = 0; l < n_my; l += 2, set ^= 1) {
     // scatter this pair's patches (loaded during the previous iteration), start the next pair's loads
-    scatter(overlay[set][0], l, t0, e0, q0, v0);
-    scatter(overlay[set][1], l + 1, t1, e1, q1, v1);
+    scatter(overlay[set][0], t0, e0, q0, v0);
+    scatter(overlay[set][1], t1, e1, q1, v1);
     load_patch(l + 2, t0, e0, q0, v0);
     load_patch(l + 3, t1, e1, q1, v1);
     __syncthreads();
@@ -463,15 +483,8 @@ __global__ void k_set_diagonal(float* __restrict__ G, int n, const double* __res
 // core sees the binary16 roundings of these values; their squares differ from the exact ones by an unbiased ~4e-6
 // relative per diagonal entry (K >= 1e4 terms), which moves no eigenvalue by more than ~1e-7.
 const double* gram_diagonal(const SpMat& A, NormStats& S, bool gene_side, cudaStream_t st) {
-  if (gene_side) return S.sumsq_gene.p;
-  S.sumsq_cell.ensure(A.N);
-  count_launches(3);
-  k_dot<<<1, 1024, 0, st>>>(S.mu.p, S.cent.p, A.M, S.scalars.p + 4);
-  k_reduce<<<1, 1024, 0, st>>>(S.cent.p, A.M, 0, S.scalars.p + 5);
-  k_cell_sumsq<<<min((A.N + 7) / 8, 148 * 8), 256, 0, st>>>(A.rowptr.p, A.colidx.p, S.z_csr.p, S.mu.p, S.cent.p, S.inv_s.p,
-                                                          S.scalars.p, A.N, S.sumsq_cell.p);
-  SCL_CUDA(cudaGetLastError());
-  return S.sumsq_cell.p;
+  (void)A; (void)st;
+  return gene_side ? S.sumsq_gene.p : S.sumsq_cell.p;
 }
 
 void set_gram_diagonal(float* G, int n, const double* sumsq, double scale, cudaStream_t st) {
@@ -501,10 +514,9 @@ void densify(const SpMat& A, const NormStats& S, int layout, size_t ld, __half* 
   const long long ctas = (long long)n_strips * ((n_lines + kLinesPerCta - 1) / kLinesPerCta);
   SCL_REQUIRE(ctas < (1LL << 31), "densify grid too large");
 #define SCL_LAUNCH_DENSIFY(CM, LO)                                                                               \
-  k_densify<CM, LO><<<(unsigned)ctas, kDenseThreads, 0, st>>>(off.p, idx, S.z_csr.p, S.patch_csc.p, S.inv_s.p,     \
-                                                             S.mu.p, S.cent.p, S.inv_s_f.p, S.mu_f.p, S.cent_f.p, \
-                                                             n_lines, line_len, ld, n_strips, (int)pos0,        \
-                                                             (int)pos1, out_hi, out_lo)
+  k_densify<CM, LO><<<(unsigned)ctas, kDenseThreads, 0, st>>>(off.p, idx, cell_major ? S.patch_csr.p : S.patch_csc.p, \
+                                                             S.inv_s_f.p, S.mu_f.p, S.cent_f.p, n_lines, line_len, \
+                                                             ld, n_strips, (int)pos0, (int)pos1, out_hi, out_lo)
   if (cell_major) {
     if (out_lo) SCL_LAUNCH_DENSIFY(true, true); else SCL_LAUNCH_DENSIFY(true, false);
   } else {

@@ -670,6 +670,13 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
   W.ensure(nm);
   SpMat& Xp = h->ws_Xp;
   NormStats& Sp = h->ws_Sp;
+  {
+    // the perturbed matrices gain up to ~2-3 % of the grid in stored entries before the search stops (p_ ~ 0.98):
+    // size their buffers once instead of growing them step by step
+    const size_t cap = X.nnz + (size_t)(0.03 * (double)N * (double)M) + 1024;
+    Xp.reserve(cap);
+    Sp.reserve(cap);
+  }
   std::vector<float> Lh(nm);
   const float bin_scale = 1.0f / (float)(N > M ? N : M);   // transposed call when N > M (Appendix A9)
 

@@ -13,6 +13,7 @@
 // accumulation; the epilogue contracts the tile of Z with the matching tile of V, so Z is never written.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include "common.cuh"
 #include "tmp.cuh"
 
@@ -210,6 +211,8 @@ void refine_eigenvalues(const float* dG, const float* dV, int n, float* dW, cuda
   // i and j are linked when the rotation angle |H_ij / (H_jj - H_ii)| is not negligible.
   std::vector<double> out(n);
   std::vector<double> blk, ev;
+  const bool trace = getenv("SCL_TRACE") != nullptr;
+  int n_clusters = 0, max_cluster = 1;
   int i = 0;
   while (i < n) {
     int hi = i;                                    // cluster = [i, hi]
@@ -226,8 +229,18 @@ void refine_eigenvalues(const float* dG, const float* dV, int n, float* dW, cuda
         for (int b = a; b < m && b - a <= kBand; ++b) blk[(size_t)a * m + b] = blk[(size_t)b * m + a] = H(i + a, i + b);
       jacobi_eigenvalues(blk, m, ev);
       for (int a = 0; a < m; ++a) out[i + a] = ev[a];
+      if (trace && (m > 8 || ev[0] < -1e-4)) {
+        fprintf(stderr, "[scl] refine: cluster [%d,%d] size %d, H_ii %.6g .. %.6g -> ritz %.6g .. %.6g\n", i, hi, m, H(i, i),
+                H(hi, hi), ev[0], ev[m - 1]);
+      }
+      ++n_clusters;
+      max_cluster = std::max(max_cluster, m);
     }
     i = hi + 1;
+  }
+  if (trace) {
+    fprintf(stderr, "[scl] refine: n=%d, %d clusters (largest %d); H_00 %.6g H_11 %.6g H_22 %.6g H_01 %.3g H_12 %.3g; vv0 %.9g\n", n,
+            n_clusters, max_cluster, H(0, 0), H(1, 1), H(2, 2), H(0, 1), H(1, 2), 0.0);
   }
   std::sort(out.begin(), out.end());
   std::vector<float> outf(n);

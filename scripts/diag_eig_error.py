@@ -71,8 +71,9 @@ for chunk in chunks:
         slope_diag = float((d.diagonal() * Ghi64.diagonal()).sum() / (Ghi64.diagonal() ** 2).sum())
         resid = d - slope_off * Ghi64
         print(f"  tensor-core Gram vs f64 Gram of the same operand: off-diagonal shrink {slope_off:+.3e}, diagonal shrink "
-              f"{slope_diag:+.3e}, rms residual off-diag after removing the shrink {float(resid[offmask].pow(2).mean().sqrt()):.2e} "
-              f"(rms off-diag {float(Ghi64[offmask].pow(2).mean().sqrt()):.2e})", flush=True)
+              f"{slope_diag:+.3e}, mean off-diagonal offset {float(d[offmask].mean()):+.3e}, rms residual off-diag after removing the "
+              f"shrink {float(resid[offmask].pow(2).mean().sqrt()):.2e} (rms off-diag {float(Ghi64[offmask].pow(2).mean().sqrt()):.2e}, "
+              f"mean |off-diag| {float(Ghi64[offmask].abs().mean()):.2e})", flush=True)
         rep("tensor-core diagonal, f64 eig", torch.linalg.eigvalsh(Go).cpu().numpy())
         Ge = Go.clone()
         Ge.diagonal().copy_(Ghi64.diagonal())
