@@ -321,16 +321,25 @@ def main():
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "MEASURED_PEAKS.json (sustained bf16 / copy)" if peaks else "fallback of B200_PROFILING.md"
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
+    # captures of the same kernels at this workload's shapes (profiles/r1_traffic.json; null for other workloads)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload, {})
+    except Exception:
+        pass
     gram_tf = prof.gram_alg_flops / (prof.gram_gemm_ms * 1e-3) / 1e12 if prof.gram_gemm_ms > 0 else 0.0
     dens_gbs = prof.densify_alg_bytes / (prof.densify_ms * 1e-3) / 1e9 if prof.densify_ms > 0 else 0.0
     roofline = {"kernel": "k_gemm_umma (tcgen05 Gram, syrk schedule)", "bound": "tensor", "achieved": gram_tf,
-                "peak": tf_peak, "unit": "TFLOP/s", "frac": gram_tf / tf_peak, "traffic": None,
+                "peak": tf_peak, "unit": "TFLOP/s", "frac": gram_tf / tf_peak, "traffic": traffic.get("k_gemm_umma"),
                 "peak_source": peak_src, "launches": int(prof.gram_gemm_launches),
                 "avg_ms_per_launch": prof.gram_gemm_ms / max(1, prof.gram_gemm_launches),
                 "alg_flops_per_launch": prof.gram_alg_flops / max(1, prof.gram_gemm_launches),
                 "hbm_kernel": {"kernel": "k_densify (fused log1p/z-score/L2 normalise -> binary16 operand)",
                                "bound": "hbm", "achieved": dens_gbs, "peak": hbm_peak, "unit": "GB/s",
-                               "frac": dens_gbs / hbm_peak, "launches": int(prof.densify_launches)}}
+                               "frac": dens_gbs / hbm_peak, "launches": int(prof.densify_launches),
+                               "alg_bytes_per_launch": prof.densify_alg_bytes / max(1, prof.densify_launches),
+                               "traffic": traffic.get("k_densify")}}
     stage_ms = {"gram_gemm": prof.gram_gemm_ms, "other_gemm": prof.other_gemm_ms, "densify": prof.densify_ms,
                 "stats": prof.stats_ms, "sparse": prof.sparse_ms, "syevd_library": prof.syevd_ms,
                 "syevd_calls": int(prof.syevd_calls), "refine_f64": prof.refine_ms, "small": prof.small_ms, "total": ms}
