@@ -246,11 +246,14 @@ class Handle:
 
 
 def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="mean", *, draws=None, seed=0,
-           gram_mode=_lib.SCL_GRAM_FP16, exact_perturb=False, verbose=True, device=0, return_handle=False):
+           gram_mode=_lib.SCL_GRAM_FP16, exact_perturb=False, verbose=True, device=0, return_handle=False, comm=None, handle=None):
     """Drop-in for scLENS.sclens (:649-832).  Returns the reference's result dictionary with
     string keys (":pca" -> "pca", ...; "λ" is also available as "lambda").  ``sig_id`` is
     0-based here (the Julia shim adds 1).  ``draws`` optionally injects the random draws
-    (an object with the fields of oracle Draws) for parity runs."""
+    (an object with the fields of oracle Draws) for parity runs.  ``comm=(nccl_unique_id_bytes, rank, world)``
+    makes this call one rank of a cooperative multi-GPU pass (one process per GPU; every rank passes the same
+    counts and receives the same results).  ``handle`` reuses an existing Handle (its device workspaces, cuSOLVER
+    state and, if initialised, its NCCL communicator) instead of creating one; the caller keeps ownership."""
     if device_ != "gpu":
         raise ValueError('sclens_b200 implements device_="gpu" only (no CPU fallback exists)')
     if centering != "mean":
@@ -259,8 +262,11 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
         print("Extracting matrices")                                    # :661
     X, cell_id, gene_id = df2sparr(inp_df)
     N, M = X.shape
-    h = Handle(device=device, gram_mode=gram_mode, verbose=verbose, seed=seed, exact_perturb=exact_perturb)
+    own = handle is None
+    h = Handle(device=device, gram_mode=gram_mode, verbose=verbose, seed=seed, exact_perturb=exact_perturb) if own else handle
     try:
+        if comm is not None:
+            h.comm_init(*comm)
         h.set_counts(X)
         if draws is not None:
             if getattr(draws, "z_idx1", None) is not None:
@@ -317,5 +323,5 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
         })
         return (results, h) if return_handle else results
     finally:
-        if not return_handle:
+        if own and not return_handle:
             h.close()

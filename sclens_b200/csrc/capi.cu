@@ -472,6 +472,7 @@ int32_t scl_bench_normalize(scl_handle* h, int32_t layout, int32_t with_lo, int3
     for (int r = -1; r < reps; ++r) {   // r = -1: warm-up
       SCL_CUDA(cudaEventRecord(e0, h->st));
       compute_norm_stats(X, S, h->st);
+      ensure_patch(X, S, layout, h->st);
       SCL_CUDA(cudaEventRecord(e1, h->st));
       densify(X, S, layout, ld, hi.p, with_lo ? lo.p : nullptr, h->st);
       SCL_CUDA(cudaEventRecord(e2, h->st));

@@ -87,12 +87,17 @@ struct NormStats {
   DBuf<float> mu_f, cent_f, inv_sigma_f;
   DBuf<double> scalars;             // [0]=|mu|^2 [1]=mean(l) [2]=sum(1/s) [3]=sum(1/s^2) [4]=mu.c [5]=|c|^2
   DBuf<double> sumsq_gene, sumsq_cell;   // exact sums of squares of the normalised matrix's columns / rows
-  // per non-zero intermediates, evaluated once by the statistics passes and reused by the later ones
-  DBuf<double> y_csc;               // log1p(x_ij / r_i), CSC order
-  DBuf<double> z_csr;               // y_ij / sigma_j, CSR order
-  DBuf<float> patch_csc, patch_csr; // final value (z_ij - mu_j)/s_i - c_j of every stored entry, in CSC / CSR order
+  // parameters gathered per stored entry by the statistics passes, packed so one 32-byte sector holds them all
+  DBuf<double2> cell_par;           // {1/r_i, 1/s_i}
+  DBuf<double4> gene_par;           // {1/sigma_j, mu_j, c_j, -}
+  DBuf<double> red_partial;         // scratch of the multi-block reductions
+  DBuf<unsigned int> red_counter;
+  // final value (z_ij - mu_j)/s_i - c_j of every stored entry, in CSC / CSR order: the writer's sparse patch for the
+  // gene-major / cell-major layout, computed on first use (ensure_patch)
+  DBuf<float> patch_csc, patch_csr;
+  bool have_patch[2] = {false, false};
   void reserve(size_t nnz_cap) {
-    y_csc.ensure(nnz_cap); z_csr.ensure(nnz_cap); patch_csc.ensure(nnz_cap); patch_csr.ensure(nnz_cap);
+    patch_csc.ensure(nnz_cap); patch_csr.ensure(nnz_cap);
   }
 };
 
@@ -119,9 +124,11 @@ double noise_baseline_device(int nm, int n_rep, uint64_t seed, cudaStream_t st);
 
 // ---- normalize.cu ----
 void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st);
+// sparse patch of the writer for `layout` (and, for layout 1, the cell-side Gram diagonal); no-op when already present
+void ensure_patch(const SpMat& A, NormStats& S, int layout, cudaStream_t st);
 // layout 0: gene-major out[M][ld] (column-major N x M); 1: cell-major out[N][ld]
 // [pos0,pos1): range of positions of every line to emit (default: the whole padded line) - the cell block of a rank
-void densify(const SpMat& A, const NormStats& S, int layout, size_t ld, __half* out_hi, __half* out_lo,
+void densify(const SpMat& A, NormStats& S, int layout, size_t ld, __half* out_hi, __half* out_lo,
              cudaStream_t st, long long pos0 = 0, long long pos1 = -1);
 // exact Float64 Gram diagonal (unscaled) of the normalised matrix on its gene side / cell side
 const double* gram_diagonal(const SpMat& A, NormStats& S, bool gene_side, cudaStream_t st);

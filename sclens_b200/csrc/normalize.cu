@@ -35,9 +35,27 @@ __device__ __forceinline__ double block_sum(double v, double* red /* >= 32 */) {
   return s;
 }
 
+// ---- log1p on [0, 1] -------------------------------------------------------------------------
+// u = x_ij / r_i lies in (0, 1] and is almost always tiny (a count over a cell's total).  log1p(u) = 2 atanh(s),
+// s = u / (2 + u): for u <= 1/16, s^2 <= 9.2e-4 and the odd series truncated after s^13 is exact to < 1e-22
+// relative, so the result carries the rounding of the division and of the last FMA only (~1 ulp).  A third of the
+// Float64 instructions of the library log1p; the statistics passes re-evaluate it instead of storing y per entry.
+__device__ __forceinline__ double log1p_unit(double u) {
+  if (!(fabs(u) <= 0.0625)) return log1p(u);
+  const double s = u / (2.0 + u), w = s * s;
+  double p = 1.0 / 13.0;
+  p = fma(p, w, 1.0 / 11.0);
+  p = fma(p, w, 1.0 / 9.0);
+  p = fma(p, w, 1.0 / 7.0);
+  p = fma(p, w, 1.0 / 5.0);
+  p = fma(p, w, 1.0 / 3.0);
+  const double s2 = s + s;
+  return fma(s2 * w, p, s2);
+}
+
 // ---- per-cell total counts (CSR, one warp per cell) -------------------------------------
 __global__ void k_row_sum(const uint32_t* __restrict__ rowptr, const float* __restrict__ rval, int N,
-                          double* __restrict__ tgc) {
+                          double* __restrict__ tgc, double2* __restrict__ cell_par) {
   const int lane = threadIdx.x & 31;
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nrows_per_grid = (gridDim.x * blockDim.x) >> 5;
@@ -45,254 +63,332 @@ __global__ void k_row_sum(const uint32_t* __restrict__ rowptr, const float* __re
     double s = 0;
     for (uint32_t t = rowptr[row] + lane; t < rowptr[row + 1]; t += 32) s += (double)rval[t];
     s = warp_sum(s);
-    if (lane == 0) tgc[row] = s;
-  }
-}
-
-// ---- per-gene mean / corrected std of y (CSC, one warp per gene) --------------------------
-// y = log1p(x / r_i) is evaluated once per non-zero and kept (Float64, CSC order) for k_gene_center.  Four
-// independent entries per lane and iteration keep enough loads in flight to hide the gather latency; the
-// lane-strided order and the shuffle tree are fixed, so the sums are deterministic.
-static constexpr int kStatUnroll = 4;
-
-__global__ void __launch_bounds__(256) k_gene_stats(const uint32_t* __restrict__ colptr,
-                                                    const uint32_t* __restrict__ rowval,
-                                                    const float* __restrict__ val, const double* __restrict__ tgc,
-                                                    int N, int M, double* __restrict__ y_csc, double* __restrict__ ybar,
-                                                    double* __restrict__ sigma, double* __restrict__ mu,
-                                                    float* __restrict__ mu_f, float* __restrict__ inv_sigma_f) {
-  const int lane = threadIdx.x & 31;
-  int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int per_grid = (gridDim.x * blockDim.x) >> 5;
-  for (int jj = j; jj < M; jj += per_grid) {
-    const int j = M - 1 - jj;   // genes arrive sorted by mean expression (:224): densest columns first, short tail
-    const uint32_t b = colptr[j], e = colptr[j + 1];
-    double s1 = 0, s2 = 0;
-    for (uint32_t t = b + lane; t < e; t += 32 * kStatUnroll) {
-      float v[kStatUnroll];
-      double r[kStatUnroll];
-#pragma unroll
-      for (int u = 0; u < kStatUnroll; ++u) {
-        const uint32_t tt = t + 32 * u;
-        const bool ok = tt < e;
-        v[u] = ok ? val[tt] : 0.f;
-        r[u] = tgc[ok ? rowval[tt] : 0];
-      }
-#pragma unroll
-      for (int u = 0; u < kStatUnroll; ++u) {
-        const uint32_t tt = t + 32 * u;
-        if (tt < e) {
-          const double y = log1p((double)v[u] * (1.0 / r[u]));
-          y_csc[tt] = y;
-          s1 += y;
-          s2 = fma(y, y, s2);
-        }
-      }
-    }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
     if (lane == 0) {
-      // sum over all N cells of (y - m)^2 with y = 0 at the implicit zeros: sum y^2 - N m^2
-      const double m = s1 / (double)N;
-      double var = (s2 - (double)N * m * m) / (double)(N - 1);
-      if (var < 0) var = 0;
-      const double sd = sqrt(var);
-      ybar[j] = m;
-      sigma[j] = sd;
-      mu[j] = m / sd;
-      mu_f[j] = (float)(m / sd);
-      inv_sigma_f[j] = (float)(1.0 / sd);
+      tgc[row] = s;
+      cell_par[row] = make_double2(1.0 / s, 0.0);
     }
   }
 }
 
-// ---- small deterministic reductions (one block) -------------------------------------------
-// mode 0: out = sum v^2 ; mode 1: out = mean v ; mode 2: out = sum v
-__global__ void __launch_bounds__(1024) k_reduce(const double* __restrict__ v, int n, int mode,
-                                                 double* __restrict__ out) {
-  __shared__ double red[32];
-  double s = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    double x = v[i];
-    s += mode == 0 ? x * x : x;
+// ---- line passes ----------------------------------------------------------------------------
+// Every statistics pass walks the lines of one orientation (genes: CSC, cells: CSR), gathers the other side's
+// parameters per stored entry (packed so that one 32-byte sector holds everything a pass needs: cell_par[i] =
+// {1/r_i, 1/s_i}, gene_par[j] = {1/sigma_j, mu_j, c_j, -}) and reduces a few Float64 sums per line.  Line lengths
+// are heavy-tailed (a gene expressed everywhere holds N entries, the median gene a few hundred), so a line of up
+// to kHeavyLine entries is reduced by one warp and a longer one by the whole CTA; lines are dealt to CTAs round-robin
+// (densest genes first when the caller asks for reversed order).  Lane/thread-strided partial sums and fixed
+// shuffle / shared-memory trees: the sums depend on the line's length only, never on scheduling (deterministic).
+static constexpr int kStatUnroll = 4;
+static constexpr int kStatThreads = 256;
+static constexpr uint32_t kHeavyLine = 1024;
+
+template <class Op>
+__device__ __forceinline__ void line_span(const Op& op, const typename Op::Ctx& cx, uint32_t b, uint32_t e, int first,
+                                          int stride, double (&acc)[Op::NACC]) {
+  for (uint32_t t = b + first; t < e; t += stride * kStatUnroll) {
+    typename Op::Ld ld[kStatUnroll];
+#pragma unroll
+    for (int u = 0; u < kStatUnroll; ++u) {
+      const uint32_t tt = t + stride * u;
+      op.load(tt, tt < e, ld[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kStatUnroll; ++u) {
+      const uint32_t tt = t + stride * u;
+      if (tt < e) op.accum(tt, cx, ld[u], acc);
+    }
   }
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) *out = mode == 1 ? s / (double)n : s;
 }
 
-// ---- per-cell l2 norm after mean shift (CSR, one warp per cell) ---------------------------
-// z = y / sigma_j is kept (Float64, CSR order): the cell-major writer turns it into its sparse patch.
-__global__ void __launch_bounds__(256) k_cell_l2(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ colidx,
-                                                 const float* __restrict__ rval, const double* __restrict__ tgc,
-                                                 const double* __restrict__ sigma, const double* __restrict__ mu,
-                                                 const double* __restrict__ scalars, int N, double* __restrict__ z_csr,
-                                                 double* __restrict__ l2) {
-  const int lane = threadIdx.x & 31;
-  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nrows_per_grid = (gridDim.x * blockDim.x) >> 5;
-  const double mu2 = scalars[0];
-  for (; row < N; row += nrows_per_grid) {
-    const double inv_r = 1.0 / tgc[row];
-    const uint32_t b = rowptr[row], e = rowptr[row + 1];
-    double a = 0, bb = 0;
-    for (uint32_t t = b + lane; t < e; t += 32 * kStatUnroll) {
-      float v[kStatUnroll];
-      double sg[kStatUnroll], m[kStatUnroll];
+template <class Op>
+__global__ void __launch_bounds__(kStatThreads) k_lines(const Op op, const uint32_t* __restrict__ ptr, int n_lines,
+                                                        int reversed) {
+  __shared__ double red[Op::NACC][kStatThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // lines of at most kHeavyLine entries: one warp each
+  for (long long li = blockIdx.x + (long long)warp * gridDim.x; li < n_lines; li += (long long)gridDim.x * (kStatThreads / 32)) {
+    const int line = reversed ? n_lines - 1 - (int)li : (int)li;
+    const uint32_t b = ptr[line], e = ptr[line + 1];
+    if (e - b > kHeavyLine) continue;
+    const typename Op::Ctx cx = op.begin(line);
+    double acc[Op::NACC];
 #pragma unroll
-      for (int u = 0; u < kStatUnroll; ++u) {
-        const uint32_t tt = t + 32 * u;
-        const bool ok = tt < e;
-        const uint32_t c = ok ? colidx[tt] : 0;
-        v[u] = ok ? rval[tt] : 0.f;
-        sg[u] = sigma[c];
-        m[u] = mu[c];
-      }
+    for (int a = 0; a < Op::NACC; ++a) acc[a] = 0;
+    line_span(op, cx, b, e, lane, 32, acc);
 #pragma unroll
-      for (int u = 0; u < kStatUnroll; ++u) {
-        const uint32_t tt = t + 32 * u;
-        if (tt < e) {
-          const double z = log1p((double)v[u] * inv_r) / sg[u];
-          z_csr[tt] = z;
-          a = fma(z, z, a);
-          bb = fma(z, m[u], bb);
-        }
-      }
+    for (int a = 0; a < Op::NACC; ++a) acc[a] = warp_sum(acc[a]);
+    if (lane == 0) op.finish(line, cx, acc);
+  }
+  // longer lines: the whole CTA (the loop and its branch are uniform over the CTA)
+  for (long long li = blockIdx.x; li < n_lines; li += gridDim.x) {
+    const int line = reversed ? n_lines - 1 - (int)li : (int)li;
+    const uint32_t b = ptr[line], e = ptr[line + 1];
+    if (e - b <= kHeavyLine) continue;
+    const typename Op::Ctx cx = op.begin(line);
+    double acc[Op::NACC];
+#pragma unroll
+    for (int a = 0; a < Op::NACC; ++a) acc[a] = 0;
+    line_span(op, cx, b, e, tid, kStatThreads, acc);
+#pragma unroll
+    for (int a = 0; a < Op::NACC; ++a) acc[a] = warp_sum(acc[a]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < Op::NACC; ++a) red[a][warp] = acc[a];
     }
-    a = warp_sum(a);
-    bb = warp_sum(bb);
-    if (lane == 0) l2[row] = sqrt(a - 2.0 * bb + mu2);
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int a = 0; a < Op::NACC; ++a) {
+        double t = 0;
+        for (int w = 0; w < kStatThreads / 32; ++w) t += red[a][w];
+        acc[a] = t;
+      }
+      op.finish(line, cx, acc);
+    }
+  }
+}
+
+// per-gene mean / corrected std of y = log1p(x / r_i)  (:681-686)
+struct GeneStatsOp {
+  static constexpr int NACC = 2;
+  const uint32_t* __restrict__ rowval;
+  const float* __restrict__ val;
+  const double2* __restrict__ cell_par;
+  int N;
+  double *ybar, *sigma, *mu;
+  float *mu_f, *inv_sigma_f;
+  double4* gene_par;
+  struct Ctx {};
+  struct Ld { float v; double inv_r; };
+  __device__ __forceinline__ Ctx begin(int) const { return Ctx(); }
+  __device__ __forceinline__ void load(uint32_t t, bool ok, Ld& l) const {
+    l.v = ok ? val[t] : 0.f;
+    l.inv_r = cell_par[ok ? rowval[t] : 0].x;
+  }
+  __device__ __forceinline__ void accum(uint32_t, const Ctx&, const Ld& l, double (&acc)[NACC]) const {
+    const double y = log1p_unit((double)l.v * l.inv_r);
+    acc[0] += y;
+    acc[1] = fma(y, y, acc[1]);
+  }
+  __device__ __forceinline__ void finish(int j, const Ctx&, const double (&acc)[NACC]) const {
+    // sum over all N cells of (y - m)^2 with y = 0 at the implicit zeros: sum y^2 - N m^2
+    const double m = acc[0] / (double)N;
+    double var = (acc[1] - (double)N * m * m) / (double)(N - 1);
+    if (var < 0) var = 0;
+    const double sd = sqrt(var);
+    ybar[j] = m;
+    sigma[j] = sd;
+    mu[j] = m / sd;
+    mu_f[j] = (float)(m / sd);
+    inv_sigma_f[j] = (float)(1.0 / sd);
+    gene_par[j] = make_double4(1.0 / sd, m / sd, 0.0, 0.0);
+  }
+};
+
+// per-cell l2 norm after the mean shift, from the sparse entries only  (:688-689, :603)
+struct CellL2Op {
+  static constexpr int NACC = 2;
+  const uint32_t* __restrict__ colidx;
+  const float* __restrict__ rval;
+  const double2* __restrict__ cell_par;
+  const double4* __restrict__ gene_par;
+  const double* __restrict__ scalars;
+  double* l2;
+  struct Ctx { double inv_r; };
+  struct Ld { float v; double inv_sd, mu; };
+  __device__ __forceinline__ Ctx begin(int row) const { return Ctx{cell_par[row].x}; }
+  __device__ __forceinline__ void load(uint32_t t, bool ok, Ld& l) const {
+    l.v = ok ? rval[t] : 0.f;
+    const double2 g = *reinterpret_cast<const double2*>(&gene_par[ok ? colidx[t] : 0]);
+    l.inv_sd = g.x;
+    l.mu = g.y;
+  }
+  __device__ __forceinline__ void accum(uint32_t, const Ctx& cx, const Ld& l, double (&acc)[NACC]) const {
+    const double z = log1p_unit((double)l.v * cx.inv_r) * l.inv_sd;
+    acc[0] = fma(z, z, acc[0]);
+    acc[1] = fma(z, l.mu, acc[1]);
+  }
+  __device__ __forceinline__ void finish(int row, const Ctx&, const double (&acc)[NACC]) const {
+    l2[row] = sqrt(acc[0] - 2.0 * acc[1] + scalars[0]);
+  }
+};
+
+// per-gene centre after cell scaling (:695) and the gene's exact sum of squares over all cells (the Gram diagonal
+// when genes are the Gram side): background in closed form plus a correction per stored entry,
+//   sum_i w^2 = sum_i bg_i^2 + sum_nz (u^2 - 2 u bg),   u = z/s_i,  bg = mu_j/s_i + c_j,  w = u - bg.
+struct GeneCenterOp {
+  static constexpr int NACC = 3;
+  const uint32_t* __restrict__ rowval;
+  const float* __restrict__ val;
+  const double2* __restrict__ cell_par;
+  const double* __restrict__ scalars;
+  int N;
+  double4* gene_par;
+  double *cent, *sumsq_gene;
+  float* cent_f;
+  struct Ctx { double inv_sd, mu; };
+  struct Ld { float v; double2 c; };
+  __device__ __forceinline__ Ctx begin(int j) const {
+    const double2 g = *reinterpret_cast<const double2*>(&gene_par[j]);
+    return Ctx{g.x, g.y};
+  }
+  __device__ __forceinline__ void load(uint32_t t, bool ok, Ld& l) const {
+    l.v = ok ? val[t] : 0.f;
+    l.c = cell_par[ok ? rowval[t] : 0];
+  }
+  __device__ __forceinline__ void accum(uint32_t, const Ctx& cx, const Ld& l, double (&acc)[NACC]) const {
+    const double uu = log1p_unit((double)l.v * l.c.x) * cx.inv_sd * l.c.y;
+    acc[0] += uu;
+    acc[1] = fma(uu, uu, acc[1]);
+    acc[2] = fma(uu, l.c.y, acc[2]);
+  }
+  __device__ __forceinline__ void finish(int j, const Ctx& cx, const double (&acc)[NACC]) const {
+    const double sum_inv_s = scalars[2], sum_inv_s2 = scalars[3], m = cx.mu;
+    const double su = acc[0], suu = acc[1], sui = acc[2];
+    const double c = (su - m * sum_inv_s) / (double)N;
+    cent[j] = c;
+    cent_f[j] = (float)c;
+    gene_par[j].z = c;
+    sumsq_gene[j] = m * m * sum_inv_s2 + 2.0 * m * c * sum_inv_s + (double)N * c * c + suu - 2.0 * m * sui - 2.0 * c * su;
+  }
+};
+
+// gene-major writer's sparse patch: the final value (z_ij - mu_j)/s_i - c_j of every stored entry, evaluated in
+// Float64 and rounded once to Float32 (CSC order)
+struct GenePatchOp {
+  static constexpr int NACC = 1;
+  const uint32_t* __restrict__ rowval;
+  const float* __restrict__ val;
+  const double2* __restrict__ cell_par;
+  const double4* __restrict__ gene_par;
+  float* patch_csc;
+  struct Ctx { double inv_sd, mu, c; };
+  struct Ld { float v; double2 c; };
+  __device__ __forceinline__ Ctx begin(int j) const {
+    const double4 g = gene_par[j];
+    return Ctx{g.x, g.y, g.z};
+  }
+  __device__ __forceinline__ void load(uint32_t t, bool ok, Ld& l) const {
+    l.v = ok ? val[t] : 0.f;
+    l.c = cell_par[ok ? rowval[t] : 0];
+  }
+  __device__ __forceinline__ void accum(uint32_t t, const Ctx& cx, const Ld& l, double (&)[NACC]) const {
+    patch_csc[t] = (float)((log1p_unit((double)l.v * l.c.x) * cx.inv_sd - cx.mu) * l.c.y - cx.c);
+  }
+  __device__ __forceinline__ void finish(int, const Ctx&, const double (&)[NACC]) const {}
+};
+
+// cell-major writer's sparse patch (CSR order) and the exact sum of squares of every cell's normalised row (the Gram
+// diagonal when cells are the Gram side): sum_j (mu_j/s_i + c_j)^2 in closed form from |mu|^2, mu.c, |c|^2, plus
+// w^2 - bg^2 at the stored entries.
+struct CellFinishOp {
+  static constexpr int NACC = 1;
+  const uint32_t* __restrict__ colidx;
+  const float* __restrict__ rval;
+  const double2* __restrict__ cell_par;
+  const double4* __restrict__ gene_par;
+  const double* __restrict__ scalars;
+  float* patch_csr;
+  double* sumsq_cell;
+  struct Ctx { double inv_r, is; };
+  struct Ld { float v; double4 g; };
+  __device__ __forceinline__ Ctx begin(int row) const {
+    const double2 c = cell_par[row];
+    return Ctx{c.x, c.y};
+  }
+  __device__ __forceinline__ void load(uint32_t t, bool ok, Ld& l) const {
+    l.v = ok ? rval[t] : 0.f;
+    l.g = gene_par[ok ? colidx[t] : 0];
+  }
+  __device__ __forceinline__ void accum(uint32_t t, const Ctx& cx, const Ld& l, double (&acc)[NACC]) const {
+    const double z = log1p_unit((double)l.v * cx.inv_r) * l.g.x;
+    const double bg = cx.is * l.g.y + l.g.z, w = (z - l.g.y) * cx.is - l.g.z;
+    patch_csr[t] = (float)w;
+    acc[0] += w * w - bg * bg;
+  }
+  __device__ __forceinline__ void finish(int row, const Ctx& cx, const double (&acc)[NACC]) const {
+    const double mu2 = scalars[0], muc = scalars[4], c2 = scalars[5];
+    sumsq_cell[row] = cx.is * cx.is * mu2 + 2.0 * cx.is * muc + c2 + acc[0];
+  }
+};
+
+// ---- small deterministic reductions over the per-line vectors ---------------------------------
+// Each block reduces a strided slice with a fixed tree and writes its partial sums; the block that finishes last
+// adds the partials in block order and derives the scalars, so the result does not depend on scheduling.
+//   MODE 0: a = mu            -> scalars[0] = |mu|^2
+//   MODE 1: a = l             -> scalars[1] = mean(l), [2] = sum(1/s), [3] = sum(1/s^2),  s_i = l_i / mean(l)
+//   MODE 2: a = mu, b = cent  -> scalars[4] = mu.c, [5] = |c|^2
+static constexpr int kRedBlocks = 64;
+template <int MODE>
+__global__ void __launch_bounds__(256) k_reduce_vec(const double* __restrict__ a, const double* __restrict__ b, int n,
+                                                    double* __restrict__ partial /* [3][kRedBlocks] */,
+                                                    unsigned int* __restrict__ counter, double* __restrict__ scalars) {
+  __shared__ double red[3][8];
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double x = a[i];
+    if (MODE == 0) {
+      s0 = fma(x, x, s0);
+    } else if (MODE == 1) {
+      const double r = 1.0 / x;
+      s0 += x;
+      s1 += r;
+      s2 = fma(r, r, s2);
+    } else {
+      const double y = b[i];
+      s0 = fma(x, y, s0);
+      s1 = fma(y, y, s1);
+    }
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = s0; red[1][warp] = s1; red[2][warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0, t1 = 0, t2 = 0;
+    for (int w = 0; w < 8; ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
+    partial[0 * kRedBlocks + blockIdx.x] = t0;
+    partial[1 * kRedBlocks + blockIdx.x] = t1;
+    partial[2 * kRedBlocks + blockIdx.x] = t2;
+    __threadfence();
+    if (atomicAdd(counter, 1u) == gridDim.x - 1) {
+      __threadfence();
+      t0 = t1 = t2 = 0;
+      const volatile double* vp = partial;
+      for (unsigned g = 0; g < gridDim.x; ++g) {
+        t0 += vp[0 * kRedBlocks + g];
+        t1 += vp[1 * kRedBlocks + g];
+        t2 += vp[2 * kRedBlocks + g];
+      }
+      if (MODE == 0) {
+        scalars[0] = t0;
+      } else if (MODE == 1) {
+        const double mean = t0 / (double)n;
+        scalars[1] = mean;
+        scalars[2] = mean * t1;
+        scalars[3] = mean * mean * t2;
+      } else {
+        scalars[4] = t0;
+        scalars[5] = t1;
+      }
+      *counter = 0;   // ready for the next launch on this stream
+    }
   }
 }
 
 __global__ void k_inv_s(const double* __restrict__ l2, const double* __restrict__ scalars, int N,
-                        double* __restrict__ inv_s, float* __restrict__ inv_s_f) {
+                        double* __restrict__ inv_s, float* __restrict__ inv_s_f, double2* __restrict__ cell_par) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) {
     double v = scalars[1] / l2[i];
     inv_s[i] = v;
     inv_s_f[i] = (float)v;
+    cell_par[i].y = v;
   }
 }
 
-// ---- per-gene centre after cell scaling (CSC, one warp per gene) ---------------------------
-// Also emits the gene-major writer's sparse patch - the final value (z_ij - mu_j)/s_i - c_j of every stored entry,
-// evaluated in Float64 and rounded once to Float32 (CSC order) - and the gene's exact sum of squares over all cells
-// (the Gram diagonal when genes are the Gram side): background in closed form plus a correction per stored entry,
-//   sum_i w^2 = sum_i bg_i^2 + sum_nz (u^2 - 2 u bg),   u = z/s_i,  bg = mu_j/s_i + c_j,  w = u - bg.
-__global__ void __launch_bounds__(256) k_gene_center(const uint32_t* __restrict__ colptr,
-                                                     const uint32_t* __restrict__ rowval,
-                                                     const double* __restrict__ y_csc,
-                                                     const double* __restrict__ sigma, const double* __restrict__ mu,
-                                                     const double* __restrict__ inv_s,
-                                                     const double* __restrict__ scalars, int N, int M,
-                                                     float* __restrict__ patch_csc, double* __restrict__ cent,
-                                                     float* __restrict__ cent_f, double* __restrict__ sumsq_gene) {
-  const int lane = threadIdx.x & 31;
-  int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int per_grid = (gridDim.x * blockDim.x) >> 5;
-  const double sum_inv_s = scalars[2], sum_inv_s2 = scalars[3];
-  for (int jj = j; jj < M; jj += per_grid) {
-    const int j = M - 1 - jj;   // densest columns first
-    const uint32_t b = colptr[j], e = colptr[j + 1];
-    const double sd = sigma[j], m = mu[j];
-    double su = 0, suu = 0, sui = 0;    // sum u, sum u^2, sum u/s_i
-    for (uint32_t t = b + lane; t < e; t += 32 * kStatUnroll) {
-      double y[kStatUnroll], is[kStatUnroll];
-#pragma unroll
-      for (int u = 0; u < kStatUnroll; ++u) {
-        const uint32_t tt = t + 32 * u;
-        const bool ok = tt < e;
-        y[u] = ok ? y_csc[tt] : 0.0;
-        is[u] = inv_s[ok ? rowval[tt] : 0];
-      }
-#pragma unroll
-      for (int u = 0; u < kStatUnroll; ++u) {
-        const double uu = y[u] / sd * is[u];      // 0 for the padding lanes (y = 0)
-        su += uu;
-        suu = fma(uu, uu, suu);
-        sui = fma(uu, is[u], sui);
-      }
-    }
-    su = warp_sum(su);
-    suu = warp_sum(suu);
-    sui = warp_sum(sui);
-    const double c = (su - m * sum_inv_s) / (double)N;
-    if (lane == 0) {
-      cent[j] = c;
-      cent_f[j] = (float)c;
-      sumsq_gene[j] = m * m * sum_inv_s2 + 2.0 * m * c * sum_inv_s + (double)N * c * c + suu - 2.0 * m * sui - 2.0 * c * su;
-    }
-    for (uint32_t t = b + lane; t < e; t += 32 * kStatUnroll) {
-      double y[kStatUnroll], is[kStatUnroll];
-#pragma unroll
-      for (int u = 0; u < kStatUnroll; ++u) {
-        const uint32_t tt = t + 32 * u;
-        const bool ok = tt < e;
-        y[u] = ok ? y_csc[tt] : 0.0;
-        is[u] = inv_s[ok ? rowval[tt] : 0];
-      }
-#pragma unroll
-      for (int u = 0; u < kStatUnroll; ++u) {
-        const uint32_t tt = t + 32 * u;
-        if (tt < e) patch_csc[tt] = (float)((y[u] / sd - m) * is[u] - c);
-      }
-    }
-  }
-}
-
-// out[0] = sum a_i b_i (one block, deterministic)
-__global__ void __launch_bounds__(1024) k_dot(const double* __restrict__ a, const double* __restrict__ b, int n,
-                                              double* __restrict__ out) {
-  __shared__ double red[32];
-  double s = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s += a[i] * b[i];
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) *out = s;
-}
-
-// ---- cell-side finishing pass (CSR, one warp per cell) --------------------------------------
-// Emits the cell-major writer's sparse patch - the final value (z_ij - mu_j)/s_i - c_j of every stored entry, Float64
-// rounded once to Float32, CSR order - and the exact sum of squares of every cell's normalised row (the Gram diagonal
-// when cells are the Gram side): sum_j (mu_j/s_i + c_j)^2 in closed form from |mu|^2, mu.c, |c|^2, plus w^2 - bg^2 at
-// the stored entries.
-__global__ void __launch_bounds__(256) k_cell_finish(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ colidx,
-                                                     const double* __restrict__ z_csr, const double* __restrict__ mu,
-                                                     const double* __restrict__ cent, const double* __restrict__ inv_s,
-                                                     const double* __restrict__ scalars, int N,
-                                                     float* __restrict__ patch_csr, double* __restrict__ sumsq_cell) {
-  const int lane = threadIdx.x & 31;
-  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nrows_per_grid = (gridDim.x * blockDim.x) >> 5;
-  const double mu2 = scalars[0], muc = scalars[4], c2 = scalars[5];
-  for (; row < N; row += nrows_per_grid) {
-    const double is = inv_s[row];
-    const uint32_t b = rowptr[row], e = rowptr[row + 1];
-    double dq = 0;
-    for (uint32_t t = b + lane; t < e; t += 32 * kStatUnroll) {
-      double z[kStatUnroll], m[kStatUnroll], cc[kStatUnroll];
-#pragma unroll
-      for (int u = 0; u < kStatUnroll; ++u) {
-        const uint32_t tt = t + 32 * u;
-        const bool ok = tt < e;
-        const uint32_t c = ok ? colidx[tt] : 0;
-        z[u] = ok ? z_csr[tt] : 0.0;
-        m[u] = mu[c];
-        cc[u] = cent[c];
-      }
-#pragma unroll
-      for (int u = 0; u < kStatUnroll; ++u) {
-        const uint32_t tt = t + 32 * u;
-        if (tt < e) {
-          const double bg = is * m[u] + cc[u], w = (z[u] - m[u]) * is - cc[u];
-          patch_csr[tt] = (float)w;
-          dq += w * w - bg * bg;
-        }
-      }
-    }
-    dq = warp_sum(dq);
-    if (lane == 0) sumsq_cell[row] = is * is * mu2 + 2.0 * is * muc + c2 + dq;
-  }
-}
+static int line_grid(int n_lines) { return std::max(1, std::min(n_lines, sm_count() * 4)); }
 
 void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st) {
   const int N = A.N, M = A.M;
@@ -300,30 +396,53 @@ void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st) {
   S.tgc.ensure(N); S.l2.ensure(N); S.inv_s.ensure(N); S.inv_s_f.ensure(N);
   S.ybar.ensure(M); S.sigma.ensure(M); S.mu.ensure(M); S.cent.ensure(M);
   S.mu_f.ensure(M); S.cent_f.ensure(M); S.inv_sigma_f.ensure(M);
-  S.scalars.ensure(8);
-  S.y_csc.ensure(A.nnz); S.z_csr.ensure(A.nnz); S.patch_csc.ensure(A.nnz);
-  S.sumsq_gene.ensure(M); S.sumsq_cell.ensure(N); S.patch_csr.ensure(A.nnz);
-  count_launches(12);
+  S.cell_par.ensure(N); S.gene_par.ensure(M);
+  S.sumsq_gene.ensure(M); S.sumsq_cell.ensure(N);
+  if (!S.scalars.p) {
+    S.scalars.ensure(8);
+    S.red_partial.ensure(3 * kRedBlocks);
+    S.red_counter.ensure(1);
+    SCL_CUDA(cudaMemsetAsync(S.red_counter.p, 0, sizeof(unsigned int), st));
+  }
+  S.have_patch[0] = S.have_patch[1] = false;
+  count_launches(7);
   const int wgrid = min((N + 7) / 8, 148 * 8);
-  k_row_sum<<<wgrid, 256, 0, st>>>(A.rowptr.p, A.rval.p, N, S.tgc.p);
-  const int ggrid = min((M + 7) / 8, 148 * 8);
-  k_gene_stats<<<ggrid, 256, 0, st>>>(A.colptr.p, A.rowval.p, A.val.p, S.tgc.p, N, M, S.y_csc.p, S.ybar.p,
-                                                  S.sigma.p, S.mu.p, S.mu_f.p, S.inv_sigma_f.p);
-  k_reduce<<<1, 1024, 0, st>>>(S.mu.p, M, 0, S.scalars.p + 0);
-  k_cell_l2<<<wgrid, 256, 0, st>>>(A.rowptr.p, A.colidx.p, A.rval.p, S.tgc.p, S.sigma.p, S.mu.p, S.scalars.p, N,
-                                   S.z_csr.p, S.l2.p);
-  k_reduce<<<1, 1024, 0, st>>>(S.l2.p, N, 1, S.scalars.p + 1);
-  k_inv_s<<<(N + 255) / 256, 256, 0, st>>>(S.l2.p, S.scalars.p, N, S.inv_s.p, S.inv_s_f.p);
-  k_reduce<<<1, 1024, 0, st>>>(S.inv_s.p, N, 2, S.scalars.p + 2);
-  k_reduce<<<1, 1024, 0, st>>>(S.inv_s.p, N, 0, S.scalars.p + 3);
-  k_gene_center<<<ggrid, 256, 0, st>>>(A.colptr.p, A.rowval.p, S.y_csc.p, S.sigma.p, S.mu.p, S.inv_s.p,
-                                                   S.scalars.p, N, M, S.patch_csc.p, S.cent.p, S.cent_f.p,
-                                                   S.sumsq_gene.p);
-  k_dot<<<1, 1024, 0, st>>>(S.mu.p, S.cent.p, M, S.scalars.p + 4);
-  k_reduce<<<1, 1024, 0, st>>>(S.cent.p, M, 0, S.scalars.p + 5);
-  k_cell_finish<<<wgrid, 256, 0, st>>>(A.rowptr.p, A.colidx.p, S.z_csr.p, S.mu.p, S.cent.p, S.inv_s.p, S.scalars.p, N,
-                                       S.patch_csr.p, S.sumsq_cell.p);
+  k_row_sum<<<wgrid, 256, 0, st>>>(A.rowptr.p, A.rval.p, N, S.tgc.p, S.cell_par.p);
+  // genes arrive sorted by mean expression (:224): reversed order starts the densest columns first
+  k_lines<GeneStatsOp><<<line_grid(M), kStatThreads, 0, st>>>(
+      GeneStatsOp{A.rowval.p, A.val.p, S.cell_par.p, N, S.ybar.p, S.sigma.p, S.mu.p, S.mu_f.p, S.inv_sigma_f.p, S.gene_par.p},
+      A.colptr.p, M, 1);
+  k_reduce_vec<0><<<kRedBlocks, 256, 0, st>>>(S.mu.p, nullptr, M, S.red_partial.p, S.red_counter.p, S.scalars.p);
+  k_lines<CellL2Op><<<line_grid(N), kStatThreads, 0, st>>>(
+      CellL2Op{A.colidx.p, A.rval.p, S.cell_par.p, S.gene_par.p, S.scalars.p, S.l2.p}, A.rowptr.p, N, 0);
+  k_reduce_vec<1><<<kRedBlocks, 256, 0, st>>>(S.l2.p, nullptr, N, S.red_partial.p, S.red_counter.p, S.scalars.p);
+  k_inv_s<<<(N + 255) / 256, 256, 0, st>>>(S.l2.p, S.scalars.p, N, S.inv_s.p, S.inv_s_f.p, S.cell_par.p);
+  k_lines<GeneCenterOp><<<line_grid(M), kStatThreads, 0, st>>>(
+      GeneCenterOp{A.rowval.p, A.val.p, S.cell_par.p, S.scalars.p, N, S.gene_par.p, S.cent.p, S.sumsq_gene.p, S.cent_f.p},
+      A.colptr.p, M, 1);
   SCL_CUDA(cudaGetLastError());
+}
+
+// The writer's sparse patch for one layout (0: gene-major / CSC order, 1: cell-major / CSR order), computed on first
+// use after compute_norm_stats: a Gram on the gene side never needs the cell-side patch and vice versa.
+void ensure_patch(const SpMat& A, NormStats& S, int layout, cudaStream_t st) {
+  SCL_REQUIRE(layout == 0 || layout == 1, "layout must be 0 or 1");
+  if (S.have_patch[layout]) return;
+  if (layout == 0) {
+    S.patch_csc.ensure(A.nnz);
+    count_launches(1);
+    k_lines<GenePatchOp><<<line_grid(A.M), kStatThreads, 0, st>>>(
+        GenePatchOp{A.rowval.p, A.val.p, S.cell_par.p, S.gene_par.p, S.patch_csc.p}, A.colptr.p, A.M, 1);
+  } else {
+    S.patch_csr.ensure(A.nnz);
+    count_launches(2);
+    k_reduce_vec<2><<<kRedBlocks, 256, 0, st>>>(S.mu.p, S.cent.p, A.M, S.red_partial.p, S.red_counter.p, S.scalars.p);
+    k_lines<CellFinishOp><<<line_grid(A.N), kStatThreads, 0, st>>>(
+        CellFinishOp{A.colidx.p, A.rval.p, S.cell_par.p, S.gene_par.p, S.scalars.p, S.patch_csr.p, S.sumsq_cell.p},
+        A.rowptr.p, A.N, 0);
+  }
+  SCL_CUDA(cudaGetLastError());
+  S.have_patch[layout] = true;
 }
 
 // ---- fused densify + normalise writer -----------------------------------------------------
@@ -483,7 +602,7 @@ __global__ void k_set_diagonal(float* __restrict__ G, int n, const double* __res
 // core sees the binary16 roundings of these values; their squares differ from the exact ones by an unbiased ~4e-6
 // relative per diagonal entry (K >= 1e4 terms), which moves no eigenvalue by more than ~1e-7.
 const double* gram_diagonal(const SpMat& A, NormStats& S, bool gene_side, cudaStream_t st) {
-  (void)A; (void)st;
+  if (!gene_side) ensure_patch(A, S, 1, st);   // the cell-side sums of squares come out of the cell-major finishing pass
   return gene_side ? S.sumsq_gene.p : S.sumsq_cell.p;
 }
 
@@ -493,8 +612,9 @@ void set_gram_diagonal(float* G, int n, const double* sumsq, double scale, cudaS
   SCL_CUDA(cudaGetLastError());
 }
 
-void densify(const SpMat& A, const NormStats& S, int layout, size_t ld, __half* out_hi, __half* out_lo,
+void densify(const SpMat& A, NormStats& S, int layout, size_t ld, __half* out_hi, __half* out_lo,
              cudaStream_t st, long long pos0, long long pos1) {
+  ensure_patch(A, S, layout, st);
   count_launches(2);
   const bool cell_major = layout == 1;
   const int n_lines = cell_major ? A.N : A.M;

@@ -262,11 +262,12 @@ double quantile7(const std::vector<double>& sorted, double p) {
 // normalise A and form its Wishart matrix on the smaller side:  dG = operand * operand^T * scale
 void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf<__half>& lo, float* dG, int nm,
              float scale, bool split, bool shard) {
+  const bool gene_side = A.N > A.M;                 // contract over cells (N > M) or over genes
   {
     ProfScope ps(&h->prof, h->st, PK_STATS);
     compute_norm_stats(A, S, h->st);
+    ensure_patch(A, S, gene_side ? 0 : 1, h->st);
   }
-  const bool gene_side = A.N > A.M;                 // contract over cells (N > M) or over genes
   const int rows = gene_side ? A.M : A.N;
   const int64_t K = gene_side ? A.N : A.M;
   const size_t ld = round8((size_t)K);
@@ -385,7 +386,7 @@ void corr_colabsmax(scl_handle* h, const float* dV, int nv, const float* dW, int
 
 // out[k][N] = normalise_rows( Vk[k][M] * Xtilde^T )  i.e. columns X*v / |X*v|  (:503-505, :556-558)
 // dVrows: pointer to the first wanted eigenvector, ld_v elements between consecutive wanted ones
-static void back_project(scl_handle* h, const SpMat& A, const NormStats& S, const float* dVrows, long long ld_v, int k,
+static void back_project(scl_handle* h, const SpMat& A, NormStats& S, const float* dVrows, long long ld_v, int k,
                          float* d_out) {
   const int N = A.N, M = A.M;
   const size_t ldm = round8((size_t)M);

@@ -3,6 +3,5 @@
 mkdir -p gpurun_out
 run() { name=$1; shift; echo "=== $name" ; timeout -s KILL $1 "${@:2}" > gpurun_out/$name.log 2>&1; echo "rc=$?" >> gpurun_out/$name.log; tail -${TAILN:-6} gpurun_out/$name.log; }
 nvidia-smi -L > gpurun_out/smi_2gpu.txt
-TAILN=15 run t_multigpu 600 python -m pytest tests/test_multigpu.py -q -m gpu
-TAILN=4 run bench_B_2gpu 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29621 bench.py --gpus 2 --steps 1 --warmup 1
-TAILN=4 run bench_B_1gpu_short 400 python bench.py --gpus 1 --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline
+TAILN=15 run t_multigpu 400 python -m pytest tests/test_multigpu.py -q -m gpu
+TAILN=6 run bench_B_2gpu 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29621 bench.py --gpus 2 --steps 1 --warmup 1
