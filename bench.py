@@ -37,7 +37,9 @@ WORKLOADS = {
     "C": (68000, 20000, 1),
     "small": (2000, 3000, 3),
 }
-NOMINAL_SEARCH_STEPS = 20     # used by the reference arm, which runs before any GPU pass exists
+# search steps the reference arm assumes (it runs before any GPU pass exists): the count our own pass takes on the
+# same synthetic matrix (deterministic per workload and seed; measured on B200, profiles/r1_bench_*.json)
+NOMINAL_SEARCH_STEPS = {"B": 14, "C": 14, "small": 14}
 
 
 def log(*a):
@@ -213,7 +215,7 @@ def main():
         X = make_counts_fast(N, M, seed)
         vals = []
         for i in range(args.warmup + args.steps):
-            total, cores, sample = cpu_sample(X, NOMINAL_SEARCH_STEPS, args.n_perturb)
+            total, cores, sample = cpu_sample(X, NOMINAL_SEARCH_STEPS[args.workload], args.n_perturb)
             if i >= args.warmup:
                 vals.append(total)
         sec = float(np.mean(vals))
@@ -223,7 +225,7 @@ def main():
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port",
-                                           "sample": sample + f"; search steps nominal={NOMINAL_SEARCH_STEPS}"},
+                                           "sample": sample + f"; search steps nominal={NOMINAL_SEARCH_STEPS[args.workload]}"},
                           "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -361,6 +363,12 @@ def main():
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (Gram), f32 syevd, f64 statistics",
             "data": "synthetic", "config": config, "clocks": clk, "gpu_launches": int(launches),
             "roofline": roofline, "stage_ms_over_timed_region": stage_ms,
+            "phase_ms_last_step": {"signal_normalise_gram": si.t_gram_ms, "signal_syevd": si.t_syevd_ms, "null_matrix": si.t_null_ms,
+                                   "mp_fit_host": si.t_fit_ms, "backproject": si.t_backproject_ms,
+                                   "noise_baseline_and_zero_candidates": ri.t_baseline_ms, "search_total": ri.t_search_ms,
+                                   "search_syevd": ri.t_search_syevd_ms, "perturbations": ri.t_perturb_ms,
+                                   "scores": ri.t_score_ms, "gene_basis": ri.t_outputs_ms},
+            "gemm_tflops": {"other_gemm_2mnk": (prof.other_gemm_flops / (prof.other_gemm_ms * 1e-3) / 1e12) if prof.other_gemm_ms > 0 else 0.0},
             "result": {"n_signal": si.n_signal, "lambda_c": si.lambda_c, "n_search": ri.n_search, "p_sel": ri.p_sel,
                        "n_robust": ri.n_robust}}
     if e2e is not None:

@@ -453,6 +453,11 @@ int32_t scl_bench_gram(scl_handle* h, int32_t rows, int64_t K, int32_t mode, int
 
 /* Times the normalisation kernels on the handle's counts: the statistics pre-passes and the fused densify writer
  * (layout 0 gene-major / 1 cell-major, with_lo: also emit the low-order binary16 part). */
+int32_t scl_debug_set_tuning(int32_t stat_variant, int32_t stat_heavy, int32_t writer) {
+  scl::set_norm_tuning(stat_variant, stat_heavy, writer);
+  return SCL_OK;
+}
+
 int32_t scl_bench_normalize(scl_handle* h, int32_t layout, int32_t with_lo, int32_t reps, double* ms_stats,
                             double* ms_densify, double* alg_bytes_densify) {
   if (!h || reps <= 0) return SCL_ERR_INVALID;

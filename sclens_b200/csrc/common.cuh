@@ -130,6 +130,7 @@ void ensure_patch(const SpMat& A, NormStats& S, int layout, cudaStream_t st);
 // [pos0,pos1): range of positions of every line to emit (default: the whole padded line) - the cell block of a rank
 void densify(const SpMat& A, NormStats& S, int layout, size_t ld, __half* out_hi, __half* out_lo,
              cudaStream_t st, long long pos0 = 0, long long pos1 = -1);
+void set_norm_tuning(int stat_variant, int stat_heavy, int writer);
 // exact Float64 Gram diagonal (unscaled) of the normalised matrix on its gene side / cell side
 const double* gram_diagonal(const SpMat& A, NormStats& S, bool gene_side, cudaStream_t st);
 void set_gram_diagonal(float* G, int n, const double* sumsq, double scale, cudaStream_t st);

@@ -11,6 +11,7 @@
 //   out_ij = (z_ij - mu_j)/s_i - c_j                                             (:696)
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include "tmp.cuh"
 
 namespace scl {
@@ -78,31 +79,50 @@ __global__ void k_row_sum(const uint32_t* __restrict__ rowptr, const float* __re
 // to kHeavyLine entries is reduced by one warp and a longer one by the whole CTA; lines are dealt to CTAs round-robin
 // (densest genes first when the caller asks for reversed order).  Lane/thread-strided partial sums and fixed
 // shuffle / shared-memory trees: the sums depend on the line's length only, never on scheduling (deterministic).
-static constexpr int kStatUnroll = 4;
 static constexpr int kStatThreads = 256;
-static constexpr uint32_t kHeavyLine = 1024;
 
-template <class Op>
+// One strided walk over the entries [b, e) of a line.  The (index, value) pairs of the next step are requested before
+// the current step's gathers and Float64 arithmetic, so a warp always has a step's worth of streaming loads in flight
+// (the gathers hit L1/L2; the stream is what has to cover the HBM latency).
+template <class Op, int kStatUnroll>
 __device__ __forceinline__ void line_span(const Op& op, const typename Op::Ctx& cx, uint32_t b, uint32_t e, int first,
                                           int stride, double (&acc)[Op::NACC]) {
-  for (uint32_t t = b + first; t < e; t += stride * kStatUnroll) {
+  uint32_t t = b + first;
+  uint32_t idx[kStatUnroll], nidx[kStatUnroll];
+  float v[kStatUnroll], nv[kStatUnroll];
+#pragma unroll
+  for (int u = 0; u < kStatUnroll; ++u) {
+    const uint32_t tt = t + stride * u;
+    const bool ok = tt < e;
+    idx[u] = ok ? op.idx[tt] : 0u;
+    v[u] = ok ? op.val[tt] : 0.f;
+  }
+  while (t < e) {
+    const uint32_t tn = t + stride * kStatUnroll;
+#pragma unroll
+    for (int u = 0; u < kStatUnroll; ++u) {
+      const uint32_t tt = tn + stride * u;
+      const bool ok = tt < e;
+      nidx[u] = ok ? op.idx[tt] : 0u;
+      nv[u] = ok ? op.val[tt] : 0.f;
+    }
     typename Op::Ld ld[kStatUnroll];
 #pragma unroll
-    for (int u = 0; u < kStatUnroll; ++u) {
-      const uint32_t tt = t + stride * u;
-      op.load(tt, tt < e, ld[u]);
-    }
+    for (int u = 0; u < kStatUnroll; ++u) op.gather(idx[u], ld[u]);
 #pragma unroll
     for (int u = 0; u < kStatUnroll; ++u) {
       const uint32_t tt = t + stride * u;
-      if (tt < e) op.accum(tt, cx, ld[u], acc);
+      if (tt < e) op.accum(tt, cx, v[u], ld[u], acc);
     }
+#pragma unroll
+    for (int u = 0; u < kStatUnroll; ++u) { idx[u] = nidx[u]; v[u] = nv[u]; }
+    t = tn;
   }
 }
 
-template <class Op>
-__global__ void __launch_bounds__(kStatThreads) k_lines(const Op op, const uint32_t* __restrict__ ptr, int n_lines,
-                                                        int reversed) {
+template <class Op, int U, int MINB>
+__global__ void __launch_bounds__(kStatThreads, MINB) k_lines(const Op op, const uint32_t* __restrict__ ptr, int n_lines,
+                                                              int reversed, uint32_t kHeavyLine) {
   __shared__ double red[Op::NACC][kStatThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // lines of at most kHeavyLine entries: one warp each
@@ -114,7 +134,7 @@ __global__ void __launch_bounds__(kStatThreads) k_lines(const Op op, const uint3
     double acc[Op::NACC];
 #pragma unroll
     for (int a = 0; a < Op::NACC; ++a) acc[a] = 0;
-    line_span(op, cx, b, e, lane, 32, acc);
+    line_span<Op, U>(op, cx, b, e, lane, 32, acc);
 #pragma unroll
     for (int a = 0; a < Op::NACC; ++a) acc[a] = warp_sum(acc[a]);
     if (lane == 0) op.finish(line, cx, acc);
@@ -128,7 +148,7 @@ __global__ void __launch_bounds__(kStatThreads) k_lines(const Op op, const uint3
     double acc[Op::NACC];
 #pragma unroll
     for (int a = 0; a < Op::NACC; ++a) acc[a] = 0;
-    line_span(op, cx, b, e, tid, kStatThreads, acc);
+    line_span<Op, U>(op, cx, b, e, tid, kStatThreads, acc);
 #pragma unroll
     for (int a = 0; a < Op::NACC; ++a) acc[a] = warp_sum(acc[a]);
     __syncthreads();
@@ -152,7 +172,7 @@ __global__ void __launch_bounds__(kStatThreads) k_lines(const Op op, const uint3
 // per-gene mean / corrected std of y = log1p(x / r_i)  (:681-686)
 struct GeneStatsOp {
   static constexpr int NACC = 2;
-  const uint32_t* __restrict__ rowval;
+  const uint32_t* __restrict__ idx;   // rowval
   const float* __restrict__ val;
   const double2* __restrict__ cell_par;
   int N;
@@ -160,14 +180,11 @@ struct GeneStatsOp {
   float *mu_f, *inv_sigma_f;
   double4* gene_par;
   struct Ctx {};
-  struct Ld { float v; double inv_r; };
+  struct Ld { double inv_r; };
   __device__ __forceinline__ Ctx begin(int) const { return Ctx(); }
-  __device__ __forceinline__ void load(uint32_t t, bool ok, Ld& l) const {
-    l.v = ok ? val[t] : 0.f;
-    l.inv_r = cell_par[ok ? rowval[t] : 0].x;
-  }
-  __device__ __forceinline__ void accum(uint32_t, const Ctx&, const Ld& l, double (&acc)[NACC]) const {
-    const double y = log1p_unit((double)l.v * l.inv_r);
+  __device__ __forceinline__ void gather(uint32_t i, Ld& l) const { l.inv_r = cell_par[i].x; }
+  __device__ __forceinline__ void accum(uint32_t, const Ctx&, float v, const Ld& l, double (&acc)[NACC]) const {
+    const double y = log1p_unit((double)v * l.inv_r);
     acc[0] += y;
     acc[1] = fma(y, y, acc[1]);
   }
@@ -189,23 +206,22 @@ struct GeneStatsOp {
 // per-cell l2 norm after the mean shift, from the sparse entries only  (:688-689, :603)
 struct CellL2Op {
   static constexpr int NACC = 2;
-  const uint32_t* __restrict__ colidx;
-  const float* __restrict__ rval;
+  const uint32_t* __restrict__ idx;   // colidx
+  const float* __restrict__ val;      // rval
   const double2* __restrict__ cell_par;
   const double4* __restrict__ gene_par;
   const double* __restrict__ scalars;
   double* l2;
   struct Ctx { double inv_r; };
-  struct Ld { float v; double inv_sd, mu; };
+  struct Ld { double inv_sd, mu; };
   __device__ __forceinline__ Ctx begin(int row) const { return Ctx{cell_par[row].x}; }
-  __device__ __forceinline__ void load(uint32_t t, bool ok, Ld& l) const {
-    l.v = ok ? rval[t] : 0.f;
-    const double2 g = *reinterpret_cast<const double2*>(&gene_par[ok ? colidx[t] : 0]);
+  __device__ __forceinline__ void gather(uint32_t j, Ld& l) const {
+    const double2 g = *reinterpret_cast<const double2*>(&gene_par[j]);
     l.inv_sd = g.x;
     l.mu = g.y;
   }
-  __device__ __forceinline__ void accum(uint32_t, const Ctx& cx, const Ld& l, double (&acc)[NACC]) const {
-    const double z = log1p_unit((double)l.v * cx.inv_r) * l.inv_sd;
+  __device__ __forceinline__ void accum(uint32_t, const Ctx& cx, float v, const Ld& l, double (&acc)[NACC]) const {
+    const double z = log1p_unit((double)v * cx.inv_r) * l.inv_sd;
     acc[0] = fma(z, z, acc[0]);
     acc[1] = fma(z, l.mu, acc[1]);
   }
@@ -219,7 +235,7 @@ struct CellL2Op {
 //   sum_i w^2 = sum_i bg_i^2 + sum_nz (u^2 - 2 u bg),   u = z/s_i,  bg = mu_j/s_i + c_j,  w = u - bg.
 struct GeneCenterOp {
   static constexpr int NACC = 3;
-  const uint32_t* __restrict__ rowval;
+  const uint32_t* __restrict__ idx;   // rowval
   const float* __restrict__ val;
   const double2* __restrict__ cell_par;
   const double* __restrict__ scalars;
@@ -228,17 +244,14 @@ struct GeneCenterOp {
   double *cent, *sumsq_gene;
   float* cent_f;
   struct Ctx { double inv_sd, mu; };
-  struct Ld { float v; double2 c; };
+  struct Ld { double2 c; };
   __device__ __forceinline__ Ctx begin(int j) const {
     const double2 g = *reinterpret_cast<const double2*>(&gene_par[j]);
     return Ctx{g.x, g.y};
   }
-  __device__ __forceinline__ void load(uint32_t t, bool ok, Ld& l) const {
-    l.v = ok ? val[t] : 0.f;
-    l.c = cell_par[ok ? rowval[t] : 0];
-  }
-  __device__ __forceinline__ void accum(uint32_t, const Ctx& cx, const Ld& l, double (&acc)[NACC]) const {
-    const double uu = log1p_unit((double)l.v * l.c.x) * cx.inv_sd * l.c.y;
+  __device__ __forceinline__ void gather(uint32_t i, Ld& l) const { l.c = cell_par[i]; }
+  __device__ __forceinline__ void accum(uint32_t, const Ctx& cx, float v, const Ld& l, double (&acc)[NACC]) const {
+    const double uu = log1p_unit((double)v * l.c.x) * cx.inv_sd * l.c.y;
     acc[0] += uu;
     acc[1] = fma(uu, uu, acc[1]);
     acc[2] = fma(uu, l.c.y, acc[2]);
@@ -258,23 +271,20 @@ struct GeneCenterOp {
 // Float64 and rounded once to Float32 (CSC order)
 struct GenePatchOp {
   static constexpr int NACC = 1;
-  const uint32_t* __restrict__ rowval;
+  const uint32_t* __restrict__ idx;   // rowval
   const float* __restrict__ val;
   const double2* __restrict__ cell_par;
   const double4* __restrict__ gene_par;
   float* patch_csc;
   struct Ctx { double inv_sd, mu, c; };
-  struct Ld { float v; double2 c; };
+  struct Ld { double2 c; };
   __device__ __forceinline__ Ctx begin(int j) const {
     const double4 g = gene_par[j];
     return Ctx{g.x, g.y, g.z};
   }
-  __device__ __forceinline__ void load(uint32_t t, bool ok, Ld& l) const {
-    l.v = ok ? val[t] : 0.f;
-    l.c = cell_par[ok ? rowval[t] : 0];
-  }
-  __device__ __forceinline__ void accum(uint32_t t, const Ctx& cx, const Ld& l, double (&)[NACC]) const {
-    patch_csc[t] = (float)((log1p_unit((double)l.v * l.c.x) * cx.inv_sd - cx.mu) * l.c.y - cx.c);
+  __device__ __forceinline__ void gather(uint32_t i, Ld& l) const { l.c = cell_par[i]; }
+  __device__ __forceinline__ void accum(uint32_t t, const Ctx& cx, float v, const Ld& l, double (&)[NACC]) const {
+    patch_csc[t] = (float)((log1p_unit((double)v * l.c.x) * cx.inv_sd - cx.mu) * l.c.y - cx.c);
   }
   __device__ __forceinline__ void finish(int, const Ctx&, const double (&)[NACC]) const {}
 };
@@ -284,25 +294,22 @@ struct GenePatchOp {
 // w^2 - bg^2 at the stored entries.
 struct CellFinishOp {
   static constexpr int NACC = 1;
-  const uint32_t* __restrict__ colidx;
-  const float* __restrict__ rval;
+  const uint32_t* __restrict__ idx;   // colidx
+  const float* __restrict__ val;      // rval
   const double2* __restrict__ cell_par;
   const double4* __restrict__ gene_par;
   const double* __restrict__ scalars;
   float* patch_csr;
   double* sumsq_cell;
   struct Ctx { double inv_r, is; };
-  struct Ld { float v; double4 g; };
+  struct Ld { double4 g; };
   __device__ __forceinline__ Ctx begin(int row) const {
     const double2 c = cell_par[row];
     return Ctx{c.x, c.y};
   }
-  __device__ __forceinline__ void load(uint32_t t, bool ok, Ld& l) const {
-    l.v = ok ? rval[t] : 0.f;
-    l.g = gene_par[ok ? colidx[t] : 0];
-  }
-  __device__ __forceinline__ void accum(uint32_t t, const Ctx& cx, const Ld& l, double (&acc)[NACC]) const {
-    const double z = log1p_unit((double)l.v * cx.inv_r) * l.g.x;
+  __device__ __forceinline__ void gather(uint32_t j, Ld& l) const { l.g = gene_par[j]; }
+  __device__ __forceinline__ void accum(uint32_t t, const Ctx& cx, float v, const Ld& l, double (&acc)[NACC]) const {
+    const double z = log1p_unit((double)v * cx.inv_r) * l.g.x;
     const double bg = cx.is * l.g.y + l.g.z, w = (z - l.g.y) * cx.is - l.g.z;
     patch_csr[t] = (float)w;
     acc[0] += w * w - bg * bg;
@@ -388,7 +395,37 @@ __global__ void k_inv_s(const double* __restrict__ l2, const double* __restrict_
   }
 }
 
-static int line_grid(int n_lines) { return std::max(1, std::min(n_lines, sm_count() * 4)); }
+// Launch configuration of the line passes: (entries per lane and step, CTAs per SM) and the line length above which
+// the whole CTA takes a line.  SCL_STAT_VARIANT / SCL_STAT_HEAVY override the defaults (tuning studies only).
+struct StatTune { int variant; uint32_t heavy; int writer; };
+static StatTune& stat_tune() {
+  static StatTune t = [] {
+    StatTune x{0, 4096u, 0};
+    if (const char* v = getenv("SCL_STAT_VARIANT")) x.variant = atoi(v);
+    if (const char* v = getenv("SCL_STAT_HEAVY")) x.heavy = (uint32_t)atoi(v);
+    if (const char* v = getenv("SCL_DENSIFY")) x.writer = atoi(v);
+    return x;
+  }();
+  return t;
+}
+// tuning studies (scl_debug_set_tuning): negative values keep the current setting
+void set_norm_tuning(int stat_variant, int stat_heavy, int writer) {
+  StatTune& t = stat_tune();
+  if (stat_variant >= 0) t.variant = stat_variant;
+  if (stat_heavy > 0) t.heavy = (uint32_t)stat_heavy;
+  if (writer >= 0) t.writer = writer;
+}
+template <class Op>
+static void launch_lines(const Op& op, const uint32_t* ptr, int n_lines, int reversed, cudaStream_t st) {
+  const StatTune t = stat_tune();
+  auto grid = [&](int per_sm) { return std::max(1, std::min(n_lines, sm_count() * per_sm)); };
+  switch (t.variant) {
+    case 1: k_lines<Op, 4, 3><<<grid(3), kStatThreads, 0, st>>>(op, ptr, n_lines, reversed, t.heavy); break;
+    case 2: k_lines<Op, 8, 2><<<grid(2), kStatThreads, 0, st>>>(op, ptr, n_lines, reversed, t.heavy); break;
+    case 3: k_lines<Op, 2, 4><<<grid(4), kStatThreads, 0, st>>>(op, ptr, n_lines, reversed, t.heavy); break;
+    default: k_lines<Op, 4, 4><<<grid(4), kStatThreads, 0, st>>>(op, ptr, n_lines, reversed, t.heavy); break;
+  }
+}
 
 void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st) {
   const int N = A.N, M = A.M;
@@ -409,17 +446,16 @@ void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st) {
   const int wgrid = min((N + 7) / 8, 148 * 8);
   k_row_sum<<<wgrid, 256, 0, st>>>(A.rowptr.p, A.rval.p, N, S.tgc.p, S.cell_par.p);
   // genes arrive sorted by mean expression (:224): reversed order starts the densest columns first
-  k_lines<GeneStatsOp><<<line_grid(M), kStatThreads, 0, st>>>(
-      GeneStatsOp{A.rowval.p, A.val.p, S.cell_par.p, N, S.ybar.p, S.sigma.p, S.mu.p, S.mu_f.p, S.inv_sigma_f.p, S.gene_par.p},
-      A.colptr.p, M, 1);
+  launch_lines(GeneStatsOp{A.rowval.p, A.val.p, S.cell_par.p, N, S.ybar.p, S.sigma.p, S.mu.p, S.mu_f.p, S.inv_sigma_f.p,
+                           S.gene_par.p},
+               A.colptr.p, M, 1, st);
   k_reduce_vec<0><<<kRedBlocks, 256, 0, st>>>(S.mu.p, nullptr, M, S.red_partial.p, S.red_counter.p, S.scalars.p);
-  k_lines<CellL2Op><<<line_grid(N), kStatThreads, 0, st>>>(
-      CellL2Op{A.colidx.p, A.rval.p, S.cell_par.p, S.gene_par.p, S.scalars.p, S.l2.p}, A.rowptr.p, N, 0);
+  launch_lines(CellL2Op{A.colidx.p, A.rval.p, S.cell_par.p, S.gene_par.p, S.scalars.p, S.l2.p}, A.rowptr.p, N, 0, st);
   k_reduce_vec<1><<<kRedBlocks, 256, 0, st>>>(S.l2.p, nullptr, N, S.red_partial.p, S.red_counter.p, S.scalars.p);
   k_inv_s<<<(N + 255) / 256, 256, 0, st>>>(S.l2.p, S.scalars.p, N, S.inv_s.p, S.inv_s_f.p, S.cell_par.p);
-  k_lines<GeneCenterOp><<<line_grid(M), kStatThreads, 0, st>>>(
-      GeneCenterOp{A.rowval.p, A.val.p, S.cell_par.p, S.scalars.p, N, S.gene_par.p, S.cent.p, S.sumsq_gene.p, S.cent_f.p},
-      A.colptr.p, M, 1);
+  launch_lines(GeneCenterOp{A.rowval.p, A.val.p, S.cell_par.p, S.scalars.p, N, S.gene_par.p, S.cent.p, S.sumsq_gene.p,
+                            S.cent_f.p},
+               A.colptr.p, M, 1, st);
   SCL_CUDA(cudaGetLastError());
 }
 
@@ -431,15 +467,13 @@ void ensure_patch(const SpMat& A, NormStats& S, int layout, cudaStream_t st) {
   if (layout == 0) {
     S.patch_csc.ensure(A.nnz);
     count_launches(1);
-    k_lines<GenePatchOp><<<line_grid(A.M), kStatThreads, 0, st>>>(
-        GenePatchOp{A.rowval.p, A.val.p, S.cell_par.p, S.gene_par.p, S.patch_csc.p}, A.colptr.p, A.M, 1);
+    launch_lines(GenePatchOp{A.rowval.p, A.val.p, S.cell_par.p, S.gene_par.p, S.patch_csc.p}, A.colptr.p, A.M, 1, st);
   } else {
     S.patch_csr.ensure(A.nnz);
     count_launches(2);
     k_reduce_vec<2><<<kRedBlocks, 256, 0, st>>>(S.mu.p, S.cent.p, A.M, S.red_partial.p, S.red_counter.p, S.scalars.p);
-    k_lines<CellFinishOp><<<line_grid(A.N), kStatThreads, 0, st>>>(
-        CellFinishOp{A.colidx.p, A.rval.p, S.cell_par.p, S.gene_par.p, S.scalars.p, S.patch_csr.p, S.sumsq_cell.p},
-        A.rowptr.p, A.N, 0);
+    launch_lines(CellFinishOp{A.colidx.p, A.rval.p, S.cell_par.p, S.gene_par.p, S.scalars.p, S.patch_csr.p, S.sumsq_cell.p},
+                 A.rowptr.p, A.N, 0, st);
   }
   SCL_CUDA(cudaGetLastError());
   S.have_patch[layout] = true;
@@ -592,6 +626,152 @@ k_densify(const uint32_t* __restrict__ off, const uint32_t* __restrict__ idx, co
   }
 }
 
+// ---- TMA-store writer ---------------------------------------------------------------------------
+// Same decomposition (a CTA owns a strip of kStripW positions for kLinesPerCta lines, eight positions per thread with
+// their factors in registers), but a line's strip is composed in shared memory and leaves the SM as ONE bulk
+// asynchronous store (cp.async.bulk.global.shared, 4 KB): the background is written by its owner threads as one
+// 16-byte shared-memory store each, the stored entries are dropped on top as 2-byte stores, and no thread reads the
+// tile back, tests for patches or issues a global store.  Two lines per step, a ring of kRing steps: the stores of
+// step s stream out while steps s+1.. are composed; thread 0 waits (wait_group.read) until the stores that used a
+// ring slot have finished reading it before the slot is written again.
+static constexpr int kRing = 3;
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+
+template <bool CELL_MAJOR, bool WITH_LO>
+__global__ void __launch_bounds__(kDenseThreads)
+k_densify_tma(const uint32_t* __restrict__ off, const uint32_t* __restrict__ idx, const float* __restrict__ patch,
+              const float* __restrict__ inv_s_f, const float* __restrict__ mu_f, const float* __restrict__ cent_f,
+              int n_lines, int line_len, size_t ld, int n_strips, int pos0, int pos1, __half* __restrict__ out_hi,
+              __half* __restrict__ out_lo) {
+  extern __shared__ __align__(128) unsigned char dens_smem[];
+  __half* tile_hi = reinterpret_cast<__half*>(dens_smem);     // [kRing][2][kStripW]
+  __half* tile_lo = tile_hi + kRing * 2 * kStripW;            // [kRing][2][kStripW] (WITH_LO only)
+  __shared__ uint32_t seg[kLinesPerCta][2];
+  __shared__ float line_a[kLinesPerCta], line_c[kLinesPerCta];
+  const int tid = threadIdx.x;
+  const int strip = blockIdx.x % n_strips;
+  const int line0 = (blockIdx.x / n_strips) * kLinesPerCta;
+  const int line1 = min(n_lines, line0 + kLinesPerCta);
+  const int n_my = line1 - line0;
+  const int base = pos0 + strip * kStripW;
+  const int p0 = base + tid * kElemsPerThread;
+  const bool active = p0 < pos1;
+  const uint32_t bytes = (uint32_t)(min(kStripW, pos1 - base)) * 2u;   // multiple of 16: pos1 % 8 == 0 or pos1 == ld
+  float P[kElemsPerThread], Q[kElemsPerThread];
+  bool tail = false;
+#pragma unroll
+  for (int q = 0; q < kElemsPerThread; ++q) {
+    const int pos = p0 + q;
+    const bool ok = pos < line_len;
+    tail |= !ok;
+    if (CELL_MAJOR) {
+      P[q] = ok ? mu_f[pos] : 0.f;
+      Q[q] = ok ? -cent_f[pos] : 0.f;
+    } else {
+      P[q] = ok ? inv_s_f[pos] : 0.f;
+      Q[q] = 0.f;
+    }
+  }
+  if (tid < 2 * n_my) {
+    const int l = tid >> 1;
+    seg[l][tid & 1] = off[(size_t)(line0 + l) * (n_strips + 1) + strip + (tid & 1)];
+  } else if (tid >= 64 && tid < 64 + n_my) {
+    const int l = tid - 64;
+    line_a[l] = CELL_MAJOR ? -inv_s_f[line0 + l] : -mu_f[line0 + l];
+    line_c[l] = CELL_MAJOR ? 0.f : -cent_f[line0 + l];
+  }
+  __syncthreads();
+
+  auto load_patch = [&](int l, uint32_t& t, uint32_t& t_end, uint32_t& pos, float& v) {
+    t = 0; t_end = 0; pos = 0; v = 0.f;
+    if (l < n_my) {
+      t = seg[l][0] + tid;
+      t_end = seg[l][1];
+      if (t < t_end) {
+        pos = idx[t];
+        v = patch[t];
+      }
+    }
+  };
+  auto put = [&](__half* th, __half* tl, uint32_t r, float v) {
+    const __half h = __float2half_rn(v);
+    th[r] = h;
+    if (WITH_LO) tl[r] = __float2half_rn(v - __half2float(h));
+  };
+  auto scatter = [&](__half* th, __half* tl, uint32_t t, uint32_t t_end, uint32_t pos, float v) {
+    if (t < t_end) {
+      put(th, tl, pos - base, v);
+      for (uint32_t u = t + kDenseThreads; u < t_end; u += kDenseThreads) put(th, tl, idx[u] - base, patch[u]);
+    }
+  };
+  auto background = [&](__half* th, __half* tl, int l) {
+    const float a = line_a[l], c = line_c[l];
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = fmaf(a, P[q], CELL_MAJOR ? Q[q] : c);
+    if (!CELL_MAJOR && tail) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (p0 + q >= line_len) f[q] = 0.f;
+    }
+    __align__(16) __half2 h2[4];
+    __align__(16) __half2 l2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      h2[q] = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
+      if (WITH_LO) {
+        const float2 hb = __half22float2(h2[q]);
+        l2[q] = __floats2half2_rn(f[2 * q] - hb.x, f[2 * q + 1] - hb.y);
+      }
+    }
+    *reinterpret_cast<uint4*>(th + tid * kElemsPerThread) = *reinterpret_cast<const uint4*>(h2);
+    if (WITH_LO) *reinterpret_cast<uint4*>(tl + tid * kElemsPerThread) = *reinterpret_cast<const uint4*>(l2);
+  };
+
+  uint32_t t0, e0, q0, t1, e1, q1;
+  float v0, v1;
+  load_patch(0, t0, e0, q0, v0);
+  load_patch(1, t1, e1, q1, v1);
+  int slot = 0;
+  for (int l = 0; l < n_my; l += 2) {
+    __half* th0 = tile_hi + (size_t)(slot * 2) * kStripW;
+    __half* th1 = th0 + kStripW;
+    __half* tl0 = tile_lo + (size_t)(slot * 2) * kStripW;
+    __half* tl1 = tl0 + kStripW;
+    const bool two = l + 1 < n_my;
+    if (active) {
+      background(th0, tl0, l);
+      if (two) background(th1, tl1, l + 1);
+    }
+    __syncthreads();
+    scatter(th0, tl0, t0, e0, q0, v0);
+    scatter(th1, tl1, t1, e1, q1, v1);
+    load_patch(l + 2, t0, e0, q0, v0);
+    load_patch(l + 3, t1, e1, q1, v1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy tile writes -> visible to the bulk copy
+    // the slot the NEXT step composes in was read by the stores committed kRing - 1 steps ago
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kRing - 2) : "memory");
+    __syncthreads();
+    if (tid == 0) {
+      __half* g0 = out_hi + (size_t)(line0 + l) * ld + (size_t)base;
+      bulk_store(g0, th0, bytes);
+      if (two) bulk_store(g0 + ld, th1, bytes);
+      if (WITH_LO) {
+        __half* gl0 = out_lo + (size_t)(line0 + l) * ld + (size_t)base;
+        bulk_store(gl0, tl0, bytes);
+        if (two) bulk_store(gl0 + ld, tl1, bytes);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    slot = slot + 1 == kRing ? 0 : slot + 1;
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until read
+}
+
 // G[i][i] = scale * sumsq[i]
 __global__ void k_set_diagonal(float* __restrict__ G, int n, const double* __restrict__ sumsq, double scale) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -633,6 +813,24 @@ void densify(const SpMat& A, NormStats& S, int layout, size_t ld, __half* out_hi
   }
   const long long ctas = (long long)n_strips * ((n_lines + kLinesPerCta - 1) / kLinesPerCta);
   SCL_REQUIRE(ctas < (1LL << 31), "densify grid too large");
+  if (stat_tune().writer == 1) {   // TMA-store writer
+    const size_t smem = (size_t)kRing * 2 * kStripW * sizeof(__half) * (out_lo ? 2 : 1);
+#define SCL_LAUNCH_TMA(CM, LO)                                                                                         \
+  do {                                                                                                                 \
+    SCL_CUDA(cudaFuncSetAttribute(k_densify_tma<CM, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k_densify_tma<CM, LO><<<(unsigned)ctas, kDenseThreads, smem, st>>>(off.p, idx, cell_major ? S.patch_csr.p : S.patch_csc.p, \
+                                                                    S.inv_s_f.p, S.mu_f.p, S.cent_f.p, n_lines, line_len, \
+                                                                    ld, n_strips, (int)pos0, (int)pos1, out_hi, out_lo); \
+  } while (0)
+    if (cell_major) {
+      if (out_lo) SCL_LAUNCH_TMA(true, true); else SCL_LAUNCH_TMA(true, false);
+    } else {
+      if (out_lo) SCL_LAUNCH_TMA(false, true); else SCL_LAUNCH_TMA(false, false);
+    }
+#undef SCL_LAUNCH_TMA
+    SCL_CUDA(cudaGetLastError());
+    return;
+  }
 #define SCL_LAUNCH_DENSIFY(CM, LO)                                                                               \
   k_densify<CM, LO><<<(unsigned)ctas, kDenseThreads, 0, st>>>(off.p, idx, cell_major ? S.patch_csr.p : S.patch_csc.p, \
                                                              S.inv_s_f.p, S.mu_f.p, S.cent_f.p, n_lines, line_len, \

@@ -24,6 +24,13 @@ KEYS = [
 ]
 
 
+# extra columns picked by pattern: issue-slot use, per-pipe instruction shares, warp stall reasons (non-zero ones)
+EXTRA = re.compile(r"smsp__issue_active\.avg\.pct|smsp__inst_executed\.sum$|sm__inst_executed_pipe_[a-z0-9_]+\.avg\.pct_of_peak_sustained_active|"
+                   r"sm__pipe_[a-z0-9_]+_cycles_active\.avg\.pct_of_peak_sustained_active|"
+                   r"smsp__average_warps?_issue_stalled_[a-z_]+_per_issue_active|smsp__average_warp_latency_issue_stalled_[a-z_]+|"
+                   r"l1tex__data_bank_conflicts_pipe_lsu\.sum$|smsp__warps_eligible\.avg\.per_cycle_active|achieved_occupancy")
+
+
 def short(name: str) -> str:
     name = re.sub(r"\(.*", "", name)
     name = re.sub(r"^void ", "", name)
@@ -71,6 +78,14 @@ def full(path: str, out: str) -> None:
             for k in KEYS:
                 if k in col:
                     f.write(f"| {k} | {r[col[k]]} | {units[col[k]]} |\n")
+            for k in hdr:
+                if k not in KEYS and EXTRA.search(k):
+                    try:
+                        v = float(r[col[k]].replace(",", ""))
+                    except ValueError:
+                        continue
+                    if abs(v) >= 0.05:
+                        f.write(f"| {k} | {r[col[k]]} | {units[col[k]]} |\n")
             f.write("\n")
     print(open(out).read())
 

@@ -105,7 +105,9 @@ def test_gram_syrk(h, h1, rows, K, cg, split):
     assert np.array_equal(G, G.T)       # mirrored store: exactly symmetric
 
 
-@pytest.mark.parametrize("N,M", [(500, 800), (900, 400), (2301, 4700)])   # the last spans several writer strips
+# (2301, 4700) spans several writer strips and has gene lines above the CTA-per-line threshold of the statistics
+# passes; (260, 20000) has cell lines above it
+@pytest.mark.parametrize("N,M", [(500, 800), (900, 400), (2301, 4700), (260, 20000)])
 @pytest.mark.parametrize("layout", [0, 1])
 def test_normalize_matches_oracle(h, N, M, layout):
     X = make_counts(N, M, seed=11, K=4, de_prob=0.3, lfc_sd=1.5)
