@@ -206,9 +206,11 @@ SCL_API int32_t scl_op_scores(scl_handle* h, int32_t N, int32_t k, int32_t min_p
 SCL_API int32_t scl_bench_gram(scl_handle* h, int32_t rows, int64_t K, int32_t mode, int32_t chunk_kb, int32_t reps,
                        double* ms_avg, double* checksum);
 /* Normalisation kernels on the handle's counts (:677-696): statistics pre-passes and the fused densify writer. */
-/* Tuning studies only (process-wide): launch shape of the statistics line passes (variant 0..3), line length above
- * which a whole CTA takes a line, dense writer (0: register/overlay writer, 1: TMA bulk-store writer).  Negative /
- * zero arguments keep the current value.  Results are identical for every setting. */
+/* Tuning studies only (process-wide).  stat_variant: launch shape of the statistics passes (0-7: line passes,
+ * 8: strip passes; < 0 keeps the current one).  stat_heavy: line length above which a whole CTA takes a line
+ * (<= 0 keeps).  writer: dense writer, -1 automatic, 0 register/overlay writer, 1 TMA bulk-store writer, 2 / 3
+ * TMA bulk-store writer with one / two cp.async-staged entries per thread and line (<= -2 keeps).  Results are
+ * identical for every setting. */
 SCL_API int32_t scl_debug_set_tuning(int32_t stat_variant, int32_t stat_heavy, int32_t writer);
 SCL_API int32_t scl_bench_normalize(scl_handle* h, int32_t layout, int32_t with_lo, int32_t reps, double* ms_stats,
                             double* ms_densify, double* alg_bytes_densify);

@@ -96,6 +96,12 @@ struct NormStats {
   // gene-major / cell-major layout, computed on first use (ensure_patch)
   DBuf<float> patch_csc, patch_csr;
   bool have_patch[2] = {false, false};
+  // strip passes: offsets of every line's entries inside every strip, [0] gene lines (CSC) x cell strips, [1] cell
+  // lines (CSR) x gene strips (shared with the dense writer), and the per-(line, strip) partial sums
+  DBuf<uint32_t> off[2];
+  int off_strips[2] = {0, 0};
+  bool off_valid[2] = {false, false};
+  DBuf<double> strip_partial;
   void reserve(size_t nnz_cap) {
     patch_csc.ensure(nnz_cap); patch_csr.ensure(nnz_cap);
   }

@@ -36,6 +36,32 @@ __device__ __forceinline__ double block_sum(double v, double* red /* >= 32 */) {
   return s;
 }
 
+// ---- strips ------------------------------------------------------------------------------------
+// The dense writer and the strip passes tile a matrix into strips of kStripW positions (cells for gene lines, genes
+// for cell lines); k_strip_offsets locates every line's entries inside every strip.
+static constexpr int kElemsPerThread = 8;
+static constexpr int kStripW = kDenseThreads * kElemsPerThread;   // 2048 positions
+static constexpr int kLinesPerCta = 32;
+// overlay slot of strip-relative position r: thread r/8 reads its positions as two conflict-free float4 planes
+__device__ __forceinline__ uint32_t slot_of(uint32_t r) { return ((r & 4u) ? (uint32_t)(kStripW / 2) : 0u) + ((r >> 3) << 2) + (r & 3u); }
+
+// off[line * (n_strips + 1) + s] = first entry of the line at position >= pos0 + s * kStripW
+__global__ void k_strip_offsets(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx, int n_lines,
+                                int n_strips, int pos0, uint32_t* __restrict__ off) {
+  const long long total = (long long)n_lines * (n_strips + 1);
+  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+    const int line = (int)(w / (n_strips + 1)), s = (int)(w % (n_strips + 1));
+    const uint32_t target = (uint32_t)pos0 + (uint32_t)s * (uint32_t)kStripW;
+    uint32_t lo = ptr[line], hi = ptr[line + 1];
+    while (lo < hi) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (idx[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    off[w] = lo;
+  }
+}
+
+
 // ---- log1p on [0, 1] -------------------------------------------------------------------------
 // u = x_ij / r_i lies in (0, 1] and is almost always tiny (a count over a cell's total).  log1p(u) = 2 atanh(s),
 // s = u / (2 + u): for u <= 1/16, s^2 <= 9.2e-4 and the odd series truncated after s^13 is exact to < 1e-22
@@ -43,7 +69,18 @@ __device__ __forceinline__ double block_sum(double v, double* red /* >= 32 */) {
 // Float64 instructions of the library log1p; the statistics passes re-evaluate it instead of storing y per entry.
 __device__ __forceinline__ double log1p_unit(double u) {
   if (!(fabs(u) <= 0.0625)) return log1p(u);
-  const double s = u / (2.0 + u), w = s * s;
+  // s = u / d, d = 2 + u in [1.9375, 2.0625]: hardware reciprocal seed (2^-23), two Newton steps (-> below 2^-53),
+  // one residual correction of the quotient; no special cases can occur, so none of the library division's guards
+  const double d = 2.0 + u;
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  double s = u * r;
+  s = fma(fma(-d, s, u), r, s);
+  const double w = s * s;
   double p = 1.0 / 13.0;
   p = fma(p, w, 1.0 / 11.0);
   p = fma(p, w, 1.0 / 9.0);
@@ -120,7 +157,48 @@ __device__ __forceinline__ void line_span(const Op& op, const typename Op::Ctx& 
   }
 }
 
-template <class Op, int U, int MINB>
+// Three-stage variant: the (index, value) stream runs two steps ahead and the gathers one step ahead of the Float64
+// arithmetic, so neither the HBM latency of the stream nor the L2 latency of the gathers is waited for in a step.
+template <class Op, int U>
+__device__ __forceinline__ void line_span_deep(const Op& op, const typename Op::Ctx& cx, uint32_t b, uint32_t e, int first,
+                                               int stride, double (&acc)[Op::NACC]) {
+  uint32_t t = b + first;
+  const uint32_t step = (uint32_t)stride * U;
+  float va[U], vb[U], vc[U];
+  uint32_t ib[U], ic[U];
+  typename Op::Ld la[U], lb[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint32_t t0 = t + stride * u, t1 = t0 + step;
+    const bool ok0 = t0 < e, ok1 = t1 < e;
+    const uint32_t i0 = ok0 ? op.idx[t0] : 0u;
+    va[u] = ok0 ? op.val[t0] : 0.f;
+    ib[u] = ok1 ? op.idx[t1] : 0u;
+    vb[u] = ok1 ? op.val[t1] : 0.f;
+    op.gather(i0, la[u]);
+  }
+  while (t < e) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t t2 = t + 2 * step + stride * u;
+      const bool ok = t2 < e;
+      ic[u] = ok ? op.idx[t2] : 0u;
+      vc[u] = ok ? op.val[t2] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) op.gather(ib[u], lb[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t tt = t + stride * u;
+      if (tt < e) op.accum(tt, cx, va[u], la[u], acc);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { va[u] = vb[u]; la[u] = lb[u]; vb[u] = vc[u]; ib[u] = ic[u]; }
+    t += step;
+  }
+}
+
+template <class Op, int U, int MINB, bool DEEP = false>
 __global__ void __launch_bounds__(kStatThreads, MINB) k_lines(const Op op, const uint32_t* __restrict__ ptr, int n_lines,
                                                               int reversed, uint32_t kHeavyLine) {
   __shared__ double red[Op::NACC][kStatThreads / 32];
@@ -134,7 +212,7 @@ __global__ void __launch_bounds__(kStatThreads, MINB) k_lines(const Op op, const
     double acc[Op::NACC];
 #pragma unroll
     for (int a = 0; a < Op::NACC; ++a) acc[a] = 0;
-    line_span<Op, U>(op, cx, b, e, lane, 32, acc);
+    if (DEEP) line_span_deep<Op, U>(op, cx, b, e, lane, 32, acc); else line_span<Op, U>(op, cx, b, e, lane, 32, acc);
 #pragma unroll
     for (int a = 0; a < Op::NACC; ++a) acc[a] = warp_sum(acc[a]);
     if (lane == 0) op.finish(line, cx, acc);
@@ -148,7 +226,7 @@ __global__ void __launch_bounds__(kStatThreads, MINB) k_lines(const Op op, const
     double acc[Op::NACC];
 #pragma unroll
     for (int a = 0; a < Op::NACC; ++a) acc[a] = 0;
-    line_span<Op, U>(op, cx, b, e, tid, kStatThreads, acc);
+    if (DEEP) line_span_deep<Op, U>(op, cx, b, e, tid, kStatThreads, acc); else line_span<Op, U>(op, cx, b, e, tid, kStatThreads, acc);
 #pragma unroll
     for (int a = 0; a < Op::NACC; ++a) acc[a] = warp_sum(acc[a]);
     __syncthreads();
@@ -320,6 +398,159 @@ struct CellFinishOp {
   }
 };
 
+// ---- strip passes -----------------------------------------------------------------------------
+// The line passes above gather one 32-byte L2 sector per stored entry (the other side's parameters): 3.5 GB of L2
+// traffic per pass at 68k x 20k beside 0.9 GB of streamed entries, which is what bounds them (measured: 9 TB/s of L2
+// sectors at 1.8 TB/s of HBM).  A strip pass tiles the same work the way the dense writer does: a CTA owns a strip
+// of kStripW positions for a block of lines, copies the strip's parameters into shared memory once (16-24 bytes per
+// position) and walks the lines' segments inside the strip (found with the writer's strip-offset table), one warp
+// per segment, gathering from shared memory.  Per-(line, strip) partial sums go to a small table that a finishing
+// kernel adds in strip order - deterministic, and balanced because a unit of work is at most kStripW entries.
+static constexpr int kStripLines = 64;    // lines per CTA
+
+template <class Op>
+__global__ void __launch_bounds__(kStatThreads, 4)
+k_strips(const Op op, const uint32_t* __restrict__ off, int n_lines, int line_len, int n_strips, int reversed,
+         double* __restrict__ partial) {
+  extern __shared__ __align__(16) double strip_par[];   // [Op::NPAR][kStripW]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int strip = blockIdx.x % n_strips;
+  const int lb = blockIdx.x / n_strips;
+  const int base = strip * kStripW;
+  for (int i = tid; i < kStripW; i += kStatThreads) op.stage(strip_par, i, min(base + i, line_len - 1));
+  __syncthreads();
+  constexpr int U = 4;
+  for (int k = warp; k < kStripLines; k += kStatThreads / 32) {
+    const int li = lb * kStripLines + k;
+    if (li >= n_lines) break;
+    const int line = reversed ? n_lines - 1 - li : li;
+    const uint32_t b = off[(size_t)line * (n_strips + 1) + strip], e = off[(size_t)line * (n_strips + 1) + strip + 1];
+    double acc[Op::NACC];
+#pragma unroll
+    for (int a = 0; a < Op::NACC; ++a) acc[a] = 0;
+    if (b < e) {
+      const typename Op::Ctx cx = op.begin(line);
+      uint32_t t = b + lane;
+      uint32_t idx[U], nidx[U];
+      float v[U], nv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t tt = t + 32 * u;
+        const bool ok = tt < e;
+        idx[u] = ok ? op.idx[tt] : (uint32_t)base;
+        v[u] = ok ? op.val[tt] : 0.f;
+      }
+      while (t < e) {
+        const uint32_t tn = t + 32 * U;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t tt = tn + 32 * u;
+          const bool ok = tt < e;
+          nidx[u] = ok ? op.idx[tt] : (uint32_t)base;
+          nv[u] = ok ? op.val[tt] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t tt = t + 32 * u;
+          if (tt < e) op.accum(tt, cx, v[u], strip_par, idx[u] - (uint32_t)base, acc);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { idx[u] = nidx[u]; v[u] = nv[u]; }
+        t = tn;
+      }
+    }
+    if (Op::NACC_OUT > 0) {
+#pragma unroll
+      for (int a = 0; a < Op::NACC; ++a) acc[a] = warp_sum(acc[a]);
+      if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < Op::NACC_OUT; ++a) partial[((size_t)a * n_strips + strip) * n_lines + line] = acc[a];
+      }
+    }
+  }
+}
+
+// per-line sums = partial sums added in strip order, then the pass's closing formula
+template <class Op>
+__global__ void k_strips_finish(const Op op, const double* __restrict__ partial, int n_lines, int n_strips) {
+  const int line = blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= n_lines) return;
+  double acc[Op::NACC];
+#pragma unroll
+  for (int a = 0; a < Op::NACC; ++a) {
+    double t = 0;
+    for (int s = 0; s < n_strips; ++s) t += partial[((size_t)a * n_strips + s) * n_lines + line];
+    acc[a] = t;
+  }
+  op.finish(line, op.begin(line), acc);
+}
+
+// The strip versions of the five passes: same arithmetic and closing formulas as the line-pass operators (which they
+// wrap), parameters read from the CTA's shared-memory copy.
+struct SGeneStatsOp : GeneStatsOp {
+  static constexpr int NPAR = 1, NACC_OUT = NACC;
+  __device__ __forceinline__ void stage(double* sp, int i, int pos) const { sp[i] = cell_par[pos].x; }
+  __device__ __forceinline__ void accum(uint32_t t, const Ctx& cx, float v, const double* sp, uint32_t r, double (&acc)[NACC]) const {
+    Ld l;
+    l.inv_r = sp[r];
+    GeneStatsOp::accum(t, cx, v, l, acc);
+  }
+};
+struct SCellL2Op : CellL2Op {
+  static constexpr int NPAR = 2, NACC_OUT = NACC;
+  __device__ __forceinline__ void stage(double* sp, int i, int pos) const {
+    const double2 g = *reinterpret_cast<const double2*>(&gene_par[pos]);
+    sp[i] = g.x;
+    sp[kStripW + i] = g.y;
+  }
+  __device__ __forceinline__ void accum(uint32_t t, const Ctx& cx, float v, const double* sp, uint32_t r, double (&acc)[NACC]) const {
+    Ld l;
+    l.inv_sd = sp[r];
+    l.mu = sp[kStripW + r];
+    CellL2Op::accum(t, cx, v, l, acc);
+  }
+};
+struct SGeneCenterOp : GeneCenterOp {
+  static constexpr int NPAR = 2, NACC_OUT = NACC;
+  __device__ __forceinline__ void stage(double* sp, int i, int pos) const {
+    const double2 c = cell_par[pos];
+    sp[i] = c.x;
+    sp[kStripW + i] = c.y;
+  }
+  __device__ __forceinline__ void accum(uint32_t t, const Ctx& cx, float v, const double* sp, uint32_t r, double (&acc)[NACC]) const {
+    Ld l;
+    l.c = make_double2(sp[r], sp[kStripW + r]);
+    GeneCenterOp::accum(t, cx, v, l, acc);
+  }
+};
+struct SGenePatchOp : GenePatchOp {
+  static constexpr int NPAR = 2, NACC_OUT = 0;
+  __device__ __forceinline__ void stage(double* sp, int i, int pos) const {
+    const double2 c = cell_par[pos];
+    sp[i] = c.x;
+    sp[kStripW + i] = c.y;
+  }
+  __device__ __forceinline__ void accum(uint32_t t, const Ctx& cx, float v, const double* sp, uint32_t r, double (&acc)[NACC]) const {
+    Ld l;
+    l.c = make_double2(sp[r], sp[kStripW + r]);
+    GenePatchOp::accum(t, cx, v, l, acc);
+  }
+};
+struct SCellFinishOp : CellFinishOp {
+  static constexpr int NPAR = 3, NACC_OUT = NACC;
+  __device__ __forceinline__ void stage(double* sp, int i, int pos) const {
+    const double4 g = gene_par[pos];
+    sp[i] = g.x;
+    sp[kStripW + i] = g.y;
+    sp[2 * kStripW + i] = g.z;
+  }
+  __device__ __forceinline__ void accum(uint32_t t, const Ctx& cx, float v, const double* sp, uint32_t r, double (&acc)[NACC]) const {
+    Ld l;
+    l.g = make_double4(sp[r], sp[kStripW + r], sp[2 * kStripW + r], 0.0);
+    CellFinishOp::accum(t, cx, v, l, acc);
+  }
+};
+
 // ---- small deterministic reductions over the per-line vectors ---------------------------------
 // Each block reduces a strided slice with a fixed tree and writes its partial sums; the block that finishes last
 // adds the partials in block order and derives the scalars, so the result does not depend on scheduling.
@@ -400,7 +631,7 @@ __global__ void k_inv_s(const double* __restrict__ l2, const double* __restrict_
 struct StatTune { int variant; uint32_t heavy; int writer; };
 static StatTune& stat_tune() {
   static StatTune t = [] {
-    StatTune x{0, 4096u, 0};
+    StatTune x{4, 4096u, -1};   // writer -1: automatic (staged TMA-store writer for hi-only output, overlay writer with lo)
     if (const char* v = getenv("SCL_STAT_VARIANT")) x.variant = atoi(v);
     if (const char* v = getenv("SCL_STAT_HEAVY")) x.heavy = (uint32_t)atoi(v);
     if (const char* v = getenv("SCL_DENSIFY")) x.writer = atoi(v);
@@ -413,7 +644,7 @@ void set_norm_tuning(int stat_variant, int stat_heavy, int writer) {
   StatTune& t = stat_tune();
   if (stat_variant >= 0) t.variant = stat_variant;
   if (stat_heavy > 0) t.heavy = (uint32_t)stat_heavy;
-  if (writer >= 0) t.writer = writer;
+  if (writer >= -1) t.writer = writer;
 }
 template <class Op>
 static void launch_lines(const Op& op, const uint32_t* ptr, int n_lines, int reversed, cudaStream_t st) {
@@ -423,8 +654,67 @@ static void launch_lines(const Op& op, const uint32_t* ptr, int n_lines, int rev
     case 1: k_lines<Op, 4, 3><<<grid(3), kStatThreads, 0, st>>>(op, ptr, n_lines, reversed, t.heavy); break;
     case 2: k_lines<Op, 8, 2><<<grid(2), kStatThreads, 0, st>>>(op, ptr, n_lines, reversed, t.heavy); break;
     case 3: k_lines<Op, 2, 4><<<grid(4), kStatThreads, 0, st>>>(op, ptr, n_lines, reversed, t.heavy); break;
+    case 4: k_lines<Op, 4, 3, true><<<grid(3), kStatThreads, 0, st>>>(op, ptr, n_lines, reversed, t.heavy); break;
+    case 5: k_lines<Op, 2, 4, true><<<grid(4), kStatThreads, 0, st>>>(op, ptr, n_lines, reversed, t.heavy); break;
+    case 6: k_lines<Op, 4, 4, true><<<grid(4), kStatThreads, 0, st>>>(op, ptr, n_lines, reversed, t.heavy); break;
+    case 7: k_lines<Op, 4, 2, true><<<grid(2), kStatThreads, 0, st>>>(op, ptr, n_lines, reversed, t.heavy); break;
     default: k_lines<Op, 4, 4><<<grid(4), kStatThreads, 0, st>>>(op, ptr, n_lines, reversed, t.heavy); break;
   }
+}
+
+template <class Op>
+static void launch_strips(const Op& op, const uint32_t* off, int n_lines, int line_len, int n_strips, int reversed,
+                          double* partial, cudaStream_t st) {
+  const int blocks = (n_lines + kStripLines - 1) / kStripLines;
+  const size_t smem = (size_t)Op::NPAR * kStripW * sizeof(double);
+  count_launches(Op::NACC_OUT > 0 ? 2 : 1);
+  k_strips<Op><<<(unsigned)(blocks * n_strips), kStatThreads, smem, st>>>(op, off, n_lines, line_len, n_strips, reversed, partial);
+  if (Op::NACC_OUT > 0) k_strips_finish<Op><<<(n_lines + 255) / 256, 256, 0, st>>>(op, partial, n_lines, n_strips);
+}
+
+// strip offsets of both orientations (kept for the dense writer) and the partial-sum table
+static void prepare_strips(const SpMat& A, NormStats& S, cudaStream_t st) {
+  const int N = A.N, M = A.M;
+  const int ns_c = (N + kStripW - 1) / kStripW, ns_r = (M + kStripW - 1) / kStripW;   // strips along cells / along genes
+  S.off[0].ensure((size_t)M * (ns_c + 1));
+  S.off[1].ensure((size_t)N * (ns_r + 1));
+  S.strip_partial.ensure((size_t)3 * std::max((size_t)M * ns_c, (size_t)N * ns_r));
+  count_launches(2);
+  {
+    const long long total = (long long)M * (ns_c + 1);
+    k_strip_offsets<<<(int)std::min<long long>((total + 255) / 256, 148LL * 16), 256, 0, st>>>(A.colptr.p, A.rowval.p, M, ns_c, 0, S.off[0].p);
+  }
+  {
+    const long long total = (long long)N * (ns_r + 1);
+    k_strip_offsets<<<(int)std::min<long long>((total + 255) / 256, 148LL * 16), 256, 0, st>>>(A.rowptr.p, A.colidx.p, N, ns_r, 0, S.off[1].p);
+  }
+  S.off_strips[0] = ns_c;
+  S.off_strips[1] = ns_r;
+  S.off_valid[0] = S.off_valid[1] = true;
+}
+
+static void compute_norm_stats_strips(const SpMat& A, NormStats& S, cudaStream_t st) {
+  const int N = A.N, M = A.M;
+  prepare_strips(A, S, st);
+  const int ns_c = S.off_strips[0], ns_r = S.off_strips[1];
+  count_launches(4);
+  const int wgrid = min((N + 7) / 8, 148 * 8);
+  k_row_sum<<<wgrid, 256, 0, st>>>(A.rowptr.p, A.rval.p, N, S.tgc.p, S.cell_par.p);
+  SGeneStatsOp gs;
+  static_cast<GeneStatsOp&>(gs) = GeneStatsOp{A.rowval.p, A.val.p, S.cell_par.p, N, S.ybar.p, S.sigma.p, S.mu.p, S.mu_f.p,
+                                              S.inv_sigma_f.p, S.gene_par.p};
+  launch_strips(gs, S.off[0].p, M, N, ns_c, 1, S.strip_partial.p, st);
+  k_reduce_vec<0><<<kRedBlocks, 256, 0, st>>>(S.mu.p, nullptr, M, S.red_partial.p, S.red_counter.p, S.scalars.p);
+  SCellL2Op cl;
+  static_cast<CellL2Op&>(cl) = CellL2Op{A.colidx.p, A.rval.p, S.cell_par.p, S.gene_par.p, S.scalars.p, S.l2.p};
+  launch_strips(cl, S.off[1].p, N, M, ns_r, 0, S.strip_partial.p, st);
+  k_reduce_vec<1><<<kRedBlocks, 256, 0, st>>>(S.l2.p, nullptr, N, S.red_partial.p, S.red_counter.p, S.scalars.p);
+  k_inv_s<<<(N + 255) / 256, 256, 0, st>>>(S.l2.p, S.scalars.p, N, S.inv_s.p, S.inv_s_f.p, S.cell_par.p);
+  SGeneCenterOp gc;
+  static_cast<GeneCenterOp&>(gc) = GeneCenterOp{A.rowval.p, A.val.p, S.cell_par.p, S.scalars.p, N, S.gene_par.p, S.cent.p,
+                                                S.sumsq_gene.p, S.cent_f.p};
+  launch_strips(gc, S.off[0].p, M, N, ns_c, 1, S.strip_partial.p, st);
+  SCL_CUDA(cudaGetLastError());
 }
 
 void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st) {
@@ -442,6 +732,11 @@ void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st) {
     SCL_CUDA(cudaMemsetAsync(S.red_counter.p, 0, sizeof(unsigned int), st));
   }
   S.have_patch[0] = S.have_patch[1] = false;
+  S.off_valid[0] = S.off_valid[1] = false;
+  if (stat_tune().variant == 8) {
+    compute_norm_stats_strips(A, S, st);
+    return;
+  }
   count_launches(7);
   const int wgrid = min((N + 7) / 8, 148 * 8);
   k_row_sum<<<wgrid, 256, 0, st>>>(A.rowptr.p, A.rval.p, N, S.tgc.p, S.cell_par.p);
@@ -464,6 +759,25 @@ void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st) {
 void ensure_patch(const SpMat& A, NormStats& S, int layout, cudaStream_t st) {
   SCL_REQUIRE(layout == 0 || layout == 1, "layout must be 0 or 1");
   if (S.have_patch[layout]) return;
+  if (stat_tune().variant == 8 && S.off_valid[0] && S.off_valid[1]) {
+    if (layout == 0) {
+      S.patch_csc.ensure(A.nnz);
+      SGenePatchOp gp;
+      static_cast<GenePatchOp&>(gp) = GenePatchOp{A.rowval.p, A.val.p, S.cell_par.p, S.gene_par.p, S.patch_csc.p};
+      launch_strips(gp, S.off[0].p, A.M, A.N, S.off_strips[0], 1, S.strip_partial.p, st);
+    } else {
+      S.patch_csr.ensure(A.nnz);
+      count_launches(1);
+      k_reduce_vec<2><<<kRedBlocks, 256, 0, st>>>(S.mu.p, S.cent.p, A.M, S.red_partial.p, S.red_counter.p, S.scalars.p);
+      SCellFinishOp cf;
+      static_cast<CellFinishOp&>(cf) = CellFinishOp{A.colidx.p, A.rval.p, S.cell_par.p, S.gene_par.p, S.scalars.p, S.patch_csr.p,
+                                                    S.sumsq_cell.p};
+      launch_strips(cf, S.off[1].p, A.N, A.M, S.off_strips[1], 0, S.strip_partial.p, st);
+    }
+    SCL_CUDA(cudaGetLastError());
+    S.have_patch[layout] = true;
+    return;
+  }
   if (layout == 0) {
     S.patch_csc.ensure(A.nnz);
     count_launches(1);
@@ -487,28 +801,6 @@ void ensure_patch(const SpMat& A, NormStats& S, int layout, cudaStream_t st) {
 // one barrier per line; the next line's patch loads are in flight while the current line is written).  Every
 // thread emits one 16-byte store per line and matrix (hi, optional lo), 512 contiguous bytes per warp.
 // CELL_MAJOR=false: line = gene j (CSC), positions = cells; CELL_MAJOR=true: line = cell i (CSR), positions = genes.
-static constexpr int kElemsPerThread = 8;
-static constexpr int kStripW = kDenseThreads * kElemsPerThread;   // 2048 positions
-static constexpr int kLinesPerCta = 32;
-// overlay slot of strip-relative position r: thread r/8 reads its positions as two conflict-free float4 planes
-__device__ __forceinline__ uint32_t slot_of(uint32_t r) { return ((r & 4u) ? (uint32_t)(kStripW / 2) : 0u) + ((r >> 3) << 2) + (r & 3u); }
-
-// off[line * (n_strips + 1) + s] = first entry of the line at position >= pos0 + s * kStripW
-__global__ void k_strip_offsets(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx, int n_lines,
-                                int n_strips, int pos0, uint32_t* __restrict__ off) {
-  const long long total = (long long)n_lines * (n_strips + 1);
-  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
-    const int line = (int)(w / (n_strips + 1)), s = (int)(w % (n_strips + 1));
-    const uint32_t target = (uint32_t)pos0 + (uint32_t)s * (uint32_t)kStripW;
-    uint32_t lo = ptr[line], hi = ptr[line + 1];
-    while (lo < hi) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (idx[mid] < target) lo = mid + 1; else hi = mid;
-    }
-    off[w] = lo;
-  }
-}
-
 template <bool CELL_MAJOR, bool WITH_LO>
 __global__ void __launch_bounds__(kDenseThreads)
 k_densify(const uint32_t* __restrict__ off, const uint32_t* __restrict__ idx, const float* __restrict__ patch,
@@ -772,6 +1064,155 @@ k_densify_tma(const uint32_t* __restrict__ off, const uint32_t* __restrict__ idx
   if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until read
 }
 
+// ---- TMA-store writer with staged patches ---------------------------------------------------------
+// As k_densify_tma, but the (position, value) pairs of a line's strip reach the scatter through shared memory:
+// every thread requests its own entries of the NEXT step's lines with 4-byte cp.async copies at the top of a step
+// (up to KP entries per thread and line, i.e. KP * 256 entries per strip-line; lines denser than that take the
+// direct path for the remainder) and reads them back a full step later, after cp.async.wait_group - no register
+// scoreboard is held across the step and no thread waits for another's loads.
+template <bool CELL_MAJOR, bool WITH_LO, int KP>
+__global__ void __launch_bounds__(kDenseThreads)
+k_densify_tma2(const uint32_t* __restrict__ off, const uint32_t* __restrict__ idx, const float* __restrict__ patch,
+               const float* __restrict__ inv_s_f, const float* __restrict__ mu_f, const float* __restrict__ cent_f,
+               int n_lines, int line_len, size_t ld, int n_strips, int pos0, int pos1, __half* __restrict__ out_hi,
+               __half* __restrict__ out_lo) {
+  extern __shared__ __align__(128) unsigned char dens_smem[];
+  __half* tile_hi = reinterpret_cast<__half*>(dens_smem);                              // [kRing][2][kStripW]
+  __half* tile_lo = tile_hi + (WITH_LO ? kRing * 2 * kStripW : 0);                     // [kRing][2][kStripW]
+  uint32_t* st_idx = reinterpret_cast<uint32_t*>(tile_lo + kRing * 2 * kStripW);       // [2][2][KP][256]
+  float* st_val = reinterpret_cast<float*>(st_idx + 2 * 2 * KP * kDenseThreads);       // [2][2][KP][256]
+  __shared__ uint32_t seg[kLinesPerCta + 2][2];
+  __shared__ float line_a[kLinesPerCta], line_c[kLinesPerCta];
+  const int tid = threadIdx.x;
+  const int strip = blockIdx.x % n_strips;
+  const int line0 = (blockIdx.x / n_strips) * kLinesPerCta;
+  const int line1 = min(n_lines, line0 + kLinesPerCta);
+  const int n_my = line1 - line0;
+  const int base = pos0 + strip * kStripW;
+  const int p0 = base + tid * kElemsPerThread;
+  const bool active = p0 < pos1;
+  const uint32_t bytes = (uint32_t)(min(kStripW, pos1 - base)) * 2u;
+  float P[kElemsPerThread], Q[kElemsPerThread];
+  bool tail = false;
+#pragma unroll
+  for (int q = 0; q < kElemsPerThread; ++q) {
+    const int pos = p0 + q;
+    const bool ok = pos < line_len;
+    tail |= !ok;
+    if (CELL_MAJOR) {
+      P[q] = ok ? mu_f[pos] : 0.f;
+      Q[q] = ok ? -cent_f[pos] : 0.f;
+    } else {
+      P[q] = ok ? inv_s_f[pos] : 0.f;
+      Q[q] = 0.f;
+    }
+  }
+  if (tid < 2 * (kLinesPerCta + 2)) {
+    const int l = tid >> 1;
+    seg[l][tid & 1] = l < n_my ? off[(size_t)(line0 + l) * (n_strips + 1) + strip + (tid & 1)] : 0u;   // empty beyond n_my
+  } else if (tid >= 96 && tid < 96 + n_my) {
+    const int l = tid - 96;
+    line_a[l] = CELL_MAJOR ? -inv_s_f[line0 + l] : -mu_f[line0 + l];
+    line_c[l] = CELL_MAJOR ? 0.f : -cent_f[line0 + l];
+  }
+  __syncthreads();
+
+  // this thread's entries of lines l, l+1 -> staging buffer sb (one cp.async group per call, possibly empty)
+  auto stage = [&](int l, int sb) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t tb = seg[l + j][0], te = seg[l + j][1];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        const uint32_t t = tb + tid + k * kDenseThreads;
+        if (t < te) {
+          const int slot = ((sb * 2 + j) * KP + k) * kDenseThreads + tid;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(st_idx + slot)),
+                       "l"(idx + t) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(st_val + slot)),
+                       "l"(patch + t) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto put = [&](__half* th, __half* tl, uint32_t r, float v) {
+    const __half h = __float2half_rn(v);
+    th[r] = h;
+    if (WITH_LO) tl[r] = __float2half_rn(v - __half2float(h));
+  };
+  auto scatter = [&](__half* th, __half* tl, int l, int j, int sb) {
+    const uint32_t tb = seg[l + j][0], te = seg[l + j][1];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const uint32_t t = tb + tid + k * kDenseThreads;
+      if (t < te) {
+        const int slot = ((sb * 2 + j) * KP + k) * kDenseThreads + tid;
+        put(th, tl, st_idx[slot] - base, st_val[slot]);
+      }
+    }
+    for (uint32_t t = tb + tid + KP * kDenseThreads; t < te; t += kDenseThreads) put(th, tl, idx[t] - base, patch[t]);
+  };
+  auto background = [&](__half* th, __half* tl, int l) {
+    const float a = line_a[l], c = line_c[l];
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = fmaf(a, P[q], CELL_MAJOR ? Q[q] : c);
+    if (!CELL_MAJOR && tail) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (p0 + q >= line_len) f[q] = 0.f;
+    }
+    __align__(16) __half2 h2[4];
+    __align__(16) __half2 l2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      h2[q] = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
+      if (WITH_LO) {
+        const float2 hb = __half22float2(h2[q]);
+        l2[q] = __floats2half2_rn(f[2 * q] - hb.x, f[2 * q + 1] - hb.y);
+      }
+    }
+    *reinterpret_cast<uint4*>(th + tid * kElemsPerThread) = *reinterpret_cast<const uint4*>(h2);
+    if (WITH_LO) *reinterpret_cast<uint4*>(tl + tid * kElemsPerThread) = *reinterpret_cast<const uint4*>(l2);
+  };
+
+  stage(0, 0);
+  int slot = 0, sb = 0;
+  for (int l = 0; l < n_my; l += 2, sb ^= 1) {
+    stage(l + 2, sb ^ 1);     // lines beyond n_my have empty segments: an empty group
+    __half* th0 = tile_hi + (size_t)(slot * 2) * kStripW;
+    __half* th1 = th0 + kStripW;
+    __half* tl0 = tile_lo + (size_t)(slot * 2) * kStripW;
+    __half* tl1 = tl0 + kStripW;
+    const bool two = l + 1 < n_my;
+    if (active) {
+      background(th0, tl0, l);
+      if (two) background(th1, tl1, l + 1);
+    }
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // this step's staged entries (all but the newest group) have landed
+    __syncthreads();
+    scatter(th0, tl0, l, 0, sb);
+    scatter(th1, tl1, l, 1, sb);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kRing - 2) : "memory");
+    __syncthreads();
+    if (tid == 0) {
+      __half* g0 = out_hi + (size_t)(line0 + l) * ld + (size_t)base;
+      bulk_store(g0, th0, bytes);
+      if (two) bulk_store(g0 + ld, th1, bytes);
+      if (WITH_LO) {
+        __half* gl0 = out_lo + (size_t)(line0 + l) * ld + (size_t)base;
+        bulk_store(gl0, tl0, bytes);
+        if (two) bulk_store(gl0 + ld, tl1, bytes);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    slot = slot + 1 == kRing ? 0 : slot + 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // G[i][i] = scale * sumsq[i]
 __global__ void k_set_diagonal(float* __restrict__ G, int n, const double* __restrict__ sumsq, double scale) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -805,15 +1246,42 @@ void densify(const SpMat& A, NormStats& S, int layout, size_t ld, __half* out_hi
   const int n_strips = (int)((pos1 - pos0 + kStripW - 1) / kStripW);
   const uint32_t* ptr = cell_major ? A.rowptr.p : A.colptr.p;
   const uint32_t* idx = cell_major ? A.colidx.p : A.rowval.p;
-  Tmp<uint32_t> off((size_t)n_lines * (n_strips + 1), st);
-  {
+  // the strip passes leave the full-range offset table of both orientations behind; a rank's cell block needs its own
+  const bool reuse = pos0 == 0 && pos1 == (long long)ld && S.off_valid[layout] && S.off_strips[layout] == n_strips;
+  Tmp<uint32_t> off_tmp(reuse ? 1 : (size_t)n_lines * (n_strips + 1), st);
+  struct { const uint32_t* p; } off{reuse ? S.off[layout].p : off_tmp.p};
+  if (!reuse) {
     const long long total = (long long)n_lines * (n_strips + 1);
     const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-    k_strip_offsets<<<grid, 256, 0, st>>>(ptr, idx, n_lines, n_strips, (int)pos0, off.p);
+    k_strip_offsets<<<grid, 256, 0, st>>>(ptr, idx, n_lines, n_strips, (int)pos0, off_tmp.p);
   }
   const long long ctas = (long long)n_strips * ((n_lines + kLinesPerCta - 1) / kLinesPerCta);
   SCL_REQUIRE(ctas < (1LL << 31), "densify grid too large");
-  if (stat_tune().writer == 1) {   // TMA-store writer
+  // measured (profiles/r1_tune_norm_*.json): the staged TMA-store writer wins for hi-only output (4.5-4.9 TB/s vs
+  // 3.8-4.45), the overlay writer for hi+lo output at the 68k x 20k shape (5.57 vs 4.9-5.2 TB/s)
+  const int writer = stat_tune().writer == -1 ? (out_lo ? 0 : 2) : stat_tune().writer;
+  if (writer >= 2) {   // TMA-store writer with cp.async-staged patches (2: one staged entry per thread and line, 3: two)
+    const int kp = writer == 2 ? 1 : 2;
+    const size_t smem = (size_t)kRing * 2 * kStripW * sizeof(__half) * (out_lo ? 2 : 1) + (size_t)2 * 2 * kp * kDenseThreads * 8;
+#define SCL_LAUNCH_TMA2(CM, LO, KP)                                                                                     \
+  do {                                                                                                                 \
+    SCL_CUDA(cudaFuncSetAttribute(k_densify_tma2<CM, LO, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_densify_tma2<CM, LO, KP><<<(unsigned)ctas, kDenseThreads, smem, st>>>(off.p, idx, cell_major ? S.patch_csr.p : S.patch_csc.p, \
+                                                                         S.inv_s_f.p, S.mu_f.p, S.cent_f.p, n_lines, line_len, \
+                                                                         ld, n_strips, (int)pos0, (int)pos1, out_hi, out_lo); \
+  } while (0)
+#define SCL_LAUNCH_TMA2_K(CM, LO) do { if (kp == 1) SCL_LAUNCH_TMA2(CM, LO, 1); else SCL_LAUNCH_TMA2(CM, LO, 2); } while (0)
+    if (cell_major) {
+      if (out_lo) SCL_LAUNCH_TMA2_K(true, true); else SCL_LAUNCH_TMA2_K(true, false);
+    } else {
+      if (out_lo) SCL_LAUNCH_TMA2_K(false, true); else SCL_LAUNCH_TMA2_K(false, false);
+    }
+#undef SCL_LAUNCH_TMA2_K
+#undef SCL_LAUNCH_TMA2
+    SCL_CUDA(cudaGetLastError());
+    return;
+  }
+  if (writer == 1) {   // TMA-store writer
     const size_t smem = (size_t)kRing * 2 * kStripW * sizeof(__half) * (out_lo ? 2 : 1);
 #define SCL_LAUNCH_TMA(CM, LO)                                                                                         \
   do {                                                                                                                 \

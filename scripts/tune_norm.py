@@ -24,13 +24,13 @@ with Handle(seed=0) as h:
         out[tag] = {"stats_ms": a.value, "densify_ms": b.value, "densify_GBs": by.value / b.value / 1e6}
         print(tag, out[tag], flush=True)
 
-    for variant in (0, 1, 2, 3):
-        for heavy in (1024, 4096, 16384):
+    for variant in (4, 8):
+        for heavy in (4096,):
             h.lib.scl_debug_set_tuning(variant, heavy, 0)
             run(f"stats_v{variant}_heavy{heavy}")
-    h.lib.scl_debug_set_tuning(0, 4096, 0)
-    for writer in (0, 1):
+    h.lib.scl_debug_set_tuning(8, 4096, 0)
+    for writer in (0, 2, -1):
         for lo in (0, 1):
             h.lib.scl_debug_set_tuning(-1, 0, writer)
-            run(f"writer{writer}_lo{lo}", lo)
+            run(f"strips_writer{writer}_lo{lo}", lo)
 open(f"gpurun_out/tune_norm_{wl}.json", "w").write(json.dumps(out, indent=1))
