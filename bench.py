@@ -350,7 +350,7 @@ def main():
                 "peak_source": peak_src, "launches": int(prof.gram_gemm_launches),
                 "avg_ms_per_launch": prof.gram_gemm_ms / max(1, prof.gram_gemm_launches),
                 "alg_flops_per_launch": prof.gram_alg_flops / max(1, prof.gram_gemm_launches),
-                "hbm_kernel": {"kernel": "k_densify (fused log1p/z-score/L2 normalise -> binary16 operand)",
+                "hbm_kernel": {"kernel": "k_densify_tma2 (normalised dense binary16 operand: background + sparse patches composed in shared memory, TMA bulk stores)",
                                "bound": "hbm", "achieved": dens_gbs, "peak": hbm_peak, "unit": "GB/s",
                                "frac": dens_gbs / hbm_peak, "launches": int(prof.densify_launches),
                                "alg_bytes_per_launch": prof.densify_alg_bytes / max(1, prof.densify_launches),
