@@ -260,14 +260,25 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
         raise NotImplementedError('only centering="mean" (the default path) is implemented')
     if verbose:
         print("Extracting matrices")                                    # :661
+    import time as _time
+    _t = [_time.perf_counter()]
+
+    def _lap():
+        _t.append(_time.perf_counter())
+        return 1e3 * (_t[-1] - _t[-2])
+
+    host_ms = {}
     X, cell_id, gene_id = df2sparr(inp_df)
+    host_ms["df2sparr"] = _lap()
     N, M = X.shape
     own = handle is None
     h = Handle(device=device, gram_mode=gram_mode, verbose=verbose, seed=seed, exact_perturb=exact_perturb) if own else handle
+    host_ms["create_handle"] = _lap()
     try:
         if comm is not None:
             h.comm_init(*comm)
         h.set_counts(X)
+        host_ms["upload_counts_and_csr_mirror"] = _lap()
         if draws is not None:
             if getattr(draws, "z_idx1", None) is not None:
                 h.set_zero_candidates(draws.z_idx1, draws.z_idx2)
@@ -281,7 +292,9 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
                 h.push_perturb_sample(s)
         if verbose:
             print("Extracting Signals...")                              # :702
+        _lap()
         si = h.run_signal()
+        host_ms["run_signal"] = _lap()
         L, L_mp = h.L(), h.L_mp()
         results = {"L": L, "L_mp": L_mp, "λ": si.lambda_c, "lambda": si.lambda_c, "cell_id": cell_id}
         if si.n_signal == 0:                                            # :780-784
@@ -291,7 +304,9 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
         if verbose:
             print("Calculating noise baseline...")                      # :707
             print("Calculating sparsity level for the perturbation...")  # :716
+        _lap()
         ri = h.run_robustness(th=th, p_step=p_step, n_perturb=n_perturb)
+        host_ms["run_robustness"] = _lap()
         nV, nL = h.signal_evec(), h.signal_ev()
         b_, m_scores, sd_scores = h.scores()
         sig_id = h.sig_id()
@@ -313,7 +328,7 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
             "robustness_scores": {"b_": b_, "rob_score": m_scores, "m_scores": m_scores, "sd_scores": sd_scores},
             "signal_evec": nV, "signal_ev": nL, "gene_id": gene_id, "gene_basis": h.gene_basis(),
             "pass": bool(si.pass_), "rec_vals": h.rec_vals(),
-            "info": {"p_sel": ri.p_sel, "n_search": ri.n_search, "p_th": ri.p_th, "min_pc": ri.min_pc,
+            "info": {"host_ms": host_ms, "p_sel": ri.p_sel, "n_search": ri.n_search, "p_th": ri.p_th, "min_pc": ri.min_pc,
                      "n_add": ri.n_add, "ks_static": si.ks_static, "b_plus": si.b_plus, "b_minus": si.b_minus,
                      "timings_ms": {"gram": si.t_gram_ms, "syevd_signal": si.t_syevd_ms, "null": si.t_null_ms,
                                     "fit": si.t_fit_ms, "backproject": si.t_backproject_ms,
@@ -321,6 +336,7 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
                                     "search_syevd": ri.t_search_syevd_ms, "perturb": ri.t_perturb_ms,
                                     "score": ri.t_score_ms, "outputs": ri.t_outputs_ms}},
         })
+        host_ms["read_results"] = _lap()
         return (results, h) if return_handle else results
     finally:
         if own and not return_handle:
