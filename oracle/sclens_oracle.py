@@ -526,6 +526,43 @@ def sclens(X, draws: Optional[Draws] = None, rng: Optional[np.random.Generator] 
 
 
 # --------------------------------------------------------------------------------------
+# downstream consumer restated ahead of its device implementation
+# --------------------------------------------------------------------------------------
+def get_denoised(result: dict, mode: str = "gpu-ref") -> np.ndarray:
+    """get_denoised_df (:889-931) on a result dict of :func:`sclens` (or of sclens_b200.sclens): the
+    robust-signal reconstruction pca_n1 * gene_basis[sig_id, :] * sqrt(M) (:890-911, a Float32 GEMM on
+    both reference paths) pushed back through the recorded normalisation (:913-926):
+    + cent_, * norm_tgc / mean(norm_tgc), * mat2_std + mat2_mean, exp(.) - 1 clamped at 0, rows scaled to
+    sum 1, * mean(TGC).  Returns the N x M Float64 matrix of the output DataFrame (without the cell column)."""
+    gene_basis = np.asarray(result["gene_basis"])
+    sig_id = np.asarray(result["sig_id"], dtype=np.int64)
+    g_mat = gene_basis[sig_id, :]                                                     # :890
+    pca_n1 = result["pca_n1"]
+    if hasattr(pca_n1, "iloc"):                                                       # DataFrame(cell, x1..xr)
+        pca_n1 = pca_n1.iloc[:, 1:].to_numpy()
+    Xout0 = np.asarray(pca_n1, dtype=np.float32)                                      # :891
+    M = gene_basis.shape[1]
+    sqrtM = math.sqrt(M)                                                              # sqrt(size(gene_basis, 2))
+    if mode == "gpu-ref":                                                             # :893-896 (cu() is Float32)
+        d_mean = (Xout0 @ np.asarray(g_mat, dtype=np.float32)).astype(np.float32) * np.float32(sqrtM)
+    else:                                                                             # :903-905: mul! into a Float32 array
+        d_mean = (Xout0.astype(np.float64) @ np.asarray(g_mat, dtype=np.float64)).astype(np.float32) * np.float32(sqrtM)
+    rec = result["rec_vals"]
+    TGC = np.asarray(rec["TGC"], dtype=np.float64).ravel()
+    mat2_mean = np.asarray(rec["mat2_mean"], dtype=np.float64).reshape(1, -1)
+    mat2_std = np.asarray(rec["mat2_std"], dtype=np.float64).reshape(1, -1)
+    norm_tgc = np.asarray(rec["norm_tgc"], dtype=np.float64).ravel()
+    cent_ = np.asarray(rec["cent_"], dtype=np.float64).reshape(1, -1)
+    r_mat1 = d_mean.astype(np.float64) + cent_                                        # :921
+    r_mat2 = r_mat1 * (norm_tgc / norm_tgc.mean())[:, None]                           # :922
+    r_mat3 = r_mat2 * mat2_std + mat2_mean                                            # :923
+    r_mat4 = np.exp(r_mat3) - 1.0                                                     # :924
+    r_mat4[r_mat4 < -0.0] = 0.0                                                       # :925
+    r_mat4 /= r_mat4.sum(axis=1, keepdims=True)                                       # :926
+    return r_mat4 * TGC.mean()                                                        # :927
+
+
+# --------------------------------------------------------------------------------------
 # QC (parity row P0; host work in the reference too)
 # --------------------------------------------------------------------------------------
 def preprocess(X, gene_name, min_tp_c=0, min_tp_g=0, max_tp_c=np.inf, max_tp_g=np.inf, min_genes_per_cell=200,

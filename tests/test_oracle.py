@@ -190,3 +190,37 @@ def test_preprocess_matches_host_mirror():
     np.testing.assert_array_equal(a[1], b[1])
     assert not a[0][:20].any() and not a[0][30:45].any() and a[0].sum() > 300
     assert not np.isin(np.arange(100, 110), a[1]).any()
+
+
+def test_denoise_inverts_the_normalisation():
+    """get_denoised_df (:889-931) with the complete eigenbasis as "signals": pca * gene_basis * sqrt(M) is then the
+    normalised matrix itself, so the recorded normalisation is undone exactly and the output must be
+    x_ij / r_i * mean(TGC) (the clamp at 0 and the row rescaling are identities on it)."""
+    X = make_counts(120, 90, seed=5, K=3, de_prob=0.3, lfc_sd=1.5)
+    scaled, rec = orc.normalize_main(X)
+    N, M = X.shape
+    U, sv, Vt = np.linalg.svd(scaled, full_matrices=False)
+    keep = sv > 1e-9 * sv[0]
+    nV, nL = U[:, keep], (sv[keep] ** 2) / M                   # eigenpairs of scaled * scaled' / M  (:339-343)
+    sq = np.sqrt(nL)
+    result = {"pca_n1": nV * sq[None, :], "sig_id": np.arange(keep.sum()),
+              "gene_basis": (1.0 / sq)[:, None] * (nV.T @ scaled) / np.sqrt(M), "rec_vals": rec}     # :810-819
+    out = orc.get_denoised(result, mode="cpu")
+    dense = np.asarray(X.todense(), dtype=np.float64)
+    want = dense / dense.sum(axis=1, keepdims=True) * rec["TGC"].mean()
+    assert out.shape == (N, M)
+    np.testing.assert_allclose(out.sum(axis=1), rec["TGC"].mean(), rtol=1e-12)
+    # Float32 reconstruction (:891-896) of values whose exp(.) - 1 is ~1e-3: a few 1e-4 relative on the non-zeros
+    nz = dense > 0
+    np.testing.assert_allclose(out[nz], want[nz], rtol=5e-3)
+    assert np.abs(out[~nz]).max() < 1e-3 * want[nz].min()
+
+
+def test_denoise_on_a_full_run_is_a_probability_profile_per_cell(small_run):
+    X, res, _, _ = small_run
+    assert len(res["sig_id"]) > 0
+    out = orc.get_denoised(res, mode="gpu-ref")
+    assert out.shape == X.shape and np.isfinite(out).all() and (out >= 0).all()
+    np.testing.assert_allclose(out.sum(axis=1), res["rec_vals"]["TGC"].mean(), rtol=1e-10)
+    # the two reference arithmetic paths (:893-896 Float32 GEMM, :903-905 Float64 operands) agree to Float32 accuracy
+    np.testing.assert_allclose(out, orc.get_denoised(res, mode="cpu"), rtol=1e-3, atol=1e-6 * out.max())
