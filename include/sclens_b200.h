@@ -199,6 +199,14 @@ SCL_API int32_t scl_op_scores(scl_handle* h, int32_t N, int32_t k, int32_t min_p
                       const float* nV_sets, double th, float* b_, double* m_scores, double* sd_scores,
                       int32_t* sig_id, int32_t* n_robust);
 
+/* get_denoised_df (:889-931) from the entries of the result Dict: pca_n1 N x r (the :pca_n1 columns), g_mat r x M
+ * (= gene_basis[sig_id, :]), rec_vals TGC / mat2_mean / mat2_std / norm_tgc / cent_.  out: N x M column-major, Float64
+ * (out_f32 = 0, as the reference's DataFrame) or Float32.  Replaces the cu()/mul! of :893-896 and the host broadcasts
+ * of :921-927 by one fused kernel. */
+SCL_API int32_t scl_op_denoise(scl_handle* h, int32_t N, int32_t M, int32_t r, const float* pca_n1, const float* g_mat,
+                       const double* TGC, const double* mat2_mean, const double* mat2_std, const double* norm_tgc,
+                       const double* cent, int32_t out_f32, void* out);
+
 /* ---- kernel-level timing harness (device-resident synthetic operands; used by bench.py and the ncu captures) ---- */
 /* Gram / GEMM kernel alone: rows x K binary16 operand generated on the device; mode bit0 = split (hi+lo) operands,
  * bit1 = full GEMM instead of the syrk schedule; chunk_kb = k-blocks per accumulation chunk (0 = default).

@@ -105,4 +105,36 @@ function sclens(inp_df, df2sparr; device_="gpu", th=60, p_step=0.001, n_perturb=
     end
 end
 
+"""
+    get_denoised_df(inp_obj; out32=false)
+
+Drop-in for scLENS.get_denoised_df(inp_obj; device_="gpu") (src/scLENS.jl:889-931) on a result Dict of `sclens`:
+one fused device kernel behind `scl_op_denoise` instead of the cu()/mul! of :893-896 and the broadcasts of :921-927.
+"""
+function get_denoised_df(inp_obj; out32::Bool=false)
+    g_mat = Matrix{Float32}(inp_obj[:gene_basis][inp_obj[:sig_id], :])              # r x M  (:890)
+    Xout0 = Matrix{Float32}(inp_obj[:pca_n1][!, 2:end])                             # N x r  (:891)
+    N, r = size(Xout0); M = size(g_mat, 2)
+    rv = inp_obj[:rec_vals]
+    f64(x) = Vector{Float64}(vec(x))
+    out = out32 ? Matrix{Float32}(undef, N, M) : Matrix{Float64}(undef, N, M)
+    hr = Ref{Ptr{Cvoid}}(C_NULL)
+    cfg = SclConfig()
+    rc = ccall((:scl_create, LIB), Int32, (Ptr{Ptr{Cvoid}}, Ref{SclConfig}), hr, cfg)
+    rc == 0 || error("scl_create failed: ", unsafe_string(ccall((:scl_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    h = hr[]
+    try
+        check(h, ccall((:scl_op_denoise, LIB), Int32,
+                       (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float32}, Ptr{Float32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                        Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Cvoid}),
+                       h, N, M, r, Xout0, g_mat, f64(rv["TGC"]), f64(rv["mat2_mean"]), f64(rv["mat2_std"]),
+                       f64(rv["norm_tgc"]), f64(rv["cent_"]), out32 ? 1 : 0, out))
+    finally
+        ccall((:scl_destroy, LIB), Int32, (Ptr{Cvoid},), h)
+    end
+    odf = DataFrame(out, inp_obj[:gene_id])                                         # :928
+    insertcols!(odf, 1, :cell => inp_obj[:cell_id])                                 # :929
+    odf
+end
+
 end # module

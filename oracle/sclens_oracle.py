@@ -543,17 +543,19 @@ def get_denoised(result: dict, mode: str = "gpu-ref") -> np.ndarray:
     Xout0 = np.asarray(pca_n1, dtype=np.float32)                                      # :891
     M = gene_basis.shape[1]
     sqrtM = math.sqrt(M)                                                              # sqrt(size(gene_basis, 2))
+    # the product lands in a Float32 array on both paths; `.* sqrt(size(...))` multiplies by a Float64 scalar, so
+    # d_mean is the Float64 product of the Float32 GEMM result and sqrt(M)
     if mode == "gpu-ref":                                                             # :893-896 (cu() is Float32)
-        d_mean = (Xout0 @ np.asarray(g_mat, dtype=np.float32)).astype(np.float32) * np.float32(sqrtM)
+        d_mean = (Xout0 @ np.asarray(g_mat, dtype=np.float32)).astype(np.float32).astype(np.float64) * sqrtM
     else:                                                                             # :903-905: mul! into a Float32 array
-        d_mean = (Xout0.astype(np.float64) @ np.asarray(g_mat, dtype=np.float64)).astype(np.float32) * np.float32(sqrtM)
+        d_mean = (Xout0.astype(np.float64) @ np.asarray(g_mat, dtype=np.float64)).astype(np.float32).astype(np.float64) * sqrtM
     rec = result["rec_vals"]
     TGC = np.asarray(rec["TGC"], dtype=np.float64).ravel()
     mat2_mean = np.asarray(rec["mat2_mean"], dtype=np.float64).reshape(1, -1)
     mat2_std = np.asarray(rec["mat2_std"], dtype=np.float64).reshape(1, -1)
     norm_tgc = np.asarray(rec["norm_tgc"], dtype=np.float64).ravel()
     cent_ = np.asarray(rec["cent_"], dtype=np.float64).reshape(1, -1)
-    r_mat1 = d_mean.astype(np.float64) + cent_                                        # :921
+    r_mat1 = d_mean + cent_                                        # :921
     r_mat2 = r_mat1 * (norm_tgc / norm_tgc.mean())[:, None]                           # :922
     r_mat3 = r_mat2 * mat2_std + mat2_mean                                            # :923
     r_mat4 = np.exp(r_mat3) - 1.0                                                     # :924

@@ -341,3 +341,49 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
     finally:
         if own and not return_handle:
             h.close()
+
+
+def get_denoised_df(inp_obj, device_="gpu", *, device=0, handle=None, dtype=np.float64):
+    """Drop-in for scLENS.get_denoised_df (:889-931): the denoised count matrix rebuilt from the robust signals of a
+    result dictionary of :func:`sclens` (keys ``gene_basis``, ``sig_id``, ``pca_n1``, ``rec_vals``, ``gene_id``,
+    ``cell_id``).  One fused device kernel behind ``scl_op_denoise``; returns a DataFrame (cell, genes...) like the
+    reference, Float64 by default (the reference's element type) or Float32."""
+    if device_ != "gpu":
+        raise ValueError('sclens_b200 implements device_="gpu" only (no CPU fallback exists)')
+    sig_id = np.asarray(inp_obj["sig_id"], dtype=np.int64)
+    if sig_id.size == 0:
+        raise ValueError("no robust signal (sig_id is empty): nothing to reconstruct")
+    gene_basis = np.asarray(inp_obj["gene_basis"], dtype=np.float32)
+    g_mat = np.ascontiguousarray(gene_basis[sig_id, :].T)                      # r x M column-major == C order of M x r
+    pca_n1 = inp_obj["pca_n1"]
+    if pd is not None and isinstance(pca_n1, pd.DataFrame):
+        pca_n1 = pca_n1.iloc[:, 1:].to_numpy()
+    A = np.ascontiguousarray(np.asarray(pca_n1, dtype=np.float32).T)            # N x r column-major == C order of r x N
+    r, N = A.shape
+    M = g_mat.shape[0]
+    if g_mat.shape[1] != r:
+        raise ValueError("pca_n1 and gene_basis[sig_id, :] disagree on the number of robust signals")
+    rec = inp_obj["rec_vals"]
+    vec = {k: np.ascontiguousarray(np.asarray(rec[k], dtype=np.float64).ravel())
+           for k in ("TGC", "mat2_mean", "mat2_std", "norm_tgc", "cent_")}
+    if len(vec["TGC"]) != N or len(vec["norm_tgc"]) != N or any(len(vec[k]) != M for k in ("mat2_mean", "mat2_std", "cent_")):
+        raise ValueError("rec_vals do not match the shapes of pca_n1 / gene_basis")
+    dtype = np.dtype(dtype)
+    if dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+        raise ValueError("dtype must be float64 or float32")
+    out = np.empty((M, N), dtype=dtype)                                         # N x M column-major
+    own = handle is None
+    h = Handle(device=device) if own else handle
+    try:
+        h._ck(h.lib.scl_op_denoise(h.h, N, M, r, ptr(A, C.c_float), ptr(g_mat, C.c_float), ptr(vec["TGC"], C.c_double),
+                                   ptr(vec["mat2_mean"], C.c_double), ptr(vec["mat2_std"], C.c_double),
+                                   ptr(vec["norm_tgc"], C.c_double), ptr(vec["cent_"], C.c_double),
+                                   int(dtype == np.dtype(np.float32)), out.ctypes.data_as(C.c_void_p)))
+    finally:
+        if own:
+            h.close()
+    if pd is None:
+        return out.T
+    odf = pd.DataFrame(out.T, columns=[str(g) for g in inp_obj["gene_id"]])
+    odf.insert(0, "cell", np.asarray(inp_obj["cell_id"]))
+    return odf

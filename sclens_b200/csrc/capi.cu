@@ -646,4 +646,33 @@ int32_t scl_op_scores(scl_handle* h, int32_t N, int32_t k, int32_t min_pc, int32
   });
 }
 
+// get_denoised_df (:889-931) from the entries of the result Dict (all host pointers, Julia layouts)
+int32_t scl_op_denoise(scl_handle* h, int32_t N, int32_t M, int32_t r, const float* pca_n1, const float* g_mat,
+                       const double* TGC, const double* mat2_mean, const double* mat2_std, const double* norm_tgc,
+                       const double* cent, int32_t out_f32, void* out) {
+  if (!h || !pca_n1 || !g_mat || !TGC || !mat2_mean || !mat2_std || !norm_tgc || !cent || !out) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_REQUIRE(N > 0 && M > 0 && r > 0, "bad shape");
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    double mean_tgc = 0, mean_l = 0;
+    for (int i = 0; i < N; ++i) { mean_tgc += TGC[i]; mean_l += norm_tgc[i]; }
+    mean_tgc /= (double)N;
+    mean_l /= (double)N;
+    SCL_REQUIRE(mean_l > 0, "norm_tgc must be positive");
+    Tmp<float> dA((size_t)r * N, h->st), dG((size_t)r * M, h->st);
+    Tmp<double> dc(M, h->st), ds(M, h->st), dy(M, h->st), dl(N, h->st);
+    SCL_CUDA(cudaMemcpyAsync(dA.p, pca_n1, (size_t)r * N * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    SCL_CUDA(cudaMemcpyAsync(dG.p, g_mat, (size_t)r * M * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    SCL_CUDA(cudaMemcpyAsync(dc.p, cent, M * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    SCL_CUDA(cudaMemcpyAsync(ds.p, mat2_std, M * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    SCL_CUDA(cudaMemcpyAsync(dy.p, mat2_mean, M * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    SCL_CUDA(cudaMemcpyAsync(dl.p, norm_tgc, N * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    const size_t bytes = (size_t)N * M * (out_f32 ? sizeof(float) : sizeof(double));
+    Tmp<unsigned char> dout(bytes, h->st);
+    denoise(dA.p, dG.p, r, N, M, dc.p, ds.p, dy.p, dl.p, mean_l, mean_tgc, dout.p, out_f32 != 0, h->st);
+    SCL_CUDA(cudaMemcpyAsync(out, dout.p, bytes, cudaMemcpyDeviceToHost, h->st));
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+  });
+}
+
 }  // extern "C"

@@ -141,6 +141,11 @@ void set_norm_tuning(int stat_variant, int stat_heavy, int writer);
 const double* gram_diagonal(const SpMat& A, NormStats& S, bool gene_side, cudaStream_t st);
 void set_gram_diagonal(float* G, int n, const double* sumsq, double scale, cudaStream_t st);
 
+// ---- denoise.cu ----
+void denoise(const float* dA, const float* dG, int r, int N, int M, const double* cent, const double* sigma,
+             const double* ybar, const double* l2, double mean_l, double mean_tgc, void* d_out, bool out_f32,
+             cudaStream_t st);
+
 // ---- gemm_umma.cu ----
 struct GemmOperand {
   const __half* hi = nullptr;
