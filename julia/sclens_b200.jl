@@ -19,6 +19,8 @@ struct SclConfig
     gram_chunk_kb::Int32; gram_tc_diag::Int32; no_refine::Int32
     reserved::NTuple{4,Int32}
 end
+default_config(; verbose=0, seed=0) =
+    SclConfig(0, 0, 0, verbose, UInt64(seed), 0, 0, 0, 0, 0, 0, ntuple(_ -> Int32(0), 4))
 mutable struct SclSignalInfo
     N::Int32; M::Int32; nm::Int32; n_signal::Int32; n_Lmp::Int32; mp_iters::Int32; pass::Int32; gram_mode_used::Int32
     lambda_c::Float64; b_plus::Float64; b_minus::Float64; ks_static::Float64
@@ -52,7 +54,7 @@ function sclens(inp_df, df2sparr; device_="gpu", th=60, p_step=0.001, n_perturb=
     println("Extracting matrices")
     X_ = df2sparr(inp_df)::SparseMatrixCSC{Float32,UInt32}
     N, M = size(X_)
-    cfg = Ref(SclConfig(0, 0, 0, 1, UInt64(seed), 0, 0, 0, ntuple(_ -> Int32(0), 7)))
+    cfg = Ref(default_config(verbose=1, seed=seed))
     hr = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:scl_create, LIB), Int32, (Ptr{Ptr{Cvoid}}, Ptr{SclConfig}), hr, cfg)
     rc == 0 || check(C_NULL, rc)
@@ -119,9 +121,9 @@ function get_denoised_df(inp_obj; out32::Bool=false)
     f64(x) = Vector{Float64}(vec(x))
     out = out32 ? Matrix{Float32}(undef, N, M) : Matrix{Float64}(undef, N, M)
     hr = Ref{Ptr{Cvoid}}(C_NULL)
-    cfg = SclConfig()
-    rc = ccall((:scl_create, LIB), Int32, (Ptr{Ptr{Cvoid}}, Ref{SclConfig}), hr, cfg)
-    rc == 0 || error("scl_create failed: ", unsafe_string(ccall((:scl_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    cfg = Ref(default_config())
+    rc = ccall((:scl_create, LIB), Int32, (Ptr{Ptr{Cvoid}}, Ptr{SclConfig}), hr, cfg)
+    rc == 0 || check(C_NULL, rc)
     h = hr[]
     try
         check(h, ccall((:scl_op_denoise, LIB), Int32,

@@ -104,3 +104,27 @@ def test_host_only_entry_points(lib_built):
     step = C.c_int32()
     assert lib.scl_plan_search_wave(2, 8, 5, C.byref(step)) == 0 and step.value == 21
     assert lib.scl_plan_replicates(20, 0, 0, None, C.byref(cnt)) < 0
+
+
+def test_julia_shim_is_in_step_with_the_header():
+    """julia/sclens_b200.jl cannot be executed here (no Julia in the image): check statically that every symbol it
+    ccalls is declared in the header and that its struct mirrors list the same fields, in order, as the ctypes
+    mirrors (which test_struct_layouts_match_header ties to the header)."""
+    from sclens_b200 import _lib
+    src = open(os.path.join(ROOT, "julia", "sclens_b200.jl")).read()
+    called = set(re.findall(r"\(:(scl_\w+),\s*LIB\)", src))
+    assert called and called <= set(header_symbols()), called - set(header_symbols())
+    for name, mirror in (("SclConfig", _lib.Config), ("SclSignalInfo", _lib.SignalInfo), ("SclRobustInfo", _lib.RobustInfo)):
+        body = src[src.index(f"struct {name}"):]
+        body = body[:body.index("\nend")]
+        fields = re.findall(r"(\w+)::", body)
+        want = [f[0].rstrip("_") for f in mirror._fields_]
+        assert fields == want, (name, fields, want)
+    # positional constructor call has one argument per field
+    ctor = re.search(r"SclConfig\(([^\n]*)\)\n", src[src.index("default_config"):]).group(1)
+    depth, nargs = 0, 1
+    for ch in ctor:
+        depth += ch in "([{"
+        depth -= ch in ")]}"
+        nargs += ch == "," and depth == 0
+    assert nargs == len(_lib.Config._fields_)
