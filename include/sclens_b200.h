@@ -214,6 +214,10 @@ SCL_API int32_t scl_op_denoise(scl_handle* h, int32_t N, int32_t M, int32_t r, c
 SCL_API int32_t scl_bench_gram(scl_handle* h, int32_t rows, int64_t K, int32_t mode, int32_t chunk_kb, int32_t reps,
                        double* ms_avg, double* checksum);
 /* Normalisation kernels on the handle's counts (:677-696): statistics pre-passes and the fused densify writer. */
+/* Timing study of the library eigensolvers on an n x n Wishart matrix generated on the device (CUDA events around the
+ * solver call).  mode 0: Ssyevd with vectors (what the path calls), 1: values only, 2: Ssyevdx with the vectors of the
+ * il..iu smallest eigenvalues (1-based, inclusive), 3: Xsyevd (64-bit API) with vectors. */
+SCL_API int32_t scl_bench_syevd(scl_handle* h, int32_t n, int32_t mode, int32_t il, int32_t iu, double* ms);
 /* Tuning studies only (process-wide).  stat_variant: launch shape of the statistics passes (0-7: line passes,
  * 8: strip passes; < 0 keeps the current one).  stat_heavy: line length above which a whole CTA takes a line
  * (<= 0 keeps).  writer: dense writer, -1 automatic, 0 register/overlay writer, 1 TMA bulk-store writer, 2 / 3

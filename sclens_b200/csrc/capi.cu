@@ -453,6 +453,25 @@ int32_t scl_bench_gram(scl_handle* h, int32_t rows, int64_t K, int32_t mode, int
 
 /* Times the normalisation kernels on the handle's counts: the statistics pre-passes and the fused densify writer
  * (layout 0 gene-major / 1 cell-major, with_lo: also emit the low-order binary16 part). */
+// symmetric test matrix with a Marchenko-Pastur-like spectrum: G = B B^T / K from a random binary16 operand
+int32_t scl_bench_syevd(scl_handle* h, int32_t n, int32_t mode, int32_t il, int32_t iu, double* ms) {
+  if (!h || n < 8 || !ms) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    const int64_t K = 2 * (int64_t)n, ld = (K + 7) / 8 * 8;
+    Tmp<__half> op((size_t)n * ld, h->st);
+    Tmp<float> g((size_t)n * n, h->st), w(n, h->st);
+    fill_random_f16(op.p, (size_t)n * ld, 0x5eedu, 1.0f, h->st);
+    GemmArgs a;
+    a.A.hi = op.p; a.A.rows = n; a.A.K = K; a.A.ld = ld;
+    a.B = a.A;
+    a.syrk = true; a.alpha = 1.0f / (float)K; a.C = g.p; a.ldc = n;
+    a.cta_group = h->cfg.cta_group == 1 ? 1 : 2;
+    gemm_umma(a, h->st);
+    *ms = h->solver->bench(g.p, n, w.p, mode, il, iu, h->st);
+  });
+}
+
 int32_t scl_debug_set_tuning(int32_t stat_variant, int32_t stat_heavy, int32_t writer) {
   scl::set_norm_tuning(stat_variant, stat_heavy, writer);
   return SCL_OK;

@@ -58,6 +58,52 @@ void Solver::dsyevd_small(double* dA, int n, double* dW, cudaStream_t st) {
   if (info != 0) throw Error(-3, "cusolverDnDsyevd did not converge, info=" + std::to_string(info));
 }
 
+double Solver::bench(float* dA, int n, float* dW, int mode, int il, int iu, cudaStream_t st) {
+  cudaEvent_t e0, e1;
+  SCL_CUDA(cudaEventCreate(&e0));
+  SCL_CUDA(cudaEventCreate(&e1));
+  int info = 0;
+  if (mode == 0 || mode == 1) {
+    const cusolverEigMode_t jobz = mode == 0 ? CUSOLVER_EIG_MODE_VECTOR : CUSOLVER_EIG_MODE_NOVECTOR;
+    int lwork = 0;
+    SCL_SOLVER(cusolverDnSsyevd_bufferSize(impl->h, jobz, CUBLAS_FILL_MODE_UPPER, n, dA, n, dW, &lwork));
+    impl->work.ensure((size_t)lwork);
+    SCL_CUDA(cudaEventRecord(e0, st));
+    SCL_SOLVER(cusolverDnSsyevd(impl->h, jobz, CUBLAS_FILL_MODE_UPPER, n, dA, n, dW, impl->work.p, lwork, impl->info.p));
+  } else if (mode == 2) {
+    int lwork = 0, meig = 0;
+    SCL_SOLVER(cusolverDnSsyevdx_bufferSize(impl->h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, n,
+                                            dA, n, 0.f, 0.f, il, iu, &meig, dW, &lwork));
+    impl->work.ensure((size_t)lwork);
+    SCL_CUDA(cudaEventRecord(e0, st));
+    SCL_SOLVER(cusolverDnSsyevdx(impl->h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, n, dA, n,
+                                 0.f, 0.f, il, iu, &meig, dW, impl->work.p, lwork, impl->info.p));
+  } else {
+    cusolverDnParams_t params = nullptr;
+    SCL_SOLVER(cusolverDnCreateParams(&params));
+    size_t wd = 0, wh = 0;
+    SCL_SOLVER(cusolverDnXsyevd_bufferSize(impl->h, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, (int64_t)n,
+                                           CUDA_R_32F, dA, (int64_t)n, CUDA_R_32F, dW, CUDA_R_32F, &wd, &wh));
+    impl->work.ensure(wd / sizeof(float) + 1);
+    std::vector<unsigned char> hbuf(wh + 1);
+    SCL_CUDA(cudaEventRecord(e0, st));
+    SCL_SOLVER(cusolverDnXsyevd(impl->h, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, (int64_t)n, CUDA_R_32F, dA,
+                                (int64_t)n, CUDA_R_32F, dW, CUDA_R_32F, impl->work.p, wd, hbuf.data(), wh, impl->info.p));
+    SCL_CUDA(cudaEventRecord(e1, st));
+    SCL_CUDA(cudaEventSynchronize(e1));   // the host buffer must outlive the call
+    cusolverDnDestroyParams(params);
+  }
+  SCL_CUDA(cudaEventRecord(e1, st));
+  SCL_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  SCL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  SCL_CUDA(cudaMemcpy(&info, impl->info.p, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (info != 0) throw Error(-3, "eigensolver timing study: info=" + std::to_string(info));
+  return (double)ms;
+}
+
 // ---- Marchenko-Pastur / Tracy-Widom (host, Float64 on the Float32 eigenvalues) ------------
 namespace {
 struct MpParams {

@@ -14,6 +14,9 @@ struct Solver {
   // cusolverDnSsyevd('V'|'N','U'): eigenvalues ascending in dW, eigenvectors overwrite dA (col-major)
   void syevd(float* dA, int n, float* dW, bool vectors, cudaStream_t st);
   void dsyevd_small(double* dA, int n, double* dW, cudaStream_t st);
+  // timing study of the library's symmetric eigensolvers on an n x n matrix (overwritten); returns milliseconds.
+  // mode 0: Ssyevd vectors, 1: Ssyevd values only, 2: Ssyevdx vectors of the il..iu smallest, 3: Xsyevd (64-bit API) vectors
+  double bench(float* dA, int n, float* dW, int mode, int il, int iu, cudaStream_t st);
 };
 
 struct MpFit {
