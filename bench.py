@@ -1,13 +1,17 @@
 #!/usr/bin/env python
 """bench.py - sclens() throughput on synthetic data of the BASELINE.json shapes.
 
-    python bench.py --gpus N --steps K --warmup W [--workload B|C|small] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload C|B|small] [--impl reference]
+
+Workloads: C = 68k cells x 20k genes (BASELINE.json configs[2], the shape the metric is quoted on; default),
+B = 10k x 20k (configs[1]), small = 2k x 3k (smoke).
 
 One "step" = one complete sclens() pass (signal detection + robustness test, n_perturb=20) over
 the synthetic count matrix of the workload.  Our arm:
   value  cells/s with the CSC counts already resident in HBM (library stream CUDA events)
-  e2e    cells/s through the public API sclens_b200.sclens(X_host): handle creation, pinned
-         host -> device copy of the CSC, the whole path, device -> host read of every result
+  e2e    cells/s through the public API sclens_b200.sclens(X_host, handle=h): pinned host -> device copy of
+         the CSC, the whole path, device -> host read of every result; the rank's handle (library context) is
+         reused, a cold call that creates its own handle is reported beside it (B / small workloads)
   roofline   the dominant own kernel, the tcgen05 Gram: algorithmic n(n+1)K FLOP per launch over its
              CUDA-event time, against MEASURED_PEAKS.json; the HBM-bound densify kernel beside it
   cpu_baseline   the oracle (reference device_="cpu" numerics) timed on the host cores on a bounded
@@ -191,15 +195,19 @@ def cpu_sample(X, n_search, n_perturb, frac=4):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=None, help="timed passes (default: 1 at the 68k x 20k workload, 2 otherwise)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("SCLENS_BENCH_WORKLOAD", "B"), choices=sorted(WORKLOADS))
+    # default = the configuration BASELINE.json's metric is quoted on (68k x 20k, fits one GPU): 65 s per pass on one
+    # B200, so the default run is 3 warm-ups + 1 timed pass + 1 end-to-end call, about 6 minutes; B is configs[1]
+    ap.add_argument("--workload", default=os.environ.get("SCLENS_BENCH_WORKLOAD", "C"), choices=sorted(WORKLOADS))
     ap.add_argument("--n-perturb", type=int, default=20)
     ap.add_argument("--gram-mode", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 1 if args.workload == "C" else 2
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -317,7 +325,7 @@ def main():
         # one cold call (N = 1 only): the call creates and destroys its own handle - cuSOLVER state and every device
         # workspace are set up inside it.  Reported beside the headline, not as the headline.
         cold_s, cold_host_ms = None, None
-        if world == 1:
+        if world == 1 and args.workload != "C":      # at 68k x 20k the cold call would add a minute to the default run
             barrier()
             t0 = time.perf_counter()
             _, cold_host_ms = call(None)
