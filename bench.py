@@ -305,50 +305,55 @@ def main():
     # ---- e2e through the public API with host buffers (pinned), results read back
     e2e = None
     if args.e2e_steps > 0:
-        pinned = [torch.from_numpy(a).pin_memory() for a in (X.indptr.astype(np.uint32).view(np.int32),
-                                                             X.indices.astype(np.uint32).view(np.int32), X.data)]
-        Xp = sp.csc_matrix((pinned[2].numpy(), pinned[1].numpy().view(np.uint32), pinned[0].numpy().view(np.uint32)),
-                           shape=X.shape)
-        h2d = sum(int(p.numel() * p.element_size()) for p in pinned)
-        d2h = 0
+        try:
+            pinned = [torch.from_numpy(a).pin_memory() for a in (X.indptr.astype(np.uint32).view(np.int32),
+                                                                 X.indices.astype(np.uint32).view(np.int32), X.data)]
+            Xp = sp.csc_matrix((pinned[2].numpy(), pinned[1].numpy().view(np.uint32), pinned[0].numpy().view(np.uint32)),
+                               shape=X.shape)
+            h2d = sum(int(p.numel() * p.element_size()) for p in pinned)
+            d2h = 0
 
-        def call(handle):
-            out = sclens(Xp, n_perturb=args.n_perturb, gram_mode=args.gram_mode, verbose=False, seed=seed,
-                         device=local_rank, handle=handle)
-            nbytes = sum(int(np.asarray(v).nbytes) for v in (out["L"], out["L_mp"], out["signal_evec"], out["signal_ev"],
-                                                             out["gene_basis"], out["robustness_scores"]["b_"],
-                                                             out["robustness_scores"]["m_scores"],
-                                                             out["robustness_scores"]["sd_scores"], out["sig_id"]))
-            nbytes += sum(int(np.asarray(v).nbytes) for v in out["rec_vals"].values())
-            return nbytes, dict(out["info"]["host_ms"])
+            def call(handle):
+                out = sclens(Xp, n_perturb=args.n_perturb, gram_mode=args.gram_mode, verbose=False, seed=seed,
+                             device=local_rank, handle=handle)
+                nbytes = sum(int(np.asarray(v).nbytes) for v in (out["L"], out["L_mp"], out["signal_evec"], out["signal_ev"],
+                                                                 out["gene_basis"], out["robustness_scores"]["b_"],
+                                                                 out["robustness_scores"]["m_scores"],
+                                                                 out["robustness_scores"]["sd_scores"], out["sig_id"]))
+                nbytes += sum(int(np.asarray(v).nbytes) for v in out["rec_vals"].values())
+                return nbytes, dict(out["info"]["host_ms"])
 
-        # one cold call (N = 1 only): the call creates and destroys its own handle - cuSOLVER state and every device
-        # workspace are set up inside it.  Reported beside the headline, not as the headline.
-        cold_s, cold_host_ms = None, None
-        if world == 1 and args.workload != "C":      # at 68k x 20k the cold call would add a minute to the default run
-            barrier()
-            t0 = time.perf_counter()
-            _, cold_host_ms = call(None)
-            barrier()
-            cold_s = time.perf_counter() - t0
-        # the timed calls reuse the rank's handle (the library context: workspaces, cuSOLVER state, NCCL communicator),
-        # as a user running sclens() on one matrix after another would; host buffers in, every result read back
-        e2e_s = 0.0
-        e2e_host_ms = {}
-        for _ in range(args.e2e_steps):
-            barrier()
-            t0 = time.perf_counter()
-            d2h, e2e_host_ms = call(h)
-            barrier()
-            e2e_s += time.perf_counter() - t0
-        te = torch.tensor([e2e_s / args.e2e_steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
-        e2e = {"value": N / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-               "seconds_per_step": e2e_s, "host_ms_last_call": e2e_host_ms,
-               "handle": "reused across calls (device workspaces, cuSOLVER state and the NCCL communicator persist)",
-               "cold_call_seconds": cold_s, "cold_call_host_ms": cold_host_ms}
+            # one cold call (N = 1 only): the call creates and destroys its own handle - cuSOLVER state and every device
+            # workspace are set up inside it.  Reported beside the headline, not as the headline.
+            cold_s, cold_host_ms = None, None
+            if world == 1 and args.workload != "C":      # at 68k x 20k the cold call would add a minute to the default run
+                barrier()
+                t0 = time.perf_counter()
+                _, cold_host_ms = call(None)
+                barrier()
+                cold_s = time.perf_counter() - t0
+            # the timed calls reuse the rank's handle (the library context: workspaces, cuSOLVER state, NCCL communicator),
+            # as a user running sclens() on one matrix after another would; host buffers in, every result read back
+            e2e_s = 0.0
+            e2e_host_ms = {}
+            for _ in range(args.e2e_steps):
+                barrier()
+                t0 = time.perf_counter()
+                d2h, e2e_host_ms = call(h)
+                barrier()
+                e2e_s += time.perf_counter() - t0
+            te = torch.tensor([e2e_s / args.e2e_steps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            e2e_s = float(te.item())
+            e2e = {"value": N / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                   "seconds_per_step": e2e_s, "host_ms_last_call": e2e_host_ms,
+                   "handle": "reused across calls (device workspaces, cuSOLVER state and the NCCL communicator persist)",
+                   "cold_call_seconds": cold_s, "cold_call_host_ms": cold_host_ms}
+        except Exception as exc:      # the device-timed headline above must survive a failure of this leg
+            if world > 1:
+                raise                  # ranks must stay in step: a one-sided failure cannot be patched over
+            e2e = {"value": None, "unit": "cells/s", "error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank != 0:
         return
@@ -398,9 +403,13 @@ def main():
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
-        total, cores, sample = cpu_sample(X, ri.n_search, args.n_perturb)
-        line["cpu_baseline"] = {"value": N / total, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample,
-                                "seconds_per_pass_estimate": total}
+        try:
+            total, cores, sample = cpu_sample(X, ri.n_search, args.n_perturb)
+            line["cpu_baseline"] = {"value": N / total, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample,
+                                    "seconds_per_pass_estimate": total}
+        except Exception as exc:          # e.g. host memory: report it, keep the line
+            line["cpu_baseline"] = {"value": None, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {type(exc).__name__}: {exc}"[:300]}
     print(json.dumps(line))
     h.close()
     if world > 1:
