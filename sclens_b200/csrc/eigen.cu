@@ -3,6 +3,7 @@
 #include <cusolverDn.h>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include "common.cuh"
 #include "eigen.h"
 #include "tmp.cuh"
@@ -18,10 +19,22 @@ namespace scl {
 
 struct Solver::Impl {
   cusolverDnHandle_t h = nullptr;
+  cusolverDnParams_t params = nullptr;   // 64-bit API (SCL_EIG_API=1)
   DBuf<float> work;
   DBuf<double> dwork;
   DBuf<int> info;
+  std::vector<unsigned char> host_work;
 };
+
+// Which library entry point runs the full eigensolves.  0 (default): cusolverDnSsyevd, the call the reference makes
+// through CUDA.jl (:377).  1: cusolverDnXsyevd, the 64-bit generic API - 495 ms against 550 ms at n = 10^4 in a first
+// look (profiles/r1_syevd_study_10000.json); NOT yet parity-tested inside the path, hence opt-in (SCL_EIG_API bit 0).
+// Bit 1: the sparsity-search steps, which use only the n/2+1 smallest eigenvectors (:742), call cusolverDnSsyevdx with
+// an index range instead of a full solve (474 ms in the same first look); also opt-in until parity-tested.
+int eig_api() {
+  static const int v = [] { const char* e = getenv("SCL_EIG_API"); return e ? atoi(e) : 0; }();
+  return v;
+}
 
 Solver::Solver(cudaStream_t st) : impl(new Impl) {
   SCL_SOLVER(cusolverDnCreate(&impl->h));
@@ -29,6 +42,7 @@ Solver::Solver(cudaStream_t st) : impl(new Impl) {
   impl->info.ensure(1);
 }
 Solver::~Solver() {
+  if (impl->params) cusolverDnDestroyParams(impl->params);
   if (impl->h) cusolverDnDestroy(impl->h);
   delete impl;
 }
@@ -37,6 +51,21 @@ Solver::~Solver() {
 void Solver::syevd(float* dA, int n, float* dW, bool vectors, cudaStream_t st) {
   int lwork = 0;
   cusolverEigMode_t jobz = vectors ? CUSOLVER_EIG_MODE_VECTOR : CUSOLVER_EIG_MODE_NOVECTOR;
+  if (eig_api() & 1) {
+    if (!impl->params) SCL_SOLVER(cusolverDnCreateParams(&impl->params));
+    size_t wd = 0, wh = 0;
+    SCL_SOLVER(cusolverDnXsyevd_bufferSize(impl->h, impl->params, jobz, CUBLAS_FILL_MODE_UPPER, (int64_t)n, CUDA_R_32F, dA,
+                                           (int64_t)n, CUDA_R_32F, dW, CUDA_R_32F, &wd, &wh));
+    impl->work.ensure(wd / sizeof(float) + 1);
+    if (impl->host_work.size() < wh + 1) impl->host_work.resize(wh + 1);
+    SCL_SOLVER(cusolverDnXsyevd(impl->h, impl->params, jobz, CUBLAS_FILL_MODE_UPPER, (int64_t)n, CUDA_R_32F, dA, (int64_t)n,
+                                CUDA_R_32F, dW, CUDA_R_32F, impl->work.p, wd, impl->host_work.data(), wh, impl->info.p));
+    int info = 0;
+    SCL_CUDA(cudaMemcpyAsync(&info, impl->info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+    if (info != 0) throw Error(-3, "cusolverDnXsyevd did not converge, info=" + std::to_string(info));
+    return;
+  }
   SCL_SOLVER(cusolverDnSsyevd_bufferSize(impl->h, jobz, CUBLAS_FILL_MODE_UPPER, n, dA, n, dW, &lwork));
   impl->work.ensure((size_t)lwork);
   SCL_SOLVER(cusolverDnSsyevd(impl->h, jobz, CUBLAS_FILL_MODE_UPPER, n, dA, n, dW, impl->work.p, lwork, impl->info.p));
@@ -44,6 +73,21 @@ void Solver::syevd(float* dA, int n, float* dW, bool vectors, cudaStream_t st) {
   SCL_CUDA(cudaMemcpyAsync(&info, impl->info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   SCL_CUDA(cudaStreamSynchronize(st));
   if (info != 0) throw Error(-3, "cusolverDnSsyevd did not converge, info=" + std::to_string(info));
+}
+
+// eigenpairs 1..iu (ascending) of A: dW[0..iu), eigenvector i in row i of dA's memory.  Returns the number found.
+int Solver::syevdx_smallest(float* dA, int n, float* dW, int iu, cudaStream_t st) {
+  int lwork = 0, meig = 0;
+  SCL_SOLVER(cusolverDnSsyevdx_bufferSize(impl->h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, n,
+                                          dA, n, 0.f, 0.f, 1, iu, &meig, dW, &lwork));
+  impl->work.ensure((size_t)lwork);
+  SCL_SOLVER(cusolverDnSsyevdx(impl->h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, n, dA, n, 0.f,
+                               0.f, 1, iu, &meig, dW, impl->work.p, lwork, impl->info.p));
+  int info = 0;
+  SCL_CUDA(cudaMemcpyAsync(&info, impl->info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  if (info != 0) throw Error(-3, "cusolverDnSsyevdx did not converge, info=" + std::to_string(info));
+  return meig;
 }
 
 void Solver::dsyevd_small(double* dA, int n, double* dW, cudaStream_t st) {

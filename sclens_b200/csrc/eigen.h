@@ -14,10 +14,13 @@ struct Solver {
   // cusolverDnSsyevd('V'|'N','U'): eigenvalues ascending in dW, eigenvectors overwrite dA (col-major)
   void syevd(float* dA, int n, float* dW, bool vectors, cudaStream_t st);
   void dsyevd_small(double* dA, int n, double* dW, cudaStream_t st);
+  int syevdx_smallest(float* dA, int n, float* dW, int iu, cudaStream_t st);
   // timing study of the library's symmetric eigensolvers on an n x n matrix (overwritten); returns milliseconds.
   // mode 0: Ssyevd vectors, 1: Ssyevd values only, 2: Ssyevdx vectors of the il..iu smallest, 3: Xsyevd (64-bit API) vectors
   double bench(float* dA, int n, float* dW, int mode, int il, int iu, cudaStream_t st);
 };
+
+int eig_api();   // SCL_EIG_API: bit 0 = Xsyevd for the full solves, bit 1 = Ssyevdx (index range) in the search steps
 
 struct MpFit {
   std::vector<float> L_mp;

@@ -689,6 +689,7 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
   info.t_search_syevd_ms += tm.stop();
   SCL_CUDA(cudaMemcpyAsync(Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
   SCL_CUDA(cudaStreamSynchronize(st));
+  const float lmax_ref = Lh.back();   // largest eigenvalue of the binarised matrix (scale of the "positive" threshold)
   // The reference basis keeps the complete eigenbasis (oracle get_eigvec(keep_null=True); DESIGN.md,
   // deviations): null directions of the binarised matrix are kept, as in the reference whenever their
   // eigenvalues round positive, so their perturbed counterparts are not mistaken for delocalised vectors.
@@ -740,14 +741,37 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
       }
       gram_of(h, Xp, Sp, op_hi, op_lo, G.p, nm, bin_scale, split);
       t_gram += tm.stop();
-      { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G.p, nm, W.p, true, st); }
-      info.t_search_syevd_ms += tm.stop();
-      SCL_CUDA(cudaMemcpyAsync(Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
-      SCL_CUDA(cudaStreamSynchronize(st));
-      const int i0 = first_positive(Lh);
-      const int npos = nm - i0;
-      SCL_REQUIRE(npos >= n_2 + 1, "perturbed matrix has too few positive eigenvalues");
       const int nw = n_2 + 1;                                  // nV_2[:, end-n_2:end] (Appendix A13)
+      int i0 = -1;
+      if (eig_api() & 2) {
+        // opt-in: only the nw smallest positive eigenpairs are used below, so ask the library for an index range.  The
+        // "positive" threshold needs the largest eigenvalue, which a range solve does not return: the reference basis'
+        // one (same matrix without the additions) stands in.  Falls back to the full solve when the range does not
+        // reach nw positive eigenvalues.
+        const int iu = std::min(nm, nw + 64);
+        Tmp<float> Gx((size_t)nm * nm, st);
+        SCL_CUDA(cudaMemcpyAsync(Gx.p, G.p, (size_t)nm * nm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        int meig = 0;
+        { ProfScope ps(&h->prof, st, PK_SYEVD); meig = h->solver->syevdx_smallest(Gx.p, nm, W.p, iu, st); }
+        std::vector<float> Lx(meig);
+        SCL_CUDA(cudaMemcpyAsync(Lx.data(), W.p, meig * sizeof(float), cudaMemcpyDeviceToHost, st));
+        SCL_CUDA(cudaStreamSynchronize(st));
+        int j = 0;
+        while (j < meig && !(Lx[j] > 1e-5f * lmax_ref)) ++j;
+        if (j + nw <= meig) {
+          i0 = j;
+          SCL_CUDA(cudaMemcpyAsync(G.p, Gx.p, (size_t)(i0 + nw) * nm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+      }
+      if (i0 < 0) {
+        { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G.p, nm, W.p, true, st); }
+        SCL_CUDA(cudaMemcpyAsync(Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
+        SCL_CUDA(cudaStreamSynchronize(st));
+        i0 = first_positive(Lh);
+        const int npos = nm - i0;
+        SCL_REQUIRE(npos >= n_2 + 1, "perturbed matrix has too few positive eigenvalues");
+      }
+      info.t_search_syevd_ms += tm.stop();
       SCL_REQUIRE(nw >= 5, "too few noise vectors");
       const double t_step_syevd = tm.stop();
       corr_colabsmax_pre(h, Vr, G.p + (size_t)i0 * nm, nw, nm, d_d.p);
