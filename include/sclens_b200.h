@@ -120,6 +120,9 @@ SCL_API int32_t scl_comm_init(scl_handle* h, const uint8_t id[128], int32_t rank
 /* Pure host logic (testable without a GPU): which replicates / search steps a rank owns. */
 SCL_API int32_t scl_plan_replicates(int32_t n_perturb, int32_t world, int32_t rank, int32_t* out_ids, int32_t* out_n);
 SCL_API int32_t scl_plan_search_wave(int32_t wave, int32_t world, int32_t rank, int32_t* out_step);
+/* Block [k0, k1) of the Gram contraction axis (cells when N > M; padded length ld = K rounded up to 8) a rank
+ * densifies and contracts before the partial Gram matrices are summed with ncclAllReduce. */
+SCL_API int32_t scl_plan_gram_shard(int64_t K, int32_t world, int32_t rank, int64_t* out_k0, int64_t* out_k1);
 
 /* ---- inputs ------------------------------------------------------------------------ */
 /* df2sparr output (:90-120): SparseMatrixCSC{Float32,UInt32}, N cells x M genes, canonical

@@ -73,6 +73,7 @@ SIGNATURES = {
     "scl_nccl_unique_id": [C.POINTER(C.c_uint8)],
     "scl_comm_init": [_hp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32],
     "scl_plan_replicates": [C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p],
+    "scl_plan_gram_shard": [C.c_int64, C.c_int32, C.c_int32, _i64p, _i64p],
     "scl_plan_search_wave": [C.c_int32, C.c_int32, C.c_int32, _i32p],
     "scl_set_counts_csc": [_hp, C.c_int32, C.c_int32, C.c_int64, _u32p, _u32p, _f32p, C.c_int32],
     "scl_set_zero_candidates": [_hp, C.c_int64, _u32p, _u32p, C.c_int32],

@@ -186,6 +186,12 @@ int32_t scl_plan_search_wave(int32_t wave, int32_t world, int32_t rank, int32_t*
   return SCL_OK;
 }
 
+int32_t scl_plan_gram_shard(int64_t K, int32_t world, int32_t rank, int64_t* out_k0, int64_t* out_k1) {
+  if (K < 1 || world < 1 || rank < 0 || rank >= world || !out_k0 || !out_k1) return SCL_ERR_INVALID;
+  scl::plan_gram_shard(K, (K + 7) / 8 * 8, world, rank, out_k0, out_k1);
+  return SCL_OK;
+}
+
 // ---- inputs -------------------------------------------------------------------------------
 int32_t scl_set_counts_csc(scl_handle* h, int32_t N, int32_t M, int64_t nnz, const uint32_t* colptr,
                            const uint32_t* rowval, const float* nzval, int32_t index_base) {

@@ -258,6 +258,15 @@ double quantile7(const std::vector<double>& sorted, double p) {
 
 }  // namespace
 
+// Contraction-axis block of rank `rank`: whole 64-element k-blocks, ceil(kblocks / world) per rank, the last rank also
+// takes the zero padding up to ld.  Blocks are disjoint and cover [0, ld); a rank beyond the data gets an empty block.
+void plan_gram_shard(int64_t K, int64_t ld, int world, int rank, int64_t* k0, int64_t* k1) {
+  const int64_t kblocks = (K + 63) / 64, per = (kblocks + world - 1) / world;
+  *k0 = std::min<int64_t>(ld, (int64_t)rank * per * 64);     // clamped to ld (a multiple of 8), never to K: a rank whose
+  *k1 = std::min<int64_t>(ld, (int64_t)(rank + 1) * per * 64);  // block starts beyond the data gets the empty block [ld, ld)
+  if (rank == world - 1) *k1 = ld;
+}
+
 // ---------------------------------------------------------------------------------------
 // normalise A and form its Wishart matrix on the smaller side:  dG = operand * operand^T * scale
 void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf<__half>& lo, float* dG, int nm,
@@ -278,12 +287,7 @@ void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf
   // contracts only that block; the partial Gram matrices are summed over NVLink.
   int64_t k0 = 0, k1 = (int64_t)ld;
   const bool sharded = shard && multi(h);
-  if (sharded) {
-    const int64_t kblocks = (K + 63) / 64, per = (kblocks + h->world - 1) / h->world;
-    k0 = std::min<int64_t>(K, (int64_t)h->rank * per * 64);
-    k1 = std::min<int64_t>((int64_t)ld, (int64_t)(h->rank + 1) * per * 64);
-    if (h->rank == h->world - 1) k1 = (int64_t)ld;
-  }
+  if (sharded) plan_gram_shard(K, (int64_t)ld, h->world, h->rank, &k0, &k1);
   const bool have_work = k1 > k0;
   // exact Gram diagonal: the tensor core's truncating FP32 accumulation biases long same-sign sums low; the
   // diagonal (the only systematically same-sign sum) comes from the statistics passes in Float64 instead

@@ -73,3 +73,29 @@ def test_two_rank_partition_and_speculative_search():
         assert p.exitcode == 0
     res = sorted(q.get() for _ in range(2))
     assert res[0][1] == res[1][1]
+
+
+def test_gram_shard_plan_partitions_the_contraction_axis():
+    """scl_plan_gram_shard (the block of cells / genes a rank densifies and contracts before the ncclAllReduce): for
+    any length and world size the blocks are 8-aligned, ordered, disjoint and cover the padded axis exactly once."""
+    import ctypes as C
+    sys.path.insert(0, ROOT)
+    from sclens_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    lengths = list(range(1, 700, 7)) + [20000, 68000, 500000] + [int(x) for x in rng.integers(1, 2_000_000, 200)]
+    for K in lengths:
+        ld = (K + 7) // 8 * 8
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            for r in range(world):
+                k0, k1 = C.c_int64(), C.c_int64()
+                assert lib.scl_plan_gram_shard(K, world, r, C.byref(k0), C.byref(k1)) == 0
+                a, b = k0.value, k1.value
+                assert a % 8 == 0 and b % 8 == 0 and 0 <= a <= b <= ld, (K, world, r, a, b)
+                if b > a:
+                    assert a == prev, (K, world, r, a, prev)      # contiguous with the previous non-empty block
+                    prev = b
+            assert prev == ld, (K, world, prev, ld)
+    assert lib.scl_plan_gram_shard(0, 2, 0, C.byref(C.c_int64()), C.byref(C.c_int64())) != 0
+    assert lib.scl_plan_gram_shard(10, 2, 2, C.byref(C.c_int64()), C.byref(C.c_int64())) != 0
