@@ -202,6 +202,10 @@ SCL_API int32_t scl_op_scores(scl_handle* h, int32_t N, int32_t k, int32_t min_p
                       const float* nV_sets, double th, float* b_, double* m_scores, double* sd_scores,
                       int32_t* sig_id, int32_t* n_robust);
 
+/* Host tail of the scoring (:797-806) on a k x n_pairs (column-major) table of pairwise similarities: Tukey fence,
+ * median, corrected std, robust set {median > cos(th degrees)}.  Pure host code (testable without a GPU). */
+SCL_API int32_t scl_op_scores_from_pairs(const float* b_, int32_t k, int32_t n_pairs, double th, double* m_scores,
+                                 double* sd_scores, int32_t* sig_id, int32_t* n_robust);
 /* get_denoised_df (:889-931) from the entries of the result Dict: pca_n1 N x r (the :pca_n1 columns), g_mat r x M
  * (= gene_basis[sig_id, :]), rec_vals TGC / mat2_mean / mat2_std / norm_tgc / cent_.  out: N x M column-major, Float64
  * (out_f32 = 0, as the reference's DataFrame) or Float32.  Replaces the cu()/mul! of :893-896 and the host broadcasts

@@ -110,6 +110,7 @@ SIGNATURES = {
     "scl_op_topk_subspace": [_hp, C.c_int32, _f32p, C.c_int32, _f32p, _f32p, _i32p],
     "scl_op_scores": [_hp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, C.c_double, _f32p, _f64p, _f64p,
                       _i32p, _i32p],
+    "scl_op_scores_from_pairs": [_f32p, C.c_int32, C.c_int32, C.c_double, _f64p, _f64p, _i32p, _i32p],
     "scl_op_denoise": [_hp, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _f64p, _f64p, _f64p, _f64p, _f64p, C.c_int32,
                        C.c_void_p],
     "scl_bench_gram": [_hp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _f64p, _f64p],

@@ -671,6 +671,22 @@ int32_t scl_op_scores(scl_handle* h, int32_t N, int32_t k, int32_t min_pc, int32
   });
 }
 
+// host tail of the scoring (:797-806) on a given k x n_pairs similarity table: pure host code
+int32_t scl_op_scores_from_pairs(const float* b_, int32_t k, int32_t n_pairs, double th, double* m_scores, double* sd_scores,
+                                 int32_t* sig_id, int32_t* n_robust) {
+  if (!b_ || k < 1 || n_pairs < 1 || !n_robust) return SCL_ERR_INVALID;
+  return guard(nullptr, [&] {
+    std::vector<float> b(b_, b_ + (size_t)k * n_pairs);
+    std::vector<double> m, sd;
+    std::vector<int32_t> sig;
+    score_from_pairs(b, k, n_pairs, th, m, sd, sig);
+    if (m_scores) std::memcpy(m_scores, m.data(), m.size() * sizeof(double));
+    if (sd_scores) std::memcpy(sd_scores, sd.data(), sd.size() * sizeof(double));
+    if (sig_id) std::memcpy(sig_id, sig.data(), sig.size() * sizeof(int32_t));
+    *n_robust = (int32_t)sig.size();
+  });
+}
+
 // get_denoised_df (:889-931) from the entries of the result Dict (all host pointers, Julia layouts)
 int32_t scl_op_denoise(scl_handle* h, int32_t N, int32_t M, int32_t r, const float* pca_n1, const float* g_mat,
                        const double* TGC, const double* mat2_mean, const double* mat2_std, const double* norm_tgc,

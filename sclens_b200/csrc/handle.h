@@ -67,6 +67,8 @@ void refine_eigenvalues(const float* dG, const float* dV, int n, float* dW, cuda
 // pipeline.cu
 void run_signal(scl_handle* h);
 void run_robustness(scl_handle* h, double th, double p_step, int n_perturb);
+void score_from_pairs(const std::vector<float>& b_, int k, int n_pairs, double th, std::vector<double>& m,
+                      std::vector<double>& sd, std::vector<int32_t>& sig);
 void plan_gram_shard(int64_t K, int64_t ld, int world, int rank, int64_t* k0, int64_t* k1);
 // shared building blocks (also used by the scl_op_* entry points)
 // shard=true (and world > 1): every rank contracts its own slice of the long axis (cells when N > M) and the

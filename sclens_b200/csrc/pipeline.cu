@@ -527,6 +527,37 @@ void run_signal(scl_handle* h) {
   h->signal_done = true;
 }
 
+// Host tail of the robustness scoring (:797-806), pure host code: per signal, Tukey fence (type-7 quartiles,
+// q1 - 1.5 iqr <= b <= q3 + 1.5 iqr) over its n_pairs pairwise similarities, median and corrected standard deviation of
+// what is left, and the robust set {i : median_i > cos(th)}.  b_ is k x n_pairs column-major.
+void score_from_pairs(const std::vector<float>& b_, int k, int n_pairs, double th, std::vector<double>& m_scores,
+                      std::vector<double>& sd_scores, std::vector<int32_t>& sig) {
+  const double th_ = std::cos(th * M_PI / 180.0);
+  m_scores.assign(k, 0.0);
+  sd_scores.assign(k, 0.0);
+  sig.clear();
+  for (int i = 0; i < k; ++i) {
+    std::vector<double> row(n_pairs);
+    for (int q = 0; q < n_pairs; ++q) row[q] = (double)b_[(size_t)q * k + i];
+    std::vector<double> srt = row;
+    std::sort(srt.begin(), srt.end());
+    const double q1 = quantile7(srt, 0.25), q3 = quantile7(srt, 0.75), iqr = q3 - q1;
+    std::vector<double> f;
+    for (double v : srt)
+      if (q1 - 1.5 * iqr <= v && v <= q3 + 1.5 * iqr) f.push_back(v);
+    const size_t n = f.size();
+    double med = n ? ((n & 1) ? f[n / 2] : 0.5 * (f[n / 2 - 1] + f[n / 2])) : NAN;
+    double mean = 0;
+    for (double v : f) mean += v;
+    mean /= (double)std::max<size_t>(1, n);
+    double ss = 0;
+    for (double v : f) ss += (v - mean) * (v - mean);
+    m_scores[i] = med;
+    sd_scores[i] = n > 1 ? std::sqrt(ss / (double)(n - 1)) : NAN;
+    if (med > th_) sig.push_back(i);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Robustness scoring (:786-806).  d_nV: [k][N]; d_sets: [n_perturb][min_pc][N].
 void score_sets(scl_handle* h, int N, int k, int min_pc, int n_perturb, const float* d_nV, const float* d_sets,
@@ -588,31 +619,7 @@ void score_sets(scl_handle* h, int N, int k, int min_pc, int n_perturb, const fl
         for (int j = 0; j < k; ++j) mx = std::max(mx, std::fabs(hc2[(size_t)(a * k + i) * R + (size_t)(b * k + j)]));
         b_[(size_t)pair * k + i] = mx;   // column-major k x n_pairs
       }
-  // Tukey fence, median, corrected std (:797-803)
-  const double th_ = std::cos(th * M_PI / 180.0);
-  m_scores.assign(k, 0.0);
-  sd_scores.assign(k, 0.0);
-  sig.clear();
-  for (int i = 0; i < k; ++i) {
-    std::vector<double> row(n_pairs);
-    for (int q = 0; q < n_pairs; ++q) row[q] = (double)b_[(size_t)q * k + i];
-    std::vector<double> srt = row;
-    std::sort(srt.begin(), srt.end());
-    const double q1 = quantile7(srt, 0.25), q3 = quantile7(srt, 0.75), iqr = q3 - q1;
-    std::vector<double> f;
-    for (double v : srt)
-      if (q1 - 1.5 * iqr <= v && v <= q3 + 1.5 * iqr) f.push_back(v);
-    const size_t n = f.size();
-    double med = n ? ((n & 1) ? f[n / 2] : 0.5 * (f[n / 2 - 1] + f[n / 2])) : NAN;
-    double mean = 0;
-    for (double v : f) mean += v;
-    mean /= (double)std::max<size_t>(1, n);
-    double ss = 0;
-    for (double v : f) ss += (v - mean) * (v - mean);
-    m_scores[i] = med;
-    sd_scores[i] = n > 1 ? std::sqrt(ss / (double)(n - 1)) : NAN;
-    if (med > th_) sig.push_back(i);
-  }
+  score_from_pairs(b_, k, n_pairs, th, m_scores, sd_scores, sig);
 }
 
 // ---------------------------------------------------------------------------------------

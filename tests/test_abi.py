@@ -128,3 +128,45 @@ def test_julia_shim_is_in_step_with_the_header():
         depth -= ch in ")]}"
         nargs += ch == "," and depth == 0
     assert nargs == len(_lib.Config._fields_)
+
+
+def _oracle_score_tail(b_, th):
+    """Tail of oracle.robustness_scores (:797-806) on a given similarity table."""
+    import math
+    q1 = np.quantile(b_, 0.25, axis=1)
+    q3 = np.quantile(b_, 0.75, axis=1)
+    iqr = q3 - q1
+    m, sd = np.zeros(b_.shape[0]), np.zeros(b_.shape[0])
+    for s in range(b_.shape[0]):
+        row = b_[s]
+        f = row[(q1[s] - 1.5 * iqr[s] <= row) & (row <= q3[s] + 1.5 * iqr[s])]
+        m[s] = np.median(f)
+        sd[s] = np.std(f, ddof=1) if len(f) > 1 else np.nan
+    return m, sd, np.nonzero(m > math.cos(math.radians(th)))[0]
+
+
+@pytest.mark.parametrize("k,n_pairs,seed", [(7, 190, 0), (3, 1, 1), (5, 3, 2), (12, 45, 3), (1, 6, 4)])
+def test_score_tail_matches_oracle(lib_built, k, n_pairs, seed):
+    """scl_op_scores_from_pairs (Tukey fence, median, corrected std, robust set) is pure host code: compare with the
+    oracle's restatement of :797-806, including one pair only (n_perturb = 2), outliers and tied values."""
+    from sclens_b200 import _lib
+    from sclens_b200._lib import ptr
+    lib = _lib.load()
+    rng = np.random.default_rng(seed)
+    b = rng.uniform(0.3, 1.0, size=(k, n_pairs)).astype(np.float32)
+    if n_pairs > 4:
+        b[0, :2] = 0.01                       # outliers below the fence
+        b[-1, :] = np.float32(0.75)           # all tied: iqr = 0, everything kept
+        b[k // 2, ::2] = b[k // 2, 1]         # many ties
+    bf = np.asfortranarray(b)                 # k x n_pairs column-major
+    m, sd = np.empty(k), np.empty(k)
+    sig = np.empty(k, np.int32)
+    nrob = C.c_int32()
+    for th in (60.0, 30.0, 75.0):
+        assert lib.scl_op_scores_from_pairs(ptr(bf, C.c_float), k, n_pairs, th, ptr(m, C.c_double), ptr(sd, C.c_double),
+                                            ptr(sig, C.c_int32), C.byref(nrob)) == 0
+        wm, wsd, wsig = _oracle_score_tail(b.astype(np.float64), th)
+        np.testing.assert_allclose(m, wm, rtol=1e-12)
+        np.testing.assert_allclose(sd, wsd, rtol=1e-9, atol=1e-15, equal_nan=True)
+        assert sig[:nrob.value].tolist() == wsig.tolist()
+    assert lib.scl_op_scores_from_pairs(ptr(bf, C.c_float), 0, n_pairs, 60.0, None, None, None, C.byref(nrob)) < 0
