@@ -170,3 +170,34 @@ def test_score_tail_matches_oracle(lib_built, k, n_pairs, seed):
         np.testing.assert_allclose(sd, wsd, rtol=1e-9, atol=1e-15, equal_nan=True)
         assert sig[:nrob.value].tolist() == wsig.tolist()
     assert lib.scl_op_scores_from_pairs(ptr(bf, C.c_float), 0, n_pairs, 60.0, None, None, None, C.byref(nrob)) < 0
+
+
+def test_df2sparr_host_mirror():
+    """df2sparr (:90-120) on the host: DataFrame with the cell column first and dense or pandas-sparse gene columns,
+    scipy matrices and ndarrays all become the same canonical Float32 CSC (sorted, duplicates summed, stored zeros
+    dropped) with the ids the result dictionary carries."""
+    import pandas as pd
+    import scipy.sparse as sp
+    from sclens_b200 import df2sparr
+    rng = np.random.default_rng(0)
+    dense = rng.poisson(0.3, size=(40, 17)).astype(np.float32)
+    dense[:, 5] = 0                                    # an all-zero gene stays a (empty) column
+    genes = [f"G{j}" for j in range(17)]
+    cells = [f"cell{i}" for i in range(40)]
+    df = pd.DataFrame(dense, columns=genes)
+    df.insert(0, "cell", cells)
+    X, cid, gid = df2sparr(df)
+    assert sp.isspmatrix_csc(X) and X.dtype == np.float32 and X.shape == (40, 17)
+    assert X.has_canonical_format and (X.data > 0).all()
+    np.testing.assert_array_equal(X.toarray(), dense)
+    assert cid.tolist() == cells and list(gid) == genes
+    sdf = pd.DataFrame({g: pd.arrays.SparseArray(dense[:, j], fill_value=0) for j, g in enumerate(genes)})
+    sdf.insert(0, "cell", cells)
+    Xs, _, _ = df2sparr(sdf)
+    assert (Xs != X).nnz == 0 and np.array_equal(Xs.indptr, X.indptr) and np.array_equal(Xs.indices, X.indices)
+    # COO input with duplicates and an explicit zero: summed / dropped like sparse(I, J, V) followed by dropzeros
+    coo = sp.coo_matrix((np.array([1, 2, 0, 3], np.float32), (np.array([0, 0, 1, 2]), np.array([1, 1, 0, 3]))), shape=(4, 5))
+    Xc, cid2, gid2 = df2sparr(coo)
+    assert Xc.nnz == 2 and Xc[0, 1] == 3 and Xc[2, 3] == 3 and cid2[0] == "c0" and gid2[4] == "g4"
+    Xn, _, _ = df2sparr(dense)
+    assert (Xn != X).nnz == 0
