@@ -201,3 +201,30 @@ def test_df2sparr_host_mirror():
     assert Xc.nnz == 2 and Xc[0, 1] == 3 and Xc[2, 3] == 3 and cid2[0] == "c0" and gid2[4] == "g4"
     Xn, _, _ = df2sparr(dense)
     assert (Xn != X).nnz == 0
+
+
+def test_get_denoised_df_validates_before_touching_the_device(lib_built):
+    """get_denoised_df (:889-931 mirror): shape / dtype / device_ errors are raised on the host; a well-formed call
+    without a GPU fails loudly at handle creation (no CPU fallback)."""
+    import torch
+    from sclens_b200 import SclError, get_denoised_df
+    N, M, k = 12, 9, 4
+    rng = np.random.default_rng(0)
+    res = {"gene_basis": rng.standard_normal((k, M)).astype(np.float32), "sig_id": np.array([0, 2]),
+           "pca_n1": rng.standard_normal((N, 2)).astype(np.float32), "cell_id": np.arange(N), "gene_id": np.arange(M),
+           "rec_vals": {"TGC": np.ones(N), "mat2_mean": np.zeros((1, M)), "mat2_std": np.ones((1, M)),
+                        "norm_tgc": np.ones(N), "cent_": np.zeros((1, M))}}
+    with pytest.raises(ValueError):
+        get_denoised_df(res, device_="cpu")
+    with pytest.raises(ValueError):
+        get_denoised_df(dict(res, sig_id=np.array([], dtype=np.int64)))
+    with pytest.raises(ValueError):
+        get_denoised_df(dict(res, pca_n1=res["pca_n1"][:, :1]))
+    with pytest.raises(ValueError):
+        get_denoised_df(dict(res, rec_vals=dict(res["rec_vals"], TGC=np.ones(N + 1))))
+    with pytest.raises(ValueError):
+        get_denoised_df(res, dtype=np.float16)
+    if not torch.cuda.is_available():
+        with pytest.raises(SclError) as e:
+            get_denoised_df(res)
+        assert e.value.code == -4
