@@ -200,12 +200,22 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     # default = the configuration BASELINE.json's metric is quoted on (68k x 20k, fits one GPU): 65 s per pass on one
     # B200, so the default run is 3 warm-ups + 1 timed pass + 1 end-to-end call, about 6 minutes; B is configs[1]
-    ap.add_argument("--workload", default=os.environ.get("SCLENS_BENCH_WORKLOAD", "C"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("SCLENS_BENCH_WORKLOAD"), choices=sorted(WORKLOADS))
     ap.add_argument("--n-perturb", type=int, default=20)
     ap.add_argument("--gram-mode", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    workload_note = None
+    if args.workload is None:
+        # 66 s per pass at 68k x 20k on one B200 (profiles/r1_bench_C_1gpu.json): keep the metric's own shape unless the
+        # requested W + K passes (+ end-to-end call + CPU sample) would run past half an hour on ONE GPU - the rule does
+        # not look at --gpus, so every point of a scaling series runs the same workload
+        est = (args.warmup + (args.steps or 1) + 2) * 66.0
+        args.workload = "C" if est <= 1800.0 else "B"
+        if args.workload == "B":
+            workload_note = (f"{args.warmup}+{args.steps} passes of the 68k x 20k workload were estimated at {est:.0f} s; "
+                             "fell back to BASELINE.json configs[1] (10k x 20k) - pass --workload C to force the metric's shape")
     if args.steps is None:
         args.steps = 1 if args.workload == "C" else 2
 
@@ -216,6 +226,8 @@ def main():
     config = {"workload": f"{args.workload}: synthetic {N} cells x {M} genes, ~92% sparse, n_perturb={args.n_perturb}, "
                           f"full MP/TW fit + sparsity search + stability", "N": N, "M": M,
               "l2": "inputs exceed L2 (dense operand >= 400 MB)", "parallelism": f"replicates+search x{world}"}
+    if workload_note:
+        config["workload_note"] = workload_note
 
     if args.impl == "reference":
         if rank != 0:
