@@ -86,6 +86,8 @@ typedef struct {
   double p_sel;              /* "Selected perturb sparisty"            (:762) */
   double p_th;               /* noise baseline                         (:712) */
   double t_baseline_ms, t_search_ms, t_search_syevd_ms, t_perturb_ms, t_score_ms, t_outputs_ms;
+  int32_t n_subspace_fallbacks; /* replicates whose block subspace iteration gave up and took the exact solve of :775 */
+  int32_t reserved;
 } scl_robust_info;
 
 /* Kernel-class timings (CUDA events on the library's stream) and algorithmic work counters,
@@ -100,6 +102,10 @@ typedef struct {
   int64_t kernel_launches;    /* kernels of this library launched by the process since load */
   double refine_ms;           /* Float64 Rayleigh-quotient refinement of the data spectrum */
   double small_ms;            /* calibration, reductions, collectives and other small kernels */
+  double stats_alg_bytes;     /* statistics line passes: 40 nnz per normalisation (4 nnz row sums, 3 x 8 nnz, 12 nnz patch pass) */
+  int64_t stats_calls;        /* normalisations (one set of statistics passes each) */
+  double comm_ms;             /* NCCL collectives on the library stream (Gram all-reduce, broadcasts of results) */
+  double comm_bytes;          /* payload bytes of those collectives as this rank sees them */
 } scl_profile;
 
 /* ---- lifecycle --------------------------------------------------------------------- */
@@ -120,6 +126,9 @@ SCL_API int32_t scl_comm_init(scl_handle* h, const uint8_t id[128], int32_t rank
 /* Pure host logic (testable without a GPU): which replicates / search steps a rank owns. */
 SCL_API int32_t scl_plan_replicates(int32_t n_perturb, int32_t world, int32_t rank, int32_t* out_ids, int32_t* out_n);
 SCL_API int32_t scl_plan_search_wave(int32_t wave, int32_t world, int32_t rank, int32_t* out_step);
+/* Task list of scl_run_pass: wave `wave` gives rank `rank` task t = wave * world + rank; t = 0 data matrix, 1 null matrix,
+ * 2 reference basis of the binarised matrix, t >= 3 sparsity-search step t - 3 (out_search_step, else -1). */
+SCL_API int32_t scl_plan_pass_task(int32_t wave, int32_t world, int32_t rank, int32_t* out_task, int32_t* out_search_step);
 /* Block [k0, k1) of the Gram contraction axis (cells when N > M; padded length ld = K rounded up to 8) a rank
  * densifies and contracts before the partial Gram matrices are summed with ncclAllReduce. */
 SCL_API int32_t scl_plan_gram_shard(int64_t K, int32_t world, int32_t rank, int64_t* out_k0, int64_t* out_k1);
@@ -146,6 +155,13 @@ SCL_API int32_t scl_clear_draws(scl_handle* h);
 SCL_API int32_t scl_run_signal(scl_handle* h, scl_signal_info* out);
 /* :709-819: noise baseline, sparsity search, perturbations, robustness scores, outputs. */
 SCL_API int32_t scl_run_robustness(scl_handle* h, double th, double p_step, int32_t n_perturb, scl_robust_info* out);
+
+/* Both stages as ONE call (:664-819).  On one GPU it is scl_run_signal followed by scl_run_robustness (skipped, with a
+ * zeroed scl_robust_info, when there is no signal).  After scl_comm_init it is one pass shared by all ranks: cell-sharded
+ * Gram matrices reduced to the rank that solves them, and the pass's eigensolves - data, null, binarised reference, search
+ * steps - dealt to the ranks wave by wave.  Every rank must call it with the same arguments and ends with the same results. */
+SCL_API int32_t scl_run_pass(scl_handle* h, double th, double p_step, int32_t n_perturb, scl_signal_info* sout,
+                             scl_robust_info* rout);
 
 /* ---- results (caller-allocated; sizes from the info structs) ------------------------- */
 SCL_API int32_t scl_get_L(scl_handle* h, float* L /* nm, ascending, unfiltered (:378) */);
@@ -180,6 +196,12 @@ SCL_API int32_t scl_op_gemm_tn(scl_handle* h, int32_t m, int32_t n, int64_t K, i
                        float alpha, int32_t c_colmajor, float* C);
 /* _get_eigen (:375-382): cuSOLVER syevd('V','U'), ascending. V may be NULL (values only). */
 SCL_API int32_t scl_op_syevd(scl_handle* h, int32_t n, const float* A, float* L, float* V, double* ms);
+/* The same solve with the library's tridiagonal stage replaced by this library's own (tridiag.cu): cusolverDnSsytrd ->
+ * Float64 Sturm multisection + twisted factorisation -> cusolverDnSormtr.  L: all n eigenvalues ascending; V: the
+ * eigenvectors with ascending 0-based indices [v0, v1) as columns (n x (v1 - v0) column-major; v0 == v1: values only, V
+ * may be NULL).  out (may be NULL): [ms Ssytrd, ms tridiagonal stage, ms Sormtr, eigenvalue clusters, eigenvalues in
+ * clusters, 1 if the solve fell back to Ssyevd]. */
+SCL_API int32_t scl_op_syevd_tri(scl_handle* h, int32_t n, const float* A, int32_t v0, int32_t v1, float* L, float* V, double out[6]);
 /* _mp_calculation + _tw + mp_check (:424-487) on host doubles. out: [lambda_c,b_plus,b_minus,
  * ks_static, n_Lmp, mp_iters, pass, n_signal]. */
 SCL_API int32_t scl_op_mp_fit(const float* L, int32_t nL, const float* Lr, int32_t nLr, double out[8]);
@@ -202,6 +224,18 @@ SCL_API int32_t scl_op_scores(scl_handle* h, int32_t N, int32_t k, int32_t min_p
                       const float* nV_sets, double th, float* b_, double* m_scores, double* sd_scores,
                       int32_t* sig_id, int32_t* n_robust);
 
+/* ---- device-side draws of a production run (no injected draws), exposed for their own tests ----------------------- */
+/* z_idx1 / z_idx2 of :668-673 drawn on the device from the handle's counts with `seed`: nnz uniform grid positions,
+ * minus the stored entries, distinct in first-occurrence order.  *n = number of candidates; z1 / z2 (0-based rows / columns,
+ * capacity >= nnz) may be NULL to ask for the count only.  The handle keeps the draw as its zero-candidate set. */
+SCL_API int32_t scl_op_draw_zero_candidates(scl_handle* h, uint64_t seed, int64_t* n, uint32_t* z1, uint32_t* z2);
+/* The uniform draws behind it, restated on the host (pure function of seed and draw index): rows[t], cols[t] of draw t. */
+SCL_API int32_t scl_op_zero_candidate_draws(uint64_t seed, int64_t n_draws, int32_t N, int32_t M, uint32_t* rows, uint32_t* cols);
+/* p_th of :709-712 drawn on the device: mean over n_rep of max |N(0, 1/nm)| over nm samples. */
+SCL_API int32_t scl_op_noise_baseline(scl_handle* h, int32_t nm, int32_t n_rep, uint64_t seed, double* p_th);
+/* sample(1:n_cand, n_take, replace=false) of :731 / :772 on the handle's zero candidates: the (row, col) pairs taken. */
+SCL_API int32_t scl_op_draw_subset(scl_handle* h, int64_t n_take, uint64_t seed, uint32_t* rows, uint32_t* cols);
+
 /* Host tail of the scoring (:797-806) on a k x n_pairs (column-major) table of pairwise similarities: Tukey fence,
  * median, corrected std, robust set {median > cos(th degrees)}.  Pure host code (testable without a GPU). */
 SCL_API int32_t scl_op_scores_from_pairs(const float* b_, int32_t k, int32_t n_pairs, double th, double* m_scores,
@@ -223,8 +257,15 @@ SCL_API int32_t scl_bench_gram(scl_handle* h, int32_t rows, int64_t K, int32_t m
 /* Normalisation kernels on the handle's counts (:677-696): statistics pre-passes and the fused densify writer. */
 /* Timing study of the library eigensolvers on an n x n Wishart matrix generated on the device (CUDA events around the
  * solver call).  mode 0: Ssyevd with vectors (what the path calls), 1: values only, 2: Ssyevdx with the vectors of the
- * il..iu smallest eigenvalues (1-based, inclusive), 3: Xsyevd (64-bit API) with vectors. */
+ * il..iu smallest eigenvalues (1-based, inclusive), 3: Xsyevd (64-bit API) with vectors, 4: Ssytrd alone (the
+ * tridiagonalisation half of a one-stage solve), 5: Sormtr alone (back-transformation of an n x n block), 6 / 7 / 8: the
+ * own tridiagonal stage with all vectors / the vectors il..iu / values only.  mode + 16: solve the data Gram matrix of the
+ * last scl_run_signal (needs n == nm) instead of the synthetic one. */
 SCL_API int32_t scl_bench_syevd(scl_handle* h, int32_t n, int32_t mode, int32_t il, int32_t iu, double* ms);
+/* `nsolves` independent Ssyevd solves (mode 0: with vectors, 1: values only) of n x n Wishart matrices issued at the same
+ * time from `nsolves` host threads, each with its own stream and cuSOLVER handle; ms_wall = host wall time until all
+ * are done (after one untimed round).  Answers whether independent eigensolves (sparsity-search steps) overlap on ONE GPU. */
+SCL_API int32_t scl_bench_syevd_concurrent(scl_handle* h, int32_t n, int32_t nsolves, int32_t mode, double* ms_wall);
 /* Tuning studies only (process-wide).  stat_variant: launch shape of the statistics passes (0-7: line passes,
  * 8: strip passes; < 0 keeps the current one).  stat_heavy: line length above which a whole CTA takes a line
  * (<= 0 keeps).  writer: dense writer, -1 automatic, 0 register/overlay writer, 1 TMA bulk-store writer, 2 / 3

@@ -34,6 +34,7 @@ mutable struct SclRobustInfo
     p_sel::Float64; p_th::Float64
     t_baseline_ms::Float64; t_search_ms::Float64; t_search_syevd_ms::Float64
     t_perturb_ms::Float64; t_score_ms::Float64; t_outputs_ms::Float64
+    n_subspace_fallbacks::Int32; reserved::Int32
     SclRobustInfo() = new()
 end
 

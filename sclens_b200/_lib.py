@@ -40,7 +40,8 @@ class RobustInfo(C.Structure):
     _fields_ = [("n_search", C.c_int32), ("n_perturb", C.c_int32), ("min_pc", C.c_int32), ("n_robust", C.c_int32),
                 ("n_add", C.c_int64), ("p_sel", C.c_double), ("p_th", C.c_double), ("t_baseline_ms", C.c_double),
                 ("t_search_ms", C.c_double), ("t_search_syevd_ms", C.c_double), ("t_perturb_ms", C.c_double),
-                ("t_score_ms", C.c_double), ("t_outputs_ms", C.c_double)]
+                ("t_score_ms", C.c_double), ("t_outputs_ms", C.c_double), ("n_subspace_fallbacks", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class Profile(C.Structure):
@@ -49,7 +50,9 @@ class Profile(C.Structure):
                 ("gram_gemm_launches", C.c_int64), ("other_gemm_launches", C.c_int64), ("densify_launches", C.c_int64),
                 ("sparse_calls", C.c_int64), ("syevd_calls", C.c_int64), ("gram_alg_flops", C.c_double),
                 ("other_gemm_flops", C.c_double), ("densify_alg_bytes", C.c_double), ("sparse_alg_bytes", C.c_double),
-                ("kernel_launches", C.c_int64), ("refine_ms", C.c_double), ("small_ms", C.c_double)]
+                ("kernel_launches", C.c_int64), ("refine_ms", C.c_double), ("small_ms", C.c_double),
+                ("stats_alg_bytes", C.c_double), ("stats_calls", C.c_int64), ("comm_ms", C.c_double),
+                ("comm_bytes", C.c_double)]
 
 
 _u32p = C.POINTER(C.c_uint32)
@@ -74,6 +77,7 @@ SIGNATURES = {
     "scl_comm_init": [_hp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32],
     "scl_plan_replicates": [C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p],
     "scl_plan_gram_shard": [C.c_int64, C.c_int32, C.c_int32, _i64p, _i64p],
+    "scl_plan_pass_task": [C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p],
     "scl_plan_search_wave": [C.c_int32, C.c_int32, C.c_int32, _i32p],
     "scl_set_counts_csc": [_hp, C.c_int32, C.c_int32, C.c_int64, _u32p, _u32p, _f32p, C.c_int32],
     "scl_set_zero_candidates": [_hp, C.c_int64, _u32p, _u32p, C.c_int32],
@@ -84,6 +88,7 @@ SIGNATURES = {
     "scl_clear_draws": [_hp],
     "scl_run_signal": [_hp, C.POINTER(SignalInfo)],
     "scl_run_robustness": [_hp, C.c_double, C.c_double, C.c_int32, C.POINTER(RobustInfo)],
+    "scl_run_pass": [_hp, C.c_double, C.c_double, C.c_int32, C.POINTER(SignalInfo), C.POINTER(RobustInfo)],
     "scl_get_L": [_hp, _f32p],
     "scl_get_Lmp": [_hp, _f32p],
     "scl_get_signal_ev": [_hp, _f32p],
@@ -101,6 +106,7 @@ SIGNATURES = {
     "scl_op_gemm_tn": [_hp, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _u16p, _u16p, _u16p, _u16p,
                        C.c_float, C.c_int32, _f32p],
     "scl_op_syevd": [_hp, C.c_int32, _f32p, _f32p, _f32p, _f64p],
+    "scl_op_syevd_tri": [_hp, C.c_int32, _f32p, C.c_int32, C.c_int32, _f32p, _f32p, _f64p],
     "scl_op_mp_fit": [_f32p, C.c_int32, _f32p, C.c_int32, _f64p],
     "scl_op_permute_null": [_hp, C.c_int32, C.c_int32, C.c_int64, _u32p, _u32p, _f32p, _u32p, _u32p, _i64p, _u32p,
                             _u32p, _f32p],
@@ -110,11 +116,16 @@ SIGNATURES = {
     "scl_op_topk_subspace": [_hp, C.c_int32, _f32p, C.c_int32, _f32p, _f32p, _i32p],
     "scl_op_scores": [_hp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, C.c_double, _f32p, _f64p, _f64p,
                       _i32p, _i32p],
+    "scl_op_draw_zero_candidates": [_hp, C.c_uint64, _i64p, _u32p, _u32p],
+    "scl_op_zero_candidate_draws": [C.c_uint64, C.c_int64, C.c_int32, C.c_int32, _u32p, _u32p],
+    "scl_op_noise_baseline": [_hp, C.c_int32, C.c_int32, C.c_uint64, _f64p],
+    "scl_op_draw_subset": [_hp, C.c_int64, C.c_uint64, _u32p, _u32p],
     "scl_op_scores_from_pairs": [_f32p, C.c_int32, C.c_int32, C.c_double, _f64p, _f64p, _i32p, _i32p],
     "scl_op_denoise": [_hp, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _f64p, _f64p, _f64p, _f64p, _f64p, C.c_int32,
                        C.c_void_p],
     "scl_bench_gram": [_hp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _f64p, _f64p],
     "scl_bench_syevd": [_hp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f64p],
+    "scl_bench_syevd_concurrent": [_hp, C.c_int32, C.c_int32, C.c_int32, _f64p],
     "scl_debug_set_tuning": [C.c_int32, C.c_int32, C.c_int32],
     "scl_bench_normalize": [_hp, C.c_int32, C.c_int32, C.c_int32, _f64p, _f64p, _f64p],
 }

@@ -84,6 +84,7 @@ class Handle:
         self.sinfo: Optional[SignalInfo] = None
         self.rinfo: Optional[RobustInfo] = None
         self.N = self.M = 0
+        self.world, self.rank = 1, 0
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h:
@@ -135,8 +136,11 @@ class Handle:
         self._ck(self.lib.scl_push_perturb_sample(self.h, len(s), ptr(s, C.c_uint32), 0))
 
     def comm_init(self, uid: bytes, rank: int, world: int):
+        """Join the NCCL communicator of a cooperative pass.  A handle that already is rank `rank` of `world` keeps its
+        communicator (the library ignores the new id), so sclens(handle=h, comm=...) can be called again and again."""
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         self._ck(self.lib.scl_comm_init(self.h, buf, rank, world))
+        self.world, self.rank = world, rank
 
     def profile(self) -> Profile:
         p = Profile()
@@ -166,6 +170,15 @@ class Handle:
         self._ck(self.lib.scl_run_robustness(self.h, float(th), float(p_step), int(n_perturb), C.byref(info)))
         self.rinfo = info
         return info
+
+    def run_pass(self, th=60.0, p_step=0.001, n_perturb=20):
+        """Both stages in one call (scl_run_pass): on several ranks the eigensolves of the pass are dealt to the ranks.
+        Returns (SignalInfo, RobustInfo); RobustInfo is None when there is no signal (:780-784)."""
+        si, ri = SignalInfo(), RobustInfo()
+        self._ck(self.lib.scl_run_pass(self.h, float(th), float(p_step), int(n_perturb), C.byref(si), C.byref(ri)))
+        self.sinfo = si
+        self.rinfo = ri if si.n_signal > 0 else None
+        return si, self.rinfo
 
     # ---- results
     def _getf(self, fn, n, dtype=np.float32, ctype=C.c_float):
@@ -293,8 +306,14 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
         if verbose:
             print("Extracting Signals...")                              # :702
         _lap()
-        si = h.run_signal()
-        host_ms["run_signal"] = _lap()
+        cooperative = h.world > 1
+        if cooperative:
+            # one pass shared by the ranks: the eigensolves of both stages are dealt out together (scl_run_pass)
+            si, ri = h.run_pass(th=th, p_step=p_step, n_perturb=n_perturb)
+            host_ms["run_pass"] = _lap()
+        else:
+            si = h.run_signal()
+            host_ms["run_signal"] = _lap()
         L, L_mp = h.L(), h.L_mp()
         results = {"L": L, "L_mp": L_mp, "λ": si.lambda_c, "lambda": si.lambda_c, "cell_id": cell_id}
         if si.n_signal == 0:                                            # :780-784
@@ -304,9 +323,10 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
         if verbose:
             print("Calculating noise baseline...")                      # :707
             print("Calculating sparsity level for the perturbation...")  # :716
-        _lap()
-        ri = h.run_robustness(th=th, p_step=p_step, n_perturb=n_perturb)
-        host_ms["run_robustness"] = _lap()
+        if not cooperative:
+            _lap()
+            ri = h.run_robustness(th=th, p_step=p_step, n_perturb=n_perturb)
+            host_ms["run_robustness"] = _lap()
         nV, nL = h.signal_evec(), h.signal_ev()
         b_, m_scores, sd_scores = h.scores()
         sig_id = h.sig_id()
@@ -329,7 +349,7 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
             "signal_evec": nV, "signal_ev": nL, "gene_id": gene_id, "gene_basis": h.gene_basis(),
             "pass": bool(si.pass_), "rec_vals": h.rec_vals(),
             "info": {"host_ms": host_ms, "p_sel": ri.p_sel, "n_search": ri.n_search, "p_th": ri.p_th, "min_pc": ri.min_pc,
-                     "n_add": ri.n_add, "ks_static": si.ks_static, "b_plus": si.b_plus, "b_minus": si.b_minus,
+                     "n_add": ri.n_add, "n_subspace_fallbacks": ri.n_subspace_fallbacks, "ks_static": si.ks_static, "b_plus": si.b_plus, "b_minus": si.b_minus,
                      "timings_ms": {"gram": si.t_gram_ms, "syevd_signal": si.t_syevd_ms, "null": si.t_null_ms,
                                     "fit": si.t_fit_ms, "backproject": si.t_backproject_ms,
                                     "baseline": ri.t_baseline_ms, "search": ri.t_search_ms,

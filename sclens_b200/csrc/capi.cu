@@ -1,6 +1,8 @@
 // extern "C" surface of libsclens_b200.so (see include/sclens_b200.h).
 #include "nccl_dyn.h"
+#include <chrono>
 #include <cstring>
+#include <thread>
 #include "handle.h"
 #include "tmp.cuh"
 
@@ -110,6 +112,10 @@ int32_t scl_get_profile(scl_handle* h, scl_profile* out) {
   out->kernel_launches = g_kernel_launches.load();
   out->refine_ms = p.ms[PK_REFINE];
   out->small_ms = p.ms[PK_SMALL];
+  out->stats_alg_bytes = p.stats_alg_bytes;
+  out->stats_calls = p.calls[PK_STATS];
+  out->comm_ms = p.ms[PK_COMM];
+  out->comm_bytes = p.comm_bytes;
   return SCL_OK;
 }
 
@@ -156,6 +162,11 @@ int32_t scl_comm_init(scl_handle* h, const uint8_t id[128], int32_t rank, int32_
   if (!h) return SCL_ERR_INVALID;
   return guard(h, [&] {
     SCL_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+    if (h->nccl && h->world == world && h->rank == rank) return;   // already this rank of this world: keep the communicator
+    if (h->nccl) {                                                 // a different world: the old communicator goes first
+      nccl_api().CommDestroy((ncclComm_t)h->nccl);
+      h->nccl = nullptr;
+    }
     h->world = world;
     h->rank = rank;
     if (world == 1) return;
@@ -183,6 +194,13 @@ int32_t scl_plan_replicates(int32_t n_perturb, int32_t world, int32_t rank, int3
 int32_t scl_plan_search_wave(int32_t wave, int32_t world, int32_t rank, int32_t* out_step) {
   if (wave < 0 || world < 1 || rank < 0 || rank >= world || !out_step) return SCL_ERR_INVALID;
   *out_step = wave * world + rank;
+  return SCL_OK;
+}
+
+int32_t scl_plan_pass_task(int32_t wave, int32_t world, int32_t rank, int32_t* out_task, int32_t* out_search_step) {
+  if (wave < 0 || world < 1 || rank < 0 || rank >= world || !out_task) return SCL_ERR_INVALID;
+  *out_task = wave * world + rank;
+  if (out_search_step) *out_search_step = *out_task >= 3 ? *out_task - 3 : -1;
   return SCL_OK;
 }
 
@@ -281,6 +299,17 @@ int32_t scl_run_robustness(scl_handle* h, double th, double p_step, int32_t n_pe
     run_robustness(h, th, p_step, n_perturb);
   });
   if (rc == SCL_OK && out) *out = h->rinfo;
+  return rc;
+}
+
+int32_t scl_run_pass(scl_handle* h, double th, double p_step, int32_t n_perturb, scl_signal_info* sout, scl_robust_info* rout) {
+  if (!h) return SCL_ERR_INVALID;
+  int32_t rc = guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    run_pass(h, th, p_step, n_perturb);
+  });
+  if (rc == SCL_OK && sout) *sout = h->sinfo;
+  if (rc == SCL_OK && rout) *rout = h->rinfo;
   return rc;
 }
 
@@ -474,7 +503,129 @@ int32_t scl_bench_syevd(scl_handle* h, int32_t n, int32_t mode, int32_t il, int3
     a.syrk = true; a.alpha = 1.0f / (float)K; a.C = g.p; a.ldc = n;
     a.cta_group = h->cfg.cta_group == 1 ? 1 : 2;
     gemm_umma(a, h->st);
-    *ms = h->solver->bench(g.p, n, w.p, mode, il, iu, h->st);
+    if (mode & 16) {   // the data Gram matrix of the last scl_run_signal instead of the synthetic one
+      SCL_REQUIRE(h->signal_done && h->ws_Gkeep.p && h->sinfo.nm == n, "mode bit 4 needs a finished scl_run_signal of the same size");
+      SCL_CUDA(cudaMemcpyAsync(g.p, h->ws_Gkeep.p, (size_t)n * n * sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+    }
+    *ms = h->solver->bench(g.p, n, w.p, mode & 15, il, iu, h->st);
+  });
+}
+
+int32_t scl_op_syevd_tri(scl_handle* h, int32_t n, const float* A, int32_t v0, int32_t v1, float* L, float* V, double* out_ms) {
+  if (!h || !A || !L || n < 2 || v0 < 0 || v1 < v0 || v1 > n || (v1 > v0 && !V)) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    Tmp<float> g((size_t)n * n, h->st), w(n, h->st);
+    SCL_CUDA(cudaMemcpyAsync(g.p, A, (size_t)n * n * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    const bool own = h->solver->syevd_tri(g.p, n, w.p, v0, v1, h->st);
+    SCL_CUDA(cudaMemcpyAsync(L, w.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    if (v1 > v0)
+      SCL_CUDA(cudaMemcpyAsync(V, g.p + (size_t)v0 * n, (size_t)(v1 - v0) * n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+    if (out_ms) {
+      for (int i = 0; i < 3; ++i) out_ms[i] = h->solver->tri_ms[i];
+      out_ms[3] = (double)h->solver->tri_clusters;
+      out_ms[4] = (double)h->solver->tri_clustered;
+      out_ms[5] = own ? 0.0 : 1.0;
+    }
+  });
+}
+
+int32_t scl_op_draw_zero_candidates(scl_handle* h, uint64_t seed, int64_t* n, uint32_t* z1, uint32_t* z2) {
+  if (!h || !n) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_REQUIRE(h->have_X, "scl_set_counts_csc must be called first");
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    h->n_cand = draw_zero_candidates_device(h->X, seed, h->z1, h->z2, h->st);
+    h->have_zc = true;
+    *n = (int64_t)h->n_cand;
+    if (z1) SCL_CUDA(cudaMemcpyAsync(z1, h->z1.p, h->n_cand * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    if (z2) SCL_CUDA(cudaMemcpyAsync(z2, h->z2.p, h->n_cand * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+  });
+}
+
+int32_t scl_op_zero_candidate_draws(uint64_t seed, int64_t n_draws, int32_t N, int32_t M, uint32_t* rows, uint32_t* cols) {
+  if (n_draws < 0 || N < 1 || M < 1 || !rows || !cols) return SCL_ERR_INVALID;
+  const uint64_t grid = (uint64_t)N * (uint64_t)M;
+  for (int64_t t = 0; t < n_draws; ++t) {
+    const uint64_t g = zero_candidate_position_host(seed, (uint64_t)t, grid);
+    rows[t] = (uint32_t)(g % (uint64_t)N);
+    cols[t] = (uint32_t)(g / (uint64_t)N);
+  }
+  return SCL_OK;
+}
+
+int32_t scl_op_noise_baseline(scl_handle* h, int32_t nm, int32_t n_rep, uint64_t seed, double* p_th) {
+  if (!h || nm < 1 || n_rep < 1 || !p_th) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    *p_th = noise_baseline_device(nm, n_rep, seed, h->st);
+  });
+}
+
+int32_t scl_op_draw_subset(scl_handle* h, int64_t n_take, uint64_t seed, uint32_t* rows, uint32_t* cols) {
+  if (!h || n_take < 0 || !rows || !cols) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_REQUIRE(h->have_zc || h->n_cand > 0, "no zero candidates on the handle (scl_set_zero_candidates / scl_op_draw_zero_candidates)");
+    SCL_REQUIRE((size_t)n_take <= h->n_cand, "sample larger than the candidate pool");
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    Tmp<uint32_t> r((size_t)std::max<int64_t>(1, n_take), h->st), c((size_t)std::max<int64_t>(1, n_take), h->st);
+    draw_subset_device(h->z1.p, h->z2.p, h->n_cand, (size_t)n_take, seed, r.p, c.p, h->st);
+    SCL_CUDA(cudaMemcpyAsync(rows, r.p, (size_t)n_take * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    SCL_CUDA(cudaMemcpyAsync(cols, c.p, (size_t)n_take * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    SCL_CUDA(cudaStreamSynchronize(h->st));
+  });
+}
+
+int32_t scl_bench_syevd_concurrent(scl_handle* h, int32_t n, int32_t nsolves, int32_t mode, double* ms_wall) {
+  if (!h || n < 8 || nsolves < 1 || nsolves > 8 || !ms_wall) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    const int64_t K = 2 * (int64_t)n, ld = (K + 7) / 8 * 8;
+    Tmp<__half> op((size_t)n * ld, h->st);
+    fill_random_f16(op.p, (size_t)n * ld, 0x5eedu, 1.0f, h->st);
+    struct Lane {
+      cudaStream_t st = nullptr;
+      std::unique_ptr<Solver> solver;
+      DBuf<float> g, w;
+      std::string err;
+    };
+    std::vector<Lane> lanes(nsolves);
+    for (auto& L : lanes) {
+      SCL_CUDA(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+      L.solver.reset(new Solver(L.st));
+      L.g.ensure((size_t)n * n);
+      L.w.ensure(n);
+    }
+    auto fill = [&](Lane& L) {
+      GemmArgs a;
+      a.A.hi = op.p; a.A.rows = n; a.A.K = K; a.A.ld = ld;
+      a.B = a.A;
+      a.syrk = true; a.alpha = 1.0f / (float)K; a.C = L.g.p; a.ldc = n;
+      a.cta_group = h->cfg.cta_group == 1 ? 1 : 2;
+      gemm_umma(a, h->st);
+    };
+    // one warm-up solve per lane (workspace allocation, library initialisation), then the timed concurrent round
+    for (int round = 0; round < 2; ++round) {
+      for (auto& L : lanes) fill(L);
+      SCL_CUDA(cudaStreamSynchronize(h->st));
+      const auto t0 = std::chrono::steady_clock::now();
+      std::vector<std::thread> th;
+      for (auto& L : lanes)
+        th.emplace_back([&L, n, mode, dev = h->cfg.device] {
+          try {
+            cudaSetDevice(dev);
+            L.solver->syevd(L.g.p, n, L.w.p, mode == 0, L.st);
+            cudaStreamSynchronize(L.st);
+          } catch (const std::exception& e) { L.err = e.what(); }
+        });
+      for (auto& t : th) t.join();
+      *ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      for (auto& L : lanes)
+        if (!L.err.empty()) throw Error(SCL_ERR_CUSOLVER, L.err);
+    }
+    for (auto& L : lanes) { L.solver.reset(); cudaStreamDestroy(L.st); }
   });
 }
 

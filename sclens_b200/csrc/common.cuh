@@ -122,6 +122,8 @@ void permute_null(const SpMat& base, const uint32_t* d_perm, const uint32_t* d_r
 void draw_null_device(const SpMat& base, uint64_t seed, SpMat& out, cudaStream_t st);
 size_t draw_zero_candidates_device(const SpMat& base, uint64_t seed, DBuf<uint32_t>& z1, DBuf<uint32_t>& z2,
                                    cudaStream_t st);
+// grid position (row + N * col) of the t-th uniform draw behind draw_zero_candidates_device, on the host (tests)
+uint64_t zero_candidate_position_host(uint64_t seed, uint64_t t, uint64_t grid);
 void draw_subset_device(const uint32_t* z1, const uint32_t* z2, size_t n_cand, size_t n_take, uint64_t seed,
                         uint32_t* out_row, uint32_t* out_col, cudaStream_t st);
 void gather_pairs(const uint32_t* z1, const uint32_t* z2, const uint32_t* d_idx, size_t n, uint32_t* out_row,
@@ -135,7 +137,8 @@ void ensure_patch(const SpMat& A, NormStats& S, int layout, cudaStream_t st);
 // layout 0: gene-major out[M][ld] (column-major N x M); 1: cell-major out[N][ld]
 // [pos0,pos1): range of positions of every line to emit (default: the whole padded line) - the cell block of a rank
 void densify(const SpMat& A, NormStats& S, int layout, size_t ld, __half* out_hi, __half* out_lo,
-             cudaStream_t st, long long pos0 = 0, long long pos1 = -1);
+             cudaStream_t st, long long pos0 = 0, long long pos1 = -1, size_t slice_stride = 0);
+// slice_stride != 0: out_hi / out_lo hold ONLY the positions [pos0, pos1) of every line, slice_stride elements apart
 void set_norm_tuning(int stat_variant, int stat_heavy, int writer);
 // exact Float64 Gram diagonal (unscaled) of the normalised matrix on its gene side / cell side
 const double* gram_diagonal(const SpMat& A, NormStats& S, bool gene_side, cudaStream_t st);

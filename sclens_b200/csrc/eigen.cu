@@ -21,6 +21,8 @@ struct Solver::Impl {
   cusolverDnHandle_t h = nullptr;
   cusolverDnParams_t params = nullptr;   // 64-bit API (SCL_EIG_API=1)
   DBuf<float> work;
+  DBuf<float> tri_d, tri_e, tri_tau, tri_z, tri_keep;   // own tridiagonal stage: T, reflector scalars, vectors, matrix copy
+  DBuf<double> tri_w;
   DBuf<double> dwork;
   DBuf<int> info;
   std::vector<unsigned char> host_work;
@@ -32,7 +34,11 @@ struct Solver::Impl {
 // Bit 1: the sparsity-search steps, which use only the n/2+1 smallest eigenvectors (:742), call cusolverDnSsyevdx with
 // an index range instead of a full solve (474 ms in the same first look); also opt-in until parity-tested.
 int eig_api() {
-  static const int v = [] { const char* e = getenv("SCL_EIG_API"); return e ? atoi(e) : 0; }();
+  // default 12: the own tridiagonal stage for every solve (bit 2) with index-range vectors in the search steps (bit 3);
+  // measured at n = 20 000 on the 68k x 20k data Gram matrix (profiles/r2_eig_study2.json): 2.85 s against 3.65 s for
+  // Ssyevd with all vectors, 2.70 s for the smallest half, 2.47 s against 3.20 s for values only.  SCL_EIG_API=0 is
+  // the plain library solve (the call the reference makes).
+  static const int v = [] { const char* e = getenv("SCL_EIG_API"); return e ? atoi(e) : 12; }();
   return v;
 }
 
@@ -47,8 +53,70 @@ Solver::~Solver() {
   delete impl;
 }
 
+bool Solver::syevd_tri(float* dA, int n, float* dW, int v0, int v1, cudaStream_t st) {
+  SCL_REQUIRE(n >= 2 && 0 <= v0 && v0 <= v1 && v1 <= n, "bad eigenvector index range");
+  const int m = v1 - v0;
+  const size_t nn = (size_t)n * n;
+  cudaEvent_t ev[4];
+  for (auto& e : ev) SCL_CUDA(cudaEventCreate(&e));
+  impl->tri_d.ensure(n); impl->tri_e.ensure(n); impl->tri_tau.ensure(n); impl->tri_w.ensure(n);
+  impl->tri_keep.ensure(nn);
+  if (m) impl->tri_z.ensure((size_t)m * n);
+  SCL_CUDA(cudaMemcpyAsync(impl->tri_keep.p, dA, nn * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  int lw1 = 0, lw2 = 0;
+  SCL_SOLVER(cusolverDnSsytrd_bufferSize(impl->h, CUBLAS_FILL_MODE_LOWER, n, dA, n, impl->tri_d.p, impl->tri_e.p, impl->tri_tau.p, &lw1));
+  if (m)
+    SCL_SOLVER(cusolverDnSormtr_bufferSize(impl->h, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, m, dA, n,
+                                           impl->tri_tau.p, impl->tri_z.p, n, &lw2));
+  impl->work.ensure((size_t)std::max(lw1, lw2) + 1);
+  SCL_CUDA(cudaEventRecord(ev[0], st));
+  SCL_SOLVER(cusolverDnSsytrd(impl->h, CUBLAS_FILL_MODE_LOWER, n, dA, n, impl->tri_d.p, impl->tri_e.p, impl->tri_tau.p,
+                              impl->work.p, lw1, impl->info.p));
+  SCL_CUDA(cudaEventRecord(ev[1], st));
+  TridiagStats ts;
+  bool ok = tridiag_eigen(impl->tri_d.p, impl->tri_e.p, n, impl->tri_w.p, dW, v0, v1, impl->tri_z.p, n, st, &ts);
+  SCL_CUDA(cudaEventRecord(ev[2], st));
+  tri_clusters = ts.clusters;
+  tri_clustered = ts.clustered;
+  int info = 0;
+  if (ok && m) {
+    SCL_SOLVER(cusolverDnSormtr(impl->h, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, m, dA, n, impl->tri_tau.p,
+                                impl->tri_z.p, n, impl->work.p, lw2, impl->info.p));
+    SCL_CUDA(cudaMemcpyAsync(dA + (size_t)v0 * n, impl->tri_z.p, (size_t)m * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  SCL_CUDA(cudaEventRecord(ev[3], st));
+  SCL_CUDA(cudaMemcpyAsync(&info, impl->info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < 3; ++i) {
+    float t = 0;
+    cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+    tri_ms[i] = t;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (info != 0) ok = false;
+  if (!ok) {
+    // loud, not silent: counted, and reported by the timing entry points
+    ++tri_fallbacks;
+    fprintf(stderr, "[scl] own tridiagonal stage failed (info=%d); this solve falls back to cusolverDnSsyevd\n", info);
+    SCL_CUDA(cudaMemcpyAsync(dA, impl->tri_keep.p, nn * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    int lwork = 0;
+    const cusolverEigMode_t jobz = m ? CUSOLVER_EIG_MODE_VECTOR : CUSOLVER_EIG_MODE_NOVECTOR;
+    SCL_SOLVER(cusolverDnSsyevd_bufferSize(impl->h, jobz, CUBLAS_FILL_MODE_UPPER, n, dA, n, dW, &lwork));
+    impl->work.ensure((size_t)lwork);
+    SCL_SOLVER(cusolverDnSsyevd(impl->h, jobz, CUBLAS_FILL_MODE_UPPER, n, dA, n, dW, impl->work.p, lwork, impl->info.p));
+    SCL_CUDA(cudaMemcpyAsync(&info, impl->info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+    if (info != 0) throw Error(-3, "cusolverDnSsyevd did not converge, info=" + std::to_string(info));
+  }
+  return ok;
+}
+
 // A (n x n, symmetric, full) is overwritten by the eigenvectors when vectors=true.
 void Solver::syevd(float* dA, int n, float* dW, bool vectors, cudaStream_t st) {
+  if (eig_api() & 4) {
+    syevd_tri(dA, n, dW, 0, vectors ? n : 0, st);
+    return;
+  }
   int lwork = 0;
   cusolverEigMode_t jobz = vectors ? CUSOLVER_EIG_MODE_VECTOR : CUSOLVER_EIG_MODE_NOVECTOR;
   if (eig_api() & 1) {
@@ -122,6 +190,32 @@ double Solver::bench(float* dA, int n, float* dW, int mode, int il, int iu, cuda
     SCL_CUDA(cudaEventRecord(e0, st));
     SCL_SOLVER(cusolverDnSsyevdx(impl->h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, n, dA, n,
                                  0.f, 0.f, il, iu, &meig, dW, impl->work.p, lwork, impl->info.p));
+  } else if (mode >= 6 && mode <= 8) {
+    // own tridiagonal stage: 6 = all vectors, 7 = vectors il..iu (1-based inclusive), 8 = values only
+    const int v0 = mode == 7 ? il - 1 : 0, v1 = mode == 6 ? n : (mode == 7 ? iu : 0);
+    SCL_CUDA(cudaEventRecord(e0, st));
+    syevd_tri(dA, n, dW, v0, v1, st);
+  } else if (mode == 4 || mode == 5) {
+    // the two library halves of a one-stage solve, timed apart: 4 = Ssytrd (tridiagonalisation) alone, 5 = Sormtr
+    // (back-transformation of an n x n block by the reflectors of a previous Ssytrd) alone
+    Tmp<float> d(n, st), e(n, st), tau(n, st);
+    int lw1 = 0, lw2 = 0;
+    SCL_SOLVER(cusolverDnSsytrd_bufferSize(impl->h, CUBLAS_FILL_MODE_LOWER, n, dA, n, d.p, e.p, tau.p, &lw1));
+    Tmp<float> Cm(mode == 5 ? (size_t)n * n : 1, st);
+    if (mode == 5)
+      SCL_SOLVER(cusolverDnSormtr_bufferSize(impl->h, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, n, dA, n, tau.p,
+                                             Cm.p, n, &lw2));
+    impl->work.ensure((size_t)std::max(lw1, lw2));
+    if (mode == 4) SCL_CUDA(cudaEventRecord(e0, st));
+    SCL_SOLVER(cusolverDnSsytrd(impl->h, CUBLAS_FILL_MODE_LOWER, n, dA, n, d.p, e.p, tau.p, impl->work.p, lw1, impl->info.p));
+    if (mode == 5) {
+      SCL_CUDA(cudaMemsetAsync(Cm.p, 0, (size_t)n * n * sizeof(float), st));
+      SCL_CUDA(cudaEventRecord(e0, st));
+      SCL_SOLVER(cusolverDnSormtr(impl->h, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, n, dA, n, tau.p, Cm.p, n,
+                                  impl->work.p, lw2, impl->info.p));
+      SCL_CUDA(cudaEventRecord(e1, st));
+      SCL_CUDA(cudaEventSynchronize(e1));
+    }
   } else {
     cusolverDnParams_t params = nullptr;
     SCL_SOLVER(cusolverDnCreateParams(&params));

@@ -15,12 +15,30 @@ struct Solver {
   void syevd(float* dA, int n, float* dW, bool vectors, cudaStream_t st);
   void dsyevd_small(double* dA, int n, double* dW, cudaStream_t st);
   int syevdx_smallest(float* dA, int n, float* dW, int iu, cudaStream_t st);
+  // Own middle stage (tridiag.cu): cusolverDnSsytrd -> Float64 multisection + twisted factorisation -> cusolverDnSormtr.
+  // All n eigenvalues ascending in dW; the eigenvectors with ascending indices [v0, v1) in rows [v0, v1) of dA's memory
+  // (v0 == v1: values only); the other rows of dA are overwritten with scratch.  Falls back to Ssyevd on a kept copy of
+  // the matrix (all vectors) when the twisted factorisation fails; returns true when it did not have to.
+  bool syevd_tri(float* dA, int n, float* dW, int v0, int v1, cudaStream_t st);
+  // milliseconds of the last syevd_tri call: [0] Ssytrd, [1] eigenvalues + eigenvectors of T, [2] Sormtr + copy
+  double tri_ms[3] = {0, 0, 0};
+  int tri_clusters = 0, tri_clustered = 0, tri_fallbacks = 0;
   // timing study of the library's symmetric eigensolvers on an n x n matrix (overwritten); returns milliseconds.
   // mode 0: Ssyevd vectors, 1: Ssyevd values only, 2: Ssyevdx vectors of the il..iu smallest, 3: Xsyevd (64-bit API) vectors
   double bench(float* dA, int n, float* dW, int mode, int il, int iu, cudaStream_t st);
 };
 
-int eig_api();   // SCL_EIG_API: bit 0 = Xsyevd for the full solves, bit 1 = Ssyevdx (index range) in the search steps
+struct TridiagStats {
+  int clusters = 0, clustered = 0;   // groups of eigenvalues closer than 1e-9 |T| and how many eigenvalues they hold
+};
+// tridiag.cu: all eigenvalues (ascending; Float64 w64 and Float32 w32) of the symmetric tridiagonal (d32, e32) and the unit
+// eigenvectors with ascending indices [v0, v1) as rows of Z; false when they came out non-finite / too degenerate
+bool tridiag_eigen(const float* d32, const float* e32, int n, double* w64, float* w32, int v0, int v1, float* Z,
+                   long long ldz, cudaStream_t st, TridiagStats* stats);
+
+// SCL_EIG_API: bit 0 = Xsyevd for the full solves, bit 1 = Ssyevdx (index range) in the search steps, bit 2 = own tridiagonal
+// stage (Ssytrd + tridiag.cu + Sormtr) for every solve, bit 3 = with bit 2: vectors of the index range the search step uses only
+int eig_api();
 
 struct MpFit {
   std::vector<float> L_mp;

@@ -67,6 +67,7 @@ void refine_eigenvalues(const float* dG, const float* dV, int n, float* dW, cuda
 // pipeline.cu
 void run_signal(scl_handle* h);
 void run_robustness(scl_handle* h, double th, double p_step, int n_perturb);
+void run_pass(scl_handle* h, double th, double p_step, int n_perturb);
 void score_from_pairs(const std::vector<float>& b_, int k, int n_pairs, double th, std::vector<double>& m,
                       std::vector<double>& sd, std::vector<int32_t>& sig);
 void plan_gram_shard(int64_t K, int64_t ld, int world, int rank, int64_t* k0, int64_t* k1);
@@ -74,7 +75,7 @@ void plan_gram_shard(int64_t K, int64_t ld, int world, int rank, int64_t* k0, in
 // shard=true (and world > 1): every rank contracts its own slice of the long axis (cells when N > M) and the
 // partial Gram matrices are summed with ncclAllReduce
 void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf<__half>& lo, float* dG, int nm,
-             float scale, bool split, bool shard = false);
+             float scale, bool split, bool shard = false, int reduce_root = -1);
 void corr_colabsmax(scl_handle* h, const float* dV, int nv, const float* dW, int nw, int n, float* d_out);
 void topk_subspace(scl_handle* h, const float* dG, int n, int k, float* dL, float* dV, int* iters);
 void score_sets(scl_handle* h, int N, int k, int min_pc, int n_perturb, const float* d_nV, const float* d_sets,

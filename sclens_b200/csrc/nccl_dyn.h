@@ -17,6 +17,7 @@ struct NcclApi {
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
   decltype(&ncclAllReduce) AllReduce = nullptr;
   decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclReduce) Reduce = nullptr;
   decltype(&ncclBroadcast) Broadcast = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
@@ -36,6 +37,7 @@ inline const NcclApi& nccl_api() {
     SCL_NCCL_SYM(GetErrorString, "ncclGetErrorString");
     SCL_NCCL_SYM(AllReduce, "ncclAllReduce");
     SCL_NCCL_SYM(AllGather, "ncclAllGather");
+    SCL_NCCL_SYM(Reduce, "ncclReduce");
     SCL_NCCL_SYM(Broadcast, "ncclBroadcast");
     SCL_NCCL_SYM(GroupStart, "ncclGroupStart");
     SCL_NCCL_SYM(GroupEnd, "ncclGroupEnd");

@@ -1234,7 +1234,7 @@ void set_gram_diagonal(float* G, int n, const double* sumsq, double scale, cudaS
 }
 
 void densify(const SpMat& A, NormStats& S, int layout, size_t ld, __half* out_hi, __half* out_lo,
-             cudaStream_t st, long long pos0, long long pos1) {
+             cudaStream_t st, long long pos0, long long pos1, size_t slice_stride) {
   ensure_patch(A, S, layout, st);
   count_launches(2);
   const bool cell_major = layout == 1;
@@ -1243,11 +1243,19 @@ void densify(const SpMat& A, NormStats& S, int layout, size_t ld, __half* out_hi
   SCL_REQUIRE(ld % 8 == 0 && ld >= (size_t)line_len, "leading dimension must be a multiple of 8 and >= line length");
   if (pos1 < 0) { pos0 = 0; pos1 = (long long)ld; }
   SCL_REQUIRE(pos0 % 8 == 0 && pos0 >= 0 && pos1 <= (long long)ld && pos1 > pos0 && (pos1 % 8 == 0 || pos1 == (long long)ld), "bad densify range");
+  if (slice_stride) {
+    // sliced output (a rank's block of the contraction axis): the buffer holds positions [pos0, pos1) only, lines
+    // slice_stride apart - the kernels address out + line * stride + position, so the base moves back by pos0
+    SCL_REQUIRE(slice_stride % 8 == 0 && (long long)slice_stride >= pos1 - pos0, "bad slice stride");
+    out_hi -= pos0;
+    if (out_lo) out_lo -= pos0;
+    ld = slice_stride;
+  }
   const int n_strips = (int)((pos1 - pos0 + kStripW - 1) / kStripW);
   const uint32_t* ptr = cell_major ? A.rowptr.p : A.colptr.p;
   const uint32_t* idx = cell_major ? A.colidx.p : A.rowval.p;
   // the strip passes leave the full-range offset table of both orientations behind; a rank's cell block needs its own
-  const bool reuse = pos0 == 0 && pos1 == (long long)ld && S.off_valid[layout] && S.off_strips[layout] == n_strips;
+  const bool reuse = !slice_stride && pos0 == 0 && pos1 == (long long)ld && S.off_valid[layout] && S.off_strips[layout] == n_strips;
   Tmp<uint32_t> off_tmp(reuse ? 1 : (size_t)n_lines * (n_strips + 1), st);
   struct { const uint32_t* p; } off{reuse ? S.off[layout].p : off_tmp.p};
   if (!reuse) {

@@ -247,6 +247,37 @@ __global__ void k_unscale_values(float* __restrict__ w, int n, const double* __r
   if (i < n) w[i] = (float)((double)w[i] / factor[0]);
 }
 
+// lower triangle (row r: columns 0..r) of an n x n matrix <-> packed array of n(n+1)/2 floats.  The partial Gram
+// matrices of the ranks travel packed: half the bytes of the square over NVLink.
+__global__ void k_pack_lower(const float* __restrict__ G, int n, float* __restrict__ P) {
+  for (int r = blockIdx.y; r < n; r += gridDim.y) {
+    const float* src = G + (size_t)r * n;
+    float* dst = P + (size_t)r * (r + 1) / 2;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= r; c += gridDim.x * blockDim.x) dst[c] = src[c];
+  }
+}
+// square tiles: element (r, c), r >= c, is written to (r, c) and (c, r) through a padded shared-memory transpose
+__global__ void __launch_bounds__(256) k_unpack_lower_mirror(const float* __restrict__ P, int n, float* __restrict__ G) {
+  __shared__ float t[32][33];
+  const int tr = blockIdx.y, tc = blockIdx.x;
+  if (tc > tr) return;
+  const int r0 = tr * 32, c0 = tc * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < n && c <= r) {
+      v = P[(size_t)r * (r + 1) / 2 + c];
+      G[(size_t)r * n + c] = v;
+    }
+    t[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;   // mirrored element (c, r) = value at (r, c)
+    if (r < n && c < r) G[(size_t)c * n + r] = t[tx][i];
+  }
+}
+
 double quantile7(const std::vector<double>& sorted, double p) {
   const size_t n = sorted.size();
   if (n == 1) return sorted[0];
@@ -270,37 +301,41 @@ void plan_gram_shard(int64_t K, int64_t ld, int world, int rank, int64_t* k0, in
 // ---------------------------------------------------------------------------------------
 // normalise A and form its Wishart matrix on the smaller side:  dG = operand * operand^T * scale
 void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf<__half>& lo, float* dG, int nm,
-             float scale, bool split, bool shard) {
+             float scale, bool split, bool shard, int reduce_root) {
   const bool gene_side = A.N > A.M;                 // contract over cells (N > M) or over genes
   {
     ProfScope ps(&h->prof, h->st, PK_STATS);
     compute_norm_stats(A, S, h->st);
     ensure_patch(A, S, gene_side ? 0 : 1, h->st);
+    h->prof.stats_alg_bytes += 40.0 * (double)A.nnz;   // 4 nnz (row sums) + 3 x 8 nnz + 12 nnz (patch pass)
   }
   const int rows = gene_side ? A.M : A.N;
   const int64_t K = gene_side ? A.N : A.M;
   const size_t ld = round8((size_t)K);
   SCL_REQUIRE(rows == nm, "Gram size mismatch");
-  hi.ensure((size_t)rows * ld);
-  if (split) lo.ensure((size_t)rows * ld);
   // Multi-GPU: rank g owns the g-th block of the contraction axis (a cell block when N > M).  It densifies and
-  // contracts only that block; the partial Gram matrices are summed over NVLink.
+  // contracts only that block - the operand buffer holds just that slice (rows x (k1 - k0)) - and the partial Gram
+  // matrices are summed over NVLink.
   int64_t k0 = 0, k1 = (int64_t)ld;
   const bool sharded = shard && multi(h);
   if (sharded) plan_gram_shard(K, (int64_t)ld, h->world, h->rank, &k0, &k1);
   const bool have_work = k1 > k0;
+  const size_t lds = sharded ? (size_t)std::max<int64_t>(8, k1 - k0) : ld;   // row stride of the operand buffer
+  hi.ensure((size_t)rows * lds);
+  if (split) lo.ensure((size_t)rows * lds);
   // exact Gram diagonal: the tensor core's truncating FP32 accumulation biases long same-sign sums low; the
   // diagonal (the only systematically same-sign sum) comes from the statistics passes in Float64 instead
   if (have_work) {
     {
       ProfScope ps(&h->prof, h->st, PK_DENSIFY);
-      densify(A, S, gene_side ? 0 : 1, ld, hi.p, split ? lo.p : nullptr, h->st, k0, k1);
+      densify(A, S, gene_side ? 0 : 1, ld, hi.p, split ? lo.p : nullptr, h->st, k0, k1, sharded ? lds : 0);
       const double frac = (double)(k1 - k0) / (double)ld;
       h->prof.densify_alg_bytes += frac * (8.0 * (double)A.nnz + (double)A.N * A.M * (split ? 4.0 : 2.0)) + 4.0 * (A.M + 1);
     }
     const int64_t Ks = std::min<int64_t>(K, k1) - k0;
     GemmArgs g;
-    g.A.hi = hi.p + k0; g.A.lo = split ? lo.p + k0 : nullptr; g.A.rows = rows; g.A.K = Ks; g.A.ld = (int64_t)ld;
+    const int64_t o0 = sharded ? 0 : k0;   // a slice buffer starts at the rank's first position
+    g.A.hi = hi.p + o0; g.A.lo = split ? lo.p + o0 : nullptr; g.A.rows = rows; g.A.K = Ks; g.A.ld = (int64_t)lds;
     g.B = g.A;
     g.syrk = true;
     g.alpha = scale;
@@ -319,21 +354,38 @@ void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf
   // exact values of the calibration samples over this rank's part of the contraction
   const bool calibrate = h->cfg.gram_tc_diag == 0 && nm >= 64;
   Tmp<double> ex(kCalibSamples, h->st);
-  h->gram_factor.ensure(1);
+  h->gram_factor.ensure(4);
   if (calibrate) {
     ProfScope ps(&h->prof, h->st, PK_SMALL);
     count_launches(1);
     if (have_work)
-      k_sample_dots<<<kCalibSamples, 256, 0, h->st>>>(hi.p, split ? lo.p : nullptr, (long long)ld, (long long)k0,
+      k_sample_dots<<<kCalibSamples, 256, 0, h->st>>>(hi.p, split ? lo.p : nullptr, (long long)lds,
+                                                      (long long)(sharded ? 0 : k0),
                                                       (long long)(std::min<int64_t>(K, k1) - k0), rows, ex.p);
     else
       SCL_CUDA(cudaMemsetAsync(ex.p, 0, kCalibSamples * sizeof(double), h->st));
     SCL_CUDA(cudaGetLastError());
   }
   if (sharded) {
-    ProfScope ps(&h->prof, h->st, PK_SMALL);
-    SCL_NCCL(nccl_api().AllReduce(dG, dG, (size_t)nm * nm, ncclFloat, ncclSum, (ncclComm_t)h->nccl, h->st));
-    if (calibrate) SCL_NCCL(nccl_api().AllReduce(ex.p, ex.p, kCalibSamples, ncclDouble, ncclSum, (ncclComm_t)h->nccl, h->st));
+    // packed lower triangle, summed in FP32 (rank order fixed by NCCL's algorithm choice for a given world size); to the
+    // one rank that solves this matrix when the caller names it, to every rank otherwise
+    ProfScope ps(&h->prof, h->st, PK_COMM);
+    const size_t np = (size_t)nm * (nm + 1) / 2;
+    Tmp<float> packed(np, h->st);
+    count_launches(2);
+    k_pack_lower<<<dim3(8, (unsigned)std::min(nm, 16384)), 256, 0, h->st>>>(dG, nm, packed.p);
+    SCL_CUDA(cudaGetLastError());
+    if (reduce_root >= 0) {
+      SCL_NCCL(nccl_api().Reduce(packed.p, packed.p, np, ncclFloat, ncclSum, reduce_root, (ncclComm_t)h->nccl, h->st));
+      if (calibrate) SCL_NCCL(nccl_api().Reduce(ex.p, ex.p, kCalibSamples, ncclDouble, ncclSum, reduce_root, (ncclComm_t)h->nccl, h->st));
+    } else {
+      SCL_NCCL(nccl_api().AllReduce(packed.p, packed.p, np, ncclFloat, ncclSum, (ncclComm_t)h->nccl, h->st));
+      if (calibrate) SCL_NCCL(nccl_api().AllReduce(ex.p, ex.p, kCalibSamples, ncclDouble, ncclSum, (ncclComm_t)h->nccl, h->st));
+    }
+    const unsigned nt = (unsigned)((nm + 31) / 32);
+    k_unpack_lower_mirror<<<dim3(nt, nt), 256, 0, h->st>>>(packed.p, nm, dG);
+    SCL_CUDA(cudaGetLastError());
+    h->prof.comm_bytes += 4.0 * (double)np + (calibrate ? 8.0 * kCalibSamples : 0.0);
   }
   // every rank holds the complete statistics, so the full-length diagonal is written after the reduction
   if (h->cfg.gram_tc_diag != 1) {
@@ -353,11 +405,16 @@ void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf
   }
 }
 
-// eigenvalues of the matrix gram_of() produced last -> eigenvalues of the Gram matrix itself
-void unscale_eigenvalues(scl_handle* h, float* dW, int n) {
+// eigenvalues of the matrix gram_of() produced last (slot 0) or of one whose factor was saved -> eigenvalues of the Gram
+// matrix itself
+void unscale_eigenvalues(scl_handle* h, float* dW, int n, int slot = 0) {
   count_launches(1);
-  k_unscale_values<<<(n + 255) / 256, 256, 0, h->st>>>(dW, n, h->gram_factor.p);
+  k_unscale_values<<<(n + 255) / 256, 256, 0, h->st>>>(dW, n, h->gram_factor.p + slot);
   SCL_CUDA(cudaGetLastError());
+}
+// keep the factor of the Gram matrix gram_of() produced last while other matrices are formed (slots 1..3)
+void save_gram_factor(scl_handle* h, int slot) {
+  SCL_CUDA(cudaMemcpyAsync(h->gram_factor.p + slot, h->gram_factor.p, sizeof(double), cudaMemcpyDeviceToDevice, h->st));
 }
 
 // d[j] = max_i |<V_i, W_j>|  (:742) with V pre-converted to binary16 hi/lo rows
@@ -414,6 +471,76 @@ static void back_project(scl_handle* h, const SpMat& A, NormStats& S, const floa
 }
 
 // ---------------------------------------------------------------------------------------
+namespace {
+
+// rec_vals (:676-695) and the ascending spectrum :L of the data matrix to the host
+void fetch_signal_outputs(scl_handle* h, const float* dW, int nm, bool sorted_needed) {
+  cudaStream_t st = h->st;
+  const int N = h->X.N, M = h->X.M;
+  h->L.resize(nm);
+  SCL_CUDA(cudaMemcpyAsync(h->L.data(), dW, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
+  h->rec_tgc.resize(N); h->rec_l2.resize(N); h->rec_mean.resize(M); h->rec_std.resize(M); h->rec_cent.resize(M);
+  SCL_CUDA(cudaMemcpyAsync(h->rec_tgc.data(), h->S_main.tgc.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaMemcpyAsync(h->rec_l2.data(), h->S_main.l2.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaMemcpyAsync(h->rec_mean.data(), h->S_main.ybar.p, M * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaMemcpyAsync(h->rec_std.data(), h->S_main.sigma.p, M * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaMemcpyAsync(h->rec_cent.data(), h->S_main.cent.p, M * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  for (float v : h->L)
+    if (!std::isfinite(v)) throw Error(SCL_ERR_CUSOLVER, "non-finite eigenvalue (the reference's CPU fallback :379-381 is an error here)");
+  // Rayleigh quotients of neighbouring bulk eigenvectors can swap by ~1e-6 relative: :L is ascending (:378); the
+  // signal eigenvalues are far apart, so their pairing with the eigenvectors is untouched
+  if (sorted_needed) std::sort(h->L.begin(), h->L.end());
+}
+
+// MP / TW fit (:537-538/:576-577) from :L and the null spectrum; Lr[1:end-1] drops the largest null eigenvalue
+void fit_signal(scl_handle* h, const std::vector<float>& Lr) {
+  scl_signal_info& info = h->sinfo;
+  const int nm = info.nm;
+  auto c0 = std::chrono::steady_clock::now();
+  MpFit fit = mp_fit(h->L.data(), nm, Lr.data(), nm - 1);
+  info.t_fit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count();
+  h->Lmp = fit.L_mp;
+  info.n_signal = fit.n_signal;
+  info.n_Lmp = (int)fit.L_mp.size();
+  info.mp_iters = fit.iters;
+  info.pass = fit.pass ? 1 : 0;
+  info.lambda_c = fit.lambda_c;
+  info.b_plus = fit.b_plus;
+  info.b_minus = fit.b_minus;
+  info.ks_static = fit.ks_static;
+  if (h->cfg.verbose) printf("(Using gpu) number of signal ev: %d\n", info.n_signal);
+  const int k = info.n_signal;
+  h->nL.resize(k);
+  for (int i = 0; i < k; ++i) h->nL[i] = h->L[nm - 1 - i];
+}
+
+// signal eigenvectors, descending (:541-551), as cell-space unit vectors (:556-558).  top: eigenvector of the largest
+// eigenvalue, the next ones ld_top floats further (negative: walking backwards through the solver's ascending rows)
+void project_signal(scl_handle* h, const float* top, long long ld_top) {
+  const int N = h->X.N, M = h->X.M, k = h->sinfo.n_signal;
+  h->d_nV.ensure((size_t)std::max(1, k) * N);
+  if (k > 0) {
+    if (N > M)
+      back_project(h, h->X, h->S_main, top, ld_top, k, h->d_nV.p);
+    else
+      copy_rows(top, ld_top, h->d_nV.p, N, k, N, h->st);
+  }
+}
+
+void make_null_matrix(scl_handle* h) {
+  const SpMat& X = h->X;
+  ProfScope ps(&h->prof, h->st, PK_SPARSE);
+  if (h->have_null_draws)
+    permute_null(X, h->null_perm.p, h->null_rows.p, h->Xnull, h->st);
+  else
+    draw_null_device(X, h->cfg.seed, h->Xnull, h->st);
+  h->prof.sparse_alg_bytes += 20.0 * (double)X.nnz;
+  SCL_REQUIRE(h->Xnull.N == X.N && h->Xnull.M == X.M, "null matrix shape");
+}
+
+}  // namespace
+
 void run_signal(scl_handle* h) {
   SCL_REQUIRE(h->have_X, "scl_set_counts_csc must be called first");
   cudaStream_t st = h->st;
@@ -451,33 +578,11 @@ void run_signal(scl_handle* h) {
     refine_eigenvalues(Gkeep.p, G.p, nm, W.p, st);
   }
   unscale_eigenvalues(h, W.p, nm);
-  h->L.resize(nm);
-  SCL_CUDA(cudaMemcpyAsync(h->L.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
-  // rec_vals (:676-695)
-  h->rec_tgc.resize(N); h->rec_l2.resize(N); h->rec_mean.resize(M); h->rec_std.resize(M); h->rec_cent.resize(M);
-  SCL_CUDA(cudaMemcpyAsync(h->rec_tgc.data(), h->S_main.tgc.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
-  SCL_CUDA(cudaMemcpyAsync(h->rec_l2.data(), h->S_main.l2.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
-  SCL_CUDA(cudaMemcpyAsync(h->rec_mean.data(), h->S_main.ybar.p, M * sizeof(double), cudaMemcpyDeviceToHost, st));
-  SCL_CUDA(cudaMemcpyAsync(h->rec_std.data(), h->S_main.sigma.p, M * sizeof(double), cudaMemcpyDeviceToHost, st));
-  SCL_CUDA(cudaMemcpyAsync(h->rec_cent.data(), h->S_main.cent.p, M * sizeof(double), cudaMemcpyDeviceToHost, st));
-  SCL_CUDA(cudaStreamSynchronize(st));
-  for (float v : h->L)
-    if (!std::isfinite(v)) throw Error(SCL_ERR_CUSOLVER, "non-finite eigenvalue (the reference's CPU fallback :379-381 is an error here)");
-  // Rayleigh quotients of neighbouring bulk eigenvectors can swap by ~1e-6 relative: :L is ascending (:378); the
-  // signal eigenvalues are far apart, so their pairing with the eigenvectors is untouched
-  if (refine) std::sort(h->L.begin(), h->L.end());
+  fetch_signal_outputs(h, W.p, nm, refine);
   tm.stop();
 
   // --- null matrix (:701) and its spectrum (:531-532/:571-572)
-  {
-    ProfScope ps(&h->prof, st, PK_SPARSE);
-    if (h->have_null_draws)
-      permute_null(X, h->null_perm.p, h->null_rows.p, h->Xnull, st);
-    else
-      draw_null_device(X, h->cfg.seed, h->Xnull, st);
-    h->prof.sparse_alg_bytes += 20.0 * (double)X.nnz;
-  }
-  SCL_REQUIRE(h->Xnull.N == N && h->Xnull.M == M, "null matrix shape");
+  make_null_matrix(h);
   info.t_null_ms += tm.stop();
   {
     NormStats& Sn = h->ws_Sn;
@@ -492,35 +597,10 @@ void run_signal(scl_handle* h) {
     std::vector<float> Lr(nm);
     SCL_CUDA(cudaMemcpyAsync(Lr.data(), W2.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
     SCL_CUDA(cudaStreamSynchronize(st));
-    // --- MP / TW fit (:537-538/:576-577); Lr[1:end-1] drops the largest null eigenvalue
-    auto c0 = std::chrono::steady_clock::now();
-    MpFit fit = mp_fit(h->L.data(), nm, Lr.data(), nm - 1);
-    info.t_fit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count();
-    h->Lmp = fit.L_mp;
-    info.n_signal = fit.n_signal;
-    info.n_Lmp = (int)fit.L_mp.size();
-    info.mp_iters = fit.iters;
-    info.pass = fit.pass ? 1 : 0;
-    info.lambda_c = fit.lambda_c;
-    info.b_plus = fit.b_plus;
-    info.b_minus = fit.b_minus;
-    info.ks_static = fit.ks_static;
+    fit_signal(h, Lr);
   }
-  if (h->cfg.verbose) printf("(Using gpu) number of signal ev: %d\n", info.n_signal);
   tm.stop();
-
-  // --- signal eigenpairs, descending (:541-551), cell-space vectors (:556-558)
-  const int k = info.n_signal;
-  h->nL.resize(k);
-  for (int i = 0; i < k; ++i) h->nL[i] = h->L[nm - 1 - i];
-  h->d_nV.ensure((size_t)std::max(1, k) * N);
-  if (k > 0) {
-    const float* top = G.p + (size_t)(nm - 1) * nm;   // eigenvector of the largest eigenvalue; walk backwards
-    if (N > M)
-      back_project(h, X, h->S_main, top, -(long long)nm, k, h->d_nV.p);
-    else
-      copy_rows(top, -(long long)nm, h->d_nV.p, N, k, N, st);
-  }
+  project_signal(h, G.p + (size_t)(nm - 1) * nm, -(long long)nm);
   SCL_CUDA(cudaStreamSynchronize(st));
   info.t_backproject_ms = tm.stop();
   h->prof.resolve();
@@ -654,185 +734,228 @@ int first_positive(const std::vector<float>& L) {
 
 }  // namespace
 
-void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
-  SCL_REQUIRE(h->signal_done, "scl_run_signal must succeed first");
-  if (h->sinfo.n_signal == 0) throw Error(SCL_ERR_NOSIGNAL, "warning: There is no signal");
-  SCL_REQUIRE(n_perturb >= 2, "n_perturb must be >= 2");
+namespace {
+
+// reference loop state of the sparsity search (:722-760): second-smallest values are fed in step order, whoever evaluated
+// them (this rank sequentially, or the ranks of a wave speculatively) - the outcome is the sequential loop's
+struct SearchState {
+  double p_step, p_th;
+  int tank_n = 5;
+  std::vector<double> tank2;            // row 2 of tank_ (second smallest of d_arr per step)
+  std::vector<double> p_of_step{0.999};
+  double p_ = 0.999;
+  int step = 0;
+  bool stop = false;
+  double p_at(int s_) {
+    while ((int)p_of_step.size() <= s_) p_of_step.push_back(p_of_step.back() - p_step);   // :760, same rounding drift
+    return p_of_step[s_];
+  }
+  // the sequential loop reaches step s only if no earlier step stopped it: every earlier p_ was >= 0.9 (:756)
+  bool reachable(int s_) { return s_ == 0 || p_at(s_ - 1) >= 0.9; }
+  long long n_add(int s_, int N, int M) { return (long long)std::nearbyint((1.0 - p_at(s_)) * (double)M * (double)N); }   // :726
+  // d2 >= 0: second-smallest of d_arr; -1: the candidate pool is smaller than this step's additions (:727-730)
+  void feed(scl_handle* h, int s_, double d2) {
+    if (stop) return;
+    p_ = p_at(s_);
+    if (d2 == -1.0) {
+      p_ += p_step;
+      stop = true;
+      return;
+    }
+    SCL_REQUIRE(d2 >= 0, "sparsity search consumed a step that was never evaluated");
+    tank2.push_back(d2);
+    h->trace_p.push_back(p_);
+    h->trace_d.push_back(d2);
+    if (h->cfg.verbose) printf("%.9g\n", d2);
+    ++step;
+    int below = 0;
+    const int cnt = (int)tank2.size() < tank_n ? (int)tank2.size() : tank_n;
+    for (int q = 0; q < cnt; ++q)
+      if (tank2[tank2.size() - 1 - q] < p_th) ++below;
+    if (below > tank_n - 1 || p_ < 0.9) {                    // :756
+      p_ += (double)(tank_n - 1) * p_step;
+      stop = true;
+    }
+  }
+};
+
+// device state shared by the search steps of one pass
+struct SearchCtx {
+  float bin_scale = 0, lmax_ref = 0;
+  int n_2 = 0, nw = 0;
+  GemmOperand Vr;
+  std::vector<float> Lh;
+};
+
+// noise baseline (:709-713), zero candidates (:668-673), buffers of the perturbed matrices
+void robust_prepare(scl_handle* h) {
+  cudaStream_t st = h->st;
+  const SpMat& X = h->X;
+  const int nm = std::min(X.N, X.M);
+  scl_robust_info& info = h->rinfo;
+  info = scl_robust_info{};
+  h->robust_done = false;
+  const double p_th = h->have_pth ? h->p_th : noise_baseline_device(nm, 5000, h->cfg.seed, st);
+  info.p_th = p_th;
+  if (h->cfg.verbose) printf("spth_: %.17g\n", p_th);
+  if (!h->have_zc) h->n_cand = draw_zero_candidates_device(X, h->cfg.seed, h->z1, h->z2, st);
+  h->ws_G.ensure((size_t)nm * nm);
+  h->ws_W.ensure(nm);
+  // the perturbed matrices gain up to ~2-3 % of the grid in stored entries before the search stops (p_ ~ 0.98):
+  // size their buffers once instead of growing them step by step
+  const size_t cap = X.nnz + (size_t)(0.03 * (double)X.N * (double)X.M) + 1024;
+  h->ws_Xp.reserve(cap);
+  h->ws_Sp.reserve(cap);
+  h->trace_p.clear();
+  h->trace_d.clear();
+}
+
+// reference basis of the binarised matrix (:717-721): Gram matrix into ws_G and its full eigenbasis in place
+void binref_solve(scl_handle* h, SearchCtx& c) {
+  cudaStream_t st = h->st;
+  const SpMat& X = h->X;
+  const int N = X.N, M = X.M, nm = std::min(N, M);
+  const bool split = h->cfg.gram_mode == SCL_GRAM_FP16X3;
+  perturb_merge(X, nullptr, nullptr, 0, true, h->ws_Xp, st);
+  gram_of(h, h->ws_Xp, h->ws_Sp, h->ws_op_hi, h->ws_op_lo, h->ws_G.p, nm, c.bin_scale, split);
+  { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(h->ws_G.p, nm, h->ws_W.p, true, st); }
+}
+
+// The reference basis keeps the complete eigenbasis (oracle get_eigvec(keep_null=True); DESIGN.md, deviations): null
+// directions of the binarised matrix are kept, as in the reference whenever their eigenvalues round positive, so their
+// perturbed counterparts are not mistaken for delocalised vectors.  hi/lo binary16 rows, the GEMM's K-major operand.
+void binref_operand(scl_handle* h, SearchCtx& c, bool convert) {
+  const int nm = std::min(h->X.N, h->X.M);
+  const size_t ldv = round8((size_t)nm);
+  h->ws_vr_hi.ensure((size_t)nm * ldv);
+  h->ws_vr_lo.ensure((size_t)nm * ldv);
+  if (convert) strided_split_f32_to_f16(h->ws_G.p, nm, nm, nm, (int64_t)ldv, h->ws_vr_hi.p, h->ws_vr_lo.p, h->st, kUnitScale);
+  c.Vr.hi = h->ws_vr_hi.p; c.Vr.lo = h->ws_vr_lo.p; c.Vr.rows = nm; c.Vr.K = nm; c.Vr.ld = (int64_t)ldv;
+}
+
+void search_ctx_init(scl_handle* h, SearchCtx& c) {
+  const int N = h->X.N, M = h->X.M, nm = std::min(N, M);
+  c.bin_scale = 1.0f / (float)(N > M ? N : M);   // transposed call when N > M (Appendix A9)
+  c.n_2 = (int)std::nearbyint((double)nm / 2.0);   // round(Int, .) ties-to-even (:722); the reference basis is complete
+  c.nw = c.n_2 + 1;                                // nV_2[:, end-n_2:end] (Appendix A13)
+  c.Lh.assign(nm, 0.f);
+  SCL_REQUIRE(c.nw >= 5, "too few noise vectors");
+}
+
+// heavy part of search step s_ (:726-740): additions, merge, normalise, Gram, eigenvectors of the nw smallest positive
+// eigenvalues, left in rows [i0, i0 + nw) of ws_G.  Returns i0, or -1 when the candidate pool is exhausted (:727-730).
+int search_step_solve(scl_handle* h, SearchCtx& c, SearchState& ss, int s_, scl_robust_info& info, Timer& tm, double& t_gram) {
+  cudaStream_t st = h->st;
+  const SpMat& X = h->X;
+  const int N = X.N, M = X.M, nm = std::min(N, M), nw = c.nw;
+  const bool split = h->cfg.gram_mode == SCL_GRAM_FP16X3;
+  const long long nnzidx = ss.n_add(s_, N, M);
+  if ((long long)h->n_cand < nnzidx) return -1;
+  DBuf<float>&G = h->ws_G, &W = h->ws_W;
+  SpMat& Xp = h->ws_Xp;
+  NormStats& Sp = h->ws_Sp;
+  tm.stop();
+  Tmp<uint32_t> a_row((size_t)std::max<long long>(1, nnzidx), st), a_col((size_t)std::max<long long>(1, nnzidx), st);
+  make_additions(h, h->search_sples, (size_t)s_, (size_t)nnzidx, h->cfg.seed + 0x5eed0000ull + (uint64_t)s_, a_row.p, a_col.p);
+  {
+    ProfScope ps(&h->prof, st, PK_SPARSE);
+    perturb_merge(X, a_row.p, a_col.p, (size_t)nnzidx, true, Xp, st);
+    h->prof.sparse_alg_bytes += 8.0 * (double)X.nnz + 12.0 * (double)nnzidx;
+  }
+  gram_of(h, Xp, Sp, h->ws_op_hi, h->ws_op_lo, G.p, nm, c.bin_scale, split);
+  t_gram += tm.stop();
+  int i0 = -1;
+  if ((eig_api() & 12) == 12) {
+    // own tridiagonal stage, vectors of the index range this step reads only (the nw smallest positive eigenpairs plus a
+    // margin for non-positive eigenvalues); all eigenvalues come back, so the "positive" threshold is exact
+    const int iu = std::min(nm, nw + 64);
+    { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd_tri(G.p, nm, W.p, 0, iu, st); }
+    SCL_CUDA(cudaMemcpyAsync(c.Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+    const int j = first_positive(c.Lh);
+    if (j + nw <= iu) {
+      i0 = j;
+    } else {   // more than 64 non-positive eigenvalues: rebuild the Gram matrix and take the full solve below
+      gram_of(h, Xp, Sp, h->ws_op_hi, h->ws_op_lo, G.p, nm, c.bin_scale, split);
+    }
+  } else if (eig_api() & 2) {
+    // opt-in: only the nw smallest positive eigenpairs are used below, so ask the library for an index range.  The
+    // "positive" threshold needs the largest eigenvalue, which a range solve does not return: the reference basis'
+    // one (same matrix without the additions) stands in.  Falls back to the full solve when the range does not
+    // reach nw positive eigenvalues.
+    const int iu = std::min(nm, nw + 64);
+    Tmp<float> Gx((size_t)nm * nm, st);
+    SCL_CUDA(cudaMemcpyAsync(Gx.p, G.p, (size_t)nm * nm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    int meig = 0;
+    { ProfScope ps(&h->prof, st, PK_SYEVD); meig = h->solver->syevdx_smallest(Gx.p, nm, W.p, iu, st); }
+    std::vector<float> Lx(meig);
+    SCL_CUDA(cudaMemcpyAsync(Lx.data(), W.p, meig * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+    int j = 0;
+    while (j < meig && !(Lx[j] > 1e-5f * c.lmax_ref)) ++j;
+    if (j + nw <= meig) {
+      i0 = j;
+      SCL_CUDA(cudaMemcpyAsync(G.p, Gx.p, (size_t)(i0 + nw) * nm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  if (i0 < 0) {
+    { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G.p, nm, W.p, true, st); }
+    SCL_CUDA(cudaMemcpyAsync(c.Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+    i0 = first_positive(c.Lh);
+    SCL_REQUIRE(nm - i0 >= c.n_2 + 1, "perturbed matrix has too few positive eigenvalues");
+  }
+  info.t_search_syevd_ms += tm.stop();
+  return i0;
+}
+
+// d_arr of :742 for the vectors search_step_solve left in ws_G; returns its second-smallest value (:747-748)
+double search_step_corr(scl_handle* h, SearchCtx& c, int i0) {
+  cudaStream_t st = h->st;
+  const int nm = std::min(h->X.N, h->X.M), nw = c.nw;
+  Tmp<float> d_d(nw, st);
+  corr_colabsmax_pre(h, c.Vr, h->ws_G.p + (size_t)i0 * nm, nw, nm, d_d.p);
+  std::vector<float> d_host(nw);
+  SCL_CUDA(cudaMemcpyAsync(d_host.data(), d_d.p, nw * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  std::partial_sort(d_host.begin(), d_host.begin() + 5, d_host.end());
+  return (double)d_host[1];
+}
+
+// every rank learns whether any rank failed in the section just finished; all of them throw together instead of leaving
+// the healthy ones blocked in the next collective
+void sync_errors(scl_handle* h, const std::string& mine) {
+  if (!multi(h)) {
+    if (!mine.empty()) throw Error(SCL_ERR_INVALID, mine);
+    return;
+  }
+  Tmp<int> flag(1, h->st);
+  const int f = mine.empty() ? 0 : 1 + h->rank;
+  SCL_CUDA(cudaMemcpyAsync(flag.p, &f, sizeof(int), cudaMemcpyHostToDevice, h->st));
+  SCL_NCCL(nccl_api().AllReduce(flag.p, flag.p, 1, ncclInt, ncclMax, (ncclComm_t)h->nccl, h->st));
+  int any = 0;
+  SCL_CUDA(cudaMemcpyAsync(&any, flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  SCL_CUDA(cudaStreamSynchronize(h->st));
+  if (!mine.empty()) throw Error(SCL_ERR_INVALID, mine);
+  if (any) throw Error(SCL_ERR_NCCL, "rank " + std::to_string(any - 1) + " failed in this stage of the cooperative pass; all ranks abort");
+}
+
+// perturbations (:767-778), robustness scores (:786-807), gene_basis (:813-819)
+void robust_tail(scl_handle* h, double th, int n_perturb, double p_, Timer& tm) {
   cudaStream_t st = h->st;
   const SpMat& X = h->X;
   const int N = X.N, M = X.M, nm = std::min(N, M);
   const bool split = h->cfg.gram_mode == SCL_GRAM_FP16X3;
   scl_robust_info& info = h->rinfo;
-  info = scl_robust_info{};
-  h->robust_done = false;
-  Timer tm(st);
-
-  // --- noise baseline (:709-713)
-  const double p_th = h->have_pth ? h->p_th : noise_baseline_device(nm, 5000, h->cfg.seed, st);
-  info.p_th = p_th;
-  if (h->cfg.verbose) printf("spth_: %.17g\n", p_th);
-  if (!h->have_zc) {
-    h->n_cand = draw_zero_candidates_device(X, h->cfg.seed, h->z1, h->z2, st);
-  }
-  info.t_baseline_ms = tm.stop();
-
   DBuf<__half>&op_hi = h->ws_op_hi, &op_lo = h->ws_op_lo;
   DBuf<float>&G = h->ws_G, &W = h->ws_W;
-  G.ensure((size_t)nm * nm);
-  W.ensure(nm);
   SpMat& Xp = h->ws_Xp;
   NormStats& Sp = h->ws_Sp;
-  {
-    // the perturbed matrices gain up to ~2-3 % of the grid in stored entries before the search stops (p_ ~ 0.98):
-    // size their buffers once instead of growing them step by step
-    const size_t cap = X.nnz + (size_t)(0.03 * (double)N * (double)M) + 1024;
-    Xp.reserve(cap);
-    Sp.reserve(cap);
-  }
   std::vector<float> Lh(nm);
-  const float bin_scale = 1.0f / (float)(N > M ? N : M);   // transposed call when N > M (Appendix A9)
-
-  // --- reference basis of the binarised matrix (:717-721)
-  perturb_merge(X, nullptr, nullptr, 0, true, Xp, st);
-  gram_of(h, Xp, Sp, op_hi, op_lo, G.p, nm, bin_scale, split);
-  double t_gram = tm.stop();
-  { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G.p, nm, W.p, true, st); }
-  info.t_search_syevd_ms += tm.stop();
-  SCL_CUDA(cudaMemcpyAsync(Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
-  SCL_CUDA(cudaStreamSynchronize(st));
-  const float lmax_ref = Lh.back();   // largest eigenvalue of the binarised matrix (scale of the "positive" threshold)
-  // The reference basis keeps the complete eigenbasis (oracle get_eigvec(keep_null=True); DESIGN.md,
-  // deviations): null directions of the binarised matrix are kept, as in the reference whenever their
-  // eigenvalues round positive, so their perturbed counterparts are not mistaken for delocalised vectors.
-  const int i0r = 0;
-  const int npos_ref = nm;
-  const int n_2 = (int)std::nearbyint((double)npos_ref / 2.0);   // round(Int, .) ties-to-even (:722)
-  const size_t ldv = round8((size_t)nm);
-  DBuf<__half>&vr_hi = h->ws_vr_hi, &vr_lo = h->ws_vr_lo;
-  vr_hi.ensure((size_t)npos_ref * ldv);
-  vr_lo.ensure((size_t)npos_ref * ldv);
-  strided_split_f32_to_f16(G.p + (size_t)i0r * nm, npos_ref, nm, nm, (int64_t)ldv, vr_hi.p, vr_lo.p, st, kUnitScale);
-  GemmOperand Vr;
-  Vr.hi = vr_hi.p; Vr.lo = vr_lo.p; Vr.rows = npos_ref; Vr.K = nm; Vr.ld = (int64_t)ldv;
-
-  // --- sparsity search (:715-762)
-  // Steps are independent given their draws; only the stop rule is sequential.  With G ranks, wave w evaluates
-  // steps w*G .. w*G+G-1 speculatively (rank g takes step w*G+g, p_ = 0.999 - step*p_step accumulated exactly as
-  // the reference's repeated `p_ -= p_step`), the second-smallest values are gathered, and the stop rule is applied
-  // in step order - the result is identical to the sequential loop (SURVEY.md 8e).  G = 1 is the plain loop.
-  const int G_ = multi(h) ? h->world : 1;
-  const int tank_n = 5;
-  std::vector<double> tank2;   // row 2 of tank_ (second smallest of d_arr per step)
-  h->trace_p.clear();
-  h->trace_d.clear();
-  Tmp<float> d_d(nm, st);
-  Tmp<double> wave_dev(G_, st);
-  std::vector<float> d_host;
-  std::vector<double> p_of_step(1, 0.999);
-  auto p_at = [&](int s_) {
-    while ((int)p_of_step.size() <= s_) p_of_step.push_back(p_of_step.back() - p_step);   // :760, same rounding drift
-    return p_of_step[s_];
-  };
-  double p_ = 0.999;
-  int step = 0;
-  bool stop = false;
-  for (int wave = 0; !stop; ++wave) {
-    const int my_step = wave * G_ + (multi(h) ? h->rank : 0);
-    const double my_p = p_at(my_step);
-    const long long nnzidx = (long long)std::nearbyint((1.0 - my_p) * (double)M * (double)N);   // :726
-    double my_d2 = -1.0;   // sentinel: candidate pool exhausted at this step (:727-730)
-    if ((long long)h->n_cand >= nnzidx && my_p > 0.85) {
-      Tmp<uint32_t> a_row((size_t)std::max<long long>(1, nnzidx), st), a_col((size_t)std::max<long long>(1, nnzidx), st);
-      make_additions(h, h->search_sples, (size_t)my_step, (size_t)nnzidx, h->cfg.seed + 0x5eed0000ull + (uint64_t)my_step,
-                     a_row.p, a_col.p);
-      {
-        ProfScope ps(&h->prof, st, PK_SPARSE);
-        perturb_merge(X, a_row.p, a_col.p, (size_t)nnzidx, true, Xp, st);
-        h->prof.sparse_alg_bytes += 8.0 * (double)X.nnz + 12.0 * (double)nnzidx;
-      }
-      gram_of(h, Xp, Sp, op_hi, op_lo, G.p, nm, bin_scale, split);
-      t_gram += tm.stop();
-      const int nw = n_2 + 1;                                  // nV_2[:, end-n_2:end] (Appendix A13)
-      int i0 = -1;
-      if (eig_api() & 2) {
-        // opt-in: only the nw smallest positive eigenpairs are used below, so ask the library for an index range.  The
-        // "positive" threshold needs the largest eigenvalue, which a range solve does not return: the reference basis'
-        // one (same matrix without the additions) stands in.  Falls back to the full solve when the range does not
-        // reach nw positive eigenvalues.
-        const int iu = std::min(nm, nw + 64);
-        Tmp<float> Gx((size_t)nm * nm, st);
-        SCL_CUDA(cudaMemcpyAsync(Gx.p, G.p, (size_t)nm * nm * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        int meig = 0;
-        { ProfScope ps(&h->prof, st, PK_SYEVD); meig = h->solver->syevdx_smallest(Gx.p, nm, W.p, iu, st); }
-        std::vector<float> Lx(meig);
-        SCL_CUDA(cudaMemcpyAsync(Lx.data(), W.p, meig * sizeof(float), cudaMemcpyDeviceToHost, st));
-        SCL_CUDA(cudaStreamSynchronize(st));
-        int j = 0;
-        while (j < meig && !(Lx[j] > 1e-5f * lmax_ref)) ++j;
-        if (j + nw <= meig) {
-          i0 = j;
-          SCL_CUDA(cudaMemcpyAsync(G.p, Gx.p, (size_t)(i0 + nw) * nm * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        }
-      }
-      if (i0 < 0) {
-        { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G.p, nm, W.p, true, st); }
-        SCL_CUDA(cudaMemcpyAsync(Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
-        SCL_CUDA(cudaStreamSynchronize(st));
-        i0 = first_positive(Lh);
-        const int npos = nm - i0;
-        SCL_REQUIRE(npos >= n_2 + 1, "perturbed matrix has too few positive eigenvalues");
-      }
-      info.t_search_syevd_ms += tm.stop();
-      SCL_REQUIRE(nw >= 5, "too few noise vectors");
-      const double t_step_syevd = tm.stop();
-      corr_colabsmax_pre(h, Vr, G.p + (size_t)i0 * nm, nw, nm, d_d.p);
-      d_host.resize(nw);
-      SCL_CUDA(cudaMemcpyAsync(d_host.data(), d_d.p, nw * sizeof(float), cudaMemcpyDeviceToHost, st));
-      SCL_CUDA(cudaStreamSynchronize(st));
-      std::partial_sort(d_host.begin(), d_host.begin() + 5, d_host.end());
-      my_d2 = (double)d_host[1];
-      if (getenv("SCL_TRACE"))
-        fprintf(stderr, "[scl] search step %d: n_add %lld, eigenvalue copy+sync %.2f ms, corr %.2f ms\n", my_step, nnzidx, t_step_syevd, tm.stop());
-    }
-    std::vector<double> wave_d2(G_, my_d2);
-    if (G_ > 1) {
-      SCL_CUDA(cudaMemcpyAsync(wave_dev.p + h->rank, &my_d2, sizeof(double), cudaMemcpyHostToDevice, st));
-      SCL_NCCL(nccl_api().AllGather(wave_dev.p + h->rank, wave_dev.p, 1, ncclDouble, (ncclComm_t)h->nccl, st));
-      SCL_CUDA(cudaMemcpyAsync(wave_d2.data(), wave_dev.p, G_ * sizeof(double), cudaMemcpyDeviceToHost, st));
-      SCL_CUDA(cudaStreamSynchronize(st));
-    }
-    // the reference's loop body, in step order
-    for (int g = 0; g < G_ && !stop; ++g) {
-      p_ = p_at(wave * G_ + g);
-      if (wave_d2[g] < 0) {            // lastindex(z_idx1) < nnzidx  (:727-730)
-        p_ += p_step;
-        stop = true;
-        break;
-      }
-      tank2.push_back(wave_d2[g]);
-      h->trace_p.push_back(p_);
-      h->trace_d.push_back(wave_d2[g]);
-      if (h->cfg.verbose) printf("%.9g\n", wave_d2[g]);
-      ++step;
-      int below = 0;
-      const int cnt = (int)tank2.size() < tank_n ? (int)tank2.size() : tank_n;
-      for (int q = 0; q < cnt; ++q)
-        if (tank2[tank2.size() - 1 - q] < p_th) ++below;
-      if (below > tank_n - 1 || p_ < 0.9) {                    // :756
-        p_ += (double)(tank_n - 1) * p_step;
-        stop = true;
-      }
-    }
-  }
-  info.n_search = step;
-  info.p_sel = p_;
-  info.t_search_ms = t_gram + tm.stop();
-  if (h->cfg.verbose) printf("Selected perturb sparisty: %.17g\n", p_);
-
-  // --- perturbations (:767-778)
   const int k = h->sinfo.n_signal;
-  const int min_pc = (int)std::ceil((double)k * 1.5);
-  SCL_REQUIRE(min_pc <= nm / 2, "too many signals for the perturbation stage");
+  // :776 takes min(min_pc, number of positive eigenpairs) columns per replicate; a replicate with fewer gets zero
+  // columns for the rest (a zero column never wins an argmax of |.|, so the scores are the reference's)
+  const int min_pc = std::min((int)std::ceil((double)k * 1.5), nm);
   const long long n_add = (long long)std::nearbyint((1.0 - p_) * (double)M * (double)N);     // :772
   SCL_REQUIRE((long long)h->n_cand >= n_add, "zero-candidate pool smaller than the perturbation size");
   info.min_pc = min_pc;
@@ -840,47 +963,74 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
   info.n_perturb = n_perturb;
   h->d_sets.ensure((size_t)n_perturb * min_pc * N);
   h->set_L.assign((size_t)n_perturb * min_pc, 0.f);
-  const bool exact = h->cfg.exact_perturb != 0;
+  // the block subspace iteration needs room for its block (k + 64 vectors, at most 256, at most n / 2); anything else -
+  // tiny matrices, signal-rich inputs, a replicate that does not converge - takes the exact solve the reference makes
+  const int sub_b = std::min(256, ((min_pc + (h->cfg.subspace_extra > 0 ? h->cfg.subspace_extra : 64) + 31) / 32) * 32);
+  const bool can_subspace = min_pc + 16 <= sub_b && sub_b * 2 <= nm;
+  const bool exact = h->cfg.exact_perturb != 0 || !can_subspace;
   Tmp<float> topL(min_pc, st), topV((size_t)min_pc * nm, st);
   Tmp<float> setL_dev((size_t)n_perturb * min_pc, st);
-  for (int r = 0; r < n_perturb; ++r) {
-    if (multi(h) && r % h->world != h->rank) continue;   // replicate r belongs to rank r mod G (scl_plan_replicates)
-    Tmp<uint32_t> a_row((size_t)std::max<long long>(1, n_add), st), a_col((size_t)std::max<long long>(1, n_add), st);
-    make_additions(h, h->perturb_sples, (size_t)r, (size_t)n_add, h->cfg.seed + 0xbeef0000ull + (uint64_t)r, a_row.p, a_col.p);
-    {
-      ProfScope ps(&h->prof, st, PK_SPARSE);
-      perturb_merge(X, a_row.p, a_col.p, (size_t)n_add, false, Xp, st);                        // :774
-      h->prof.sparse_alg_bytes += 8.0 * (double)X.nnz + 12.0 * (double)n_add;
+  std::string err;
+  try {
+    for (int r = 0; r < n_perturb; ++r) {
+      if (multi(h) && r % h->world != h->rank) continue;   // replicate r belongs to rank r mod G (scl_plan_replicates)
+      Tmp<uint32_t> a_row((size_t)std::max<long long>(1, n_add), st), a_col((size_t)std::max<long long>(1, n_add), st);
+      make_additions(h, h->perturb_sples, (size_t)r, (size_t)n_add, h->cfg.seed + 0xbeef0000ull + (uint64_t)r, a_row.p, a_col.p);
+      {
+        ProfScope ps(&h->prof, st, PK_SPARSE);
+        perturb_merge(X, a_row.p, a_col.p, (size_t)n_add, false, Xp, st);                        // :774
+        h->prof.sparse_alg_bytes += 8.0 * (double)X.nnz + 12.0 * (double)n_add;
+      }
+      gram_of(h, Xp, Sp, op_hi, op_lo, G.p, nm, 1.0f / (float)M, split);                         // :775 -> :492/:512
+      float* set_r = h->d_sets.p + (size_t)r * min_pc * N;
+      const float* vec0 = nullptr;
+      long long ldvec = 0;
+      int have = min_pc;
+      bool solved = false;
+      if (!exact) {
+        try {
+          int iters = 0;
+          topk_subspace(h, G.p, nm, min_pc, topL.p, topV.p, &iters);
+          unscale_eigenvalues(h, topL.p, min_pc);
+          SCL_CUDA(cudaMemcpyAsync(&h->set_L[(size_t)r * min_pc], topL.p, min_pc * sizeof(float), cudaMemcpyDeviceToHost, st));
+          vec0 = topV.p;
+          ldvec = nm;
+          solved = true;
+        } catch (const Error& e) {
+          if (e.code != SCL_ERR_CUSOLVER) throw;
+          ++info.n_subspace_fallbacks;   // did not converge / lost rank: the Gram matrix is intact, solve it exactly
+        }
+      }
+      if (!solved) {
+        {
+          ProfScope ps(&h->prof, st, PK_SYEVD);
+          if (eig_api() & 4) h->solver->syevd_tri(G.p, nm, W.p, nm - min_pc, nm, st);
+          else h->solver->syevd(G.p, nm, W.p, true, st);
+        }
+        unscale_eigenvalues(h, W.p, nm);
+        SCL_CUDA(cudaMemcpyAsync(Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
+        SCL_CUDA(cudaStreamSynchronize(st));
+        have = std::min(min_pc, nm - first_positive(Lh));
+        for (int i = 0; i < have; ++i) h->set_L[(size_t)r * min_pc + i] = Lh[nm - 1 - i];
+        vec0 = G.p + (size_t)(nm - 1) * nm;
+        ldvec = -(long long)nm;
+      }
+      if (have < min_pc) SCL_CUDA(cudaMemsetAsync(set_r + (size_t)have * N, 0, (size_t)(min_pc - have) * N * sizeof(float), st));
+      if (have > 0) {
+        if (N > M)
+          back_project(h, Xp, Sp, vec0, ldvec, have, set_r);
+        else
+          copy_rows(vec0, ldvec, set_r, N, have, N, st);
+      }
     }
-    gram_of(h, Xp, Sp, op_hi, op_lo, G.p, nm, 1.0f / (float)M, split);                         // :775 -> :492/:512
-    float* set_r = h->d_sets.p + (size_t)r * min_pc * N;
-    const float* vec0;
-    long long ldvec;
-    if (exact) {
-      { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G.p, nm, W.p, true, st); }
-      unscale_eigenvalues(h, W.p, nm);
-      SCL_CUDA(cudaMemcpyAsync(Lh.data(), W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
-      SCL_CUDA(cudaStreamSynchronize(st));
-      SCL_REQUIRE(nm - first_positive(Lh) >= min_pc, "too few positive eigenvalues in a replicate");
-      for (int i = 0; i < min_pc; ++i) h->set_L[(size_t)r * min_pc + i] = Lh[nm - 1 - i];
-      vec0 = G.p + (size_t)(nm - 1) * nm;
-      ldvec = -(long long)nm;
-    } else {
-      int iters = 0;
-      topk_subspace(h, G.p, nm, min_pc, topL.p, topV.p, &iters);
-      unscale_eigenvalues(h, topL.p, min_pc);
-      SCL_CUDA(cudaMemcpyAsync(&h->set_L[(size_t)r * min_pc], topL.p, min_pc * sizeof(float), cudaMemcpyDeviceToHost, st));
-      vec0 = topV.p;
-      ldvec = nm;
-    }
-    if (N > M)
-      back_project(h, Xp, Sp, vec0, ldvec, min_pc, set_r);
-    else
-      copy_rows(vec0, ldvec, set_r, N, min_pc, N, st);
+    SCL_CUDA(cudaStreamSynchronize(st));
+  } catch (const std::exception& e) {
+    err = e.what();
   }
-  SCL_CUDA(cudaStreamSynchronize(st));
+  sync_errors(h, err);
   if (multi(h)) {
     // every rank scores all replicates: N x min_pc blocks travel once over NVLink from their owner
+    ProfScope ps(&h->prof, st, PK_COMM);
     SCL_CUDA(cudaMemcpyAsync(setL_dev.p, h->set_L.data(), h->set_L.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     SCL_NCCL(nccl_api().GroupStart());
     for (int r = 0; r < n_perturb; ++r) {
@@ -892,6 +1042,7 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
     SCL_NCCL(nccl_api().GroupEnd());
     SCL_CUDA(cudaMemcpyAsync(h->set_L.data(), setL_dev.p, h->set_L.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
     SCL_CUDA(cudaStreamSynchronize(st));
+    h->prof.comm_bytes += 4.0 * (double)n_perturb * min_pc * (N + 1);
   }
   info.t_perturb_ms = tm.stop();
 
@@ -930,6 +1081,246 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
   info.t_outputs_ms = tm.stop();
   h->prof.resolve();
   h->robust_done = true;
+}
+
+}  // namespace
+
+void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
+  SCL_REQUIRE(h->signal_done, "scl_run_signal must succeed first");
+  if (h->sinfo.n_signal == 0) throw Error(SCL_ERR_NOSIGNAL, "warning: There is no signal");
+  SCL_REQUIRE(n_perturb >= 2, "n_perturb must be >= 2");
+  cudaStream_t st = h->st;
+  const int nm = std::min(h->X.N, h->X.M);
+  scl_robust_info& info = h->rinfo;
+  Timer tm(st);
+  robust_prepare(h);
+  info.t_baseline_ms = tm.stop();
+
+  // --- reference basis of the binarised matrix (:717-721)
+  SearchCtx c;
+  search_ctx_init(h, c);
+  binref_solve(h, c);
+  SCL_CUDA(cudaMemcpyAsync(c.Lh.data(), h->ws_W.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  c.lmax_ref = c.Lh.back();   // largest eigenvalue of the binarised matrix (scale of the "positive" threshold)
+  binref_operand(h, c, true);
+  info.t_search_syevd_ms += tm.stop();
+
+  // --- sparsity search (:715-762)
+  // Steps are independent given their draws; only the stop rule is sequential.  With G ranks, wave w evaluates
+  // steps w*G .. w*G+G-1 speculatively (rank g takes step w*G+g, p_ = 0.999 - step*p_step accumulated exactly as
+  // the reference's repeated `p_ -= p_step`), the second-smallest values are gathered, and the stop rule is applied
+  // in step order - the result is identical to the sequential loop (SURVEY.md 8e).  G = 1 is the plain loop.
+  // (scl_run_pass spreads the three solves above over the ranks as well.)
+  const int G_ = multi(h) ? h->world : 1;
+  SearchState ss;
+  ss.p_step = p_step;
+  ss.p_th = info.p_th;
+  Tmp<double> wave_dev(G_, st);
+  double t_gram = 0;
+  for (int wave = 0; !ss.stop; ++wave) {
+    const int my_step = wave * G_ + (multi(h) ? h->rank : 0);
+    double my_d2 = -2.0;   // not evaluated: the sequential loop cannot reach this step
+    std::string err;
+    try {
+      if (ss.reachable(my_step)) {
+        const int i0 = search_step_solve(h, c, ss, my_step, info, tm, t_gram);
+        my_d2 = i0 < 0 ? -1.0 : search_step_corr(h, c, i0);
+      }
+    } catch (const std::exception& e) {
+      err = e.what();
+    }
+    std::vector<double> wave_d2(G_, my_d2);
+    if (G_ > 1) {
+      sync_errors(h, err);
+      SCL_CUDA(cudaMemcpyAsync(wave_dev.p + h->rank, &my_d2, sizeof(double), cudaMemcpyHostToDevice, st));
+      SCL_NCCL(nccl_api().AllGather(wave_dev.p + h->rank, wave_dev.p, 1, ncclDouble, (ncclComm_t)h->nccl, st));
+      SCL_CUDA(cudaMemcpyAsync(wave_d2.data(), wave_dev.p, G_ * sizeof(double), cudaMemcpyDeviceToHost, st));
+      SCL_CUDA(cudaStreamSynchronize(st));
+    } else if (!err.empty()) {
+      throw Error(SCL_ERR_INVALID, err);
+    }
+    for (int g = 0; g < G_; ++g) ss.feed(h, wave * G_ + g, wave_d2[g]);   // the reference's loop body, in step order
+  }
+  info.n_search = ss.step;
+  info.p_sel = ss.p_;
+  info.t_search_ms = t_gram + tm.stop();
+  if (h->cfg.verbose) printf("Selected perturb sparisty: %.17g\n", ss.p_);
+  robust_tail(h, th, n_perturb, ss.p_, tm);
+}
+
+// One complete sclens() pass (:664-819).  One rank: run_signal, then run_robustness.  Several ranks: ONE pass shared by all
+// of them - the Gram matrices of the data and null matrices are contracted cell block by cell block on every rank and
+// reduced (packed triangle) to the rank that solves them, and the pass's eigensolves form one task list
+//   [data, null, binarised reference, search step 0, search step 1, ...]          task t -> rank t mod G, wave t div G
+// so that the three solves that used to run redundantly on every rank share a wave with the first search steps.  What a
+// later task needs from an earlier one travels once over NVLink: the two spectra (for the MP/TW fit every rank repeats),
+// the k signal eigenvectors, and the reference basis as binary16 hi/lo rows.  Search steps keep their eigenvectors until the
+// basis has arrived.  The stop rule consumes the steps in order, so the outcome is the sequential loop's.
+void run_pass(scl_handle* h, double th, double p_step, int n_perturb) {
+  if (!multi(h)) {
+    run_signal(h);
+    h->rinfo = scl_robust_info{};
+    if (h->sinfo.n_signal == 0) return;   // :780-784
+    run_robustness(h, th, p_step, n_perturb);
+    return;
+  }
+  SCL_REQUIRE(h->have_X, "scl_set_counts_csc must be called first");
+  SCL_REQUIRE(n_perturb >= 2, "n_perturb must be >= 2");
+  cudaStream_t st = h->st;
+  const SpMat& X = h->X;
+  const int N = X.N, M = X.M, nm = std::min(N, M), G_ = h->world, me = h->rank;
+  const bool split = h->cfg.gram_mode == SCL_GRAM_FP16X3;
+  scl_signal_info& sinfo = h->sinfo;
+  sinfo = scl_signal_info{};
+  sinfo.N = N; sinfo.M = M; sinfo.nm = nm;
+  sinfo.gram_mode_used = h->cfg.gram_mode;
+  h->signal_done = false;
+  const int r_data = 0, r_null = 1 % G_, r_bin = 2 % G_;
+  const bool refine = !h->cfg.no_refine;
+  DBuf<float>&G = h->ws_G, &W = h->ws_W, &G2 = h->ws_G2, &W2 = h->ws_W2;
+  G.ensure((size_t)nm * nm); W.ensure(nm); G2.ensure((size_t)nm * nm); W2.ensure(nm);
+  Timer tm(st);
+  std::string err;
+  SearchCtx c;
+  SearchState ss;
+  scl_robust_info& rinfo = h->rinfo;
+  double t_gram = 0;
+  // --- cooperative part: both sharded Gram matrices, the draws every rank repeats identically
+  try {
+    gram_of(h, X, h->S_main, h->ws_op_hi, h->ws_op_lo, G.p, nm, 1.0f / (float)M, split, /*shard=*/true, r_data);
+    save_gram_factor(h, 1);
+    if (me == r_data && refine) {
+      h->ws_Gkeep.ensure((size_t)nm * nm);
+      SCL_CUDA(cudaMemcpyAsync(h->ws_Gkeep.p, G.p, (size_t)nm * nm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    make_null_matrix(h);
+    sinfo.t_null_ms = tm.stop();
+    gram_of(h, h->Xnull, h->ws_Sn, h->ws_op_hi, h->ws_op_lo, G2.p, nm, 1.0f / (float)M, split, /*shard=*/true, r_null);
+    save_gram_factor(h, 2);
+    sinfo.t_gram_ms = tm.stop();
+    robust_prepare(h);
+    rinfo.t_baseline_ms = tm.stop();
+    search_ctx_init(h, c);
+    binref_operand(h, c, false);
+    ss.p_step = p_step;
+    ss.p_th = rinfo.p_th;
+  } catch (const std::exception& e) {
+    err = e.what();
+  }
+  sync_errors(h, err);
+
+  Tmp<double> wave_dev(G_, st);
+  Tmp<float> lmax_dev(1, st);
+  bool have_fit = false, have_basis = false;
+  std::vector<float> Lr(nm);
+  for (int wave = 0; !ss.stop; ++wave) {
+    const int task = wave * G_ + me;
+    int i0 = -2;            // search step of this rank in this wave: -2 none / unreachable, -1 pool exhausted, >= 0 solved
+    const int my_step = task - 3;
+    err.clear();
+    try {
+      if (task == 0) {                  // data matrix (:530/:570)
+        { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G.p, nm, W.p, true, st); }
+        sinfo.t_syevd_ms += tm.stop();
+        if (refine) {
+          ProfScope ps(&h->prof, st, PK_REFINE);
+          refine_eigenvalues(h->ws_Gkeep.p, G.p, nm, W.p, st);
+        }
+        unscale_eigenvalues(h, W.p, nm, 1);
+      }
+      if (task == 1) {                  // null matrix, values only (:531-532/:571-572)
+        { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G2.p, nm, W2.p, false, st); }
+        unscale_eigenvalues(h, W2.p, nm, 2);
+        sinfo.t_syevd_ms += tm.stop();
+      }
+      if (task == 2) {                  // reference basis of the binarised matrix (:717-721)
+        tm.stop();
+        binref_solve(h, c);
+        // its largest eigenvalue (scale of the "positive" threshold) before the data spectrum arrives in the same buffer
+        SCL_CUDA(cudaMemcpyAsync(lmax_dev.p, W.p + (nm - 1), sizeof(float), cudaMemcpyDeviceToDevice, st));
+        rinfo.t_search_syevd_ms += tm.stop();
+      }
+      if (my_step >= 0 && ss.reachable(my_step)) i0 = search_step_solve(h, c, ss, my_step, rinfo, tm, t_gram);
+      SCL_CUDA(cudaStreamSynchronize(st));
+    } catch (const std::exception& e) {
+      err = e.what();
+    }
+    sync_errors(h, err);
+    err.clear();
+    double my_d2 = i0 == -1 ? -1.0 : -2.0;
+    try {
+      // --- what later tasks need from this wave's, in task order
+      const bool fit_now = !have_fit && wave >= 1 / G_;       // tasks 0 and 1 are done (wave 0 when G >= 2)
+      const bool basis_now = !have_basis && wave >= 2 / G_;   // task 2 is done (wave 0 when G >= 3, wave 1 when G = 2)
+      if (fit_now) {
+        ProfScope ps(&h->prof, st, PK_COMM);
+        SCL_NCCL(nccl_api().Broadcast(W.p, W.p, nm, ncclFloat, r_data, (ncclComm_t)h->nccl, st));
+        SCL_NCCL(nccl_api().Broadcast(W2.p, W2.p, nm, ncclFloat, r_null, (ncclComm_t)h->nccl, st));
+        h->prof.comm_bytes += 8.0 * nm;
+      }
+      if (fit_now) {
+        fetch_signal_outputs(h, W.p, nm, refine);
+        SCL_CUDA(cudaMemcpyAsync(Lr.data(), W2.p, nm * sizeof(float), cudaMemcpyDeviceToHost, st));
+        SCL_CUDA(cudaStreamSynchronize(st));
+        fit_signal(h, Lr);
+        const int k = sinfo.n_signal;
+        // the k leading eigenvectors leave the solving rank before its buffer is reused (G = 2: by the reference basis)
+        Tmp<float> top((size_t)std::max(1, k) * nm, st);
+        if (k > 0) {
+          if (me == r_data) copy_rows(G.p + (size_t)(nm - 1) * nm, -(long long)nm, top.p, nm, k, nm, st);
+          ProfScope ps(&h->prof, st, PK_COMM);
+          SCL_NCCL(nccl_api().Broadcast(top.p, top.p, (size_t)k * nm, ncclFloat, r_data, (ncclComm_t)h->nccl, st));
+          h->prof.comm_bytes += 4.0 * (double)k * nm;
+        }
+        tm.stop();
+        project_signal(h, top.p, (long long)nm);
+        SCL_CUDA(cudaStreamSynchronize(st));
+        sinfo.t_backproject_ms = tm.stop();
+        h->signal_done = true;
+        have_fit = true;
+      }
+      if (basis_now) {
+        if (me == r_bin) binref_operand(h, c, true);
+        ProfScope ps(&h->prof, st, PK_COMM);
+        const size_t cnt = (size_t)nm * (size_t)c.Vr.ld;
+        SCL_NCCL(nccl_api().Broadcast(h->ws_vr_hi.p, h->ws_vr_hi.p, cnt, ncclHalf, r_bin, (ncclComm_t)h->nccl, st));
+        SCL_NCCL(nccl_api().Broadcast(h->ws_vr_lo.p, h->ws_vr_lo.p, cnt, ncclHalf, r_bin, (ncclComm_t)h->nccl, st));
+        SCL_NCCL(nccl_api().Broadcast(lmax_dev.p, lmax_dev.p, 1, ncclFloat, r_bin, (ncclComm_t)h->nccl, st));
+        SCL_CUDA(cudaMemcpyAsync(&c.lmax_ref, lmax_dev.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+        SCL_CUDA(cudaStreamSynchronize(st));
+        h->prof.comm_bytes += 4.0 * (double)cnt;
+        have_basis = true;
+      }
+      if (i0 >= 0) {
+        SCL_REQUIRE(have_basis, "search step finished before the reference basis");
+        tm.stop();
+        my_d2 = search_step_corr(h, c, i0);
+        t_gram += tm.stop();
+      }
+    } catch (const std::exception& e) {
+      err = e.what();
+    }
+    sync_errors(h, err);
+    if (sinfo.n_signal == 0 && have_fit) {   // :780-784: nothing to test
+      h->prof.resolve();
+      return;
+    }
+    std::vector<double> wave_d2(G_, -2.0);
+    SCL_CUDA(cudaMemcpyAsync(wave_dev.p + me, &my_d2, sizeof(double), cudaMemcpyHostToDevice, st));
+    SCL_NCCL(nccl_api().AllGather(wave_dev.p + me, wave_dev.p, 1, ncclDouble, (ncclComm_t)h->nccl, st));
+    SCL_CUDA(cudaMemcpyAsync(wave_d2.data(), wave_dev.p, G_ * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+    for (int g = 0; g < G_; ++g) {
+      const int s_ = wave * G_ + g - 3;
+      if (s_ >= 0) ss.feed(h, s_, wave_d2[g]);
+    }
+  }
+  rinfo.n_search = ss.step;
+  rinfo.p_sel = ss.p_;
+  rinfo.t_search_ms = t_gram + tm.stop();
+  if (h->cfg.verbose) printf("Selected perturb sparisty: %.17g\n", ss.p_);
+  robust_tail(h, th, n_perturb, ss.p_, tm);
 }
 
 }  // namespace scl

@@ -8,7 +8,7 @@
 
 namespace scl {
 
-enum ProfKind { PK_GRAM_GEMM = 0, PK_OTHER_GEMM, PK_DENSIFY, PK_STATS, PK_SPARSE, PK_SYEVD, PK_SMALL, PK_REFINE, PK_COUNT };
+enum ProfKind { PK_GRAM_GEMM = 0, PK_OTHER_GEMM, PK_DENSIFY, PK_STATS, PK_SPARSE, PK_SYEVD, PK_SMALL, PK_REFINE, PK_COMM, PK_COUNT };
 
 struct ProfEvent {
   cudaEvent_t a, b;
@@ -22,6 +22,8 @@ struct Prof {
   double other_gemm_flops = 0;    // 2 m n k
   double densify_alg_bytes = 0;   // 8 nnz + 4(M+1) + N*M*s_out
   double sparse_alg_bytes = 0;    // 20 nnz (+12 n_add)
+  double stats_alg_bytes = 0;     // 40 nnz per normalisation
+  double comm_bytes = 0;          // payload of the NCCL collectives
   std::vector<ProfEvent> pending;
   void resolve();
   void reset();

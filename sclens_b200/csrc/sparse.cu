@@ -615,17 +615,48 @@ void draw_null_device(const SpMat& base, uint64_t seed, SpMat& out, cudaStream_t
   build_csr_mirror(out, st);
 }
 
-// Zero candidates (:668-673): T distinct grid positions from a Feistel bijection of [0,N*M),
-// minus the non-zero set (binary search in the gene's sorted row list), compacted in order.
+// Zero candidates (:668-673), the reference's own recipe on the device: nnz independent uniform grid positions (draw t
+// is a pure function of (seed, t): counter-based, no state), minus the non-zero set (binary search in the gene's sorted
+// row list), de-duplicated keeping the FIRST occurrence, in draw order - `setdiff(sample_idx, z_idset)`.  First occurrence
+// is decided deterministically: an open-addressing table holds, per drawn position, the smallest draw index that hit it
+// (the table stores draw indices only - the position of a stored draw is recomputed from its index).
+__host__ __device__ inline uint64_t zc_position(uint64_t seed, uint64_t t, uint64_t grid) {
+  const uint64_t h = mix64(seed ^ mix64(t + 0x632be59bd9b4e019ull));
+#ifdef __CUDA_ARCH__
+  return __umul64hi(h, grid);
+#else
+  return (uint64_t)(((unsigned __int128)h * grid) >> 64);
+#endif
+}
+
+__global__ void k_zc_insert(uint64_t seed, uint64_t grid, size_t n_draw, uint32_t* __restrict__ table, uint32_t mask) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; t < n_draw; t += stride) {
+    const uint64_t pos = zc_position(seed, t, grid);
+    uint32_t slot = (uint32_t)mix64(pos) & mask;
+    while (true) {
+      const uint32_t cur = atomicCAS(table + slot, 0xffffffffu, (uint32_t)t);
+      if (cur == 0xffffffffu) break;                                   // claimed an empty slot
+      if (zc_position(seed, cur, grid) == pos) {                       // the slot of this position: keep the earliest draw
+        atomicMin(table + slot, (uint32_t)t);
+        break;
+      }
+      slot = (slot + 1) & mask;
+    }
+  }
+}
+
 __global__ void k_zero_cand_flags(const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ rowval, int N,
-                                  Feistel f, size_t T, uint32_t* __restrict__ cand_row, uint32_t* __restrict__ cand_col,
+                                  uint64_t seed, uint64_t grid, const uint32_t* __restrict__ table, uint32_t mask, size_t T,
+                                  uint32_t* __restrict__ cand_row, uint32_t* __restrict__ cand_col,
                                   uint32_t* __restrict__ block_cnt) {
   __shared__ uint32_t wc[8];
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   bool keep = false;
   uint32_t r = 0, c = 0;
   if (i < T) {
-    uint64_t g = f(i);
+    const uint64_t g = zc_position(seed, i, grid);
     c = (uint32_t)(g / (uint64_t)N);
     r = (uint32_t)(g % (uint64_t)N);
     uint32_t lo = colptr[c], hi = colptr[c + 1];
@@ -634,6 +665,15 @@ __global__ void k_zero_cand_flags(const uint32_t* __restrict__ colptr, const uin
       if (rowval[mid] < r) lo = mid + 1; else hi = mid;
     }
     keep = !(lo < colptr[c + 1] && rowval[lo] == r);
+    if (keep) {   // first occurrence of this position among the draws?
+      uint32_t slot = (uint32_t)mix64(g) & mask;
+      while (true) {
+        const uint32_t cur = table[slot];
+        if (cur == 0xffffffffu) { keep = false; break; }               // cannot happen: every draw was inserted
+        if (zc_position(seed, cur, grid) == g) { keep = cur == (uint32_t)i; break; }
+        slot = (slot + 1) & mask;
+      }
+    }
     cand_row[i] = keep ? r : 0xffffffffu;
     cand_col[i] = c;
   }
@@ -667,23 +707,26 @@ __global__ void k_zero_cand_compact(const uint32_t* __restrict__ cand_row, const
   }
 }
 
-// Large exclusive scan (block counts can exceed 1024*chunk comfortably handled by k_exclusive_scan).
 size_t draw_zero_candidates_device(const SpMat& base, uint64_t seed, DBuf<uint32_t>& z1, DBuf<uint32_t>& z2,
                                    cudaStream_t st) {
-  count_launches(3);
+  count_launches(4);
   const uint64_t grid = (uint64_t)base.N * (uint64_t)base.M;
-  // expected number of distinct positions among nnz uniform draws (the reference draws nnz pairs)
-  double d = (double)base.nnz / (double)grid;
-  size_t T = (size_t)llround((double)grid * (1.0 - exp(-d)));
-  if (T > grid) T = grid;
-  SCL_REQUIRE(T > 0, "empty matrix");
-  Feistel f = Feistel::make(grid, mix64(seed ^ 0x7a65726full));
+  const size_t T = base.nnz;                        // the reference draws length(nz_val) pairs (:669)
+  SCL_REQUIRE(T > 0 && T < 0xffffffffull, "empty matrix, or too many stored entries for 32-bit draw indices");
+  const uint64_t key = mix64(seed ^ 0x7a65726full);
+  size_t cap = 1;
+  while (cap < 2 * T) cap <<= 1;                    // load factor <= 1/2
+  SCL_REQUIRE(cap <= (1ull << 32), "draw table too large");
+  const uint32_t mask = (uint32_t)(cap - 1);
+  Tmp<uint32_t> table(cap, st);
+  SCL_CUDA(cudaMemsetAsync(table.p, 0xff, cap * sizeof(uint32_t), st));
+  k_zc_insert<<<grid_for(T, 256), 256, 0, st>>>(key, grid, T, table.p, mask);
   const int threads = 256;
   const size_t blocks = (T + threads - 1) / threads;
   SCL_REQUIRE(blocks < (1ull << 31), "too many candidate blocks");
   Tmp<uint32_t> crow(T, st), ccol(T, st), bcnt(blocks + 1, st), boff(blocks + 1, st);
-  k_zero_cand_flags<<<(unsigned)blocks, threads, 0, st>>>(base.colptr.p, base.rowval.p, base.N, f, T, crow.p, ccol.p,
-                                                          bcnt.p);
+  k_zero_cand_flags<<<(unsigned)blocks, threads, 0, st>>>(base.colptr.p, base.rowval.p, base.N, key, grid, table.p, mask, T,
+                                                          crow.p, ccol.p, bcnt.p);
   exclusive_scan(bcnt.p, boff.p, (int)blocks, st);
   uint32_t total = 0;
   SCL_CUDA(cudaMemcpyAsync(&total, boff.p + blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -693,6 +736,11 @@ size_t draw_zero_candidates_device(const SpMat& base, uint64_t seed, DBuf<uint32
   k_zero_cand_compact<<<(unsigned)blocks, threads, 0, st>>>(crow.p, ccol.p, T, boff.p, z1.p, z2.p);
   SCL_CUDA(cudaGetLastError());
   return total;
+}
+
+// the draw the kernels make, restated for the tests: grid position of draw t (host)
+uint64_t zero_candidate_position_host(uint64_t seed, uint64_t t, uint64_t grid) {
+  return zc_position(mix64(seed ^ 0x7a65726full), t, grid);
 }
 
 // sample(1:n_cand, n_take, replace=false) (:731, :772) as the first n_take images of a keyed

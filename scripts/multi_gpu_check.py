@@ -22,10 +22,13 @@ shape = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1200, 90
 X = make_counts(*shape, seed=21, K=5, de_prob=0.3, lfc_sd=1.5)
 
 
-def run(h):
+def run(h, one_call=False):
     t0 = time.perf_counter()
-    si = h.run_signal()
-    ri = h.run_robustness(n_perturb=8)
+    if one_call:      # scl_run_pass: the pass's eigensolves (data, null, reference basis, search steps) dealt to the ranks
+        si, ri = h.run_pass(n_perturb=8)
+    else:             # the two stage calls: every rank repeats the three serial solves
+        si = h.run_signal()
+        ri = h.run_robustness(n_perturb=8)
     dt = time.perf_counter() - t0
     b, m, sd = h.scores()
     return dict(L=h.L(), nL=h.signal_ev(), nV=h.signal_evec(), n_signal=si.n_signal, lam=si.lambda_c, p_sel=ri.p_sel,
@@ -41,8 +44,9 @@ if rank == 0:
 dist.broadcast(uid, 0)
 h.comm_init(bytes(uid.cpu().tolist()), rank, world)
 h.set_counts(X)
-multi = run(h)
-multi2 = run(h)
+staged = run(h)
+multi = run(h, one_call=True)
+multi2 = run(h, one_call=True)
 dist.barrier()
 ok = True
 if rank == 0:
@@ -52,13 +56,14 @@ if rank == 0:
         single = run(h1)
     print(f"world={world} shape={shape} multi {multi2['dt']:.2f}s single {single['dt']:.2f}s n_signal {multi['n_signal']} "
           f"p_sel {multi['p_sel']} n_search {multi['n_search']}", flush=True)
-    assert multi["n_signal"] == single["n_signal"] and multi["n_search"] == single["n_search"] and multi["p_sel"] == single["p_sel"]
-    np.testing.assert_allclose(multi["L"][10:], single["L"][10:], rtol=2e-5)
-    np.testing.assert_allclose(multi["trace"][1], single["trace"][1], rtol=2e-2)
-    np.testing.assert_allclose(multi["m"], single["m"], atol=2e-2)
-    np.testing.assert_array_equal(multi["sig"], single["sig"])
-    cos = np.abs(np.sum(multi["nV"] * single["nV"], axis=0))
-    assert cos.min() > 1 - 1e-5
+    for name, got in (("scl_run_pass", multi), ("scl_run_pass again", multi2), ("scl_run_signal + scl_run_robustness", staged)):
+        assert got["n_signal"] == single["n_signal"] and got["n_search"] == single["n_search"] and got["p_sel"] == single["p_sel"], name
+        np.testing.assert_allclose(got["L"][10:], single["L"][10:], rtol=2e-5, err_msg=name)
+        np.testing.assert_allclose(got["trace"][1], single["trace"][1], rtol=2e-2, err_msg=name)
+        np.testing.assert_allclose(got["m"], single["m"], atol=2e-2, err_msg=name)
+        np.testing.assert_array_equal(got["sig"], single["sig"], err_msg=name)
+        cos = np.abs(np.sum(got["nV"] * single["nV"], axis=0))
+        assert cos.min() > 1 - 1e-5, name
     print("MULTI_GPU_CHECK_OK", flush=True)
 # every rank must hold identical results
 t = torch.tensor([multi["p_sel"], float(multi["n_search"]), float(len(multi["sig"])), float(multi["m"].sum())], device=dev, dtype=torch.float64)

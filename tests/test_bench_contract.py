@@ -23,9 +23,13 @@ def test_reference_arm_prints_one_contract_line():
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["metric"] == "sclens_cells_per_s" and j["unit"] == "cells/s"
     assert j["higher_is_better"] is True and j["value"] > 0 and j["steps"] == 1 and j["warmup"] == 0
+    assert j["steps_requested"] == 1 and j["warmup_requested"] == 0
     assert j["config"]["workload"].startswith("small") and j["data"] == "synthetic" and j["vs_baseline"] is None
     cb = j["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "sub-matrix" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "measured once at FULL size" in cb["sample"]
+    # the stages are measured, not modelled: seconds per stage at the full shape of the workload, measured once
+    assert cb["frac"] == 1 and cb["measured_at"] == [2000, 3000] and cb["eig_n"] == 2000
+    assert set(cb["stage_seconds"]) == {"normalise", "gram_f64", "eigen_vectors", "corr"} and min(cb["stage_seconds"].values()) > 0
     assert j["e2e"] == {"value": j["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -68,3 +68,45 @@ def test_moderate_size_matches_oracle_eigenvalues():
     keep = Lref >= si.b_minus
     assert np.max(np.abs(L[keep] - Lref[keep]) / Lref[keep]) < 1e-4
     assert si.n_signal == int((Lref > si.lambda_c).sum())
+
+
+def test_signal_stage_headline_shape_68k_x_20k():
+    """BASELINE.json configs[2], the shape the metric is quoted on (N > M: gene-side Gram, contraction over 68 000 cells in
+    17 promoted chunks, bias calibration, Float64 refinement, back-projection): every eigenvalue >= b_minus within 1e-4 of a
+    Float64 evaluation of the same normalised matrix, exact signal count = 7, trace identity (/root/reference/src/scLENS.jl:526-594)."""
+    import torch
+    from bench import WORKLOADS, make_counts_fast
+    N, M, seed = WORKLOADS["C"]
+    X = make_counts_fast(N, M, seed, device=torch.device("cuda", 0))
+    with Handle(gram_mode=SCL_GRAM_FP16, seed=seed) as h:
+        h.set_counts(X)
+        si = h.run_signal()
+        L = h.L().astype(np.float64)
+        nV, nL = h.signal_evec(), h.signal_ev()
+        ld = (N + 7) // 8 * 8
+        hi = np.empty((M, ld), np.uint16)
+        lo = np.empty((M, ld), np.uint16)
+        colptr, rowval, val = _lib.as_u32(X.indptr), _lib.as_u32(X.indices), _lib.as_f32(X.data)
+        h._ck(h.lib.scl_op_normalize(h.h, N, M, X.nnz, ptr(colptr, C.c_uint32), ptr(rowval, C.c_uint32),
+                                     ptr(val, C.c_float), 0, ld, ptr(hi, C.c_uint16), ptr(lo, C.c_uint16),
+                                     None, None, None, None, None))
+    A = torch.from_numpy(hi.view(np.float16)).cuda().double()
+    A += torch.from_numpy(lo.view(np.float16)).cuda().double()           # M x ld, gene-major: column j of scaled_X
+    del hi, lo
+    G = A @ A.T / M                                                       # X'X / size(X,2)  (:337-338)
+    Lref, Vref = torch.linalg.eigh(G)
+    Lref = Lref.cpu().numpy()
+    keep = Lref >= si.b_minus
+    rel = np.abs(L[keep] - Lref[keep]) / Lref[keep]
+    assert rel.max() < 1e-4, rel.max()                                    # north star
+    assert si.n_signal == int((Lref > si.lambda_c).sum()) == 7            # bit-exact signal count
+    tr = float((A * A).sum().item()) / M
+    assert abs(L.sum() - tr) / tr < 2e-5
+    # cell-space signal vectors (:556-558): X v / |X v| of the Float64 eigenvectors, up to sign
+    k = si.n_signal
+    Vk = Vref[:, -k:].flip(1)                                             # descending
+    U = (A[:, :N].T @ Vk)
+    U /= U.norm(dim=0, keepdim=True)
+    cos = np.abs(np.sum(U.cpu().numpy() * nV.astype(np.float64), axis=0))
+    assert np.arccos(np.clip(cos, 0, 1)).max() < 5e-3
+    np.testing.assert_allclose(nL, Lref[::-1][:k], rtol=1e-4)

@@ -99,3 +99,44 @@ def test_gram_shard_plan_partitions_the_contraction_axis():
             assert prev == ld, (K, world, prev, ld)
     assert lib.scl_plan_gram_shard(0, 2, 0, C.byref(C.c_int64()), C.byref(C.c_int64())) != 0
     assert lib.scl_plan_gram_shard(10, 2, 2, C.byref(C.c_int64()), C.byref(C.c_int64())) != 0
+
+
+def test_pass_task_plan_deals_every_solve_once_and_in_order():
+    """scl_plan_pass_task (the wave schedule of scl_run_pass): tasks 0 (data), 1 (null), 2 (reference basis) and every search
+    step are owned by exactly one (wave, rank); the reference basis never lands in a later wave than the first search step,
+    and a host simulation of the waves - stop rule fed in task order - ends exactly like the sequential loop."""
+    import ctypes as C
+    sys.path.insert(0, ROOT)
+    from sclens_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    d2_all = np.concatenate([0.3 - 0.01 * np.arange(9), 0.1 + 0.001 * rng.standard_normal(40)])
+    p_th = 0.15
+    want = sequential_stop(d2_all, p_th)
+    for world in (1, 2, 3, 4, 8):
+        seen = {}
+        for wave in range(6):
+            for r in range(world):
+                t, s = C.c_int32(), C.c_int32()
+                assert lib.scl_plan_pass_task(wave, world, r, C.byref(t), C.byref(s)) == 0
+                assert t.value not in seen
+                seen[t.value] = (wave, r)
+                assert s.value == (t.value - 3 if t.value >= 3 else -1)
+        assert sorted(seen) == list(range(6 * world))
+        assert seen[2][0] <= seen[3][0] and seen[0][0] <= seen[2][0] and seen[1][0] <= seen[2][0]
+        # waves until the stop rule fires: steps of a wave are consumed in task order
+        p_, tank, n_steps, stop, wave = 0.999, [], 0, None, 0
+        while stop is None:
+            for r in range(world):
+                s = wave * world + r - 3
+                if s < 0 or stop is not None:
+                    continue
+                tank.append(d2_all[s])
+                n_steps += 1
+                if (sum(x < p_th for x in tank[-5:]) > 4) or p_ < 0.9:
+                    stop = (n_steps, p_ + 4 * 0.001)
+                    break
+                p_ -= 0.001
+            wave += 1
+        assert stop[0] == want[0] and stop[1] == want[1], (world, stop, want)
+    assert lib.scl_plan_pass_task(0, 2, 2, C.byref(C.c_int32()), None) != 0

@@ -262,6 +262,154 @@ def test_syevd_and_mp_fit(h):
     assert abs(out[3] - chk["ks_static"]) < 1e-9 and bool(out[6]) == chk["pass"]
 
 
+def _tri_solve(h, G, v0, v1):
+    n = G.shape[0]
+    L, V, out = np.empty(n, np.float32), np.empty((max(1, v1 - v0), n), np.float32), np.zeros(6)
+    h._ck(h.lib.scl_op_syevd_tri(h.h, n, ptr(G, C.c_float), v0, v1, ptr(L, C.c_float), ptr(V, C.c_float), ptr(out, C.c_double)))
+    return L, V[: v1 - v0].T, out
+
+
+@pytest.mark.parametrize("case", ["wishart", "centred", "wide_range_of_scales"])
+def test_syevd_tri_matches_float64(h, case):
+    """Own tridiagonal stage (Ssytrd -> Float64 multisection + twisted factorisation -> Sormtr) against numpy's Float64
+    eigh of the same FP32 matrix: same tolerances as the library solve above, all vectors / an index range / values only."""
+    rng = np.random.default_rng(5)
+    n = 640
+    A = rng.standard_normal((n, 900))
+    if case == "centred":
+        A -= A.mean(axis=0)                       # one exactly-null direction (column-centred N <= M matrix)
+    if case == "wide_range_of_scales":
+        A *= np.exp(rng.normal(0, 2.0, size=(n, 1)))   # graded rows: eigenvalues over ~6 decades
+    G = (A @ A.T / 900).astype(np.float32)
+    Lref, Vref = np.linalg.eigh(G.astype(np.float64))
+    scale = float(Lref[-1])
+    L, V, out = _tri_solve(h, G, 0, n)
+    assert out[5] == 0, "fell back to the library solver"
+    np.testing.assert_allclose(L, Lref, rtol=2e-5, atol=2e-6 * scale)
+    G64 = G.astype(np.float64)
+    assert np.max(np.abs(G64 @ V - V * L[None, :])) < 5e-5 * max(1.0, scale)
+    assert np.max(np.abs(V.T.astype(np.float64) @ V - np.eye(n))) < 5e-5
+    # index range (what a sparsity-search step asks for) and values only give the same numbers
+    v0, v1 = 3, n // 2 + 40
+    L2, V2, _ = _tri_solve(h, G, v0, v1)
+    np.testing.assert_array_equal(L2, L)
+    assert np.max(np.abs(np.abs(np.sum(V2 * V[:, v0:v1], axis=0)) - 1.0)) < 1e-5
+    L3, _, _ = _tri_solve(h, G, 0, 0)
+    np.testing.assert_array_equal(L3, L)
+
+
+def test_syevd_tri_exact_multiplicities(h):
+    """Every eigenvalue exactly double (two identical diagonal blocks) plus a block of exact zeros: twisted factorisation alone
+    would return parallel vectors; the cluster pass (inverse iteration + Gram-Schmidt inside the cluster) must give an
+    orthonormal basis of every eigenspace."""
+    rng = np.random.default_rng(6)
+    nb = 150
+    A = rng.standard_normal((nb, 300))
+    B = (A @ A.T / 300).astype(np.float32)
+    n = 2 * nb + 20
+    G = np.zeros((n, n), np.float32)
+    G[:nb, :nb] = B
+    G[nb:2 * nb, nb:2 * nb] = B
+    perm = rng.permutation(n)
+    G = np.ascontiguousarray(G[np.ix_(perm, perm)])
+    L, V, out = _tri_solve(h, G, 0, n)
+    assert out[5] == 0, out
+    Lref = np.linalg.eigvalsh(G.astype(np.float64))
+    np.testing.assert_allclose(L, Lref, rtol=2e-5, atol=5e-6)
+    assert np.max(np.abs(G.astype(np.float64) @ V - V * L[None, :])) < 5e-5
+    assert np.max(np.abs(V.T.astype(np.float64) @ V - np.eye(n))) < 5e-5
+    # a diagonal matrix stays exactly tridiagonal (e = 0) with exactly repeated eigenvalues: this is the case that reaches
+    # the cluster pass (the FP32 tridiagonalisation above splits the pairs by ~1e-7, far above the 1e-9 |T| cluster gap)
+    vals = np.repeat(rng.uniform(0.5, 3.0, size=60), 3).astype(np.float32)
+    vals = np.concatenate([vals, np.zeros(7, np.float32)])
+    vals = vals[rng.permutation(len(vals))]
+    D = np.diag(vals).astype(np.float32)
+    L, V, out = _tri_solve(h, D, 0, len(vals))
+    assert out[5] == 0 and out[3] == 61 and out[4] == len(vals), out
+    np.testing.assert_allclose(L, np.sort(vals), rtol=1e-6, atol=1e-7)
+    assert np.max(np.abs(D.astype(np.float64) @ V - V * L[None, :])) < 1e-5
+    assert np.max(np.abs(V.T.astype(np.float64) @ V - np.eye(len(vals)))) < 1e-5
+
+
+class _QueuedDraws:
+    """Stands in for numpy's Generator inside the oracle: hands out arrays that were drawn elsewhere, in call order."""
+
+    def __init__(self, *arrays):
+        self.q = list(arrays)
+
+    def integers(self, lo, hi, size=None, dtype=np.int64):
+        a = self.q.pop(0)
+        assert len(a) == size and a.min() >= lo and a.max() < hi
+        return a.astype(dtype)
+
+
+@pytest.mark.parametrize("shape,seed", [((300, 500), 11), ((700, 260), 12), ((64, 40), 13)])
+def test_device_zero_candidates_follow_the_reference_recipe(shape, seed):
+    """Production draw of z_idx1 / z_idx2 (:668-673) on the device: fed the same uniform draws (restated on the host from the
+    library's counter-based generator), the oracle's setdiff / first-occurrence step must give the same two vectors, bit for bit."""
+    N, M = shape
+    X = make_counts(N, M, seed=seed, K=3, de_prob=0.3, lfc_sd=1.5) if N >= 200 else \
+        sp.random(N, M, density=0.3, random_state=seed, format="csc", dtype=np.float32)
+    X = sp.csc_matrix(X, dtype=np.float32)
+    X.data[:] = np.maximum(1.0, np.round(X.data * 5))
+    X.sort_indices()
+    with Handle(seed=seed) as hh:
+        hh.set_counts(X)
+        n = C.c_int64()
+        hh._ck(hh.lib.scl_op_draw_zero_candidates(hh.h, 1000 + seed, C.byref(n), None, None))
+        z1, z2 = np.empty(max(1, X.nnz), np.uint32), np.empty(max(1, X.nnz), np.uint32)
+        n2 = C.c_int64()
+        hh._ck(hh.lib.scl_op_draw_zero_candidates(hh.h, 1000 + seed, C.byref(n2), ptr(z1, C.c_uint32), ptr(z2, C.c_uint32)))
+        assert n2.value == n.value                    # deterministic for a given seed
+        z1, z2 = z1[: n.value], z2[: n.value]
+        rows, cols = np.empty(X.nnz, np.uint32), np.empty(X.nnz, np.uint32)
+        assert hh.lib.scl_op_zero_candidate_draws(1000 + seed, X.nnz, N, M, ptr(rows, C.c_uint32), ptr(cols, C.c_uint32)) == 0
+        want1, want2 = orc.draw_zero_candidates(X, _QueuedDraws(rows, cols))
+        np.testing.assert_array_equal(z1, np.asarray(want1, np.uint32))
+        np.testing.assert_array_equal(z2, np.asarray(want2, np.uint32))
+        # properties that do not depend on the generator: inside the grid, distinct, disjoint from the stored entries,
+        # and as many as nnz uniform draws leave: NM(1 - exp(-nnz/NM)) distinct positions, a fraction (1 - density) of them zeros
+        key = z2.astype(np.int64) * N + z1
+        assert z1.max() < N and z2.max() < M and len(np.unique(key)) == len(key)
+        nzr, nzc = X.nonzero()
+        assert not np.isin(key, nzc.astype(np.int64) * N + nzr).any()
+        grid = N * M
+        expect = grid * (1 - np.exp(-X.nnz / grid)) * (1 - X.nnz / grid)
+        assert abs(n.value - expect) < 6 * np.sqrt(expect) + 3
+        # the draws themselves are uniform on the grid: chi-square of the row and column marginals (large shapes only)
+        if N >= 200:
+            for v, k in ((rows, N), (cols, M)):
+                cnt = np.bincount(v, minlength=k)
+                chi2 = ((cnt - len(v) / k) ** 2 / (len(v) / k)).sum()
+                assert abs(chi2 - (k - 1)) < 6 * np.sqrt(2 * (k - 1)), (chi2, k)
+        # sample(1:n_cand, n_take, replace=false) (:731, :772): distinct members of the pool; n_take = n_cand is a permutation
+        for n_take in (n.value // 3, n.value):
+            r, c = np.empty(max(1, n_take), np.uint32), np.empty(max(1, n_take), np.uint32)
+            hh._ck(hh.lib.scl_op_draw_subset(hh.h, n_take, 77, ptr(r, C.c_uint32), ptr(c, C.c_uint32)))
+            k2 = c[:n_take].astype(np.int64) * N + r[:n_take]
+            assert len(np.unique(k2)) == n_take and np.isin(k2, key).all()
+        r2, c2 = np.empty(n.value, np.uint32), np.empty(n.value, np.uint32)
+        hh._ck(hh.lib.scl_op_draw_subset(hh.h, n.value // 3, 78, ptr(r2, C.c_uint32), ptr(c2, C.c_uint32)))
+        assert not np.array_equal(r2[: n.value // 3], r[: n.value // 3])     # another seed, another sample
+
+
+def test_device_noise_baseline_matches_the_oracle_expectation(h):
+    """p_th (:709-712) from the device generator against the oracle's draw_noise_baseline: both estimate
+    E max_{nm} |N(0, 1/nm)| from 5000 replicates, so they agree within a few standard errors of that mean."""
+    for nm in (450, 2000):
+        ref = np.array([np.max(np.abs(np.random.default_rng(s).normal(0, np.sqrt(1 / nm), size=nm))) for s in range(4000)])
+        se = ref.std(ddof=1) / np.sqrt(5000)
+        want = orc.draw_noise_baseline(nm, np.random.default_rng(5), n_rep=5000)
+        got = []
+        for seed in (1, 2, 3):
+            p = C.c_double()
+            h._ck(h.lib.scl_op_noise_baseline(h.h, nm, 5000, seed, C.byref(p)))
+            got.append(p.value)
+            assert abs(p.value - ref.mean()) < 5 * se * np.sqrt(1 + 5000 / 4000), (nm, p.value, ref.mean(), se)
+            assert abs(p.value - want) < 7 * se
+        assert len(set(got)) == 3          # seeds matter
+
+
 def test_corr_colabsmax(h):
     rng = np.random.default_rng(9)
     n, nv, nw = 700, 650, 331
