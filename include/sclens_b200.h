@@ -63,7 +63,9 @@ typedef struct {
   int32_t gram_tc_diag;  /* numerics studies. 0: exact Float64 Gram diagonal + calibration of the tensor core's
                             accumulation bias (default); 1: the raw tensor-core result; 2: exact diagonal only */
   int32_t no_refine;     /* 1: return the FP32 eigensolver's eigenvalues as they are (no Float64 Rayleigh-quotient refinement) */
-  int32_t reserved[4];
+  int32_t centering;     /* 0: centering="mean" (default, :677-696); 1: centering="median" (:294-299, :653-654): per-gene median of
+                            log1p(x / r_i) over all cells as the centre, rows rescaled to the mean row norm, no re-centring */
+  int32_t reserved[3];
 } scl_config;
 
 typedef struct {

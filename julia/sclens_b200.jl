@@ -17,10 +17,11 @@ struct SclConfig
     seed::UInt64
     subspace_extra::Int32; subspace_degree::Int32; exact_perturb::Int32
     gram_chunk_kb::Int32; gram_tc_diag::Int32; no_refine::Int32
-    reserved::NTuple{4,Int32}
+    centering::Int32
+    reserved::NTuple{3,Int32}
 end
-default_config(; verbose=0, seed=0) =
-    SclConfig(0, 0, 0, verbose, UInt64(seed), 0, 0, 0, 0, 0, 0, ntuple(_ -> Int32(0), 4))
+default_config(; verbose=0, seed=0, centering=0) =
+    SclConfig(0, 0, 0, verbose, UInt64(seed), 0, 0, 0, 0, 0, 0, centering, ntuple(_ -> Int32(0), 3))
 mutable struct SclSignalInfo
     N::Int32; M::Int32; nm::Int32; n_signal::Int32; n_Lmp::Int32; mp_iters::Int32; pass::Int32; gram_mode_used::Int32
     lambda_c::Float64; b_plus::Float64; b_minus::Float64; ks_static::Float64
@@ -51,11 +52,11 @@ Drop-in for `scLENS.sclens` (src/scLENS.jl:649).  `df2sparr` is the reference's 
 """
 function sclens(inp_df, df2sparr; device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="mean", seed=0)
     device_ == "gpu" || error("sclens_b200 implements device_=\"gpu\" only")
-    centering == "mean" || error("only centering=\"mean\" is implemented")
+    centering in ("mean", "median") || (println("Warning: The specified centering method is not supported in the current algorithm. scLENS will automatically use mean centering."); centering = "mean")   # :655-657
     println("Extracting matrices")
     X_ = df2sparr(inp_df)::SparseMatrixCSC{Float32,UInt32}
     N, M = size(X_)
-    cfg = Ref(default_config(verbose=1, seed=seed))
+    cfg = Ref(default_config(verbose=1, seed=seed, centering=(centering == "median" ? 1 : 0)))
     hr = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:scl_create, LIB), Int32, (Ptr{Ptr{Cvoid}}, Ptr{SclConfig}), hr, cfg)
     rc == 0 || check(C_NULL, rc)
@@ -88,12 +89,14 @@ function sclens(inp_df, df2sparr; device_="gpu", th=60, p_step=0.001, n_perturb=
         ri.n_robust > 0 && check(h, ccall((:scl_get_sig_id, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}), h, sig0))
         sig_id = Int.(sig0) .+ 1                                       # back to 1-based
         rec_vals = Dict{String,Union{VecOrMat{Float64}}}()
-        tgc = Vector{Float64}(undef, N); l2 = Vector{Float64}(undef, N)
-        mn = Matrix{Float64}(undef, 1, M); sd = Matrix{Float64}(undef, 1, M); ct = Matrix{Float64}(undef, 1, M)
-        check(h, ccall((:scl_get_rec_vals, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                       h, tgc, mn, sd, l2, ct))
-        rec_vals["TGC"] = tgc; rec_vals["mat2_mean"] = mn; rec_vals["mat2_std"] = sd
-        rec_vals["norm_tgc"] = l2; rec_vals["cent_"] = ct
+        if centering == "mean"                                         # the reference records them on the mean path only (:676-695)
+            tgc = Vector{Float64}(undef, N); l2 = Vector{Float64}(undef, N)
+            mn = Matrix{Float64}(undef, 1, M); sd = Matrix{Float64}(undef, 1, M); ct = Matrix{Float64}(undef, 1, M)
+            check(h, ccall((:scl_get_rec_vals, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                           h, tgc, mn, sd, l2, ct))
+            rec_vals["TGC"] = tgc; rec_vals["mat2_mean"] = mn; rec_vals["mat2_std"] = sd
+            rec_vals["norm_tgc"] = l2; rec_vals["cent_"] = ct
+        end
         println("Reconstructing reduced data...")
         Xout0 = nV .* (sqrt.(nL))'                                      # :810
         Xout1 = nV[:, sig_id] .* sqrt.(nL[sig_id])'                     # :811

@@ -182,6 +182,25 @@ def logn_scale_pre_scale(X: sp.csc_matrix) -> np.ndarray:
     return out - out.mean(axis=0)[None, :]                                          # :305
 
 
+def logn_scale_pre_scale_median(X: sp.csc_matrix) -> np.ndarray:
+    """logn_scale(pre_scale(X)) for centering=="median" (:653-654):
+    norm_l(scaled_gdata(Matrix{Float32}(log1p.(proj_l(X))), position_="median")) - dense Float32 throughout:
+    per-gene median over ALL cells (`mapslices(median, X, dims=1)` :298) and corrected std (:307), (X - median) / std
+    (:326), then every row rescaled to the mean row norm (norm_l :608).  No re-centring afterwards."""
+    X = as_csc(X)
+    N, M = X.shape
+    rs = np.asarray(X.sum(axis=1), dtype=np.float32).ravel()
+    inv = (np.float32(1.0) / rs).astype(np.float32)
+    P = X.tocoo()
+    dense = np.zeros((N, M), dtype=np.float32)
+    dense[P.row, P.col] = np.log1p((inv[P.row] * P.data).astype(np.float32)).astype(np.float32)
+    med = np.median(dense, axis=0).astype(np.float32)                               # :298
+    std_ = dense.astype(np.float64).std(axis=0, ddof=1).astype(np.float32)          # :307
+    W = ((dense - med[None, :]) / std_[None, :]).astype(np.float32)                 # :326
+    l2 = np.sqrt((W.astype(np.float64) ** 2).sum(axis=1)).astype(np.float32)        # :608
+    return (W / l2[:, None] * np.float32(l2.astype(np.float64).mean())).astype(np.float32)
+
+
 # --------------------------------------------------------------------------------------
 # Gram + eigen
 # --------------------------------------------------------------------------------------
@@ -418,8 +437,9 @@ def robustness_scores(nV: np.ndarray, nV_set: List[np.ndarray], th: float):
 # --------------------------------------------------------------------------------------
 def sclens(X, draws: Optional[Draws] = None, rng: Optional[np.random.Generator] = None,
            mode: str = "cpu", th: float = 60, p_step: float = 0.001, n_perturb: int = 20,
-           null_gene_order=None, n_baseline: int = 5000, verbose: bool = False):
-    """sclens (:649-832), centering="mean".  ``mode`` = "cpu" | "gpu-ref".
+           null_gene_order=None, n_baseline: int = 5000, verbose: bool = False, centering: str = "mean"):
+    """sclens (:649-832), centering="mean" (default) or "median" (:653-654: no rec_vals, every matrix through
+    logn_scale_pre_scale_median).  ``mode`` = "cpu" | "gpu-ref".
 
     Draws missing from ``draws`` are generated from ``rng`` and recorded, so the returned
     bundle can be replayed through the CUDA path.  Returns (result dict, Draws, info)."""
@@ -433,13 +453,18 @@ def sclens(X, draws: Optional[Draws] = None, rng: Optional[np.random.Generator] 
         draws.z_idx1, draws.z_idx2 = draw_zero_candidates(X, rng)
     z1, z2 = draws.z_idx1, draws.z_idx2
 
-    scaled_X, rec_vals = normalize_main(X)                                            # :677-696
+    if centering == "median":
+        logn = logn_scale_pre_scale_median
+        scaled_X, rec_vals = logn(X).astype(np.float64), {}                           # :696-698 (the else branch)
+    else:
+        logn = logn_scale_pre_scale
+        scaled_X, rec_vals = normalize_main(X)                                        # :677-696
     if draws.null_perm is None:
         draws.null_perm, draws.null_rows = draw_null(X, rng, null_gene_order)
     X_r = build_null(X, draws.null_perm, draws.null_rows)                             # :701
     info["null"] = X_r
     nL, nV, L, L_mp, lambda_c, b_min, b_plus, n_it = get_sigev(
-        scaled_X, logn_scale_pre_scale(X_r), mode)                                    # :704
+        scaled_X, logn(X_r), mode)                                    # :704
     info.update(b_min=b_min, b_plus=b_plus, mp_iters=n_it)
     mpc = mp_check(L_mp)                                                              # :706
     nm = min(N, M)
@@ -456,7 +481,7 @@ def sclens(X, draws: Optional[Draws] = None, rng: Optional[np.random.Generator] 
     p_ = 0.999
     Xb = X.copy()
     Xb.data = np.ones_like(Xb.data)
-    nb = logn_scale_pre_scale(Xb)
+    nb = logn(Xb)
     Vr2 = get_eigvec(nb.T if N > M else nb, mode, keep_null=True)[1]                  # :717-721
     n_2 = julia_round(Vr2.shape[1] / 2)                                               # :722
     tank = np.zeros((5, 0))
@@ -475,7 +500,7 @@ def sclens(X, draws: Optional[Draws] = None, rng: Optional[np.random.Generator] 
             draws.search_sple.append(sple)
         assert len(sple) == nnzidx
         Pb = perturbed_matrix(X, z1, z2, sple, binarise=True)
-        npb = logn_scale_pre_scale(Pb)
+        npb = logn(Pb)
         nV_2 = get_eigvec(npb.T if N > M else npb, mode)[1]                           # :733-739
         W = nV_2[:, nV_2.shape[1] - n_2 - 1:]                                         # end-n_2:end
         d_arr = np.nanmax(np.abs(corr_mat(Vr2, W, mode)), axis=0)                     # :742
@@ -503,7 +528,7 @@ def sclens(X, draws: Optional[Draws] = None, rng: Optional[np.random.Generator] 
             sple = rng.choice(len(z1), size=n_add, replace=False).astype(np.uint32)
             draws.perturb_sple.append(sple)
         tmp_X = perturbed_matrix(X, z1, z2, sple, binarise=False)                     # :774
-        tL, tV = get_eigvec(logn_scale_pre_scale(tmp_X), mode)                        # :775
+        tL, tV = get_eigvec(logn(tmp_X), mode)                        # :775
         k = min(min_pc, tV.shape[1])
         nV_set.append(np.asarray(tV[:, :k], dtype=np.float64))
         nL_set.append(tL[:k])

@@ -24,7 +24,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("gram_mode", C.c_int32), ("cta_group", C.c_int32), ("verbose", C.c_int32),
                 ("seed", C.c_uint64), ("subspace_extra", C.c_int32), ("subspace_degree", C.c_int32),
                 ("exact_perturb", C.c_int32), ("gram_chunk_kb", C.c_int32), ("gram_tc_diag", C.c_int32),
-                ("no_refine", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("no_refine", C.c_int32), ("centering", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class SignalInfo(C.Structure):

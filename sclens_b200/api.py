@@ -72,11 +72,13 @@ class Handle:
 
     def __init__(self, device: int = 0, gram_mode: int = _lib.SCL_GRAM_FP16, cta_group: int = 0, verbose: bool = False,
                  seed: int = 0, exact_perturb: bool = False, subspace_extra: int = 0, subspace_degree: int = 0,
-                 gram_chunk_kb: int = 0, gram_tc_diag: int = 0, no_refine: bool = False):
+                 gram_chunk_kb: int = 0, gram_tc_diag: int = 0, no_refine: bool = False, centering: str = "mean"):
         self.lib = _lib.load()
         cfg = Config(device=device, gram_mode=gram_mode, cta_group=cta_group, verbose=int(verbose), seed=seed,
                      subspace_extra=subspace_extra, subspace_degree=subspace_degree, exact_perturb=int(exact_perturb),
-                     gram_chunk_kb=int(gram_chunk_kb), gram_tc_diag=int(gram_tc_diag), no_refine=int(no_refine))
+                     gram_chunk_kb=int(gram_chunk_kb), gram_tc_diag=int(gram_tc_diag), no_refine=int(no_refine),
+                     centering=1 if centering == "median" else 0)
+        self.centering = "median" if centering == "median" else "mean"
         self.h = C.c_void_p()
         rc = self.lib.scl_create(C.byref(self.h), C.byref(cfg))
         if rc != 0:
@@ -269,8 +271,12 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
     state and, if initialised, its NCCL communicator) instead of creating one; the caller keeps ownership."""
     if device_ != "gpu":
         raise ValueError('sclens_b200 implements device_="gpu" only (no CPU fallback exists)')
-    if centering != "mean":
-        raise NotImplementedError('only centering="mean" (the default path) is implemented')
+    if centering not in ("mean", "median"):                             # :655-657
+        print("Warning: The specified centering method is not supported in the current algorithm. scLENS will automatically "
+              "use mean centering.")
+        centering = "mean"
+    if handle is not None and handle.centering != centering:
+        raise ValueError(f"the handle was created for centering={handle.centering!r}")
     if verbose:
         print("Extracting matrices")                                    # :661
     import time as _time
@@ -285,7 +291,8 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
     host_ms["df2sparr"] = _lap()
     N, M = X.shape
     own = handle is None
-    h = Handle(device=device, gram_mode=gram_mode, verbose=verbose, seed=seed, exact_perturb=exact_perturb) if own else handle
+    h = Handle(device=device, gram_mode=gram_mode, verbose=verbose, seed=seed, exact_perturb=exact_perturb,
+               centering=centering) if own else handle
     host_ms["create_handle"] = _lap()
     try:
         if comm is not None:
@@ -347,7 +354,7 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
             "pca": frame(Xout0), "pca_n1": frame(Xout1), "sig_id": sig_id,
             "robustness_scores": {"b_": b_, "rob_score": m_scores, "m_scores": m_scores, "sd_scores": sd_scores},
             "signal_evec": nV, "signal_ev": nL, "gene_id": gene_id, "gene_basis": h.gene_basis(),
-            "pass": bool(si.pass_), "rec_vals": h.rec_vals(),
+            "pass": bool(si.pass_), "rec_vals": h.rec_vals() if centering == "mean" else {},   # mean path only (:676-695)
             "info": {"host_ms": host_ms, "p_sel": ri.p_sel, "n_search": ri.n_search, "p_th": ri.p_th, "min_pc": ri.min_pc,
                      "n_add": ri.n_add, "n_subspace_fallbacks": ri.n_subspace_fallbacks, "ks_static": si.ks_static, "b_plus": si.b_plus, "b_minus": si.b_minus,
                      "timings_ms": {"gram": si.t_gram_ms, "syevd_signal": si.t_syevd_ms, "null": si.t_null_ms,

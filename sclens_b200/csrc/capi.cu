@@ -113,7 +113,7 @@ int32_t scl_get_profile(scl_handle* h, scl_profile* out) {
   out->refine_ms = p.ms[PK_REFINE];
   out->small_ms = p.ms[PK_SMALL];
   out->stats_alg_bytes = p.stats_alg_bytes;
-  out->stats_calls = p.calls[PK_STATS];
+  out->stats_calls = p.stats_norms;
   out->comm_ms = p.ms[PK_COMM];
   out->comm_bytes = p.comm_bytes;
   return SCL_OK;

@@ -102,6 +102,10 @@ struct NormStats {
   int off_strips[2] = {0, 0};
   bool off_valid[2] = {false, false};
   DBuf<double> strip_partial;
+  // centering="median" (:294-299, :653-654): per-gene median of y = log1p(x / r_i) over ALL cells replaces the mean as the
+  // centre and there is no final re-centring (c_j = 0); everything downstream reads mu_j and c_j and is unchanged
+  int centering = 0;                // 0 mean (default path), 1 median
+  DBuf<double> median;
   void reserve(size_t nnz_cap) {
     patch_csc.ensure(nnz_cap); patch_csr.ensure(nnz_cap);
   }

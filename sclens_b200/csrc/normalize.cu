@@ -257,6 +257,7 @@ struct GeneStatsOp {
   double *ybar, *sigma, *mu;
   float *mu_f, *inv_sigma_f;
   double4* gene_par;
+  const double* centre = nullptr;    // per-gene median of y (centering="median"); nullptr: the mean is the centre
   struct Ctx {};
   struct Ld { double inv_r; };
   __device__ __forceinline__ Ctx begin(int) const { return Ctx(); }
@@ -272,12 +273,13 @@ struct GeneStatsOp {
     double var = (acc[1] - (double)N * m * m) / (double)(N - 1);
     if (var < 0) var = 0;
     const double sd = sqrt(var);
+    const double ctr = centre ? centre[j] : m;
     ybar[j] = m;
     sigma[j] = sd;
-    mu[j] = m / sd;
-    mu_f[j] = (float)(m / sd);
+    mu[j] = ctr / sd;
+    mu_f[j] = (float)(ctr / sd);
     inv_sigma_f[j] = (float)(1.0 / sd);
-    gene_par[j] = make_double4(1.0 / sd, m / sd, 0.0, 0.0);
+    gene_par[j] = make_double4(1.0 / sd, ctr / sd, 0.0, 0.0);
   }
 };
 
@@ -321,6 +323,7 @@ struct GeneCenterOp {
   double4* gene_par;
   double *cent, *sumsq_gene;
   float* cent_f;
+  int no_center = 0;                 // centering="median": norm_l is the last step, no re-centring (:653-654)
   struct Ctx { double inv_sd, mu; };
   struct Ld { double2 c; };
   __device__ __forceinline__ Ctx begin(int j) const {
@@ -337,7 +340,7 @@ struct GeneCenterOp {
   __device__ __forceinline__ void finish(int j, const Ctx& cx, const double (&acc)[NACC]) const {
     const double sum_inv_s = scalars[2], sum_inv_s2 = scalars[3], m = cx.mu;
     const double su = acc[0], suu = acc[1], sui = acc[2];
-    const double c = (su - m * sum_inv_s) / (double)N;
+    const double c = no_center ? 0.0 : (su - m * sum_inv_s) / (double)N;
     cent[j] = c;
     cent_f[j] = (float)c;
     gene_par[j].z = c;
@@ -693,6 +696,58 @@ static void prepare_strips(const SpMat& A, NormStats& S, cudaStream_t st) {
   S.off_valid[0] = S.off_valid[1] = true;
 }
 
+// ---- per-gene median of y = log1p(x / r_i) over all N cells (centering="median", :294-299) --------------------------
+// `mapslices(median, X, dims=1)` on the dense Float32 matrix: the N - nnz_j implicit zeros sort first, so the value at sorted
+// position k is 0 for k < zeros and the (k - zeros)-th smallest stored value otherwise; the median is the mean of positions
+// floor((N-1)/2) and ceil((N-1)/2).  Stored values are selected by an 8-bit radix select over the bit pattern of
+// u = x / r_i (positive doubles order like their bit patterns, and y is increasing in u): one CTA per gene, eight passes.
+__device__ double radix_select_u(const uint32_t* __restrict__ rowval, const float* __restrict__ val, uint32_t b, uint32_t e,
+                                 const double2* __restrict__ cell_par, uint32_t rank, uint32_t* hist) {
+  unsigned long long prefix = 0, mask = 0;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t t = b + threadIdx.x; t < e; t += blockDim.x) {
+      const unsigned long long key = (unsigned long long)__double_as_longlong((double)val[t] * cell_par[rowval[t]].x);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xff], 1u);
+    }
+    __syncthreads();
+    // bucket holding the wanted rank (every thread walks the 256 counters: uniform result, no broadcast needed)
+    uint32_t acc = 0;
+    int bucket = 0;
+    for (; bucket < 256; ++bucket) {
+      const uint32_t c = hist[bucket];
+      if (rank < acc + c) break;
+      acc += c;
+    }
+    rank -= acc;
+    prefix |= (unsigned long long)bucket << shift;
+    mask |= 0xffull << shift;
+    __syncthreads();
+  }
+  return __longlong_as_double((long long)prefix);
+}
+
+__global__ void __launch_bounds__(256) k_gene_median(const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ rowval,
+                                                     const float* __restrict__ val, const double2* __restrict__ cell_par, int N,
+                                                     int M, double* __restrict__ med) {
+  __shared__ uint32_t hist[256];
+  for (int j = blockIdx.x; j < M; j += gridDim.x) {
+    const uint32_t b = colptr[j], e = colptr[j + 1], nz = e - b, zeros = (uint32_t)N - nz;
+    const uint32_t k1 = (uint32_t)(N - 1) / 2, k2 = (uint32_t)N / 2;     // the two middle positions (equal when N is odd)
+    double m = 0.0;
+    if (k2 >= zeros) {                                                   // otherwise both middle values are zeros
+      const double u2 = radix_select_u(rowval, val, b, e, cell_par, k2 - zeros, hist);
+      const double y2 = log1p(u2);
+      double y1 = 0.0;
+      if (k1 == k2) y1 = y2;
+      else if (k1 >= zeros) y1 = log1p(radix_select_u(rowval, val, b, e, cell_par, k1 - zeros, hist));
+      m = 0.5 * (y1 + y2);
+    }
+    if (threadIdx.x == 0) med[j] = m;
+  }
+}
+
 static void compute_norm_stats_strips(const SpMat& A, NormStats& S, cudaStream_t st) {
   const int N = A.N, M = A.M;
   prepare_strips(A, S, st);
@@ -733,23 +788,29 @@ void compute_norm_stats(const SpMat& A, NormStats& S, cudaStream_t st) {
   }
   S.have_patch[0] = S.have_patch[1] = false;
   S.off_valid[0] = S.off_valid[1] = false;
-  if (stat_tune().variant == 8) {
+  const bool median = S.centering == 1;
+  if (stat_tune().variant == 8 && !median) {
     compute_norm_stats_strips(A, S, st);
     return;
   }
   count_launches(7);
   const int wgrid = min((N + 7) / 8, 148 * 8);
   k_row_sum<<<wgrid, 256, 0, st>>>(A.rowptr.p, A.rval.p, N, S.tgc.p, S.cell_par.p);
+  if (median) {
+    S.median.ensure(M);
+    count_launches(1);
+    k_gene_median<<<min(M, 148 * 8), 256, 0, st>>>(A.colptr.p, A.rowval.p, A.val.p, S.cell_par.p, N, M, S.median.p);
+  }
   // genes arrive sorted by mean expression (:224): reversed order starts the densest columns first
   launch_lines(GeneStatsOp{A.rowval.p, A.val.p, S.cell_par.p, N, S.ybar.p, S.sigma.p, S.mu.p, S.mu_f.p, S.inv_sigma_f.p,
-                           S.gene_par.p},
+                           S.gene_par.p, median ? S.median.p : nullptr},
                A.colptr.p, M, 1, st);
   k_reduce_vec<0><<<kRedBlocks, 256, 0, st>>>(S.mu.p, nullptr, M, S.red_partial.p, S.red_counter.p, S.scalars.p);
   launch_lines(CellL2Op{A.colidx.p, A.rval.p, S.cell_par.p, S.gene_par.p, S.scalars.p, S.l2.p}, A.rowptr.p, N, 0, st);
   k_reduce_vec<1><<<kRedBlocks, 256, 0, st>>>(S.l2.p, nullptr, N, S.red_partial.p, S.red_counter.p, S.scalars.p);
   k_inv_s<<<(N + 255) / 256, 256, 0, st>>>(S.l2.p, S.scalars.p, N, S.inv_s.p, S.inv_s_f.p, S.cell_par.p);
   launch_lines(GeneCenterOp{A.rowval.p, A.val.p, S.cell_par.p, S.scalars.p, N, S.gene_par.p, S.cent.p, S.sumsq_gene.p,
-                            S.cent_f.p},
+                            S.cent_f.p, median ? 1 : 0},
                A.colptr.p, M, 1, st);
   SCL_CUDA(cudaGetLastError());
 }

@@ -305,9 +305,11 @@ void gram_of(scl_handle* h, const SpMat& A, NormStats& S, DBuf<__half>& hi, DBuf
   const bool gene_side = A.N > A.M;                 // contract over cells (N > M) or over genes
   {
     ProfScope ps(&h->prof, h->st, PK_STATS);
+    S.centering = h->cfg.centering;
     compute_norm_stats(A, S, h->st);
     ensure_patch(A, S, gene_side ? 0 : 1, h->st);
     h->prof.stats_alg_bytes += 40.0 * (double)A.nnz;   // 4 nnz (row sums) + 3 x 8 nnz + 12 nnz (patch pass)
+    h->prof.stats_norms += 1;
   }
   const int rows = gene_side ? A.M : A.N;
   const int64_t K = gene_side ? A.N : A.M;

@@ -24,6 +24,7 @@ struct Prof {
   double sparse_alg_bytes = 0;    // 20 nnz (+12 n_add)
   double stats_alg_bytes = 0;     // 40 nnz per normalisation
   double comm_bytes = 0;          // payload of the NCCL collectives
+  long stats_norms = 0;           // normalisations (one set of statistics passes each)
   std::vector<ProfEvent> pending;
   void resolve();
   void reset();

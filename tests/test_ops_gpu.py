@@ -331,6 +331,35 @@ def test_syevd_tri_exact_multiplicities(h):
     assert np.max(np.abs(V.T.astype(np.float64) @ V - np.eye(len(vals)))) < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(301, 420), (400, 250)])
+def test_normalize_median_centering_matches_oracle(shape):
+    """centering="median" (:653-654): the dense operand against the oracle's Float32 restatement, with genes expressed in
+    most cells (non-zero medians, both parities of N) and the usual sparse genes (median = an implicit zero)."""
+    N, M = shape
+    X = make_counts(N, M, seed=5, K=3, de_prob=0.3, lfc_sd=1.5).tolil()
+    rng = np.random.default_rng(0)
+    for j in range(8):
+        col = rng.poisson(4.0 if j < 6 else 0.7, size=(N, 1)).astype(np.float32)   # j >= 6: close to half the cells
+        X[:, j] = col
+    X = sp.csc_matrix(X, dtype=np.float32)
+    X.eliminate_zeros()
+    X.sort_indices()
+    want = orc.logn_scale_pre_scale_median(X).astype(np.float64)
+    with Handle(centering="median") as hh:
+        for layout in (0, 1):
+            lines, length = (M, N) if layout == 0 else (N, M)
+            ld = (length + 7) // 8 * 8
+            hi = np.empty((lines, ld), np.uint16)
+            lo = np.empty((lines, ld), np.uint16)
+            colptr, rowval, val = _lib.as_u32(X.indptr), _lib.as_u32(X.indices), _lib.as_f32(X.data)
+            hh._ck(hh.lib.scl_op_normalize(hh.h, N, M, X.nnz, ptr(colptr, C.c_uint32), ptr(rowval, C.c_uint32),
+                                           ptr(val, C.c_float), layout, ld, ptr(hi, C.c_uint16), ptr(lo, C.c_uint16),
+                                           None, None, None, None, None))
+            got = hi.view(np.float16).astype(np.float64) + lo.view(np.float16).astype(np.float64)
+            got = got[:, :length].T if layout == 0 else got[:, :length]
+            np.testing.assert_allclose(got, want, rtol=3e-4, atol=3e-5)       # the oracle itself is Float32 here
+
+
 class _QueuedDraws:
     """Stands in for numpy's Generator inside the oracle: hands out arrays that were drawn elsewhere, in call order."""
 

@@ -224,3 +224,30 @@ def test_denoise_on_a_full_run_is_a_probability_profile_per_cell(small_run):
     np.testing.assert_allclose(out.sum(axis=1), res["rec_vals"]["TGC"].mean(), rtol=1e-10)
     # the two reference arithmetic paths (:893-896 Float32 GEMM, :903-905 Float64 operands) agree to Float32 accuracy
     np.testing.assert_allclose(out, orc.get_denoised(res, mode="cpu"), rtol=1e-3, atol=1e-6 * out.max())
+
+
+def test_median_centering_restatement_properties():
+    """centering="median" (:653-654, :294-299, :608): undoing the row scaling leaves every gene with median 0 and corrected
+    std 1 over all cells; every row has the same l2 norm; genes expressed in at most half the cells keep their zeros at
+    the common background -0/std = 0 before scaling (their median is an implicit zero)."""
+    from sclens_b200.synth import make_counts
+    X = make_counts(301, 420, seed=5, K=3, de_prob=0.3, lfc_sd=1.5).tolil()
+    rng = np.random.default_rng(0)
+    for j in range(6):                                   # a few genes expressed in most cells: non-zero medians
+        X[:, j] = rng.poisson(4.0, size=(301, 1)).astype(np.float32)
+    X = sp.csc_matrix(X, dtype=np.float32)
+    X.eliminate_zeros()
+    out = orc.logn_scale_pre_scale_median(X).astype(np.float64)
+    l2 = np.sqrt((out ** 2).sum(axis=1))
+    np.testing.assert_allclose(l2, l2.mean(), rtol=1e-5)
+    # rows were scaled by mean(l2_raw)/l2_raw; the raw matrix is out * l2_raw / mean(l2_raw): recover it up to that factor
+    rs = np.asarray(X.sum(axis=1)).ravel()
+    Y = np.zeros(X.shape)
+    C = X.tocoo()
+    Y[C.row, C.col] = np.log1p(C.data / rs[C.row])
+    W = (Y - np.median(Y, axis=0)) / Y.std(axis=0, ddof=1)
+    want = W / np.sqrt((W ** 2).sum(axis=1))[:, None] * np.sqrt((W ** 2).sum(axis=1)).mean()
+    np.testing.assert_allclose(out, want, rtol=2e-4, atol=2e-5)
+    assert (np.median(Y, axis=0)[:6] > 0).all() and (np.median(Y, axis=0)[6:] == 0).sum() > 300
+    res, draws, info = orc.sclens(X, rng=np.random.default_rng(3), mode="cpu", n_perturb=3, n_baseline=100, centering="median")
+    assert res["rec_vals"] == {} and len(res["signal_ev"]) >= 1 and 0.9 <= info["p_sel"] <= 0.999
