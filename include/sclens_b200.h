@@ -152,6 +152,26 @@ SCL_API int32_t scl_push_search_sample(scl_handle* h, int64_t n, const uint32_t*
 SCL_API int32_t scl_push_perturb_sample(scl_handle* h, int64_t n, const uint32_t* sple_idx, int32_t index_base); /* :772 */
 SCL_API int32_t scl_clear_draws(scl_handle* h);
 
+/* ---- QC on the device ------------------------------------------- */
+/* Thresholds of scLENS.preprocess (:160-162), same names, same defaults in the host mirrors. */
+typedef struct {
+  double min_tp_c, min_tp_g, max_tp_c, max_tp_g;      /* total counts per cell / gene: strict bounds (:186-187, :193-194) */
+  int32_t min_genes_per_cell, max_genes_per_cell;     /* >= / < ; max 0 = off (:195, :213) */
+  int32_t min_cells_per_gene, reserved;               /* >= (:188) */
+  double mito_percent, ribo_percent;                  /* Float32 share strictly below percent/100; 0 = off (:198-211) */
+} scl_qc_params;
+/* preprocess (:160-236) on raw counts (N cells x M genes, CSC): cell / gene filters, drop of genes left empty, stable sort
+ * of the survivors by their Float32 mean.  gene_flags[j]: bit 0 = mitochondrial name (r"^(?i)mt-." :196), bit 1 = ribosomal
+ * (r"^(?i)RP[SL]." :197) - the caller matches the names.  Outputs: *n_cells / *n_genes / *out_nnz (0 cells: "There is no high
+ * quality cells and genes" :231-234), fc_idx (kept cells, ascending, 0-based, capacity N) and gene_idx (kept genes in output
+ * order, capacity M).  The filtered matrix becomes the handle's counts, as if passed to scl_set_counts_csc; read it back
+ * with scl_get_counts_csc. */
+SCL_API int32_t scl_op_preprocess(scl_handle* h, int32_t N, int32_t M, int64_t nnz, const uint32_t* colptr, const uint32_t* rowval,
+                                  const float* nzval, int32_t index_base, const uint8_t* gene_flags, const scl_qc_params* p,
+                                  int32_t* n_cells, int32_t* n_genes, int64_t* out_nnz, int32_t* fc_idx, int32_t* gene_idx);
+/* The handle's counts as canonical 0-based CSC (colptr M+1, rowval / nzval nnz). */
+SCL_API int32_t scl_get_counts_csc(scl_handle* h, uint32_t* colptr, uint32_t* rowval, float* nzval);
+
 /* ---- the path ---------------------------------------------------------------------- */
 /* :664-706: normalise, null matrix, get_sigev, mp_check. */
 SCL_API int32_t scl_run_signal(scl_handle* h, scl_signal_info* out);

@@ -44,6 +44,12 @@ class RobustInfo(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class QcParams(C.Structure):
+    _fields_ = [("min_tp_c", C.c_double), ("min_tp_g", C.c_double), ("max_tp_c", C.c_double), ("max_tp_g", C.c_double),
+                ("min_genes_per_cell", C.c_int32), ("max_genes_per_cell", C.c_int32), ("min_cells_per_gene", C.c_int32),
+                ("reserved", C.c_int32), ("mito_percent", C.c_double), ("ribo_percent", C.c_double)]
+
+
 class Profile(C.Structure):
     _fields_ = [("gram_gemm_ms", C.c_double), ("other_gemm_ms", C.c_double), ("densify_ms", C.c_double),
                 ("stats_ms", C.c_double), ("sparse_ms", C.c_double), ("syevd_ms", C.c_double),
@@ -86,6 +92,9 @@ SIGNATURES = {
     "scl_push_search_sample": [_hp, C.c_int64, _u32p, C.c_int32],
     "scl_push_perturb_sample": [_hp, C.c_int64, _u32p, C.c_int32],
     "scl_clear_draws": [_hp],
+    "scl_op_preprocess": [_hp, C.c_int32, C.c_int32, C.c_int64, _u32p, _u32p, _f32p, C.c_int32, C.POINTER(C.c_uint8),
+                          C.POINTER(QcParams), _i32p, _i32p, _i64p, _i32p, _i32p],
+    "scl_get_counts_csc": [_hp, _u32p, _u32p, _f32p],
     "scl_run_signal": [_hp, C.POINTER(SignalInfo)],
     "scl_run_robustness": [_hp, C.c_double, C.c_double, C.c_int32, C.POINTER(RobustInfo)],
     "scl_run_pass": [_hp, C.c_double, C.c_double, C.c_int32, C.POINTER(SignalInfo), C.POINTER(RobustInfo)],

@@ -370,6 +370,76 @@ def sclens(inp_df, device_="gpu", th=60, p_step=0.001, n_perturb=20, centering="
             h.close()
 
 
+def qc_indices_device(X, gene_name, min_tp_c=0, min_tp_g=0, max_tp_c=np.inf, max_tp_g=np.inf, min_genes_per_cell=200,
+                      max_genes_per_cell=0, min_cells_per_gene=15, mito_percent=5.0, ribo_percent=0.0, *, device=0, handle=None):
+    """The filters of scLENS.preprocess (:183-225) on the device (``scl_op_preprocess``): returns ``(fc_idx, gene_idx,
+    filtered CSC)`` - kept cells (ascending), kept genes in output order (stable sort by Float32 mean) and the filtered
+    matrix - or None when nothing survives.  The filtered matrix stays on the handle as its counts, so ``sclens(...,
+    handle=h)`` can follow without another upload.  Only the regular expressions over the gene names run on the host."""
+    import re
+    X = sp.csc_matrix(X, dtype=np.float32)
+    if not X.has_canonical_format:
+        X.sum_duplicates()
+    X.eliminate_zeros()
+    X.sort_indices()
+    N, M = X.shape
+    flags = np.zeros(M, np.uint8)
+    for j, g in enumerate(gene_name):
+        g = str(g)
+        flags[j] = (1 if re.match(r"^mt-.", g, flags=re.I) else 0) | (2 if re.match(r"^RP[SL].", g, flags=re.I) else 0)   # :196-197
+    qp = _lib.QcParams(min_tp_c=float(min_tp_c), min_tp_g=float(min_tp_g), max_tp_c=float(max_tp_c), max_tp_g=float(max_tp_g),
+                       min_genes_per_cell=int(min_genes_per_cell), max_genes_per_cell=int(max_genes_per_cell),
+                       min_cells_per_gene=int(min_cells_per_gene), mito_percent=float(mito_percent), ribo_percent=float(ribo_percent))
+    own = handle is None
+    h = Handle(device=device) if own else handle
+    try:
+        colptr, rowval, val = as_u32(X.indptr), as_u32(X.indices), as_f32(X.data)
+        nc, ng, nnz = C.c_int32(), C.c_int32(), C.c_int64()
+        fc, gi = np.empty(N, np.int32), np.empty(M, np.int32)
+        h._ck(h.lib.scl_op_preprocess(h.h, N, M, X.nnz, ptr(colptr, C.c_uint32), ptr(rowval, C.c_uint32), ptr(val, C.c_float), 0,
+                                      flags.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(qp), C.byref(nc), C.byref(ng),
+                                      C.byref(nnz), ptr(fc, C.c_int32), ptr(gi, C.c_int32)))
+        if nc.value == 0 or ng.value == 0:
+            return None
+        h.N, h.M = nc.value, ng.value
+        oc, orow, oval = np.empty(ng.value + 1, np.uint32), np.empty(max(1, nnz.value), np.uint32), np.empty(max(1, nnz.value), np.float32)
+        h._ck(h.lib.scl_get_counts_csc(h.h, ptr(oc, C.c_uint32), ptr(orow, C.c_uint32), ptr(oval, C.c_float)))
+        out = sp.csc_matrix((oval[:nnz.value], orow[:nnz.value].astype(np.int64), oc.astype(np.int64)), shape=(nc.value, ng.value))
+        return fc[:nc.value].copy(), gi[:ng.value].copy(), out
+    finally:
+        if own:
+            h.close()
+
+
+def preprocess(tmp_df, min_tp_c=0, min_tp_g=0, max_tp_c=np.inf, max_tp_g=np.inf, min_genes_per_cell=200, max_genes_per_cell=0,
+               min_cells_per_gene=15, mito_percent=5.0, ribo_percent=0.0, *, verbose=True, device=0, handle=None):
+    """Drop-in for scLENS.preprocess (:160-236) with the filters on the device: DataFrame (col 0 'cell', then genes) ->
+    filtered DataFrame with genes sorted by mean expression, or None ("There is no high quality cells and genes")."""
+    cell_name = tmp_df.iloc[:, 0].to_numpy()
+    gene_name = np.asarray(tmp_df.columns[1:], dtype=object)
+    body = tmp_df.iloc[:, 1:]
+    if all(isinstance(t, pd.SparseDtype) for t in body.dtypes):
+        X = sp.csc_matrix(body.sparse.to_coo(), dtype=np.float32)
+    else:
+        X = sp.csc_matrix(body.to_numpy(dtype=np.float32))
+    X.eliminate_zeros()
+    if verbose:
+        print("Inp_spec")                                                                  # :168-169
+        print(f"data size: {tmp_df.shape}, sparsity: {1 - X.nnz / (X.shape[0] * X.shape[1])}")
+    res = qc_indices_device(X, gene_name, min_tp_c, min_tp_g, max_tp_c, max_tp_g, min_genes_per_cell, max_genes_per_cell,
+                            min_cells_per_gene, mito_percent, ribo_percent, device=device, handle=handle)
+    if res is None:
+        if verbose:
+            print("There is no high quality cells and genes")                              # :232
+        return None
+    fc_idx, gene_idx, out = res
+    o_df = pd.DataFrame.sparse.from_spmatrix(out, columns=gene_name[gene_idx])
+    o_df.insert(0, "cell", cell_name[fc_idx])
+    if verbose:
+        print(f"After filtering>> data size: {o_df.shape}, sparsity: {1 - out.nnz / (out.shape[0] * out.shape[1])}")   # :229
+    return o_df
+
+
 def get_denoised_df(inp_obj, device_="gpu", *, device=0, handle=None, dtype=np.float64):
     """Drop-in for scLENS.get_denoised_df (:889-931): the denoised count matrix rebuilt from the robust signals of a
     result dictionary of :func:`sclens` (keys ``gene_basis``, ``sig_id``, ``pca_n1``, ``rec_vals``, ``gene_id``,

@@ -233,6 +233,10 @@ int32_t scl_set_zero_candidates(scl_handle* h, int64_t n, const uint32_t* z1, co
   if (!h) return SCL_ERR_INVALID;
   return guard(h, [&] {
     SCL_REQUIRE(h->have_X && n >= 0 && (n == 0 || (z1 && z2)), "bad zero candidates");
+    SCL_REQUIRE(index_base == 0 || index_base == 1, "index_base must be 0 or 1");
+    for (int64_t t = 0; t < n; ++t)   // the merge kernels index lines with them
+      SCL_REQUIRE(z1[t] - (uint32_t)index_base < (uint32_t)h->X.N && z2[t] - (uint32_t)index_base < (uint32_t)h->X.M,
+                  "zero candidate outside the N x M grid");
     upload_u32(h->z1, z1, (size_t)n, index_base, h->st);
     upload_u32(h->z2, z2, (size_t)n, index_base, h->st);
     SCL_CUDA(cudaStreamSynchronize(h->st));
@@ -259,8 +263,9 @@ int32_t scl_set_noise_baseline(scl_handle* h, double p_th) {
   return SCL_OK;
 }
 
-static int32_t push_sample(scl_handle* h, std::vector<std::vector<uint32_t>>& q, int64_t n, const uint32_t* s, int32_t base) {
-  if (!h || n < 0 || (n > 0 && !s)) return SCL_ERR_INVALID;
+static int32_t push_sample(scl_handle* h, int which, int64_t n, const uint32_t* s, int32_t base) {
+  if (!h || n < 0 || (n > 0 && !s) || (base != 0 && base != 1)) return SCL_ERR_INVALID;
+  std::vector<std::vector<uint32_t>>& q = which == 0 ? h->search_sples : h->perturb_sples;
   std::vector<uint32_t> v(s, s + n);
   if (base)
     for (auto& x : v) x -= (uint32_t)base;
@@ -268,10 +273,10 @@ static int32_t push_sample(scl_handle* h, std::vector<std::vector<uint32_t>>& q,
   return SCL_OK;
 }
 int32_t scl_push_search_sample(scl_handle* h, int64_t n, const uint32_t* s, int32_t base) {
-  return push_sample(h, h->search_sples, n, s, base);
+  return push_sample(h, 0, n, s, base);
 }
 int32_t scl_push_perturb_sample(scl_handle* h, int64_t n, const uint32_t* s, int32_t base) {
-  return push_sample(h, h->perturb_sples, n, s, base);
+  return push_sample(h, 1, n, s, base);
 }
 int32_t scl_clear_draws(scl_handle* h) {
   if (!h) return SCL_ERR_INVALID;
@@ -300,6 +305,43 @@ int32_t scl_run_robustness(scl_handle* h, double th, double p_step, int32_t n_pe
   });
   if (rc == SCL_OK && out) *out = h->rinfo;
   return rc;
+}
+
+int32_t scl_op_preprocess(scl_handle* h, int32_t N, int32_t M, int64_t nnz, const uint32_t* colptr, const uint32_t* rowval,
+                          const float* nzval, int32_t index_base, const uint8_t* gene_flags, const scl_qc_params* p,
+                          int32_t* n_cells, int32_t* n_genes, int64_t* out_nnz, int32_t* fc_idx, int32_t* gene_idx) {
+  if (!h || !colptr || !rowval || !nzval || !gene_flags || !p || !n_cells || !n_genes || N < 1 || M < 1 || nnz < 1) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    SpMat raw;
+    upload_csc(raw, N, M, (size_t)nnz, colptr, rowval, nzval, index_base, h->st);
+    Tmp<uint8_t> flags(M, h->st);
+    SCL_CUDA(cudaMemcpyAsync(flags.p, gene_flags, (size_t)M, cudaMemcpyHostToDevice, h->st));
+    std::vector<int32_t> fc, gi;
+    SpMat out;
+    const bool any = preprocess_device(raw, flags.p, *p, fc, gi, out, h->st);
+    *n_cells = any ? out.N : 0;
+    *n_genes = any ? out.M : 0;
+    if (out_nnz) *out_nnz = any ? (int64_t)out.nnz : 0;
+    if (!any) return;
+    if (fc_idx) std::memcpy(fc_idx, fc.data(), fc.size() * sizeof(int32_t));
+    if (gene_idx) std::memcpy(gene_idx, gi.data(), gi.size() * sizeof(int32_t));
+    h->X.swap(out);
+    h->have_X = true;
+    h->signal_done = h->robust_done = false;
+    h->have_zc = h->have_null_draws = h->have_pth = false;
+    h->search_sples.clear();
+    h->perturb_sples.clear();
+  });
+}
+
+int32_t scl_get_counts_csc(scl_handle* h, uint32_t* colptr, uint32_t* rowval, float* nzval) {
+  if (!h || !colptr || !rowval || !nzval) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_REQUIRE(h->have_X, "no counts on the handle");
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    download_csc(h->X, colptr, rowval, nzval, h->st);
+  });
 }
 
 int32_t scl_run_pass(scl_handle* h, double th, double p_step, int32_t n_perturb, scl_signal_info* sout, scl_robust_info* rout) {

@@ -71,6 +71,9 @@ void run_pass(scl_handle* h, double th, double p_step, int n_perturb);
 void score_from_pairs(const std::vector<float>& b_, int k, int n_pairs, double th, std::vector<double>& m,
                       std::vector<double>& sd, std::vector<int32_t>& sig);
 void plan_gram_shard(int64_t K, int64_t ld, int world, int rank, int64_t* k0, int64_t* k1);
+// preprocess.cu
+bool preprocess_device(const SpMat& X, const uint8_t* d_gene_flags, const scl_qc_params& p, std::vector<int32_t>& fc_idx,
+                       std::vector<int32_t>& gene_idx, SpMat& out, cudaStream_t st);
 // shared building blocks (also used by the scl_op_* entry points)
 // shard=true (and world > 1): every rank contracts its own slice of the long axis (cells when N > M) and the
 // partial Gram matrices are summed with ncclAllReduce

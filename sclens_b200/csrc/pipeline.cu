@@ -714,6 +714,7 @@ void make_additions(scl_handle* h, const std::vector<std::vector<uint32_t>>& inj
   if (index < injected.size()) {
     const std::vector<uint32_t>& s = injected[index];
     SCL_REQUIRE(s.size() == n_add, "injected sample has the wrong length for this sparsity step");
+    for (uint32_t v : s) SCL_REQUIRE((size_t)v < h->n_cand, "injected sample index outside the zero-candidate pool");
     Tmp<uint32_t> d_idx(n_add, h->st);
     SCL_CUDA(cudaMemcpyAsync(d_idx.p, s.data(), n_add * sizeof(uint32_t), cudaMemcpyHostToDevice, h->st));
     gather_pairs(h->z1.p, h->z2.p, d_idx.p, n_add, d_row, d_col, h->st);

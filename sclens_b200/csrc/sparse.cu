@@ -174,6 +174,41 @@ __global__ void k_rebase(uint32_t* p, size_t n, uint32_t base) {
   for (; i < n; i += stride) p[i] -= base;
 }
 
+// canonical-form check of an uploaded CSC, one warp per column: monotone column pointers ending at nnz, rows inside
+// [0, N) and strictly increasing inside a column, strictly positive finite values.  flag[0] = first kind of violation seen.
+__global__ void __launch_bounds__(256) k_validate_csc(const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ rowval,
+                                                      const float* __restrict__ val, int N, int M, size_t nnz, int* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < M; j += (gridDim.x * blockDim.x) >> 5) {
+    const uint32_t b = colptr[j], e = colptr[j + 1];
+    if (b > e || (size_t)e > nnz || (j == 0 && b != 0) || (j == M - 1 && (size_t)e != nnz)) {
+      if (lane == 0) atomicCAS(flag, 0, 1);
+      continue;
+    }
+    for (uint32_t t = b + lane; t < e; t += 32) {
+      const uint32_t r = rowval[t];
+      const float v = val[t];
+      if (r >= (uint32_t)N) atomicCAS(flag, 0, 2);
+      else if (t > b && rowval[t - 1] >= r) atomicCAS(flag, 0, 3);
+      if (!(v > 0.f) || !(v < 3.0e38f)) atomicCAS(flag, 0, 4);
+    }
+  }
+}
+
+void validate_csc(const SpMat& A, cudaStream_t st) {
+  Tmp<int> flag(1, st);
+  SCL_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+  count_launches(1);
+  k_validate_csc<<<std::min((A.M + 7) / 8, 148 * 16), 256, 0, st>>>(A.colptr.p, A.rowval.p, A.val.p, A.N, A.M, A.nnz, flag.p);
+  SCL_CUDA(cudaGetLastError());
+  int f = 0;
+  SCL_CUDA(cudaMemcpyAsync(&f, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  static const char* what[] = {"", "column pointers are not monotone from 0 to nnz", "a row index is outside [0, N)",
+                               "row indices are not strictly increasing inside a column", "a stored value is not a positive finite number"};
+  if (f) throw Error(-1 /*SCL_ERR_INVALID*/, std::string("counts are not a canonical CSC matrix: ") + what[f]);
+}
+
 void upload_csc(SpMat& A, int N, int M, size_t nnz, const uint32_t* colptr, const uint32_t* rowval, const float* val,
                 int index_base, cudaStream_t st) {
   A.N = N; A.M = M; A.nnz = nnz;
@@ -191,6 +226,7 @@ void upload_csc(SpMat& A, int N, int M, size_t nnz, const uint32_t* colptr, cons
   }
   SCL_CUDA(cudaGetLastError());
   count_launches(index_base ? 2 : 0);
+  validate_csc(A, st);          // before anything indexes with it: the mirror builder and every line pass trust the form
   build_csr_mirror(A, st);
 }
 
