@@ -293,6 +293,11 @@ SCL_API int32_t scl_bench_syevd_concurrent(scl_handle* h, int32_t n, int32_t nso
  * (<= 0 keeps).  writer: dense writer, -1 automatic, 0 register/overlay writer, 1 TMA bulk-store writer, 2 / 3
  * TMA bulk-store writer with one / two cp.async-staged entries per thread and line (<= -2 keeps).  Results are
  * identical for every setting. */
+/* Which eigensolver path runs (process-wide; the environment variable SCL_EIG_API sets the same bits): 0 = plain
+ * cusolverDnSsyevd; bit 0 Xsyevd; bit 1 Ssyevdx in the search steps; bit 2 own tridiagonal stage (tridiag.cu) between Ssytrd
+ * and Sormtr; bit 3 (with 2) index-range vectors in the search steps; bit 4 (with 2) own tridiagonalisation (sytrd.cu).
+ * v < 0: back to the environment / default. */
+SCL_API int32_t scl_debug_set_eig_api(int32_t v);
 SCL_API int32_t scl_debug_set_tuning(int32_t stat_variant, int32_t stat_heavy, int32_t writer);
 SCL_API int32_t scl_bench_normalize(scl_handle* h, int32_t layout, int32_t with_lo, int32_t reps, double* ms_stats,
                             double* ms_densify, double* alg_bytes_densify);

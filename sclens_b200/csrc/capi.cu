@@ -671,6 +671,11 @@ int32_t scl_bench_syevd_concurrent(scl_handle* h, int32_t n, int32_t nsolves, in
   });
 }
 
+int32_t scl_debug_set_eig_api(int32_t v) {
+  scl::set_eig_api(v);
+  return SCL_OK;
+}
+
 int32_t scl_debug_set_tuning(int32_t stat_variant, int32_t stat_heavy, int32_t writer) {
   scl::set_norm_tuning(stat_variant, stat_heavy, writer);
   return SCL_OK;

@@ -3,6 +3,7 @@
 #include <cusolverDn.h>
 #include <algorithm>
 #include <cmath>
+#include <atomic>
 #include <cstdlib>
 #include "common.cuh"
 #include "eigen.h"
@@ -33,14 +34,17 @@ struct Solver::Impl {
 // look (profiles/r1_syevd_study_10000.json); NOT yet parity-tested inside the path, hence opt-in (SCL_EIG_API bit 0).
 // Bit 1: the sparsity-search steps, which use only the n/2+1 smallest eigenvectors (:742), call cusolverDnSsyevdx with
 // an index range instead of a full solve (474 ms in the same first look); also opt-in until parity-tested.
+static std::atomic<int> g_eig_api_override{-1};
 int eig_api() {
   // default 12: the own tridiagonal stage for every solve (bit 2) with index-range vectors in the search steps (bit 3);
   // measured at n = 20 000 on the 68k x 20k data Gram matrix (profiles/r2_eig_study2.json): 2.85 s against 3.65 s for
   // Ssyevd with all vectors, 2.70 s for the smallest half, 2.47 s against 3.20 s for values only.  SCL_EIG_API=0 is
   // the plain library solve (the call the reference makes).
   static const int v = [] { const char* e = getenv("SCL_EIG_API"); return e ? atoi(e) : 12; }();
-  return v;
+  const int o = g_eig_api_override.load(std::memory_order_relaxed);
+  return o >= 0 ? o : v;
 }
+void set_eig_api(int v) { g_eig_api_override.store(v, std::memory_order_relaxed); }
 
 Solver::Solver(cudaStream_t st) : impl(new Impl) {
   SCL_SOLVER(cusolverDnCreate(&impl->h));
@@ -70,8 +74,12 @@ bool Solver::syevd_tri(float* dA, int n, float* dW, int v0, int v1, cudaStream_t
                                            impl->tri_tau.p, impl->tri_z.p, n, &lw2));
   impl->work.ensure((size_t)std::max(lw1, lw2) + 1);
   SCL_CUDA(cudaEventRecord(ev[0], st));
-  SCL_SOLVER(cusolverDnSsytrd(impl->h, CUBLAS_FILL_MODE_LOWER, n, dA, n, impl->tri_d.p, impl->tri_e.p, impl->tri_tau.p,
-                              impl->work.p, lw1, impl->info.p));
+  tri_own_sytrd = (eig_api() & 16) && sytrd_lower(dA, n, impl->tri_d.p, impl->tri_e.p, impl->tri_tau.p, st);
+  if (!tri_own_sytrd)
+    SCL_SOLVER(cusolverDnSsytrd(impl->h, CUBLAS_FILL_MODE_LOWER, n, dA, n, impl->tri_d.p, impl->tri_e.p, impl->tri_tau.p,
+                                impl->work.p, lw1, impl->info.p));
+  else
+    SCL_CUDA(cudaMemsetAsync(impl->info.p, 0, sizeof(int), st));
   SCL_CUDA(cudaEventRecord(ev[1], st));
   TridiagStats ts;
   bool ok = tridiag_eigen(impl->tri_d.p, impl->tri_e.p, n, impl->tri_w.p, dW, v0, v1, impl->tri_z.p, n, st, &ts);
@@ -190,6 +198,12 @@ double Solver::bench(float* dA, int n, float* dW, int mode, int il, int iu, cuda
     SCL_CUDA(cudaEventRecord(e0, st));
     SCL_SOLVER(cusolverDnSsyevdx(impl->h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, n, dA, n,
                                  0.f, 0.f, il, iu, &meig, dW, impl->work.p, lwork, impl->info.p));
+  } else if (mode == 9) {
+    // own tridiagonalisation (sytrd.cu) alone
+    Tmp<float> d(n, st), e(n, st), tau(n, st);
+    SCL_CUDA(cudaEventRecord(e0, st));
+    if (!sytrd_lower(dA, n, d.p, e.p, tau.p, st)) throw Error(-1, "sytrd_lower does not handle this size");
+    SCL_CUDA(cudaMemsetAsync(impl->info.p, 0, sizeof(int), st));
   } else if (mode >= 6 && mode <= 8) {
     // own tridiagonal stage: 6 = all vectors, 7 = vectors il..iu (1-based inclusive), 8 = values only
     const int v0 = mode == 7 ? il - 1 : 0, v1 = mode == 6 ? n : (mode == 7 ? iu : 0);

@@ -23,6 +23,7 @@ struct Solver {
   // milliseconds of the last syevd_tri call: [0] Ssytrd, [1] eigenvalues + eigenvectors of T, [2] Sormtr + copy
   double tri_ms[3] = {0, 0, 0};
   int tri_clusters = 0, tri_clustered = 0, tri_fallbacks = 0;
+  bool tri_own_sytrd = false;   // the last syevd_tri call tridiagonalised with sytrd.cu
   // timing study of the library's symmetric eigensolvers on an n x n matrix (overwritten); returns milliseconds.
   // mode 0: Ssyevd vectors, 1: Ssyevd values only, 2: Ssyevdx vectors of the il..iu smallest, 3: Xsyevd (64-bit API) vectors
   double bench(float* dA, int n, float* dW, int mode, int il, int iu, cudaStream_t st);
@@ -37,8 +38,12 @@ bool tridiag_eigen(const float* d32, const float* e32, int n, double* w64, float
                    long long ldz, cudaStream_t st, TridiagStats* stats);
 
 // SCL_EIG_API: bit 0 = Xsyevd for the full solves, bit 1 = Ssyevdx (index range) in the search steps, bit 2 = own tridiagonal
-// stage (Ssytrd + tridiag.cu + Sormtr) for every solve, bit 3 = with bit 2: vectors of the index range the search step uses only
+// stage (Ssytrd + tridiag.cu + Sormtr) for every solve, bit 3 = with bit 2: vectors of the index range the search step uses only, bit 4 = with bit 2: own tridiagonalisation
+// (sytrd.cu) instead of cusolverDnSsytrd
+// sytrd.cu: own Householder tridiagonalisation (persistent cooperative kernel), output as ssytrd('L'); false = not handled
+bool sytrd_lower(float* dA, int n, float* d_d, float* d_e, float* d_tau, cudaStream_t st);
 int eig_api();
+void set_eig_api(int v);   // process-wide override of SCL_EIG_API (tests, timing studies); < 0: back to the environment / default
 
 struct MpFit {
   std::vector<float> L_mp;

@@ -302,16 +302,23 @@ __global__ void k_add_ptrs(const uint32_t* __restrict__ a, const uint32_t* __res
   if (i < n) out[i] = a[i] + b[i];
 }
 
+// One CTA per line.  Shared memory: base bitmap, added bitmap, and the exclusive prefix of their word popcounts
+// (4 arrays of `words` 32-bit entries).  Every stored entry and every addition then knows its output slot from two
+// popcounts - slot = (entries before it in the base line) + (additions before its position) - so the base line is read and
+// the merged line written by consecutive threads at consecutive (base) / monotone (merged) addresses: no per-bit loops, no
+// sorting, coalesced traffic.  Additions (12 % of a line at the largest perturbation) scatter into the gaps.
 __global__ void __launch_bounds__(kMergeThreads)
 k_merge_lines(const uint32_t* __restrict__ base_ptr, const uint32_t* __restrict__ base_idx,
               const float* __restrict__ base_val, const uint32_t* __restrict__ add_ptr,
               const uint32_t* __restrict__ add_pos, const uint32_t* __restrict__ out_ptr, uint32_t* __restrict__ out_idx,
               float* __restrict__ out_val, int n_lines, int line_len, int binarise, int* __restrict__ flag) {
-  extern __shared__ uint32_t bm[];   // [2][words]: base bits, added bits
+  extern __shared__ uint32_t bm[];   // [4][words]: base bits, added bits, prefix of base popcounts, prefix of added popcounts
   __shared__ unsigned long long warp_tot[kMergeThreads / 32];
   const int words = (line_len + 31) >> 5;
   uint32_t* bmB = bm;
   uint32_t* bmA = bm + words;
+  uint32_t* pfB = bm + 2 * words;
+  uint32_t* pfA = bm + 3 * words;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wpt = (words + kMergeThreads - 1) / kMergeThreads;   // contiguous words per thread
   for (int l = blockIdx.x; l < n_lines; l += gridDim.x) {
@@ -337,13 +344,13 @@ k_merge_lines(const uint32_t* __restrict__ base_ptr, const uint32_t* __restrict_
       if (atomicOr(&bmA[p >> 5], bit) & bit) bad = true;       // the same position added twice
     }
     __syncthreads();
-    // per-thread counts over its contiguous words: (merged << 32) | base
+    // exclusive prefix of the word popcounts, both bitmaps at once: (added << 32) | base
     const int w0 = min(words, tid * wpt), w1 = min(words, w0 + wpt);
     unsigned long long cnt = 0;
     for (int w = w0; w < w1; ++w) {
       const uint32_t B = bmB[w], A = bmA[w];
       if (B & A) bad = true;                                     // an addition on a stored position
-      cnt += ((unsigned long long)__popc(B | A) << 32) | (unsigned long long)__popc(B);
+      cnt += ((unsigned long long)__popc(A) << 32) | (unsigned long long)__popc(B);
     }
     unsigned long long incl = cnt;
 #pragma unroll
@@ -353,27 +360,32 @@ k_merge_lines(const uint32_t* __restrict__ base_ptr, const uint32_t* __restrict_
     }
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    unsigned long long wbase = 0;
-    for (int q = 0; q < warp; ++q) wbase += warp_tot[q];
-    const unsigned long long excl = wbase + incl - cnt;
-    uint32_t ru = (uint32_t)(excl >> 32), rb = (uint32_t)(excl & 0xffffffffull);
-    if (bad) atomicOr(flag, 1);
+    unsigned long long run = incl - cnt;
+    for (int q = 0; q < warp; ++q) run += warp_tot[q];
     for (int w = w0; w < w1; ++w) {
-      const uint32_t B = bmB[w], A = bmA[w];
-      uint32_t u = B | A;
-      while (u) {
-        const int k = __ffs(u) - 1;
-        u &= u - 1;
-        const uint32_t bit = 1u << k;
-        float v = 0.f;
-        if (B & bit) { v = binarise ? 1.f : base_val[bb + rb]; ++rb; }
-        if (A & bit) v += 1.f;
-        out_idx[ob + ru] = (uint32_t)(w * 32 + k);
-        out_val[ob + ru] = v;
-        ++ru;
-      }
+      pfB[w] = (uint32_t)(run & 0xffffffffull);
+      pfA[w] = (uint32_t)(run >> 32);
+      run += ((unsigned long long)__popc(bmA[w]) << 32) | (unsigned long long)__popc(bmB[w]);
     }
-    __syncthreads();   // bitmaps and warp_tot are reused by the next line
+    if (bad) atomicOr(flag, 1);
+    __syncthreads();
+    // stored entries: slot = rank in the base line + additions at smaller positions
+    for (uint32_t t = bb + tid; t < be; t += kMergeThreads) {
+      const uint32_t p = base_idx[t], w = p >> 5, low = (1u << (p & 31)) - 1u;
+      const uint32_t slot = (t - bb) + pfA[w] + __popc(bmA[w] & low);
+      out_idx[ob + slot] = p;
+      out_val[ob + slot] = binarise ? 1.f : base_val[t];
+    }
+    // additions: slot = additions at smaller positions + stored entries at smaller positions; value 1 (:735, :774)
+    for (uint32_t t = ab + tid; t < ae; t += kMergeThreads) {
+      const uint32_t p = add_pos[t];
+      if (p >= (uint32_t)line_len) continue;
+      const uint32_t w = p >> 5, low = (1u << (p & 31)) - 1u;
+      const uint32_t slot = pfA[w] + __popc(bmA[w] & low) + pfB[w] + __popc(bmB[w] & low);
+      out_idx[ob + slot] = p;
+      out_val[ob + slot] = 1.f;
+    }
+    __syncthreads();   // bitmaps, prefixes and warp_tot are reused by the next line
   }
 }
 
@@ -384,7 +396,7 @@ void perturb_merge(const SpMat& base, const uint32_t* d_add_row, const uint32_t*
                    bool binarise, SpMat& out, cudaStream_t st) {
   const int N = base.N, M = base.M;
   const size_t nnz = base.nnz + n_add;
-  const size_t smem_c = (size_t)2 * ((N + 31) / 32) * sizeof(uint32_t), smem_r = (size_t)2 * ((M + 31) / 32) * sizeof(uint32_t);
+  const size_t smem_c = (size_t)4 * ((N + 31) / 32) * sizeof(uint32_t), smem_r = (size_t)4 * ((M + 31) / 32) * sizeof(uint32_t);
   if (smem_c > 200 * 1024 || smem_r > 200 * 1024) {   // a line's bitmaps must fit in shared memory
     perturb_merge_general(base, d_add_row, d_add_col, n_add, binarise, out, st);
     return;

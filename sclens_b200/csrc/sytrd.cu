@@ -1,0 +1,402 @@
+// Householder tridiagonalisation of a symmetric FP32 matrix (the first and by far the longest part of the full-spectrum
+// solve, _get_eigen src/scLENS.jl:375-382): one persistent cooperative kernel, output in LAPACK ssytrd('L') form so that
+// the library's back-transformation (Sormtr) applies unchanged.
+//
+// Why not the library's: cusolverDnSsytrd is a one-stage blocked reduction whose matrix-vector half streams the whole
+// trailing SQUARE per column (4 n^3 / 3 bytes: 1.6 s at n = 20 000 at HBM speed, 2.1-2.4 s measured).  Here
+//   * the symmetric matrix-vector product reads the LOWER TRIANGLE only - every tile contributes to y twice, once through
+//     its rows and once through its columns - half the bytes;
+//   * one launch: the ~60 000 dependent steps of a 20 000-column reduction are separated by a hand-rolled grid barrier
+//     (one atomic + an acquire spin, ~2 us) instead of kernel boundaries;
+//   * the panel's corrections are applied on the fly (W is kept without its last rank-1 term, alpha_c v_c, which needs a
+//     global dot product - the term is added wherever W is read), so a column costs three barriers, not five;
+//   * results are deterministic: partial sums meet in a fixed order (per-CTA row partials in shared memory, reduced by row
+//     owners), no floating-point atomics.
+// Blocked algorithm = LAPACK slatrd / ssytrd (lower): panel of kNB columns, rank-2k update of the trailing matrix
+// A22 -= V W' + W V' (register-tiled FP32 FMA, lower triangle only) after each panel.
+#include <algorithm>
+#include <cmath>
+#include "common.cuh"
+#include "eigen.h"
+#include "tmp.cuh"
+
+namespace scl {
+namespace {
+
+constexpr int kNB = 32;        // panel width = strip width of the matrix-vector product
+constexpr int kT = 512;        // threads per CTA (one CTA per SM)
+constexpr int kW = kT / 32;
+constexpr int kTile = 128;     // rank-2k update tile (one half CTA per tile)
+
+struct SyArgs {
+  float* A;          // n x n, column-major lower triangle in, reflectors + tridiagonal out
+  int n;
+  float* W;          // n x kNB, column-major: the panel's W without its alpha_c v_c terms
+  float *d, *e, *tau;
+  float* P;          // [grid][n] row partials of the matrix-vector product
+  float* ycol;       // n: column parts of the matrix-vector product
+  double* part;      // [grid][2 kNB + 2]: panel dot products, norm / w'v partials
+  float* scal;       // [0] = A(i+1, i) after the column update
+  unsigned* bar;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+  target += gridDim.x;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum over the CTA (all threads call); result valid in every thread
+__device__ double cta_sum(double v, double* red) {
+  v = warp_sum_d(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0;
+  for (int w = 0; w < kW; ++w) s += red[w];
+  return s;
+}
+
+__global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
+  extern __shared__ __align__(16) float smem[];   // row accumulator of the matrix-vector product / update tiles
+  __shared__ double s_red[kW];
+  __shared__ float s_rowV[kNB], s_rowW[kNB], s_p[kNB], s_q[kNB], s_alpha[kNB];
+  __shared__ float s_col[kW][32];
+  __shared__ float s_pq[kW][2 * kNB];
+  __shared__ double s_scal[3];   // tau, scale, -
+  float* ysm = smem;
+  const int n = a.n, P = (int)gridDim.x, b = (int)blockIdx.x, tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t ld = (size_t)n;
+  unsigned target = gridDim.x;
+  double* part1 = a.part + (size_t)P * 2 * kNB;   // [P] squared norms
+  double* part3 = part1 + P;                      // [P] w'v
+
+  for (int k0 = 0; k0 < n; k0 += kNB) {
+    const int k1 = min(n, k0 + kNB), ncols = k1 - k0;
+    for (int c = 0; c < ncols; ++c) {
+      const int i = k0 + c, t0 = i + 1;
+      // ---- alpha of the previous column of this panel; row i of V and of W (with its alpha terms)
+      if (c > 0) {
+        if (tid == 0) {
+          double s = 0;
+          for (int q = 0; q < P; ++q) s += __ldcg(part3 + q);
+          s_alpha[c - 1] = (float)(-0.5 * s_scal[0] * s);
+        }
+        __syncthreads();
+        if (tid < c) {
+          const float v = __ldcg(a.A + (size_t)(k0 + tid) * ld + i);
+          s_rowV[tid] = v;
+          s_rowW[tid] = __ldcg(a.W + (size_t)tid * ld + i) + s_alpha[tid] * v;
+        }
+        __syncthreads();
+      }
+      // ---- phase 1: A(i:n, i) -= V(i:n, :) Wf(i, :)' + Wf(i:n, :) V(i, :)'; diagonal, sub-diagonal, |x|^2
+      double nrm = 0;
+      for (int rb = b + P * warp; rb * 32 < n; rb += P * kW) {   // row block rb belongs to CTA rb % P, warp (rb / P) % kW
+        const int r = rb * 32 + lane;
+        if (r < i || r >= n) continue;
+        float upd = 0.f;
+        for (int cp = 0; cp < c; ++cp) {
+          const float vr = __ldcg(a.A + (size_t)(k0 + cp) * ld + r);
+          const float wr = __ldcg(a.W + (size_t)cp * ld + r) + s_alpha[cp] * vr;
+          upd = fmaf(vr, s_rowW[cp], upd);
+          upd = fmaf(wr, s_rowV[cp], upd);
+        }
+        const float ar = __ldcg(a.A + (size_t)i * ld + r) - upd;
+        __stcg(a.A + (size_t)i * ld + r, ar);
+        if (r == i) a.d[i] = ar;
+        else if (r == t0) __stcg(a.scal, ar);
+        else nrm += (double)ar * (double)ar;
+      }
+      if (i == n - 1) break;   // last diagonal entry: nothing left to reduce
+      nrm = cta_sum(nrm, s_red);
+      if (tid == 0) __stcg(part1 + b, nrm);
+      grid_barrier(a.bar, target);
+
+      // ---- phase 2: reflector scalars; y = A22 v over the lower triangle; panel dot products
+      if (tid == 0) {
+        double xn2 = 0;
+        for (int q = 0; q < P; ++q) xn2 += __ldcg(part1 + q);
+        const double ain = (double)__ldcg(a.scal);
+        double beta = ain, tau = 0, scale = 0;
+        if (xn2 > 0) {
+          beta = -copysign(sqrt(ain * ain + xn2), ain);
+          tau = (beta - ain) / beta;
+          scale = 1.0 / (ain - beta);
+        }
+        s_scal[0] = tau;
+        s_scal[1] = scale;
+        if (b == 0) { a.e[i] = (float)beta; a.tau[i] = (float)tau; }
+      }
+      for (int r = t0 + tid; r < n; r += kT) ysm[r] = 0.f;
+      __syncthreads();
+      const float tau = (float)s_scal[0], scale = (float)s_scal[1];
+      const float* coli = a.A + (size_t)i * ld;
+      {
+        // panel dots p = V' v, q = Wf' v over the rows this warp owns
+        float pacc[kNB], qacc[kNB];
+#pragma unroll
+        for (int cp = 0; cp < kNB; ++cp) { pacc[cp] = 0.f; qacc[cp] = 0.f; }
+        bool any = false;
+        if (c > 0) {
+          for (int rb = b + P * warp; rb * 32 < n; rb += P * kW) {
+            const int r = rb * 32 + lane;
+            if (r < t0 || r >= n) continue;
+            any = true;
+            const float vr_i = r == t0 ? 1.f : __ldcg(coli + r) * scale;
+#pragma unroll
+            for (int cp = 0; cp < kNB; ++cp) {
+              if (cp < c) {
+                const float vr = __ldcg(a.A + (size_t)(k0 + cp) * ld + r);
+                const float wr = __ldcg(a.W + (size_t)cp * ld + r) + s_alpha[cp] * vr;
+                pacc[cp] = fmaf(vr, vr_i, pacc[cp]);
+                qacc[cp] = fmaf(wr, vr_i, qacc[cp]);
+              }
+            }
+          }
+        }
+        (void)any;
+#pragma unroll
+        for (int cp = 0; cp < kNB; ++cp) {
+          const float ps = warp_sum_f(pacc[cp]), qs = warp_sum_f(qacc[cp]);
+          if (lane == 0) { s_pq[warp][cp] = ps; s_pq[warp][kNB + cp] = qs; }
+        }
+        __syncthreads();
+        if (tid < 2 * kNB) {
+          double s = 0;
+          for (int w = 0; w < kW; ++w) s += (double)s_pq[w][tid];
+          __stcg(a.part + (size_t)b * 2 * kNB + tid, s);
+        }
+      }
+      // strips of 32 columns, dealt to the CTAs cyclically; a warp walks 32-row blocks down its strip
+      {
+        const int s0 = t0 >> 5, smax = (n - 1) >> 5;
+        for (int s = s0 + ((b - s0 % P) % P + P) % P; s <= smax; s += P) {
+          const int ja = max(32 * s, t0), jb = min(32 * s + 32, n);
+          const int jc = 32 * s + lane;
+          const float vC = (jc >= ja && jc < jb) ? (jc == t0 ? 1.f : __ldcg(coli + jc) * scale) : 0.f;
+          float colacc[32];
+#pragma unroll
+          for (int cc = 0; cc < 32; ++cc) colacc[cc] = 0.f;
+          for (int rb = s + warp; rb * 32 < n; rb += kW) {
+            const int r = rb * 32 + lane;
+            const bool rvalid = r < n && r >= t0;
+            const float vr = rvalid ? (r == t0 ? 1.f : __ldcg(coli + r) * scale) : 0.f;
+            float acc = 0.f;
+            if (rb > s) {   // rectangular part: every column of the strip lies left of the row
+#pragma unroll
+              for (int cc = 0; cc < 32; ++cc) {
+                const int j = 32 * s + cc;
+                const float vj = __shfl_sync(0xffffffffu, vC, cc);
+                if (j >= ja && j < jb) {   // uniform over the warp
+                  const float av = rvalid ? __ldcg(a.A + (size_t)j * ld + r) : 0.f;
+                  acc = fmaf(av, vj, acc);
+                  colacc[cc] = fmaf(av, vr, colacc[cc]);
+                }
+              }
+            } else {        // diagonal block: lower triangle only, the diagonal itself counted once
+#pragma unroll
+              for (int cc = 0; cc < 32; ++cc) {
+                const int j = 32 * s + cc;
+                const float vj = __shfl_sync(0xffffffffu, vC, cc);
+                if (j >= ja && j < jb) {
+                  const float av = (rvalid && r >= j) ? __ldcg(a.A + (size_t)j * ld + r) : 0.f;
+                  acc = fmaf(av, vj, acc);
+                  if (r > j) colacc[cc] = fmaf(av, vr, colacc[cc]);
+                }
+              }
+            }
+            if (rvalid) ysm[r] += acc;   // one warp per row block inside a strip; strips are separated by barriers
+          }
+          float mine = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < 32; ++cc) {
+            const float t = warp_sum_f(colacc[cc]);
+            if (lane == cc) mine = t;
+          }
+          s_col[warp][lane] = mine;
+          __syncthreads();
+          if (tid < 32) {
+            float t = 0.f;
+            for (int w = 0; w < kW; ++w) t += s_col[w][tid];
+            const int j = 32 * s + tid;
+            if (j >= ja && j < jb) __stcg(a.ycol + j, t);
+          }
+          __syncthreads();
+        }
+        float* Pb = a.P + (size_t)b * ld;
+        for (int r = t0 + tid; r < n; r += kT) __stcg(Pb + r, ysm[r]);
+      }
+      grid_barrier(a.bar, target);
+
+      // ---- phase 3: w = tau (y - V q - Wf p) on the rows this warp owns (stored without alpha v); w'v; v into A(:, i)
+      if (tid < 2 * kNB) {
+        double s = 0;
+        if ((tid & (kNB - 1)) < c)
+          for (int q = 0; q < P; ++q) s += __ldcg(a.part + (size_t)q * 2 * kNB + tid);
+        if (tid < kNB) s_p[tid] = (float)s; else s_q[tid - kNB] = (float)s;
+      }
+      __syncthreads();
+      double dot = 0;
+      for (int rb = b + P * warp; rb * 32 < n; rb += P * kW) {
+        const int r = rb * 32 + lane;
+        if (r < t0 || r >= n) continue;
+        float y = __ldcg(a.ycol + r);
+#pragma unroll 8
+        for (int q = 0; q < P; ++q) y += __ldcg(a.P + (size_t)q * ld + r);
+        const float vr_i = r == t0 ? 1.f : __ldcg(coli + r) * scale;
+        float corr = 0.f;
+        for (int cp = 0; cp < c; ++cp) {
+          const float vr = __ldcg(a.A + (size_t)(k0 + cp) * ld + r);
+          const float wr = __ldcg(a.W + (size_t)cp * ld + r) + s_alpha[cp] * vr;
+          corr = fmaf(vr, s_q[cp], corr);
+          corr = fmaf(wr, s_p[cp], corr);
+        }
+        const float w = tau * (y - corr);
+        __stcg(a.W + (size_t)c * ld + r, w);
+        dot += (double)w * (double)vr_i;
+        __stcg(a.A + (size_t)i * ld + r, vr_i);   // the reflector, its leading one stored explicitly while the panel is open
+      }
+      dot = cta_sum(dot, s_red);
+      if (tid == 0) __stcg(part3 + b, dot);
+      grid_barrier(a.bar, target);
+    }
+    if (k1 >= n) break;
+    // ---- panel end: alpha of its last column, then A22 -= V Wf' + Wf V' on the lower triangle of rows / columns >= k1
+    if (tid == 0) {
+      double s = 0;
+      for (int q = 0; q < P; ++q) s += __ldcg(part3 + q);
+      s_alpha[ncols - 1] = (float)(-0.5 * s_scal[0] * s);
+    }
+    __syncthreads();
+    {
+      const int half = tid >> 8, u = tid & 255;
+      float* Vr = smem + (size_t)half * 4 * kNB * kTile;   // [kNB][kTile] each
+      float* Wr = Vr + kNB * kTile;
+      float* Vc = Wr + kNB * kTile;
+      float* Wc = Vc + kNB * kTile;
+      const int m = n - k1, Tn = (m + kTile - 1) / kTile, n_tiles = Tn * (Tn + 1) / 2;
+      const int rx = (u & 15) * 8, cy = (u >> 4) * 8;
+      for (int t = 2 * b + half; t < n_tiles; t += 2 * P) {
+        // tile index -> (tr, tc), tc <= tr
+        int tr = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while (tr * (tr + 1) / 2 > t) --tr;
+        while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
+        const int tc = t - tr * (tr + 1) / 2;
+        const int r0 = k1 + tr * kTile, c0 = k1 + tc * kTile;
+        for (int x = u; x < kNB * kTile; x += 256) {
+          const int k = x / kTile, o = x % kTile;
+          float vr = 0.f, wr = 0.f, vc = 0.f, wc = 0.f;
+          if (k < ncols) {
+            if (r0 + o < n) {
+              vr = __ldcg(a.A + (size_t)(k0 + k) * ld + r0 + o);
+              wr = __ldcg(a.W + (size_t)k * ld + r0 + o) + s_alpha[k] * vr;
+            }
+            if (c0 + o < n) {
+              vc = __ldcg(a.A + (size_t)(k0 + k) * ld + c0 + o);
+              wc = __ldcg(a.W + (size_t)k * ld + c0 + o) + s_alpha[k] * vc;
+            }
+          }
+          Vr[x] = vr; Wr[x] = wr; Vc[x] = vc; Wc[x] = wc;
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(256) : "memory");
+        float acc[8][8];
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+#pragma unroll
+          for (int y = 0; y < 8; ++y) acc[x][y] = 0.f;
+        for (int k = 0; k < ncols; ++k) {
+          float vr[8], wr[8], vc[8], wc[8];
+          *reinterpret_cast<float4*>(vr) = *reinterpret_cast<const float4*>(Vr + k * kTile + rx);
+          *reinterpret_cast<float4*>(vr + 4) = *reinterpret_cast<const float4*>(Vr + k * kTile + rx + 4);
+          *reinterpret_cast<float4*>(wr) = *reinterpret_cast<const float4*>(Wr + k * kTile + rx);
+          *reinterpret_cast<float4*>(wr + 4) = *reinterpret_cast<const float4*>(Wr + k * kTile + rx + 4);
+          *reinterpret_cast<float4*>(vc) = *reinterpret_cast<const float4*>(Vc + k * kTile + cy);
+          *reinterpret_cast<float4*>(vc + 4) = *reinterpret_cast<const float4*>(Vc + k * kTile + cy + 4);
+          *reinterpret_cast<float4*>(wc) = *reinterpret_cast<const float4*>(Wc + k * kTile + cy);
+          *reinterpret_cast<float4*>(wc + 4) = *reinterpret_cast<const float4*>(Wc + k * kTile + cy + 4);
+#pragma unroll
+          for (int x = 0; x < 8; ++x)
+#pragma unroll
+            for (int y = 0; y < 8; ++y) acc[x][y] = fmaf(vr[x], wc[y], fmaf(wr[x], vc[y], acc[x][y]));
+        }
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+          const int cc = c0 + cy + y;
+          if (cc >= n) continue;
+#pragma unroll
+          for (int x = 0; x < 8; ++x) {
+            const int r = r0 + rx + x;
+            if (r < n && r >= cc) {
+              float* p = a.A + (size_t)cc * ld + r;
+              __stcg(p, __ldcg(p) - acc[x][y]);
+            }
+          }
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(256) : "memory");
+      }
+    }
+    grid_barrier(a.bar, target);
+  }
+}
+
+// the sub-diagonal of T goes back where ssytrd leaves it (the reflectors' leading ones were stored there while their panel was open)
+__global__ void k_restore_subdiagonal(float* __restrict__ A, int n, const float* __restrict__ e) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n - 1) A[(size_t)i * n + i + 1] = e[i];
+}
+
+}  // namespace
+
+// A: symmetric n x n (the lower triangle, column-major, is read); on return as after ssytrd('L'): d (n), e (n - 1),
+// tau (n - 1), reflectors below the sub-diagonal.  Returns false when the matrix is outside what the kernel handles (the
+// caller uses the library's Ssytrd then).
+bool sytrd_lower(float* dA, int n, float* d_d, float* d_e, float* d_tau, cudaStream_t st) {
+  if (n < 256 || n > 48000) return false;
+  int dev = 0, sms = 0, coop = 0;
+  SCL_CUDA(cudaGetDevice(&dev));
+  SCL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  SCL_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  if (!coop) return false;
+  const size_t smem = std::max((size_t)n * sizeof(float), (size_t)2 * 4 * kNB * kTile * sizeof(float));
+  if (smem > 200 * 1024) return false;
+  SCL_CUDA(cudaFuncSetAttribute(k_sytrd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  SCL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sytrd, kT, smem));
+  if (per_sm < 1) return false;
+  const int grid = sms;
+  Tmp<float> W((size_t)n * kNB, st), P((size_t)grid * n, st), ycol(n, st), scal(4, st);
+  Tmp<double> part((size_t)grid * (2 * kNB + 2), st);
+  Tmp<unsigned> bar(1, st);
+  SCL_CUDA(cudaMemsetAsync(bar.p, 0, sizeof(unsigned), st));
+  SCL_CUDA(cudaMemsetAsync(part.p, 0, (size_t)grid * (2 * kNB + 2) * sizeof(double), st));
+  SCL_CUDA(cudaMemsetAsync(d_tau, 0, (size_t)n * sizeof(float), st));
+  SCL_CUDA(cudaMemsetAsync(d_e, 0, (size_t)n * sizeof(float), st));
+  SyArgs args{dA, n, W.p, d_d, d_e, d_tau, P.p, ycol.p, part.p, scal.p, bar.p};
+  void* params[] = {&args};
+  count_launches(2);
+  SCL_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd, dim3(grid), dim3(kT), params, smem, st));
+  k_restore_subdiagonal<<<(n + 255) / 256, 256, 0, st>>>(dA, n, d_e);
+  SCL_CUDA(cudaGetLastError());
+  return true;
+}
+
+}  // namespace scl

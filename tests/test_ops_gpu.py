@@ -298,6 +298,28 @@ def test_syevd_tri_matches_float64(h, case):
     np.testing.assert_array_equal(L3, L)
 
 
+@pytest.mark.parametrize("n", [300, 1000, 2531])
+def test_own_tridiagonalisation_matches_float64(h, n):
+    """sytrd.cu (persistent cooperative Householder tridiagonalisation, lower triangle only) in place of cusolverDnSsytrd:
+    the full solve through it - eigenvalues, residuals, orthogonality - against numpy's Float64 eigh, same tolerances as the
+    library path; shapes that are not multiples of the 32-column panel or the 128 x 128 update tile."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n + 300))
+    A -= A.mean(axis=0)
+    G = (A @ A.T / A.shape[1]).astype(np.float32)
+    Lref = np.linalg.eigvalsh(G.astype(np.float64))
+    try:
+        h.lib.scl_debug_set_eig_api(4 | 8 | 16)
+        L, V, out = _tri_solve(h, G, 0, n)
+    finally:
+        h.lib.scl_debug_set_eig_api(-1)
+    assert out[5] == 0, "fell back to the library solver"
+    np.testing.assert_allclose(L, Lref, rtol=2e-5, atol=3e-6 * float(Lref[-1]))
+    G64 = G.astype(np.float64)
+    assert np.max(np.abs(G64 @ V - V * L[None, :])) < 5e-5 * max(1.0, float(Lref[-1]))
+    assert np.max(np.abs(V.T.astype(np.float64) @ V - np.eye(n))) < 5e-5
+
+
 def test_syevd_tri_exact_multiplicities(h):
     """Every eigenvalue exactly double (two identical diagonal blocks) plus a block of exact zeros: twisted factorisation alone
     would return parallel vectors; the cluster pass (inverse iteration + Gram-Schmidt inside the cluster) must give an
