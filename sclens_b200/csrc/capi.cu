@@ -443,6 +443,7 @@ int32_t scl_op_normalize(scl_handle* h, int32_t N, int32_t M, int64_t nnz, const
     SCL_CUDA(cudaSetDevice(h->cfg.device));
     SpMat A;
     NormStats S;
+    S.centering = h->cfg.centering;
     upload_csc(A, N, M, (size_t)nnz, colptr, rowval, nzval, 0, h->st);
     compute_norm_stats(A, S, h->st);
     if (out_hi) {
@@ -692,6 +693,7 @@ int32_t scl_bench_normalize(scl_handle* h, int32_t layout, int32_t with_lo, int3
     const size_t ld = (line_len + 7) / 8 * 8;
     Tmp<__half> hi(lines * ld, h->st), lo(with_lo ? lines * ld : 1, h->st);
     NormStats S;
+    S.centering = h->cfg.centering;
     cudaEvent_t e0, e1, e2;
     SCL_CUDA(cudaEventCreate(&e0));
     SCL_CUDA(cudaEventCreate(&e1));

@@ -16,6 +16,8 @@
 // A22 -= V W' + W V' (register-tiled FP32 FMA, lower triangle only) after each panel.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <vector>
 #include "common.cuh"
 #include "eigen.h"
 #include "tmp.cuh"
@@ -38,6 +40,7 @@ struct SyArgs {
   double* part;      // [grid][2 kNB + 2]: panel dot products, norm / w'v partials
   float* scal;       // [0] = A(i+1, i) after the column update
   unsigned* bar;
+  unsigned long long* prof;   // [grid][16] nanoseconds per section of CTA's thread 0 (timing studies; may be null)
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
@@ -54,6 +57,20 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
   __syncthreads();
   target += gridDim.x;
 }
+
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define SY_TICK(slot)                                   \
+  do {                                                  \
+    if (tid == 0) {                                     \
+      const unsigned long long t_ = now_ns();           \
+      tacc[slot] += t_ - tlast;                         \
+      tlast = t_;                                       \
+    }                                                   \
+  } while (0)
 
 __device__ __forceinline__ double warp_sum_d(double v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -75,17 +92,40 @@ __device__ double cta_sum(double v, double* red) {
   return s;
 }
 
+// sum of `cnt` doubles at stride `stride`, by one warp, fixed order (lane-strided partial sums, butterfly): every lane gets it
+__device__ __forceinline__ double warp_gather_sum(const double* p, int cnt, size_t stride) {
+  const int lane = threadIdx.x & 31;
+  double s = 0;
+  for (int q = lane; q < cnt; q += 32) s += __ldcg(p + (size_t)q * stride);
+  return warp_sum_d(s);
+}
+
+// panel loops: all kNB column slots are issued (clamped address, value masked) so the loads of a row leave together
+__device__ __forceinline__ void load_panel_row(const SyArgs& a, size_t ld, int k0, int c, int r, const float* s_alpha,
+                                               float (&vr)[kNB], float (&wr)[kNB]) {
+#pragma unroll
+  for (int cp = 0; cp < kNB; ++cp) {
+    const bool ok = cp < c;
+    const float v = __ldcg(a.A + (ok ? (size_t)(k0 + cp) * ld + r : 0));
+    const float w = __ldcg(a.W + (ok ? (size_t)cp * ld + r : 0));
+    vr[cp] = ok ? v : 0.f;
+    wr[cp] = ok ? fmaf(s_alpha[cp], v, w) : 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
   extern __shared__ __align__(16) float smem[];   // row accumulator of the matrix-vector product / update tiles
   __shared__ double s_red[kW];
   __shared__ float s_rowV[kNB], s_rowW[kNB], s_p[kNB], s_q[kNB], s_alpha[kNB];
   __shared__ float s_col[kW][32];
+  __shared__ float s_y[kW][32];
   __shared__ float s_pq[kW][2 * kNB];
   __shared__ double s_scal[3];   // tau, scale, -
   float* ysm = smem;
   const int n = a.n, P = (int)gridDim.x, b = (int)blockIdx.x, tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t ld = (size_t)n;
   unsigned target = gridDim.x;
+  unsigned long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = now_ns();
   double* part1 = a.part + (size_t)P * 2 * kNB;   // [P] squared norms
   double* part3 = part1 + P;                      // [P] w'v
 
@@ -95,10 +135,9 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
       const int i = k0 + c, t0 = i + 1;
       // ---- alpha of the previous column of this panel; row i of V and of W (with its alpha terms)
       if (c > 0) {
-        if (tid == 0) {
-          double s = 0;
-          for (int q = 0; q < P; ++q) s += __ldcg(part3 + q);
-          s_alpha[c - 1] = (float)(-0.5 * s_scal[0] * s);
+        if (warp == 0) {
+          const double s = warp_gather_sum(part3, P, 1);
+          if (lane == 0) s_alpha[c - 1] = (float)(-0.5 * s_scal[0] * s);
         }
         __syncthreads();
         if (tid < c) {
@@ -114,13 +153,19 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
         const int r = rb * 32 + lane;
         if (r < i || r >= n) continue;
         float upd = 0.f;
-        for (int cp = 0; cp < c; ++cp) {
-          const float vr = __ldcg(a.A + (size_t)(k0 + cp) * ld + r);
-          const float wr = __ldcg(a.W + (size_t)cp * ld + r) + s_alpha[cp] * vr;
-          upd = fmaf(vr, s_rowW[cp], upd);
-          upd = fmaf(wr, s_rowV[cp], upd);
+        const float a0 = __ldcg(a.A + (size_t)i * ld + r);
+        {
+          float vr[kNB], wr[kNB];
+          load_panel_row(a, ld, k0, c, r, s_alpha, vr, wr);
+#pragma unroll
+          for (int cp = 0; cp < kNB; ++cp) {
+            if (cp < c) {
+              upd = fmaf(vr[cp], s_rowW[cp], upd);
+              upd = fmaf(wr[cp], s_rowV[cp], upd);
+            }
+          }
         }
-        const float ar = __ldcg(a.A + (size_t)i * ld + r) - upd;
+        const float ar = a0 - upd;
         __stcg(a.A + (size_t)i * ld + r, ar);
         if (r == i) a.d[i] = ar;
         else if (r == t0) __stcg(a.scal, ar);
@@ -129,12 +174,13 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
       if (i == n - 1) break;   // last diagonal entry: nothing left to reduce
       nrm = cta_sum(nrm, s_red);
       if (tid == 0) __stcg(part1 + b, nrm);
+      SY_TICK(0);
       grid_barrier(a.bar, target);
+      SY_TICK(1);
 
       // ---- phase 2: reflector scalars; y = A22 v over the lower triangle; panel dot products
-      if (tid == 0) {
-        double xn2 = 0;
-        for (int q = 0; q < P; ++q) xn2 += __ldcg(part1 + q);
+      if (warp == 0) {
+        const double xn2 = warp_gather_sum(part1, P, 1);
         const double ain = (double)__ldcg(a.scal);
         double beta = ain, tau = 0, scale = 0;
         if (xn2 > 0) {
@@ -142,9 +188,11 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
           tau = (beta - ain) / beta;
           scale = 1.0 / (ain - beta);
         }
-        s_scal[0] = tau;
-        s_scal[1] = scale;
-        if (b == 0) { a.e[i] = (float)beta; a.tau[i] = (float)tau; }
+        if (lane == 0) {
+          s_scal[0] = tau;
+          s_scal[1] = scale;
+          if (b == 0) { a.e[i] = (float)beta; a.tau[i] = (float)tau; }
+        }
       }
       for (int r = t0 + tid; r < n; r += kT) ysm[r] = 0.f;
       __syncthreads();
@@ -162,14 +210,12 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
             if (r < t0 || r >= n) continue;
             any = true;
             const float vr_i = r == t0 ? 1.f : __ldcg(coli + r) * scale;
+            float vr[kNB], wr[kNB];
+            load_panel_row(a, ld, k0, c, r, s_alpha, vr, wr);
 #pragma unroll
             for (int cp = 0; cp < kNB; ++cp) {
-              if (cp < c) {
-                const float vr = __ldcg(a.A + (size_t)(k0 + cp) * ld + r);
-                const float wr = __ldcg(a.W + (size_t)cp * ld + r) + s_alpha[cp] * vr;
-                pacc[cp] = fmaf(vr, vr_i, pacc[cp]);
-                qacc[cp] = fmaf(wr, vr_i, qacc[cp]);
-              }
+              pacc[cp] = fmaf(vr[cp], vr_i, pacc[cp]);
+              qacc[cp] = fmaf(wr[cp], vr_i, qacc[cp]);
             }
           }
         }
@@ -186,10 +232,16 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
           __stcg(a.part + (size_t)b * 2 * kNB + tid, s);
         }
       }
+      SY_TICK(2);
       // strips of 32 columns, dealt to the CTAs cyclically; a warp walks 32-row blocks down its strip
       {
+        // strips are dealt in snake order (round 0: CTA b takes the b-th tallest, round 1: the (P-1-b)-th of the next P, ...):
+        // strip heights fall linearly, so a plain cyclic deal would give the first CTAs 60 % more rows than the last
         const int s0 = t0 >> 5, smax = (n - 1) >> 5;
-        for (int s = s0 + ((b - s0 % P) % P + P) % P; s <= smax; s += P) {
+        for (int round = 0;; ++round) {
+          const int s = s0 + round * P + ((round & 1) ? P - 1 - b : b);
+          if (s0 + round * P > smax) break;   // uniform over the grid
+          if (s > smax) continue;
           const int ja = max(32 * s, t0), jb = min(32 * s + 32, n);
           const int jc = 32 * s + lane;
           const float vC = (jc >= ja && jc < jb) ? (jc == t0 ? 1.f : __ldcg(coli + jc) * scale) : 0.f;
@@ -201,27 +253,24 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
             const bool rvalid = r < n && r >= t0;
             const float vr = rvalid ? (r == t0 ? 1.f : __ldcg(coli + r) * scale) : 0.f;
             float acc = 0.f;
-            if (rb > s) {   // rectangular part: every column of the strip lies left of the row
+            {
+              // all 32 column loads of the row block leave before the first FMA: invalid positions (columns outside the
+              // strip, rows above the diagonal or outside the matrix) read a safe address and are masked afterwards
+              float av[32];
+              const bool diag = rb == s;
 #pragma unroll
               for (int cc = 0; cc < 32; ++cc) {
                 const int j = 32 * s + cc;
-                const float vj = __shfl_sync(0xffffffffu, vC, cc);
-                if (j >= ja && j < jb) {   // uniform over the warp
-                  const float av = rvalid ? __ldcg(a.A + (size_t)j * ld + r) : 0.f;
-                  acc = fmaf(av, vj, acc);
-                  colacc[cc] = fmaf(av, vr, colacc[cc]);
-                }
+                const bool ok = rvalid && j >= ja && j < jb && (!diag || r >= j);
+                const float t = __ldcg(a.A + (ok ? (size_t)j * ld + r : 0));
+                av[cc] = ok ? t : 0.f;
               }
-            } else {        // diagonal block: lower triangle only, the diagonal itself counted once
 #pragma unroll
               for (int cc = 0; cc < 32; ++cc) {
-                const int j = 32 * s + cc;
                 const float vj = __shfl_sync(0xffffffffu, vC, cc);
-                if (j >= ja && j < jb) {
-                  const float av = (rvalid && r >= j) ? __ldcg(a.A + (size_t)j * ld + r) : 0.f;
-                  acc = fmaf(av, vj, acc);
-                  if (r > j) colacc[cc] = fmaf(av, vr, colacc[cc]);
-                }
+                acc = fmaf(av[cc], vj, acc);
+                // strictly-lower entries also feed their column's sum; on the diagonal block lane == cc is the diagonal itself
+                colacc[cc] = fmaf(av[cc], (diag && lane <= cc) ? 0.f : vr, colacc[cc]);
               }
             }
             if (rvalid) ysm[r] += acc;   // one warp per row block inside a strip; strips are separated by barriers
@@ -242,49 +291,72 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
           }
           __syncthreads();
         }
+        SY_TICK(3);
         float* Pb = a.P + (size_t)b * ld;
         for (int r = t0 + tid; r < n; r += kT) __stcg(Pb + r, ysm[r]);
       }
+      SY_TICK(4);
       grid_barrier(a.bar, target);
+      SY_TICK(5);
 
       // ---- phase 3: w = tau (y - V q - Wf p) on the rows this warp owns (stored without alpha v); w'v; v into A(:, i)
-      if (tid < 2 * kNB) {
+      for (int x = warp; x < 2 * kNB; x += kW) {   // one warp per dot product: 148 partials, fixed order
         double s = 0;
-        if ((tid & (kNB - 1)) < c)
-          for (int q = 0; q < P; ++q) s += __ldcg(a.part + (size_t)q * 2 * kNB + tid);
-        if (tid < kNB) s_p[tid] = (float)s; else s_q[tid - kNB] = (float)s;
+        if ((x & (kNB - 1)) < c) s = warp_gather_sum(a.part + x, P, 2 * kNB);
+        if (lane == 0) { if (x < kNB) s_p[x] = (float)s; else s_q[x - kNB] = (float)s; }
       }
       __syncthreads();
       double dot = 0;
-      for (int rb = b + P * warp; rb * 32 < n; rb += P * kW) {
-        const int r = rb * 32 + lane;
-        if (r < t0 || r >= n) continue;
-        float y = __ldcg(a.ycol + r);
+      {
+        // a row block's 148 partial sums are met by four warps (37 loads each); block rb belongs to CTA rb % P, warp group
+        // (rb / P) % 4.  The trip count is the same for every thread of the CTA (barriers inside).
+        const int g = warp >> 2, q4 = warp & 3;
+        const int trips = ((n + 31) / 32 + 4 * P - 1) / (4 * P);
+        for (int m = 0; m < trips; ++m) {
+          const int rb = b + P * (g + 4 * m);
+          const int r = rb * 32 + lane;
+          const bool live = r >= t0 && r < n;
+          float ys = 0.f;
+          if (live) {
 #pragma unroll 8
-        for (int q = 0; q < P; ++q) y += __ldcg(a.P + (size_t)q * ld + r);
-        const float vr_i = r == t0 ? 1.f : __ldcg(coli + r) * scale;
-        float corr = 0.f;
-        for (int cp = 0; cp < c; ++cp) {
-          const float vr = __ldcg(a.A + (size_t)(k0 + cp) * ld + r);
-          const float wr = __ldcg(a.W + (size_t)cp * ld + r) + s_alpha[cp] * vr;
-          corr = fmaf(vr, s_q[cp], corr);
-          corr = fmaf(wr, s_p[cp], corr);
+            for (int q = q4; q < P; q += 4) ys += __ldcg(a.P + (size_t)q * ld + r);
+          }
+          s_y[warp][lane] = ys;
+          __syncthreads();
+          if (live && q4 == 0) {
+            const float y = __ldcg(a.ycol + r) + ((s_y[warp][lane] + s_y[warp + 1][lane]) + (s_y[warp + 2][lane] + s_y[warp + 3][lane]));
+            const float vr_i = r == t0 ? 1.f : __ldcg(coli + r) * scale;
+            float corr = 0.f;
+            {
+              float vr[kNB], wr[kNB];
+              load_panel_row(a, ld, k0, c, r, s_alpha, vr, wr);
+#pragma unroll
+              for (int cp = 0; cp < kNB; ++cp) {
+                if (cp < c) {
+                  corr = fmaf(vr[cp], s_q[cp], corr);
+                  corr = fmaf(wr[cp], s_p[cp], corr);
+                }
+              }
+            }
+            const float w = tau * (y - corr);
+            __stcg(a.W + (size_t)c * ld + r, w);
+            dot += (double)w * (double)vr_i;
+            __stcg(a.A + (size_t)i * ld + r, vr_i);   // the reflector, its leading one stored explicitly while the panel is open
+          }
+          __syncthreads();
         }
-        const float w = tau * (y - corr);
-        __stcg(a.W + (size_t)c * ld + r, w);
-        dot += (double)w * (double)vr_i;
-        __stcg(a.A + (size_t)i * ld + r, vr_i);   // the reflector, its leading one stored explicitly while the panel is open
       }
       dot = cta_sum(dot, s_red);
       if (tid == 0) __stcg(part3 + b, dot);
+      SY_TICK(6);
       grid_barrier(a.bar, target);
+      SY_TICK(7);
     }
     if (k1 >= n) break;
     // ---- panel end: alpha of its last column, then A22 -= V Wf' + Wf V' on the lower triangle of rows / columns >= k1
-    if (tid == 0) {
-      double s = 0;
-      for (int q = 0; q < P; ++q) s += __ldcg(part3 + q);
-      s_alpha[ncols - 1] = (float)(-0.5 * s_scal[0] * s);
+    if (warp == 0) {
+      const double s = warp_gather_sum(part3, P, 1);
+      if (lane == 0) s_alpha[ncols - 1] = (float)(-0.5 * s_scal[0] * s);
     }
     __syncthreads();
     {
@@ -354,8 +426,12 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
         asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(256) : "memory");
       }
     }
+    SY_TICK(8);
     grid_barrier(a.bar, target);
+    SY_TICK(9);
   }
+  if (tid == 0 && a.prof)
+    for (int q = 0; q < 10; ++q) a.prof[(size_t)b * 16 + q] = tacc[q];
 }
 
 // the sub-diagonal of T goes back where ssytrd leaves it (the reflectors' leading ones were stored there while their panel was open)
@@ -390,12 +466,29 @@ bool sytrd_lower(float* dA, int n, float* d_d, float* d_e, float* d_tau, cudaStr
   SCL_CUDA(cudaMemsetAsync(part.p, 0, (size_t)grid * (2 * kNB + 2) * sizeof(double), st));
   SCL_CUDA(cudaMemsetAsync(d_tau, 0, (size_t)n * sizeof(float), st));
   SCL_CUDA(cudaMemsetAsync(d_e, 0, (size_t)n * sizeof(float), st));
-  SyArgs args{dA, n, W.p, d_d, d_e, d_tau, P.p, ycol.p, part.p, scal.p, bar.p};
+  static const bool trace = getenv("SCL_TRACE") != nullptr;
+  Tmp<unsigned long long> prof(trace ? (size_t)grid * 16 : 1, st);
+  SyArgs args{dA, n, W.p, d_d, d_e, d_tau, P.p, ycol.p, part.p, scal.p, bar.p, trace ? prof.p : nullptr};
   void* params[] = {&args};
   count_launches(2);
   SCL_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd, dim3(grid), dim3(kT), params, smem, st));
   k_restore_subdiagonal<<<(n + 255) / 256, 256, 0, st>>>(dA, n, d_e);
   SCL_CUDA(cudaGetLastError());
+  if (trace) {
+    std::vector<unsigned long long> hp((size_t)grid * 16);
+    SCL_CUDA(cudaMemcpyAsync(hp.data(), prof.p, hp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+    static const char* name[10] = {"phase1 (column update)", "barrier 1", "phase2 scalars + panel dots", "symv strips", "row partials out",
+                                   "barrier 2", "phase3 (w)", "barrier 3", "rank-2k update", "barrier 4"};
+    for (int q = 0; q < 10; ++q) {
+      double mn = 1e30, mx = 0, av = 0;
+      for (int g = 0; g < grid; ++g) {
+        const double v = (double)hp[(size_t)g * 16 + q] * 1e-6;
+        mn = std::min(mn, v); mx = std::max(mx, v); av += v / grid;
+      }
+      fprintf(stderr, "[scl] sytrd n=%d %-28s ms per CTA: min %9.2f  mean %9.2f  max %9.2f\n", n, name[q], mn, av, mx);
+    }
+  }
   return true;
 }
 
