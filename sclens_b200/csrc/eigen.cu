@@ -22,7 +22,7 @@ struct Solver::Impl {
   cusolverDnHandle_t h = nullptr;
   cusolverDnParams_t params = nullptr;   // 64-bit API (SCL_EIG_API=1)
   DBuf<float> work;
-  DBuf<float> tri_d, tri_e, tri_tau, tri_z, tri_keep;   // own tridiagonal stage: T, reflector scalars, vectors, matrix copy
+  DBuf<float> tri_d, tri_e, tri_tau, tri_z, tri_keep, tri_pad;   // own tridiagonal stage: T, reflector scalars, vectors, matrix copy, padded copy
   DBuf<double> tri_w;
   DBuf<double> dwork;
   DBuf<int> info;
@@ -67,16 +67,29 @@ bool Solver::syevd_tri(float* dA, int n, float* dW, int v0, int v1, cudaStream_t
   impl->tri_keep.ensure(nn);
   if (m) impl->tri_z.ensure((size_t)m * n);
   SCL_CUDA(cudaMemcpyAsync(impl->tri_keep.p, dA, nn * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // the own tridiagonalisation reads 16-byte groups of rows: a matrix whose order is not a multiple of 4 is reduced in a copy
+  // with a padded leading dimension (the reflectors stay there for Sormtr)
+  const bool want_own = (eig_api() & 16) != 0;
+  float* Aq = dA;
+  int lda = n;
+  if (want_own && (n & 3)) {
+    lda = (n + 3) & ~3;
+    impl->tri_pad.ensure((size_t)lda * n);
+    SCL_CUDA(cudaMemsetAsync(impl->tri_pad.p, 0, (size_t)lda * n * sizeof(float), st));
+    SCL_CUDA(cudaMemcpy2DAsync(impl->tri_pad.p, (size_t)lda * sizeof(float), dA, (size_t)n * sizeof(float), (size_t)n * sizeof(float),
+                               (size_t)n, cudaMemcpyDeviceToDevice, st));
+    Aq = impl->tri_pad.p;
+  }
   int lw1 = 0, lw2 = 0;
-  SCL_SOLVER(cusolverDnSsytrd_bufferSize(impl->h, CUBLAS_FILL_MODE_LOWER, n, dA, n, impl->tri_d.p, impl->tri_e.p, impl->tri_tau.p, &lw1));
+  SCL_SOLVER(cusolverDnSsytrd_bufferSize(impl->h, CUBLAS_FILL_MODE_LOWER, n, Aq, lda, impl->tri_d.p, impl->tri_e.p, impl->tri_tau.p, &lw1));
   if (m)
-    SCL_SOLVER(cusolverDnSormtr_bufferSize(impl->h, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, m, dA, n,
+    SCL_SOLVER(cusolverDnSormtr_bufferSize(impl->h, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, m, Aq, lda,
                                            impl->tri_tau.p, impl->tri_z.p, n, &lw2));
   impl->work.ensure((size_t)std::max(lw1, lw2) + 1);
   SCL_CUDA(cudaEventRecord(ev[0], st));
-  tri_own_sytrd = (eig_api() & 16) && sytrd_lower(dA, n, impl->tri_d.p, impl->tri_e.p, impl->tri_tau.p, st);
+  tri_own_sytrd = want_own && sytrd_lower(Aq, n, lda, impl->tri_d.p, impl->tri_e.p, impl->tri_tau.p, st);
   if (!tri_own_sytrd)
-    SCL_SOLVER(cusolverDnSsytrd(impl->h, CUBLAS_FILL_MODE_LOWER, n, dA, n, impl->tri_d.p, impl->tri_e.p, impl->tri_tau.p,
+    SCL_SOLVER(cusolverDnSsytrd(impl->h, CUBLAS_FILL_MODE_LOWER, n, Aq, lda, impl->tri_d.p, impl->tri_e.p, impl->tri_tau.p,
                                 impl->work.p, lw1, impl->info.p));
   else
     SCL_CUDA(cudaMemsetAsync(impl->info.p, 0, sizeof(int), st));
@@ -88,7 +101,7 @@ bool Solver::syevd_tri(float* dA, int n, float* dW, int v0, int v1, cudaStream_t
   tri_clustered = ts.clustered;
   int info = 0;
   if (ok && m) {
-    SCL_SOLVER(cusolverDnSormtr(impl->h, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, m, dA, n, impl->tri_tau.p,
+    SCL_SOLVER(cusolverDnSormtr(impl->h, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, m, Aq, lda, impl->tri_tau.p,
                                 impl->tri_z.p, n, impl->work.p, lw2, impl->info.p));
     SCL_CUDA(cudaMemcpyAsync(dA + (size_t)v0 * n, impl->tri_z.p, (size_t)m * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
@@ -202,7 +215,7 @@ double Solver::bench(float* dA, int n, float* dW, int mode, int il, int iu, cuda
     // own tridiagonalisation (sytrd.cu) alone
     Tmp<float> d(n, st), e(n, st), tau(n, st);
     SCL_CUDA(cudaEventRecord(e0, st));
-    if (!sytrd_lower(dA, n, d.p, e.p, tau.p, st)) throw Error(-1, "sytrd_lower does not handle this size");
+    if (!sytrd_lower(dA, n, n, d.p, e.p, tau.p, st)) throw Error(-1, "sytrd_lower does not handle this size (order must be a multiple of 4 here)");
     SCL_CUDA(cudaMemsetAsync(impl->info.p, 0, sizeof(int), st));
   } else if (mode >= 6 && mode <= 8) {
     // own tridiagonal stage: 6 = all vectors, 7 = vectors il..iu (1-based inclusive), 8 = values only

@@ -41,7 +41,7 @@ bool tridiag_eigen(const float* d32, const float* e32, int n, double* w64, float
 // stage (Ssytrd + tridiag.cu + Sormtr) for every solve, bit 3 = with bit 2: vectors of the index range the search step uses only, bit 4 = with bit 2: own tridiagonalisation
 // (sytrd.cu) instead of cusolverDnSsytrd
 // sytrd.cu: own Householder tridiagonalisation (persistent cooperative kernel), output as ssytrd('L'); false = not handled
-bool sytrd_lower(float* dA, int n, float* d_d, float* d_e, float* d_tau, cudaStream_t st);
+bool sytrd_lower(float* dA, int n, int lda, float* d_d, float* d_e, float* d_tau, cudaStream_t st);
 int eig_api();
 void set_eig_api(int v);   // process-wide override of SCL_EIG_API (tests, timing studies); < 0: back to the environment / default
 

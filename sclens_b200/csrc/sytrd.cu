@@ -26,16 +26,17 @@ namespace scl {
 namespace {
 
 constexpr int kNB = 32;        // panel width = strip width of the matrix-vector product
-constexpr int kT = 512;        // threads per CTA (one CTA per SM)
+constexpr int kT = 256;        // threads per CTA (one CTA per SM; 255 registers per thread for the 128 x 32 tiles held in flight)
 constexpr int kW = kT / 32;
-constexpr int kTile = 128;     // rank-2k update tile (one half CTA per tile)
+constexpr int kTile = 128;     // rank-2k update tile (8 x 8 outputs per thread)
+constexpr int kG = kW / 4;     // phase 3: four warps share the 148 partial sums of a row block
 
 struct SyArgs {
-  float* A;          // n x n, column-major lower triangle in, reflectors + tridiagonal out
-  int n;
-  float* W;          // n x kNB, column-major: the panel's W without its alpha_c v_c terms
+  float* A;          // n x n, column-major with leading dimension ld (a multiple of 4): lower triangle in, reflectors out
+  int n, ld;
+  float* W;          // ld x kNB, column-major: the panel's W without its alpha_c v_c terms
   float *d, *e, *tau;
-  float* P;          // [grid][n] row partials of the matrix-vector product
+  float* P;          // [grid][ld] row partials of the matrix-vector product
   float* ycol;       // n: column parts of the matrix-vector product
   double* part;      // [grid][2 kNB + 2]: panel dot products, norm / w'v partials
   float* scal;       // [0] = A(i+1, i) after the column update
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
   __shared__ double s_scal[3];   // tau, scale, -
   float* ysm = smem;
   const int n = a.n, P = (int)gridDim.x, b = (int)blockIdx.x, tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const size_t ld = (size_t)n;
+  const size_t ld = (size_t)a.ld;
   unsigned target = gridDim.x;
   unsigned long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = now_ns();
   double* part1 = a.part + (size_t)P * 2 * kNB;   // [P] squared norms
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
           if (b == 0) { a.e[i] = (float)beta; a.tau[i] = (float)tau; }
         }
       }
-      for (int r = t0 + tid; r < n; r += kT) ysm[r] = 0.f;
+      for (int r = (t0 & ~3) + tid; r < n; r += kT) ysm[r] = 0.f;
       __syncthreads();
       const float tau = (float)s_scal[0], scale = (float)s_scal[1];
       const float* coli = a.A + (size_t)i * ld;
@@ -248,32 +249,60 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
           float colacc[32];
 #pragma unroll
           for (int cc = 0; cc < 32; ++cc) colacc[cc] = 0.f;
-          for (int rb = s + warp; rb * 32 < n; rb += kW) {
-            const int r = rb * 32 + lane;
-            const bool rvalid = r < n && r >= t0;
-            const float vr = rvalid ? (r == t0 ? 1.f : __ldcg(coli + r) * scale) : 0.f;
-            float acc = 0.f;
-            {
-              // all 32 column loads of the row block leave before the first FMA: invalid positions (columns outside the
-              // strip, rows above the diagonal or outside the matrix) read a safe address and are masked afterwards
-              float av[32];
-              const bool diag = rb == s;
+          // a warp walks 128-row blocks down the strip, four consecutive rows per lane (one 16-byte load per column)
+          const bool full_cols = 32 * s + 32 <= n;
+          for (int R = (32 * s) / 128 + warp; R * 128 < n; R += kW) {
+            const int r = R * 128 + 4 * lane;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (full_cols && R * 128 >= 32 * s + 32 && R * 128 + 128 <= n) {
+              // below the strip's diagonal block, inside the matrix: 32 unconditional 16-byte loads in flight, then the FMAs.
+              // Columns left of t0 (first strip only) hold finished reflectors: finite values times v = 0.
+              const float* p = a.A + (size_t)(32 * s) * ld + r;
+              float4 av[32];
 #pragma unroll
-              for (int cc = 0; cc < 32; ++cc) {
-                const int j = 32 * s + cc;
-                const bool ok = rvalid && j >= ja && j < jb && (!diag || r >= j);
-                const float t = __ldcg(a.A + (ok ? (size_t)j * ld + r : 0));
-                av[cc] = ok ? t : 0.f;
-              }
+              for (int cc = 0; cc < 32; ++cc) av[cc] = __ldcg(reinterpret_cast<const float4*>(p + (size_t)cc * ld));
+              float4 vr = __ldcg(reinterpret_cast<const float4*>(coli + r));
+              vr.x *= scale; vr.y *= scale; vr.z *= scale; vr.w *= scale;
 #pragma unroll
               for (int cc = 0; cc < 32; ++cc) {
                 const float vj = __shfl_sync(0xffffffffu, vC, cc);
-                acc = fmaf(av[cc], vj, acc);
-                // strictly-lower entries also feed their column's sum; on the diagonal block lane == cc is the diagonal itself
-                colacc[cc] = fmaf(av[cc], (diag && lane <= cc) ? 0.f : vr, colacc[cc]);
+                acc[0] = fmaf(av[cc].x, vj, acc[0]);
+                acc[1] = fmaf(av[cc].y, vj, acc[1]);
+                acc[2] = fmaf(av[cc].z, vj, acc[2]);
+                acc[3] = fmaf(av[cc].w, vj, acc[3]);
+                colacc[cc] = fmaf(av[cc].x, vr.x, fmaf(av[cc].y, vr.y, fmaf(av[cc].z, vr.z, fmaf(av[cc].w, vr.w, colacc[cc]))));
+              }
+              float4* yp = reinterpret_cast<float4*>(ysm + r);   // one warp per row block inside a strip; strips are
+              float4 y4 = *yp;                                    // separated by barriers
+              y4.x += acc[0]; y4.y += acc[1]; y4.z += acc[2]; y4.w += acc[3];
+              *yp = y4;
+            } else {
+              // the block holding the strip's diagonal, the matrix edge, a partial last strip: every position is masked
+              // (outside the strip, above the diagonal, outside the matrix) and read from a safe address instead
+#pragma unroll 1
+              for (int q = 0; q < 4; ++q) {
+                const int rr = r + q;
+                const bool rvalid = rr < n && rr >= t0;
+                const float vr = rvalid ? (rr == t0 ? 1.f : __ldcg(coli + rr) * scale) : 0.f;
+                float av[32];
+#pragma unroll
+                for (int cc = 0; cc < 32; ++cc) {
+                  const int j = 32 * s + cc;
+                  const bool ok = rvalid && j >= ja && j < jb && rr >= j;
+                  const float t = __ldcg(a.A + (ok ? (size_t)j * ld + rr : 0));
+                  av[cc] = ok ? t : 0.f;
+                }
+                float ac = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < 32; ++cc) {
+                  const float vj = __shfl_sync(0xffffffffu, vC, cc);
+                  ac = fmaf(av[cc], vj, ac);
+                  // strictly-lower entries also feed their column's sum; the diagonal entry itself is counted once, above
+                  colacc[cc] = fmaf(av[cc], rr > 32 * s + cc ? vr : 0.f, colacc[cc]);
+                }
+                if (rvalid) ysm[rr] += ac;
               }
             }
-            if (rvalid) ysm[r] += acc;   // one warp per row block inside a strip; strips are separated by barriers
           }
           float mine = 0.f;
 #pragma unroll
@@ -309,11 +338,11 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
       double dot = 0;
       {
         // a row block's 148 partial sums are met by four warps (37 loads each); block rb belongs to CTA rb % P, warp group
-        // (rb / P) % 4.  The trip count is the same for every thread of the CTA (barriers inside).
+        // (rb / P) % kG.  The trip count is the same for every thread of the CTA (barriers inside).
         const int g = warp >> 2, q4 = warp & 3;
-        const int trips = ((n + 31) / 32 + 4 * P - 1) / (4 * P);
+        const int trips = ((n + 31) / 32 + kG * P - 1) / (kG * P);
         for (int m = 0; m < trips; ++m) {
-          const int rb = b + P * (g + 4 * m);
+          const int rb = b + P * (g + kG * m);
           const int r = rb * 32 + lane;
           const bool live = r >= t0 && r < n;
           float ys = 0.f;
@@ -360,36 +389,43 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
     }
     __syncthreads();
     {
-      const int half = tid >> 8, u = tid & 255;
-      float* Vr = smem + (size_t)half * 4 * kNB * kTile;   // [kNB][kTile] each
+      const int u = tid;
+      float* Vr = smem;                      // [kNB][kTile] each
       float* Wr = Vr + kNB * kTile;
       float* Vc = Wr + kNB * kTile;
       float* Wc = Vc + kNB * kTile;
       const int m = n - k1, Tn = (m + kTile - 1) / kTile, n_tiles = Tn * (Tn + 1) / 2;
       const int rx = (u & 15) * 8, cy = (u >> 4) * 8;
-      for (int t = 2 * b + half; t < n_tiles; t += 2 * P) {
+      for (int t = b; t < n_tiles; t += P) {
         // tile index -> (tr, tc), tc <= tr
         int tr = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
         while (tr * (tr + 1) / 2 > t) --tr;
         while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
         const int tc = t - tr * (tr + 1) / 2;
         const int r0 = k1 + tr * kTile, c0 = k1 + tc * kTile;
-        for (int x = u; x < kNB * kTile; x += 256) {
-          const int k = x / kTile, o = x % kTile;
-          float vr = 0.f, wr = 0.f, vc = 0.f, wc = 0.f;
+        // k1 is a multiple of 32 and ld of 4: 16-byte loads; rows beyond n inside the last group of four are padding
+        for (int x = u; x < kNB * kTile / 4; x += kT) {
+          const int k = x / (kTile / 4), o = (x % (kTile / 4)) * 4;
+          float4 vr = make_float4(0.f, 0.f, 0.f, 0.f), wr = vr, vc = vr, wc = vr;
           if (k < ncols) {
+            const float al = s_alpha[k];
             if (r0 + o < n) {
-              vr = __ldcg(a.A + (size_t)(k0 + k) * ld + r0 + o);
-              wr = __ldcg(a.W + (size_t)k * ld + r0 + o) + s_alpha[k] * vr;
+              vr = __ldcg(reinterpret_cast<const float4*>(a.A + (size_t)(k0 + k) * ld + r0 + o));
+              wr = __ldcg(reinterpret_cast<const float4*>(a.W + (size_t)k * ld + r0 + o));
+              wr.x = fmaf(al, vr.x, wr.x); wr.y = fmaf(al, vr.y, wr.y); wr.z = fmaf(al, vr.z, wr.z); wr.w = fmaf(al, vr.w, wr.w);
             }
             if (c0 + o < n) {
-              vc = __ldcg(a.A + (size_t)(k0 + k) * ld + c0 + o);
-              wc = __ldcg(a.W + (size_t)k * ld + c0 + o) + s_alpha[k] * vc;
+              vc = __ldcg(reinterpret_cast<const float4*>(a.A + (size_t)(k0 + k) * ld + c0 + o));
+              wc = __ldcg(reinterpret_cast<const float4*>(a.W + (size_t)k * ld + c0 + o));
+              wc.x = fmaf(al, vc.x, wc.x); wc.y = fmaf(al, vc.y, wc.y); wc.z = fmaf(al, vc.z, wc.z); wc.w = fmaf(al, vc.w, wc.w);
             }
           }
-          Vr[x] = vr; Wr[x] = wr; Vc[x] = vc; Wc[x] = wc;
+          *reinterpret_cast<float4*>(Vr + k * kTile + o) = vr;
+          *reinterpret_cast<float4*>(Wr + k * kTile + o) = wr;
+          *reinterpret_cast<float4*>(Vc + k * kTile + o) = vc;
+          *reinterpret_cast<float4*>(Wc + k * kTile + o) = wc;
         }
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(256) : "memory");
+        __syncthreads();
         float acc[8][8];
 #pragma unroll
         for (int x = 0; x < 8; ++x)
@@ -410,20 +446,28 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
 #pragma unroll
             for (int y = 0; y < 8; ++y) acc[x][y] = fmaf(vr[x], wc[y], fmaf(wr[x], vc[y], acc[x][y]));
         }
+        // write-back: 8 consecutive rows per column as two 16-byte read-modify-writes when they are all below the diagonal
 #pragma unroll
         for (int y = 0; y < 8; ++y) {
           const int cc = c0 + cy + y;
           if (cc >= n) continue;
+          const int rr = r0 + rx;
+          float* p = a.A + (size_t)cc * ld + rr;
+          if (rr >= cc && rr + 8 <= n) {
+            float4 lo4 = __ldcg(reinterpret_cast<const float4*>(p)), hi4 = __ldcg(reinterpret_cast<const float4*>(p + 4));
+            lo4.x -= acc[0][y]; lo4.y -= acc[1][y]; lo4.z -= acc[2][y]; lo4.w -= acc[3][y];
+            hi4.x -= acc[4][y]; hi4.y -= acc[5][y]; hi4.z -= acc[6][y]; hi4.w -= acc[7][y];
+            __stcg(reinterpret_cast<float4*>(p), lo4);
+            __stcg(reinterpret_cast<float4*>(p + 4), hi4);
+          } else {
 #pragma unroll
-          for (int x = 0; x < 8; ++x) {
-            const int r = r0 + rx + x;
-            if (r < n && r >= cc) {
-              float* p = a.A + (size_t)cc * ld + r;
-              __stcg(p, __ldcg(p) - acc[x][y]);
+            for (int x = 0; x < 8; ++x) {
+              const int r = rr + x;
+              if (r < n && r >= cc) __stcg(p + x, __ldcg(p + x) - acc[x][y]);
             }
           }
         }
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(256) : "memory");
+        __syncthreads();
       }
     }
     SY_TICK(8);
@@ -435,31 +479,31 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
 }
 
 // the sub-diagonal of T goes back where ssytrd leaves it (the reflectors' leading ones were stored there while their panel was open)
-__global__ void k_restore_subdiagonal(float* __restrict__ A, int n, const float* __restrict__ e) {
+__global__ void k_restore_subdiagonal(float* __restrict__ A, int n, int ld, const float* __restrict__ e) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n - 1) A[(size_t)i * n + i + 1] = e[i];
+  if (i < n - 1) A[(size_t)i * ld + i + 1] = e[i];
 }
 
 }  // namespace
 
-// A: symmetric n x n (the lower triangle, column-major, is read); on return as after ssytrd('L'): d (n), e (n - 1),
-// tau (n - 1), reflectors below the sub-diagonal.  Returns false when the matrix is outside what the kernel handles (the
-// caller uses the library's Ssytrd then).
-bool sytrd_lower(float* dA, int n, float* d_d, float* d_e, float* d_tau, cudaStream_t st) {
-  if (n < 256 || n > 48000) return false;
+// A: symmetric n x n, column-major with leading dimension lda (a multiple of 4, 16-byte aligned base; the lower triangle is
+// read); on return as after ssytrd('L'): d (n), e (n - 1), tau (n - 1), reflectors below the sub-diagonal.  Returns false
+// when the matrix is outside what the kernel handles (the caller uses the library's Ssytrd then).
+bool sytrd_lower(float* dA, int n, int lda, float* d_d, float* d_e, float* d_tau, cudaStream_t st) {
+  if (n < 256 || n > 48000 || lda < n || (lda & 3) || ((uintptr_t)dA & 15)) return false;
   int dev = 0, sms = 0, coop = 0;
   SCL_CUDA(cudaGetDevice(&dev));
   SCL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   SCL_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   if (!coop) return false;
-  const size_t smem = std::max((size_t)n * sizeof(float), (size_t)2 * 4 * kNB * kTile * sizeof(float));
+  const size_t smem = std::max((size_t)lda * sizeof(float), (size_t)4 * kNB * kTile * sizeof(float));
   if (smem > 200 * 1024) return false;
   SCL_CUDA(cudaFuncSetAttribute(k_sytrd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   SCL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sytrd, kT, smem));
   if (per_sm < 1) return false;
   const int grid = sms;
-  Tmp<float> W((size_t)n * kNB, st), P((size_t)grid * n, st), ycol(n, st), scal(4, st);
+  Tmp<float> W((size_t)lda * kNB, st), P((size_t)grid * lda, st), ycol(n, st), scal(4, st);
   Tmp<double> part((size_t)grid * (2 * kNB + 2), st);
   Tmp<unsigned> bar(1, st);
   SCL_CUDA(cudaMemsetAsync(bar.p, 0, sizeof(unsigned), st));
@@ -468,11 +512,11 @@ bool sytrd_lower(float* dA, int n, float* d_d, float* d_e, float* d_tau, cudaStr
   SCL_CUDA(cudaMemsetAsync(d_e, 0, (size_t)n * sizeof(float), st));
   static const bool trace = getenv("SCL_TRACE") != nullptr;
   Tmp<unsigned long long> prof(trace ? (size_t)grid * 16 : 1, st);
-  SyArgs args{dA, n, W.p, d_d, d_e, d_tau, P.p, ycol.p, part.p, scal.p, bar.p, trace ? prof.p : nullptr};
+  SyArgs args{dA, n, lda, W.p, d_d, d_e, d_tau, P.p, ycol.p, part.p, scal.p, bar.p, trace ? prof.p : nullptr};
   void* params[] = {&args};
   count_launches(2);
   SCL_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd, dim3(grid), dim3(kT), params, smem, st));
-  k_restore_subdiagonal<<<(n + 255) / 256, 256, 0, st>>>(dA, n, d_e);
+  k_restore_subdiagonal<<<(n + 255) / 256, 256, 0, st>>>(dA, n, lda, d_e);
   SCL_CUDA(cudaGetLastError());
   if (trace) {
     std::vector<unsigned long long> hp((size_t)grid * 16);
