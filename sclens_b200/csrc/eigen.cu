@@ -36,11 +36,12 @@ struct Solver::Impl {
 // an index range instead of a full solve (474 ms in the same first look); also opt-in until parity-tested.
 static std::atomic<int> g_eig_api_override{-1};
 int eig_api() {
-  // default 12: the own tridiagonal stage for every solve (bit 2) with index-range vectors in the search steps (bit 3);
-  // measured at n = 20 000 on the 68k x 20k data Gram matrix (profiles/r2_eig_study2.json): 2.85 s against 3.65 s for
-  // Ssyevd with all vectors, 2.70 s for the smallest half, 2.47 s against 3.20 s for values only.  SCL_EIG_API=0 is
-  // the plain library solve (the call the reference makes).
-  static const int v = [] { const char* e = getenv("SCL_EIG_API"); return e ? atoi(e) : 12; }();
+  // default 28: the own tridiagonal stage for every solve (bit 2) with index-range vectors in the search steps (bit 3) on
+  // the own tridiagonalisation (bit 4).  Measured at n = 20 000 (profiles/r2_eig_study2.json, r2_eig_study3_20000.json):
+  // Ssyevd with all vectors 3.65 s on the 68k x 20k data Gram matrix (2.69 s on a synthetic Wishart matrix); Ssytrd + own
+  // stage + Sormtr 2.85 s; own sytrd (1.98 s against 2.13 s for Ssytrd) + own stage + Sormtr 2.42 s, 2.25 s for the
+  // smallest half, 2.03 s for values only.  SCL_EIG_API=0 is the plain library solve (the call the reference makes).
+  static const int v = [] { const char* e = getenv("SCL_EIG_API"); return e ? atoi(e) : 28; }();
   const int o = g_eig_api_override.load(std::memory_order_relaxed);
   return o >= 0 ? o : v;
 }

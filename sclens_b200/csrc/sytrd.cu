@@ -29,7 +29,6 @@ constexpr int kNB = 32;        // panel width = strip width of the matrix-vector
 constexpr int kT = 256;        // threads per CTA (one CTA per SM; 255 registers per thread for the 128 x 32 tiles held in flight)
 constexpr int kW = kT / 32;
 constexpr int kTile = 128;     // rank-2k update tile (8 x 8 outputs per thread)
-constexpr int kG = kW / 4;     // phase 3: four warps share the 148 partial sums of a row block
 
 struct SyArgs {
   float* A;          // n x n, column-major with leading dimension ld (a multiple of 4): lower triangle in, reflectors out
@@ -119,7 +118,7 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
   __shared__ double s_red[kW];
   __shared__ float s_rowV[kNB], s_rowW[kNB], s_p[kNB], s_q[kNB], s_alpha[kNB];
   __shared__ float s_col[kW][32];
-  __shared__ float s_y[kW][32];
+  __shared__ double s_dd[kT / (2 * kNB)][2 * kNB];
   __shared__ float s_pq[kW][2 * kNB];
   __shared__ double s_scal[3];   // tau, scale, -
   float* ysm = smem;
@@ -220,11 +219,15 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
             }
           }
         }
-        (void)any;
+        if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
-        for (int cp = 0; cp < kNB; ++cp) {
-          const float ps = warp_sum_f(pacc[cp]), qs = warp_sum_f(qacc[cp]);
-          if (lane == 0) { s_pq[warp][cp] = ps; s_pq[warp][kNB + cp] = qs; }
+          for (int cp = 0; cp < kNB; ++cp) {
+            const float ps = warp_sum_f(pacc[cp]), qs = warp_sum_f(qacc[cp]);
+            if (lane == 0) { s_pq[warp][cp] = ps; s_pq[warp][kNB + cp] = qs; }
+          }
+        } else {
+          s_pq[warp][lane] = 0.f;
+          s_pq[warp][32 + lane] = 0.f;
         }
         __syncthreads();
         if (tid < 2 * kNB) {
@@ -249,14 +252,38 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
           float colacc[32];
 #pragma unroll
           for (int cc = 0; cc < 32; ++cc) colacc[cc] = 0.f;
-          // a warp walks 128-row blocks down the strip, four consecutive rows per lane (one 16-byte load per column)
+          // the strip's 32 x 32 diagonal block (lower triangle, one row per lane) goes to the last warp; below it the warps
+          // walk 128-row blocks aligned to the strip, four consecutive rows per lane: one 16-byte load per column
           const bool full_cols = 32 * s + 32 <= n;
-          for (int R = (32 * s) / 128 + warp; R * 128 < n; R += kW) {
-            const int r = R * 128 + 4 * lane;
+          if (warp == kW - 1) {
+            const int rr = 32 * s + lane;
+            const bool rvalid = rr < n && rr >= t0;
+            const float vr = rvalid ? (rr == t0 ? 1.f : __ldcg(coli + rr) * scale) : 0.f;
+            float av[32];
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) {
+              const int j = 32 * s + cc;
+              const bool ok = rvalid && j >= ja && j < jb && rr >= j;
+              const float t = __ldcg(a.A + (ok ? (size_t)j * ld + rr : 0));
+              av[cc] = ok ? t : 0.f;
+            }
+            float ac = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) {
+              const float vj = __shfl_sync(0xffffffffu, vC, cc);
+              ac = fmaf(av[cc], vj, ac);
+              // strictly-lower entries also feed their column's sum; the diagonal entry itself is counted once, above
+              colacc[cc] = fmaf(av[cc], lane > cc ? vr : 0.f, colacc[cc]);
+            }
+            if (rvalid) ysm[rr] += ac;
+          }
+          const int rbase = 32 * s + 32;
+          for (int R = warp; rbase + R * 128 < n; R += kW) {
+            const int r = rbase + R * 128 + 4 * lane;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            if (full_cols && R * 128 >= 32 * s + 32 && R * 128 + 128 <= n) {
-              // below the strip's diagonal block, inside the matrix: 32 unconditional 16-byte loads in flight, then the FMAs.
-              // Columns left of t0 (first strip only) hold finished reflectors: finite values times v = 0.
+            if (full_cols && rbase + R * 128 + 128 <= n) {
+              // inside the matrix: 32 unconditional 16-byte loads in flight, then the FMAs.  Columns left of t0 (first
+              // strip only) hold finished reflectors: finite values times v = 0.
               const float* p = a.A + (size_t)(32 * s) * ld + r;
               float4 av[32];
 #pragma unroll
@@ -277,18 +304,17 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
               y4.x += acc[0]; y4.y += acc[1]; y4.z += acc[2]; y4.w += acc[3];
               *yp = y4;
             } else {
-              // the block holding the strip's diagonal, the matrix edge, a partial last strip: every position is masked
-              // (outside the strip, above the diagonal, outside the matrix) and read from a safe address instead
+              // the matrix edge (last rows, a partial last strip): every position is masked and read from a safe address
 #pragma unroll 1
               for (int q = 0; q < 4; ++q) {
                 const int rr = r + q;
-                const bool rvalid = rr < n && rr >= t0;
-                const float vr = rvalid ? (rr == t0 ? 1.f : __ldcg(coli + rr) * scale) : 0.f;
+                const bool rvalid = rr < n;
+                const float vr = rvalid ? __ldcg(coli + rr) * scale : 0.f;
                 float av[32];
 #pragma unroll
                 for (int cc = 0; cc < 32; ++cc) {
                   const int j = 32 * s + cc;
-                  const bool ok = rvalid && j >= ja && j < jb && rr >= j;
+                  const bool ok = rvalid && j >= ja && j < jb;
                   const float t = __ldcg(a.A + (ok ? (size_t)j * ld + rr : 0));
                   av[cc] = ok ? t : 0.f;
                 }
@@ -297,8 +323,7 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
                 for (int cc = 0; cc < 32; ++cc) {
                   const float vj = __shfl_sync(0xffffffffu, vC, cc);
                   ac = fmaf(av[cc], vj, ac);
-                  // strictly-lower entries also feed their column's sum; the diagonal entry itself is counted once, above
-                  colacc[cc] = fmaf(av[cc], rr > 32 * s + cc ? vr : 0.f, colacc[cc]);
+                  colacc[cc] = fmaf(av[cc], vr, colacc[cc]);
                 }
                 if (rvalid) ysm[rr] += ac;
               }
@@ -329,51 +354,57 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
       SY_TICK(5);
 
       // ---- phase 3: w = tau (y - V q - Wf p) on the rows this warp owns (stored without alpha v); w'v; v into A(:, i)
-      for (int x = warp; x < 2 * kNB; x += kW) {   // one warp per dot product: 148 partials, fixed order
-        double s = 0;
-        if ((x & (kNB - 1)) < c) s = warp_gather_sum(a.part + x, P, 2 * kNB);
-        if (lane == 0) { if (x < kNB) s_p[x] = (float)s; else s_q[x - kNB] = (float)s; }
+      {
+        // 64 dot products x 148 partials: thread (x, quarter) sums every fourth partial of dot product x (independent loads),
+        // the four quarters meet in shared memory - fixed order
+        const int x = tid & (2 * kNB - 1), ch = tid >> 6;
+        double sx = 0;
+        if ((x & (kNB - 1)) < c)
+#pragma unroll 8
+          for (int q = ch; q < P; q += kT / (2 * kNB)) sx += __ldcg(a.part + (size_t)q * 2 * kNB + x);
+        s_dd[ch][x] = sx;
+        __syncthreads();
+        if (tid < 2 * kNB) {
+          double t = 0;
+          for (int q = 0; q < kT / (2 * kNB); ++q) t += s_dd[q][tid];
+          if (tid < kNB) s_p[tid] = (float)t; else s_q[tid - kNB] = (float)t;
+        }
       }
       __syncthreads();
       double dot = 0;
-      {
-        // a row block's 148 partial sums are met by four warps (37 loads each); block rb belongs to CTA rb % P, warp group
-        // (rb / P) % kG.  The trip count is the same for every thread of the CTA (barriers inside).
-        const int g = warp >> 2, q4 = warp & 3;
-        const int trips = ((n + 31) / 32 + kG * P - 1) / (kG * P);
-        for (int m = 0; m < trips; ++m) {
-          const int rb = b + P * (g + kG * m);
-          const int r = rb * 32 + lane;
-          const bool live = r >= t0 && r < n;
-          float ys = 0.f;
-          if (live) {
+      for (int rb = b + P * warp; rb * 32 < n; rb += P * kW) {   // row block rb belongs to CTA rb % P, warp (rb / P) % kW
+        const int r = rb * 32 + lane;
+        if (r < t0 || r >= n) continue;
+        // the row's partial sums of all CTAs: four independent chains, 32 loads in flight
+        float y0 = __ldcg(a.ycol + r), y1 = 0.f, y2 = 0.f, y3 = 0.f;
+        const float* pp = a.P + r;
+        int q = 0;
 #pragma unroll 8
-            for (int q = q4; q < P; q += 4) ys += __ldcg(a.P + (size_t)q * ld + r);
-          }
-          s_y[warp][lane] = ys;
-          __syncthreads();
-          if (live && q4 == 0) {
-            const float y = __ldcg(a.ycol + r) + ((s_y[warp][lane] + s_y[warp + 1][lane]) + (s_y[warp + 2][lane] + s_y[warp + 3][lane]));
-            const float vr_i = r == t0 ? 1.f : __ldcg(coli + r) * scale;
-            float corr = 0.f;
-            {
-              float vr[kNB], wr[kNB];
-              load_panel_row(a, ld, k0, c, r, s_alpha, vr, wr);
-#pragma unroll
-              for (int cp = 0; cp < kNB; ++cp) {
-                if (cp < c) {
-                  corr = fmaf(vr[cp], s_q[cp], corr);
-                  corr = fmaf(wr[cp], s_p[cp], corr);
-                }
-              }
-            }
-            const float w = tau * (y - corr);
-            __stcg(a.W + (size_t)c * ld + r, w);
-            dot += (double)w * (double)vr_i;
-            __stcg(a.A + (size_t)i * ld + r, vr_i);   // the reflector, its leading one stored explicitly while the panel is open
-          }
-          __syncthreads();
+        for (; q + 4 <= P; q += 4) {
+          y0 += __ldcg(pp + (size_t)q * ld);
+          y1 += __ldcg(pp + (size_t)(q + 1) * ld);
+          y2 += __ldcg(pp + (size_t)(q + 2) * ld);
+          y3 += __ldcg(pp + (size_t)(q + 3) * ld);
         }
+        for (; q < P; ++q) y0 += __ldcg(pp + (size_t)q * ld);
+        const float y = (y0 + y1) + (y2 + y3);
+        const float vr_i = r == t0 ? 1.f : __ldcg(coli + r) * scale;
+        float corr = 0.f;
+        {
+          float vr[kNB], wr[kNB];
+          load_panel_row(a, ld, k0, c, r, s_alpha, vr, wr);
+#pragma unroll
+          for (int cp = 0; cp < kNB; ++cp) {
+            if (cp < c) {
+              corr = fmaf(vr[cp], s_q[cp], corr);
+              corr = fmaf(wr[cp], s_p[cp], corr);
+            }
+          }
+        }
+        const float w = tau * (y - corr);
+        __stcg(a.W + (size_t)c * ld + r, w);
+        dot += (double)w * (double)vr_i;
+        __stcg(a.A + (size_t)i * ld + r, vr_i);   // the reflector, its leading one stored explicitly while the panel is open
       }
       dot = cta_sum(dot, s_red);
       if (tid == 0) __stcg(part3 + b, dot);
@@ -515,7 +546,12 @@ bool sytrd_lower(float* dA, int n, int lda, float* d_d, float* d_e, float* d_tau
   SyArgs args{dA, n, lda, W.p, d_d, d_e, d_tau, P.p, ycol.p, part.p, scal.p, bar.p, trace ? prof.p : nullptr};
   void* params[] = {&args};
   count_launches(2);
-  SCL_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd, dim3(grid), dim3(kT), params, smem, st));
+  // a cooperative launch is all or nothing: if the device cannot hold one CTA per SM right now (another context shares
+  // it), the launch is refused and the caller takes the library's tridiagonalisation instead
+  if (cudaLaunchCooperativeKernel((void*)k_sytrd, dim3(grid), dim3(kT), params, smem, st) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
   k_restore_subdiagonal<<<(n + 255) / 256, 256, 0, st>>>(dA, n, lda, d_e);
   SCL_CUDA(cudaGetLastError());
   if (trace) {
