@@ -384,8 +384,8 @@ def main():
     h.set_counts(X)
 
     def one_pass():
-        if signal_only:
-            return h.run_signal(), None
+        if signal_only:      # scl_run_pass with n_perturb = 0: the signal stage alone, shared by the ranks
+            return h.run_pass(th=60.0, p_step=0.001, n_perturb=0)[0], None
         return h.run_pass(th=60.0, p_step=0.001, n_perturb=args.n_perturb)
 
     def barrier():

@@ -181,7 +181,8 @@ SCL_API int32_t scl_run_robustness(scl_handle* h, double th, double p_step, int3
 /* Both stages as ONE call (:664-819).  On one GPU it is scl_run_signal followed by scl_run_robustness (skipped, with a
  * zeroed scl_robust_info, when there is no signal).  After scl_comm_init it is one pass shared by all ranks: cell-sharded
  * Gram matrices reduced to the rank that solves them, and the pass's eigensolves - data, null, binarised reference, search
- * steps - dealt to the ranks wave by wave.  Every rank must call it with the same arguments and ends with the same results. */
+ * steps - dealt to the ranks wave by wave.  Every rank must call it with the same arguments and ends with the same results.
+ * n_perturb = 0 runs the signal stage alone (rout is zeroed). */
 SCL_API int32_t scl_run_pass(scl_handle* h, double th, double p_step, int32_t n_perturb, scl_signal_info* sout,
                              scl_robust_info* rout);
 

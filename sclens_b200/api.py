@@ -179,7 +179,7 @@ class Handle:
         si, ri = SignalInfo(), RobustInfo()
         self._ck(self.lib.scl_run_pass(self.h, float(th), float(p_step), int(n_perturb), C.byref(si), C.byref(ri)))
         self.sinfo = si
-        self.rinfo = ri if si.n_signal > 0 else None
+        self.rinfo = ri if (si.n_signal > 0 and n_perturb > 0) else None
         return si, self.rinfo
 
     # ---- results

@@ -1161,15 +1161,16 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
 // the k signal eigenvectors, and the reference basis as binary16 hi/lo rows.  Search steps keep their eigenvectors until the
 // basis has arrived.  The stop rule consumes the steps in order, so the outcome is the sequential loop's.
 void run_pass(scl_handle* h, double th, double p_step, int n_perturb) {
+  const bool signal_only = n_perturb == 0;   // the signal stage alone (:664-706), still shared by the ranks
   if (!multi(h)) {
     run_signal(h);
     h->rinfo = scl_robust_info{};
-    if (h->sinfo.n_signal == 0) return;   // :780-784
+    if (h->sinfo.n_signal == 0 || signal_only) return;   // :780-784
     run_robustness(h, th, p_step, n_perturb);
     return;
   }
   SCL_REQUIRE(h->have_X, "scl_set_counts_csc must be called first");
-  SCL_REQUIRE(n_perturb >= 2, "n_perturb must be >= 2");
+  SCL_REQUIRE(n_perturb >= 2 || signal_only, "n_perturb must be >= 2 (or 0 for the signal stage alone)");
   cudaStream_t st = h->st;
   const SpMat& X = h->X;
   const int N = X.N, M = X.M, nm = std::min(N, M), G_ = h->world, me = h->rank;
@@ -1202,10 +1203,14 @@ void run_pass(scl_handle* h, double th, double p_step, int n_perturb) {
     gram_of(h, h->Xnull, h->ws_Sn, h->ws_op_hi, h->ws_op_lo, G2.p, nm, 1.0f / (float)M, split, /*shard=*/true, r_null);
     save_gram_factor(h, 2);
     sinfo.t_gram_ms = tm.stop();
-    robust_prepare(h);
-    rinfo.t_baseline_ms = tm.stop();
-    search_ctx_init(h, c);
-    binref_operand(h, c, false);
+    if (!signal_only) {
+      robust_prepare(h);
+      rinfo.t_baseline_ms = tm.stop();
+      search_ctx_init(h, c);
+      binref_operand(h, c, false);
+    } else {
+      rinfo = scl_robust_info{};
+    }
     ss.p_step = p_step;
     ss.p_th = rinfo.p_th;
   } catch (const std::exception& e) {
@@ -1237,14 +1242,14 @@ void run_pass(scl_handle* h, double th, double p_step, int n_perturb) {
         unscale_eigenvalues(h, W2.p, nm, 2);
         sinfo.t_syevd_ms += tm.stop();
       }
-      if (task == 2) {                  // reference basis of the binarised matrix (:717-721)
+      if (task == 2 && !signal_only) {  // reference basis of the binarised matrix (:717-721)
         tm.stop();
         binref_solve(h, c);
         // its largest eigenvalue (scale of the "positive" threshold) before the data spectrum arrives in the same buffer
         SCL_CUDA(cudaMemcpyAsync(lmax_dev.p, W.p + (nm - 1), sizeof(float), cudaMemcpyDeviceToDevice, st));
         rinfo.t_search_syevd_ms += tm.stop();
       }
-      if (my_step >= 0 && ss.reachable(my_step)) i0 = search_step_solve(h, c, ss, my_step, rinfo, tm, t_gram);
+      if (!signal_only && my_step >= 0 && ss.reachable(my_step)) i0 = search_step_solve(h, c, ss, my_step, rinfo, tm, t_gram);
       SCL_CUDA(cudaStreamSynchronize(st));
     } catch (const std::exception& e) {
       err = e.what();
@@ -1255,7 +1260,7 @@ void run_pass(scl_handle* h, double th, double p_step, int n_perturb) {
     try {
       // --- what later tasks need from this wave's, in task order
       const bool fit_now = !have_fit && wave >= 1 / G_;       // tasks 0 and 1 are done (wave 0 when G >= 2)
-      const bool basis_now = !have_basis && wave >= 2 / G_;   // task 2 is done (wave 0 when G >= 3, wave 1 when G = 2)
+      const bool basis_now = !signal_only && !have_basis && wave >= 2 / G_;   // task 2 is done (wave 0 when G >= 3, wave 1 when G = 2)
       if (fit_now) {
         ProfScope ps(&h->prof, st, PK_COMM);
         SCL_NCCL(nccl_api().Broadcast(W.p, W.p, nm, ncclFloat, r_data, (ncclComm_t)h->nccl, st));
@@ -1305,7 +1310,7 @@ void run_pass(scl_handle* h, double th, double p_step, int n_perturb) {
       err = e.what();
     }
     sync_errors(h, err);
-    if (sinfo.n_signal == 0 && have_fit) {   // :780-784: nothing to test
+    if (have_fit && (sinfo.n_signal == 0 || signal_only)) {   // :780-784: nothing to test (or nothing asked for)
       h->prof.resolve();
       return;
     }
