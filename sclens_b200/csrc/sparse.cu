@@ -324,6 +324,7 @@ k_merge_lines(const uint32_t* __restrict__ base_ptr, const uint32_t* __restrict_
   for (int l = blockIdx.x; l < n_lines; l += gridDim.x) {
     const uint32_t bb = base_ptr[l], be = base_ptr[l + 1], ab = add_ptr[l], ae = add_ptr[l + 1], ob = out_ptr[l];
     if (ae == ab) {   // nothing added to this line: copy
+#pragma unroll 4
       for (uint32_t t = bb + tid; t < be; t += kMergeThreads) {
         out_idx[ob + (t - bb)] = base_idx[t];
         out_val[ob + (t - bb)] = binarise ? 1.f : base_val[t];
@@ -332,9 +333,18 @@ k_merge_lines(const uint32_t* __restrict__ base_ptr, const uint32_t* __restrict_
     }
     for (int w = tid; w < 2 * words; w += kMergeThreads) bm[w] = 0u;
     __syncthreads();
-    for (uint32_t t = bb + tid; t < be; t += kMergeThreads) {
-      const uint32_t p = base_idx[t];
-      atomicOr(&bmB[p >> 5], 1u << (p & 31));
+    // four independent loads per thread in flight (a line is a few thousand entries over 256 threads: without this a thread
+    // waits for one 4-byte load at a time)
+    for (uint32_t t0 = bb + tid; t0 < be; t0 += 4 * kMergeThreads) {
+      uint32_t p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t t = t0 + u * kMergeThreads;
+        p[u] = t < be ? base_idx[t] : 0xffffffffu;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (p[u] != 0xffffffffu) atomicOr(&bmB[p[u] >> 5], 1u << (p[u] & 31));
     }
     bool bad = false;
     for (uint32_t t = ab + tid; t < ae; t += kMergeThreads) {
@@ -370,11 +380,24 @@ k_merge_lines(const uint32_t* __restrict__ base_ptr, const uint32_t* __restrict_
     if (bad) atomicOr(flag, 1);
     __syncthreads();
     // stored entries: slot = rank in the base line + additions at smaller positions
-    for (uint32_t t = bb + tid; t < be; t += kMergeThreads) {
-      const uint32_t p = base_idx[t], w = p >> 5, low = (1u << (p & 31)) - 1u;
-      const uint32_t slot = (t - bb) + pfA[w] + __popc(bmA[w] & low);
-      out_idx[ob + slot] = p;
-      out_val[ob + slot] = binarise ? 1.f : base_val[t];
+    for (uint32_t t0 = bb + tid; t0 < be; t0 += 4 * kMergeThreads) {
+      uint32_t p[4];
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t t = t0 + u * kMergeThreads;
+        const bool ok = t < be;
+        p[u] = ok ? base_idx[t] : 0xffffffffu;
+        v[u] = (ok && !binarise) ? base_val[t] : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (p[u] == 0xffffffffu) continue;
+        const uint32_t t = t0 + u * kMergeThreads, w = p[u] >> 5, low = (1u << (p[u] & 31)) - 1u;
+        const uint32_t slot = (t - bb) + pfA[w] + __popc(bmA[w] & low);
+        out_idx[ob + slot] = p[u];
+        out_val[ob + slot] = v[u];
+      }
     }
     // additions: slot = additions at smaller positions + stored entries at smaller positions; value 1 (:735, :774)
     for (uint32_t t = ab + tid; t < ae; t += kMergeThreads) {
