@@ -353,7 +353,6 @@ def main():
                           "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")      # NCCL's version banner goes to stdout otherwise: stdout is the JSON line's
     import torch
     import torch.distributed as dist
     from sclens_b200 import Handle, sclens
