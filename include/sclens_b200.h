@@ -129,7 +129,9 @@ SCL_API int32_t scl_comm_init(scl_handle* h, const uint8_t id[128], int32_t rank
 SCL_API int32_t scl_plan_replicates(int32_t n_perturb, int32_t world, int32_t rank, int32_t* out_ids, int32_t* out_n);
 SCL_API int32_t scl_plan_search_wave(int32_t wave, int32_t world, int32_t rank, int32_t* out_step);
 /* Task list of scl_run_pass: wave `wave` gives rank `rank` task t = wave * world + rank; t = 0 data matrix, 1 null matrix,
- * 2 reference basis of the binarised matrix, t >= 3 sparsity-search step t - 3 (out_search_step, else -1). */
+ * 2 reference basis of the binarised matrix, t >= 3 the sparsity-search steps in order (out_search_step, else -1) - except
+ * that with world >= 3 the slot t = world (rank 0, wave 1) is the Float64 refinement of the data spectrum and the steps
+ * after it move down by one. */
 SCL_API int32_t scl_plan_pass_task(int32_t wave, int32_t world, int32_t rank, int32_t* out_task, int32_t* out_search_step);
 /* Block [k0, k1) of the Gram contraction axis (cells when N > M; padded length ld = K rounded up to 8) a rank
  * densifies and contracts before the partial Gram matrices are summed with ncclAllReduce. */

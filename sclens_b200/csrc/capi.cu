@@ -200,7 +200,7 @@ int32_t scl_plan_search_wave(int32_t wave, int32_t world, int32_t rank, int32_t*
 int32_t scl_plan_pass_task(int32_t wave, int32_t world, int32_t rank, int32_t* out_task, int32_t* out_search_step) {
   if (wave < 0 || world < 1 || rank < 0 || rank >= world || !out_task) return SCL_ERR_INVALID;
   *out_task = wave * world + rank;
-  if (out_search_step) *out_search_step = *out_task >= 3 ? *out_task - 3 : -1;
+  if (out_search_step) *out_search_step = scl::pass_task_step(*out_task, scl::pass_refine_task(world));
   return SCL_OK;
 }
 

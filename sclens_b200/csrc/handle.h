@@ -68,6 +68,8 @@ void refine_eigenvalues(const float* dG, const float* dV, int n, float* dW, cuda
 void run_signal(scl_handle* h);
 void run_robustness(scl_handle* h, double th, double p_step, int n_perturb);
 void run_pass(scl_handle* h, double th, double p_step, int n_perturb);
+int pass_refine_task(int world);
+int pass_task_step(int task, int refine_task);
 void score_from_pairs(const std::vector<float>& b_, int k, int n_pairs, double th, std::vector<double>& m,
                       std::vector<double>& sd, std::vector<int32_t>& sig);
 void plan_gram_shard(int64_t K, int64_t ld, int world, int rank, int64_t* k0, int64_t* k1);

@@ -1152,6 +1152,16 @@ void run_robustness(scl_handle* h, double th, double p_step, int n_perturb) {
   robust_tail(h, th, n_perturb, ss.p_, tm);
 }
 
+// Task list of the shared pass: 0 data, 1 null, 2 reference basis, then the search steps - with one slot taken out for the
+// Float64 refinement of the data spectrum when there are at least three ranks: the first slot of wave 1, which is rank 0's
+// (the rank that holds the data matrix's eigenvectors), so the refinement does not lengthen wave 0 and costs rank 0 one
+// search step instead.  Fewer ranks refine right after the data solve (their rank 0 reuses the buffer in wave 1).
+int pass_refine_task(int world) { return world >= 3 ? world : -1; }
+int pass_task_step(int task, int refine_task) {
+  if (task < 3 || task == refine_task) return -1;
+  return task - 3 - ((refine_task >= 0 && task > refine_task) ? 1 : 0);
+}
+
 // One complete sclens() pass (:664-819).  One rank: run_signal, then run_robustness.  Several ranks: ONE pass shared by all
 // of them - the Gram matrices of the data and null matrices are contracted cell block by cell block on every rank and
 // reduced (packed triangle) to the rank that solves them, and the pass's eigensolves form one task list
@@ -1221,20 +1231,26 @@ void run_pass(scl_handle* h, double th, double p_step, int n_perturb) {
   Tmp<double> wave_dev(G_, st);
   Tmp<float> lmax_dev(1, st);
   bool have_fit = false, have_basis = false;
+  const int refine_task = (refine && !signal_only) ? pass_refine_task(G_) : -1;
   std::vector<float> Lr(nm);
   for (int wave = 0; !ss.stop; ++wave) {
     const int task = wave * G_ + me;
     int i0 = -2;            // search step of this rank in this wave: -2 none / unreachable, -1 pool exhausted, >= 0 solved
-    const int my_step = task - 3;
+    const int my_step = pass_task_step(task, refine_task);
     err.clear();
     try {
       if (task == 0) {                  // data matrix (:530/:570)
         { ProfScope ps(&h->prof, st, PK_SYEVD); h->solver->syevd(G.p, nm, W.p, true, st); }
         sinfo.t_syevd_ms += tm.stop();
-        if (refine) {
+        if (refine && refine_task < 0) {
           ProfScope ps(&h->prof, st, PK_REFINE);
           refine_eigenvalues(h->ws_Gkeep.p, G.p, nm, W.p, st);
         }
+        if (refine_task < 0) unscale_eigenvalues(h, W.p, nm, 1);
+      }
+      if (task == refine_task) {        // Float64 refinement of the data spectrum, in the slot after the data solve's wave
+        ProfScope ps(&h->prof, st, PK_REFINE);
+        refine_eigenvalues(h->ws_Gkeep.p, G.p, nm, W.p, st);
         unscale_eigenvalues(h, W.p, nm, 1);
       }
       if (task == 1) {                  // null matrix, values only (:531-532/:571-572)
@@ -1259,7 +1275,7 @@ void run_pass(scl_handle* h, double th, double p_step, int n_perturb) {
     double my_d2 = i0 == -1 ? -1.0 : -2.0;
     try {
       // --- what later tasks need from this wave's, in task order
-      const bool fit_now = !have_fit && wave >= 1 / G_;       // tasks 0 and 1 are done (wave 0 when G >= 2)
+      const bool fit_now = !have_fit && wave >= (refine_task >= 0 ? refine_task / G_ : 1 / G_);   // data (refined) and null spectra are in
       const bool basis_now = !signal_only && !have_basis && wave >= 2 / G_;   // task 2 is done (wave 0 when G >= 3, wave 1 when G = 2)
       if (fit_now) {
         ProfScope ps(&h->prof, st, PK_COMM);
@@ -1320,7 +1336,7 @@ void run_pass(scl_handle* h, double th, double p_step, int n_perturb) {
     SCL_CUDA(cudaMemcpyAsync(wave_d2.data(), wave_dev.p, G_ * sizeof(double), cudaMemcpyDeviceToHost, st));
     SCL_CUDA(cudaStreamSynchronize(st));
     for (int g = 0; g < G_; ++g) {
-      const int s_ = wave * G_ + g - 3;
+      const int s_ = pass_task_step(wave * G_ + g, refine_task);
       if (s_ >= 0) ss.feed(h, s_, wave_d2[g]);
     }
   }

@@ -37,7 +37,6 @@ struct SyArgs {
   float *d, *e, *tau;
   float* P;          // [grid][ld] row partials of the matrix-vector product
   float* ycol;       // n: column parts of the matrix-vector product
-  float* ycol2;      // n: the same from the lower halves of split strips (zero elsewhere)
   double* part;      // [grid][2 kNB + 2]: panel dot products, norm / w'v partials
   float* scal;       // [0] = A(i+1, i) after the column update
   unsigned* bar;
@@ -242,21 +241,10 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
       {
         // strips are dealt in snake order (round 0: CTA b takes the b-th tallest, round 1: the (P-1-b)-th of the next P, ...):
         // strip heights fall linearly, so a plain cyclic deal would give the first CTAs 60 % more rows than the last
-        // An odd number of full rounds leaves one round unpaired: its strips are cut in two halves of row blocks, CTA b takes
-        // the upper half of its b-th and the lower half of its (P-1-b)-th strip (the halves' column sums meet in phase 3).
         const int s0 = t0 >> 5, smax = (n - 1) >> 5;
-        const int n_strips = smax - s0 + 1, r_full = n_strips / P;
-        const int split_round = (r_full & 1) ? r_full - 1 : -1;
-        const int n_items = r_full + (split_round >= 0 ? 1 : 0) + ((n_strips % P) ? 1 : 0);
-        for (int item = 0; item < n_items; ++item) {
-          // item -> (round, half): rounds before the split round one item each, the split round two, then the rest
-          int round = item, half = -1;   // half -1: whole strip, 0: upper half (with the diagonal block), 1: lower half
-          if (split_round >= 0 && item >= split_round) {
-            if (item <= split_round + 1) { round = split_round; half = item - split_round; }
-            else round = item - 1;
-          }
-          const int k = (half == 1 || (half < 0 && (round & 1))) ? P - 1 - b : b;
-          const int s = s0 + round * P + k;
+        for (int round = 0;; ++round) {
+          const int s = s0 + round * P + ((round & 1) ? P - 1 - b : b);
+          if (s0 + round * P > smax) break;   // uniform over the grid
           if (s > smax) continue;
           const int ja = max(32 * s, t0), jb = min(32 * s + 32, n);
           const int jc = 32 * s + lane;
@@ -267,7 +255,7 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
           // the strip's 32 x 32 diagonal block (lower triangle, one row per lane) goes to the last warp; below it the warps
           // walk 128-row blocks aligned to the strip, four consecutive rows per lane: one 16-byte load per column
           const bool full_cols = 32 * s + 32 <= n;
-          if (warp == kW - 1 && half != 1) {
+          if (warp == kW - 1) {
             const int rr = 32 * s + lane;
             const bool rvalid = rr < n && rr >= t0;
             const float vr = rvalid ? (rr == t0 ? 1.f : __ldcg(coli + rr) * scale) : 0.f;
@@ -290,9 +278,7 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
             if (rvalid) ysm[rr] += ac;
           }
           const int rbase = 32 * s + 32;
-          const int units = (n - rbase + 127) / 128;                       // 128-row blocks below the diagonal block
-          const int u0 = half == 1 ? units / 2 : 0, u1 = half == 0 ? units / 2 : units;
-          for (int R = u0 + warp; R < u1; R += kW) {
+          for (int R = warp; rbase + R * 128 < n; R += kW) {
             const int r = rbase + R * 128 + 4 * lane;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             if (full_cols && rbase + R * 128 + 128 <= n) {
@@ -355,7 +341,7 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
             float t = 0.f;
             for (int w = 0; w < kW; ++w) t += s_col[w][tid];
             const int j = 32 * s + tid;
-            if (j >= ja && j < jb) __stcg((half == 1 ? a.ycol2 : a.ycol) + j, t);
+            if (j >= ja && j < jb) __stcg(a.ycol + j, t);
           }
           __syncthreads();
         }
@@ -390,8 +376,7 @@ __global__ void __launch_bounds__(kT, 1) k_sytrd(SyArgs a) {
         const int r = rb * 32 + lane;
         if (r < t0 || r >= n) continue;
         // the row's partial sums of all CTAs: four independent chains, 32 loads in flight
-        float y0 = __ldcg(a.ycol + r), y1 = __ldcg(a.ycol2 + r), y2 = 0.f, y3 = 0.f;
-        __stcg(a.ycol2 + r, 0.f);   // only the lower halves of a split round write it: clear for the next column
+        float y0 = __ldcg(a.ycol + r), y1 = 0.f, y2 = 0.f, y3 = 0.f;
         const float* pp = a.P + r;
         int q = 0;
 #pragma unroll 8
@@ -549,8 +534,7 @@ bool sytrd_lower(float* dA, int n, int lda, float* d_d, float* d_e, float* d_tau
   SCL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sytrd, kT, smem));
   if (per_sm < 1) return false;
   const int grid = sms;
-  Tmp<float> W((size_t)lda * kNB, st), P((size_t)grid * lda, st), ycol(n, st), ycol2(n, st), scal(4, st);
-  SCL_CUDA(cudaMemsetAsync(ycol2.p, 0, (size_t)n * sizeof(float), st));
+  Tmp<float> W((size_t)lda * kNB, st), P((size_t)grid * lda, st), ycol(n, st), scal(4, st);
   Tmp<double> part((size_t)grid * (2 * kNB + 2), st);
   Tmp<unsigned> bar(1, st);
   SCL_CUDA(cudaMemsetAsync(bar.p, 0, sizeof(unsigned), st));
@@ -559,7 +543,7 @@ bool sytrd_lower(float* dA, int n, int lda, float* d_d, float* d_e, float* d_tau
   SCL_CUDA(cudaMemsetAsync(d_e, 0, (size_t)n * sizeof(float), st));
   static const bool trace = getenv("SCL_TRACE") != nullptr;
   Tmp<unsigned long long> prof(trace ? (size_t)grid * 16 : 1, st);
-  SyArgs args{dA, n, lda, W.p, d_d, d_e, d_tau, P.p, ycol.p, ycol2.p, part.p, scal.p, bar.p, trace ? prof.p : nullptr};
+  SyArgs args{dA, n, lda, W.p, d_d, d_e, d_tau, P.p, ycol.p, part.p, scal.p, bar.p, trace ? prof.p : nullptr};
   void* params[] = {&args};
   count_launches(2);
   // a cooperative launch is all or nothing: if the device cannot hold one CTA per SM right now (another context shares

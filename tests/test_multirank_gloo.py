@@ -114,21 +114,31 @@ def test_pass_task_plan_deals_every_solve_once_and_in_order():
     p_th = 0.15
     want = sequential_stop(d2_all, p_th)
     for world in (1, 2, 3, 4, 8):
-        seen = {}
+        seen, step_of, steps = {}, {}, []
         for wave in range(6):
             for r in range(world):
                 t, s = C.c_int32(), C.c_int32()
                 assert lib.scl_plan_pass_task(wave, world, r, C.byref(t), C.byref(s)) == 0
                 assert t.value not in seen
                 seen[t.value] = (wave, r)
-                assert s.value == (t.value - 3 if t.value >= 3 else -1)
+                step_of[(wave, r)] = s.value
+                if s.value >= 0:
+                    steps.append(s.value)
         assert sorted(seen) == list(range(6 * world))
-        assert seen[2][0] <= seen[3][0] and seen[0][0] <= seen[2][0] and seen[1][0] <= seen[2][0]
+        assert steps == list(range(len(steps)))                   # every step once, in task order
+        refine_slot = [t for t in range(3, 6 * world) if step_of[seen[t]] < 0]
+        # with three ranks or more the refinement of the data spectrum takes the first slot of wave 1: rank 0's, which holds
+        # the data matrix's eigenvectors and has touched nothing else since
+        assert refine_slot == ([world] if world >= 3 else []) and all(seen[t] == (1, 0) for t in refine_slot)
+        first_step_wave = min(w for (w, r), s in step_of.items() if s == 0)
+        assert seen[2][0] <= first_step_wave and seen[0][0] <= seen[2][0] and seen[1][0] <= seen[2][0]
         # waves until the stop rule fires: steps of a wave are consumed in task order
         p_, tank, n_steps, stop, wave = 0.999, [], 0, None, 0
         while stop is None:
             for r in range(world):
-                s = wave * world + r - 3
+                t, sv = C.c_int32(), C.c_int32()
+                assert lib.scl_plan_pass_task(wave, world, r, C.byref(t), C.byref(sv)) == 0
+                s = sv.value
                 if s < 0 or stop is not None:
                     continue
                 tank.append(d2_all[s])
