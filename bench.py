@@ -221,20 +221,27 @@ def cpu_sample(X, n_search, n_perturb, frac=4):
 
 
 def reference_arm(X, workload, n_search, n_perturb, budget_s):
-    """--impl reference: the CPU path's stages measured ONCE AT FULL SIZE when that fits the budget (a 1/8-size probe
+    """--impl reference: the CPU path's stages measured ONCE AT FULL SIZE when that fits the budget (a 1/4-size probe
     predicts it), otherwise on the largest 1/frac sample that does; never repeated per requested step."""
     N, M = X.shape
     cores = os.cpu_count() or 1
     t0 = time.perf_counter()
-    tp, shp, n_p = cpu_stages(X, 8)
+    tp, shp, n_p = cpu_stages(X, 4)      # the probe: a quarter of the smaller side (LAPACK is well into its n^3 regime there)
     probe_s = time.perf_counter() - t0
     ratio = min(N, M) / n_p
     pred_full = (tp["normalise"] * (N * M) / (shp[0] * shp[1]) + tp["gram_f64"] * ratio ** 2 +
                  (tp["eigen_vectors"] + tp["corr"]) * ratio ** 3)
     frac = 1
-    while frac < 8 and pred_full / (frac ** 3) > budget_s:
+    while frac < 4 and pred_full / (frac ** 3) > budget_s:
         frac *= 2
-    if frac >= 8:
+    try:      # the Float64 dense pipeline holds ~5 copies of the N x M matrix at its peak: stay inside the host's free memory
+        import psutil
+        avail = psutil.virtual_memory().available
+        while frac < 4 and 6.0 * N * M * 8.0 / frac > 0.8 * avail:
+            frac *= 2
+    except Exception:
+        pass
+    if frac >= 4:
         t, shape, n_s, measured_s = tp, shp, n_p, probe_s
     else:
         t0 = time.perf_counter()
@@ -247,7 +254,7 @@ def reference_arm(X, workload, n_search, n_perturb, budget_s):
               + ", ".join(f"{k} {v:.2f}s" for k, v in t.items())
               + f"; one pass = {n_full} x (normalise + Gram + eigen) + {n_search} x corr"
               + ("" if frac == 1 else "; scaled to full size by N*M, n^2*K, n^3")
-              + f"; search steps nominal={n_search}, n_perturb={n_perturb}; 1/8-size probe predicted {pred_full:.0f}s for the full-size stages")
+              + f"; search steps nominal={n_search}, n_perturb={n_perturb}; 1/4-size probe predicted {pred_full:.0f}s for the full-size stages")
     return total, cores, sample, {"stage_seconds": t, "measured_at": list(shape), "eig_n": n_s, "frac": frac,
                                   "measured_wall_s": measured_s, "probe_wall_s": probe_s}
 

@@ -65,6 +65,31 @@ if rank == 0:
         cos = np.abs(np.sum(got["nV"] * single["nV"], axis=0))
         assert cos.min() > 1 - 1e-5, name
     print("MULTI_GPU_CHECK_OK", flush=True)
+# the shared pass against the ORACLE with injected draws (every rank regenerates the same seeded oracle run and injects its
+# draws; the stop rule of the search is fed by steps that different ranks evaluated)
+if len(sys.argv) <= 2:
+    from oracle import sclens_oracle as orc   # test infrastructure: this script is a test, not the product path
+    from sclens_b200 import SCL_GRAM_FP16X3, sclens
+    Xo = make_counts(900, 640, seed=21, K=5, de_prob=0.3, lfc_sd=1.5)
+    ref, draws, info = orc.sclens(Xo, rng=np.random.default_rng(7), mode="cpu", n_perturb=6, n_baseline=300)
+    with Handle(device=local, seed=7, gram_mode=SCL_GRAM_FP16X3, exact_perturb=True) as ho:
+        uid2 = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            assert ho.lib.scl_nccl_unique_id(buf) == 0
+            uid2 = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        dist.broadcast(uid2, 0)
+        out = sclens(Xo, draws=draws, n_perturb=6, gram_mode=SCL_GRAM_FP16X3, exact_perturb=True, verbose=False, handle=ho,
+                     comm=(bytes(uid2.cpu().tolist()), rank, world))
+    assert len(out["signal_ev"]) == len(ref["signal_ev"]), (rank, len(out["signal_ev"]), len(ref["signal_ev"]))
+    np.testing.assert_allclose(out["signal_ev"], ref["signal_ev"], rtol=1e-4)
+    assert out["info"]["n_search"] == info["n_search"] and out["info"]["p_sel"] == info["p_sel"], rank
+    np.testing.assert_array_equal(out["sig_id"], ref["sig_id"])
+    np.testing.assert_allclose(out["robustness_scores"]["m_scores"], ref["robustness_scores"]["m_scores"], atol=2e-2)
+    cos = np.abs(np.sum(out["signal_evec"] * np.asarray(ref["signal_evec"]), axis=0))
+    assert cos.min() > 1 - 1e-5, (rank, cos)
+    if rank == 0:
+        print("MULTI_GPU_ORACLE_OK", flush=True)
 # every rank must hold identical results
 t = torch.tensor([multi["p_sel"], float(multi["n_search"]), float(len(multi["sig"])), float(multi["m"].sum())], device=dev, dtype=torch.float64)
 ref = t.clone()
