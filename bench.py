@@ -553,7 +553,8 @@ def main():
         phase.update({"noise_baseline_and_zero_candidates": ri.t_baseline_ms, "search_total": ri.t_search_ms,
                       "search_syevd": ri.t_search_syevd_ms, "perturbations": ri.t_perturb_ms,
                       "scores": ri.t_score_ms, "gene_basis": ri.t_outputs_ms})
-        result.update({"n_search": ri.n_search, "p_sel": ri.p_sel, "n_robust": ri.n_robust})
+        result.update({"n_search": ri.n_search, "p_sel": ri.p_sel, "n_robust": ri.n_robust,
+                       "n_subspace_fallbacks": ri.n_subspace_fallbacks})
     line = {"metric": "sclens_cells_per_s", "value": value, "unit": "cells/s", "n_gpus": world, "steps": steps,
             "steps_requested": args.steps, "warmup": warm_done, "warmup_requested": args.warmup,
             "warmup_seconds": warm_s, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
