@@ -299,8 +299,20 @@ SCL_API int32_t scl_bench_syevd_concurrent(scl_handle* h, int32_t n, int32_t nso
 /* Which eigensolver path runs (process-wide; the environment variable SCL_EIG_API sets the same bits): 0 = plain
  * cusolverDnSsyevd; bit 0 Xsyevd; bit 1 Ssyevdx in the search steps; bit 2 own tridiagonal stage (tridiag.cu) between Ssytrd
  * and Sormtr; bit 3 (with 2) index-range vectors in the search steps; bit 4 (with 2) own tridiagonalisation (sytrd.cu).
+ * bit 5 (with 2) two-stage reduction (dense -> band -> tridiagonal, sy2sb.cu / sb2st.cu / backtrans.cu) for orders >= 256.
  * v < 0: back to the environment / default. */
 SCL_API int32_t scl_debug_set_eig_api(int32_t v);
+/* Stage times of the handle's last own-path eigensolve, milliseconds: out[0..4] = dense->band, band->tridiagonal, tridiagonal
+ * eigenproblem, stage-2 back-transformation, stage-1 back-transformation (all 0 unless the two-stage path ran); out[5] = 1 when
+ * the two-stage path produced the result; out[6] = number of two-stage solves of this handle that fell back to one stage;
+ * out[7] = number of own-path solves that fell back to cusolverDnSsyevd. */
+SCL_API int32_t scl_debug_last_solve(scl_handle* h, double out[8]);
+/* The stages of the two-stage reduction one by one on a host matrix A (n x n, symmetric, n a multiple of 4), for the stage-wise
+ * parity tests: AB (n x 128, band storage AB[j*128 + (i-j)]) after dense -> band; d (n), e (n-1) after band -> tridiagonal;
+ * Q2 (n x n, column v at Q2 + v*n) = the stage-2 transformation applied to the identity; Q (same layout) = Q1 Q2.  Any output
+ * pointer may be NULL.  flags[0] = panel failure flag, flags[1] = number of panels. */
+SCL_API int32_t scl_debug_two_stage(scl_handle* h, int32_t n, const float* A, float* AB, float* d, float* e, float* Q2, float* Q,
+                                    int32_t flags[2]);
 SCL_API int32_t scl_debug_set_tuning(int32_t stat_variant, int32_t stat_heavy, int32_t writer);
 SCL_API int32_t scl_bench_normalize(scl_handle* h, int32_t layout, int32_t with_lo, int32_t reps, double* ms_stats,
                             double* ms_densify, double* alg_bytes_densify);

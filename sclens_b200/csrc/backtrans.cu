@@ -1,0 +1,336 @@
+// Back-transformation of the two-stage eigensolver: Z <- Q1 Q2 Z for the eigenvectors Z of the tridiagonal matrix.
+//
+// Q2 (stage-2 reflectors, one per sweep and chase level, kBand long, consecutive sweeps shifted by one row): the reflectors
+// of kBand consecutive sweeps at one level form a parallelogram V (2 kBand - 1 rows x kBand columns) and are applied as
+// one block I - V T V'.  Generation order is sweep-major; reflectors (s, k) and (s', k') with s < s', k < k' act on disjoint
+// rows, so inside a group of sweeps the product may be taken level by level, and the eigenvectors see: groups descending,
+// levels ascending inside a group (oracle/two_stage_ref.py: apply_q2 == apply_q2_plain).  Every eigenvector is independent:
+// a CTA owns a slab of vectors, keeps the 127-row window of its slab in shared memory (consecutive levels overlap in 63
+// rows, which never leave the SM), and walks all blocks.
+// Q1 (stage-1 panels): Z[r0:] -= V (T (V' Z[r0:])) panel by panel, last panel first, on the FP32 tile engine.
+#include <algorithm>
+#include "common.cuh"
+#include "sgemm_tile.cuh"
+#include "tmp.cuh"
+#include "twostage.h"
+
+namespace scl {
+namespace {
+
+constexpr int B = kBand;
+constexpr int VS = 68;   // shared-memory stride of the reflector block and of T
+
+// T factor (stored transposed: Tt[c'][c] = T[c][c']) of every (group, level) block of stage-2 reflectors
+__global__ void __launch_bounds__(256) k_q2_tfactor(const float* __restrict__ V2, long long ldv2, const float* __restrict__ tau2,
+                                                    long long ldt2, int n, int nlev, float* __restrict__ Tq) {
+  const int k = (int)blockIdx.x, G = (int)blockIdx.y, s0 = G * B;
+  if (s0 + 1 + B * k > n - 2) return;
+  __shared__ float Vc[B][B + 1], T[B][B + 1];   // T: upper triangle = T, strictly lower triangle = the Gram matrix W (W[a][b] at T[b][a])
+  __shared__ float tau[B];
+  const int tid = (int)threadIdx.x;
+  for (int e = tid; e < B * B; e += 256) {
+    const int j = e / B, i = e % B, s = s0 + j;
+    Vc[j][i] = s < n - 2 ? V2[(size_t)s * ldv2 + (size_t)k * B + i] : 0.f;
+    if (j <= i) T[j][i] = 0.f;
+  }
+  if (tid < B) tau[tid] = s0 + tid < n - 2 ? tau2[(size_t)(s0 + tid) * ldt2 + k] : 0.f;
+  __syncthreads();
+  // W[a][b] = v_a . v_b for a < b: reflector b sits b - a rows below reflector a
+  for (int e = tid; e < B * B; e += 256) {
+    const int a = e / B, b = e % B;
+    if (a < b) {
+      const int sh = b - a;
+      float s = 0.f;
+      for (int i = 0; i + sh < B; ++i) s = fmaf(Vc[a][i + sh], Vc[b][i], s);
+      T[b][a] = s;
+    }
+  }
+  __syncthreads();
+  // forward columnwise larft: T[0:j, j] = -tau_j T[0:j, 0:j] W[0:j, j]
+  for (int j = 0; j < B; ++j) {
+    if (tid < j) {
+      float s = 0.f;
+      for (int q = tid; q < j; ++q) s = fmaf(T[tid][q], T[j][q], s);
+      T[tid][j] = -tau[j] * s;
+    } else if (tid == j) {
+      T[j][j] = tau[j];
+    }
+    __syncthreads();
+  }
+  float* out = Tq + ((size_t)G * nlev + k) * B * B;
+  for (int e = tid; e < B * B; e += 256) out[e] = (e % B) <= (e / B) ? T[e % B][e / B] : 0.f;   // out[c'][c] = T[c][c'], upper triangular
+}
+
+struct Q2Args {
+  const float* V2;
+  long long ldv2;
+  const float* Tq;
+  int n, nlev, ngroups;
+  float* Z;
+  long long ldz;
+  int mvec, nv, nvp;
+};
+
+// blockDim = 16 * (nvp / 4): thread (g = tid & 15, vg = tid >> 4) owns vectors 4 vg .. 4 vg + 3 and, per product, the
+// reflectors 4 g .. 4 g + 3 (first product, T product) or the window rows 8 g .. 8 g + 7 (second product)
+__global__ void __launch_bounds__(384, 1) k_q2_apply(Q2Args a) {
+  extern __shared__ __align__(16) float sm[];
+  const int nvp = a.nvp;
+  float* Zs = sm;                        // [128][nvp]  window rows (slot = window row & 127, see below) x vectors
+  float* Xs = Zs + 128 * nvp;            // [64][nvp]
+  float* X2s = Xs + B * nvp;             // [64][nvp]
+  float* Vs = X2s + B * nvp;             // [128][VS]   parallelogram: Vs[j + i][j] = v_j[i]
+  float* Tt = Vs + 128 * VS;             // [64][VS]
+  const int tid = (int)threadIdx.x, nthr = (int)blockDim.x;
+  const int g = tid & 15, vg = tid >> 4, v0 = vg * 4;
+  const int vec0 = (int)blockIdx.x * a.nv, nvv = min(a.nv, a.mvec - vec0);
+  const int n = a.n;
+  for (int e = tid; e < 128 * VS; e += nthr) Vs[e] = 0.f;
+  for (int e = tid; e < 128 * nvp; e += nthr) Zs[e] = 0.f;
+  __syncthreads();
+  for (int G = a.ngroups - 1; G >= 0; --G) {
+    const int s0 = G * B, base = s0 + 1;   // window row w of level k is global row base + 64 k + w, kept in slot (64 k + w) & 127
+    for (int k = 0;; ++k) {
+      const int rlo = base + B * k;
+      if (rlo > n - 2) break;
+      const bool last = rlo + B > n - 2;
+      // ---- loads: new window rows (all 127 at level 0, the upper 64 afterwards), reflectors, T
+      {
+        const int w_first = k == 0 ? 0 : B - 1;
+        const int nrow = 127 - w_first;
+        for (int e = tid; e < nrow * nvp; e += nthr) {
+          const int v = e / nrow, w = w_first + e % nrow, r = rlo + w;
+          if (v < nvp) Zs[((B * k + w) & 127) * nvp + v] = (v < nvv && r < n) ? a.Z[(size_t)(vec0 + v) * a.ldz + r] : 0.f;
+        }
+        for (int e = tid; e < B * B; e += nthr) {
+          const int j = e / B, i = e % B, s = s0 + j;
+          Vs[(j + i) * VS + j] = s < n - 2 ? a.V2[(size_t)s * a.ldv2 + (size_t)k * B + i] : 0.f;
+        }
+        const float* tq = a.Tq + ((size_t)G * a.nlev + k) * B * B;
+        for (int e = tid; e < B * B; e += nthr) Tt[(e / B) * VS + (e % B)] = tq[e];
+      }
+      __syncthreads();
+      // ---- X[c][vec] = sum_w V[w][c] Z[w][vec], w in [c, c + 63]
+      {
+        float acc[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+        const int c0 = g * 4;
+#pragma unroll 4
+        for (int w = c0; w < c0 + 67; ++w) {
+          const float4 vr = *reinterpret_cast<const float4*>(&Vs[w * VS + c0]);
+          const float4 z = *reinterpret_cast<const float4*>(&Zs[((B * k + w) & 127) * nvp + v0]);
+          const float vv[4] = {vr.x, vr.y, vr.z, vr.w}, zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(vv[x], zz[y], acc[x][y]);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+          *reinterpret_cast<float4*>(&Xs[(c0 + x) * nvp + v0]) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+      }
+      __syncthreads();
+      // ---- X2[c][vec] = sum_{c' >= c} T[c][c'] X[c'][vec]
+      {
+        float acc[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+        const int c0 = g * 4;
+#pragma unroll 4
+        for (int cp = c0; cp < B; ++cp) {
+          const float4 tr = *reinterpret_cast<const float4*>(&Tt[cp * VS + c0]);
+          const float4 x4 = *reinterpret_cast<const float4*>(&Xs[cp * nvp + v0]);
+          const float tt[4] = {tr.x, tr.y, tr.z, tr.w}, xx[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(tt[x], xx[y], acc[x][y]);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+          *reinterpret_cast<float4*>(&X2s[(c0 + x) * nvp + v0]) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+      }
+      __syncthreads();
+      // ---- Z[w][vec] -= sum_c V[w][c] X2[c][vec], c in [w - 63, w]
+      {
+        const int w0 = g * 8;
+        float acc[8][4];
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+        const int clo = max(0, w0 - (B - 1)) & ~3, chi = min(B - 1, w0 + 7);
+        for (int c = clo; c <= chi; c += 4) {
+          float4 xr[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) xr[j] = *reinterpret_cast<const float4*>(&X2s[(c + j) * nvp + v0]);
+#pragma unroll
+          for (int x = 0; x < 8; ++x) {
+            const float4 vr = *reinterpret_cast<const float4*>(&Vs[(w0 + x) * VS + c]);
+            acc[x][0] = fmaf(vr.x, xr[0].x, acc[x][0]); acc[x][1] = fmaf(vr.x, xr[0].y, acc[x][1]);
+            acc[x][2] = fmaf(vr.x, xr[0].z, acc[x][2]); acc[x][3] = fmaf(vr.x, xr[0].w, acc[x][3]);
+            acc[x][0] = fmaf(vr.y, xr[1].x, acc[x][0]); acc[x][1] = fmaf(vr.y, xr[1].y, acc[x][1]);
+            acc[x][2] = fmaf(vr.y, xr[1].z, acc[x][2]); acc[x][3] = fmaf(vr.y, xr[1].w, acc[x][3]);
+            acc[x][0] = fmaf(vr.z, xr[2].x, acc[x][0]); acc[x][1] = fmaf(vr.z, xr[2].y, acc[x][1]);
+            acc[x][2] = fmaf(vr.z, xr[2].z, acc[x][2]); acc[x][3] = fmaf(vr.z, xr[2].w, acc[x][3]);
+            acc[x][0] = fmaf(vr.w, xr[3].x, acc[x][0]); acc[x][1] = fmaf(vr.w, xr[3].y, acc[x][1]);
+            acc[x][2] = fmaf(vr.w, xr[3].z, acc[x][2]); acc[x][3] = fmaf(vr.w, xr[3].w, acc[x][3]);
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          float4* zp = reinterpret_cast<float4*>(&Zs[((B * k + w0 + x) & 127) * nvp + v0]);
+          float4 z = *zp;
+          z.x -= acc[x][0]; z.y -= acc[x][1]; z.z -= acc[x][2]; z.w -= acc[x][3];
+          *zp = z;
+        }
+      }
+      __syncthreads();
+      // ---- rows leaving the window go back to global memory (everything at the group's last level)
+      {
+        const int nrow = last ? 127 : B;
+        for (int e = tid; e < nrow * nvp; e += nthr) {
+          const int v = e / nrow, w = e % nrow, r = rlo + w;
+          if (v < nvv && r < n) a.Z[(size_t)(vec0 + v) * a.ldz + r] = Zs[((B * k + w) & 127) * nvp + v];
+        }
+      }
+      __syncthreads();
+      if (last) break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- Q1
+// Xpart[s][c][vec] = sum over rows i of chunk s of V[c][i] * Z[vec][r0 + i]
+__global__ void __launch_bounds__(256, 2) k_q1_x(const float* __restrict__ Vp, long long lda, int m, const float* __restrict__ Zr,
+                                                 long long ldz, int mvec, float* __restrict__ Xpart, long long ldx, int chunk) {
+  __shared__ __align__(16) float smem[tile::Smem<64>::floats];
+  const int vec0 = (int)blockIdx.x * tile::TM;
+  const int ka = (int)blockIdx.y * chunk, kl = min(m, ka + chunk) - ka;
+  tile::Acc<64> acc;
+  acc.clear();
+  tile::mac<64>(acc, tile::opnd(Zr + (long long)vec0 * ldz + ka, ldz, 1, mvec - vec0, kl), tile::opnd(Vp + ka, lda, 1, B, kl), kl, smem);
+  float* out = Xpart + (size_t)blockIdx.y * B * ldx;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int c = tile::Acc<64>::col(b);
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int v = vec0 + tile::Acc<64>::row(a);
+      if (v < mvec) out[(long long)c * ldx + v] = acc.v[a][b];
+    }
+  }
+}
+
+// X'[c][vec] = sum_c' T[c][c'] sum_s Xpart[s][c'][vec]   (T row-major, upper triangular); one thread per vector
+__global__ void __launch_bounds__(128) k_q1_tx(const float* __restrict__ Xpart, int nparts, long long ldx, int mvec,
+                                               const float* __restrict__ T, float* __restrict__ Xout) {
+  __shared__ float Ts[B][B + 1];
+  for (int e = (int)threadIdx.x; e < B * B; e += (int)blockDim.x) Ts[e / B][e % B] = T[e];
+  __syncthreads();
+  const int v = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (v >= mvec) return;
+  float x[B];
+#pragma unroll
+  for (int c = 0; c < B; ++c) {
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += Xpart[(size_t)p * B * ldx + (long long)c * ldx + v];
+    x[c] = s;
+  }
+#pragma unroll
+  for (int c = 0; c < B; ++c) {
+    float s = 0.f;
+#pragma unroll
+    for (int cp = c; cp < B; ++cp) s = fmaf(Ts[c][cp], x[cp], s);
+    Xout[(long long)c * ldx + v] = s;
+  }
+}
+
+// Z[vec][r0 + i] -= sum_c V[c][i] X'[c][vec]
+__global__ void __launch_bounds__(256, 2) k_q1_z(const float* __restrict__ Vp, long long lda, int m, const float* __restrict__ Xp,
+                                                 long long ldx, int mvec, float* Zr, long long ldz) {
+  __shared__ __align__(16) float smem[tile::Smem<128>::floats];
+  const int i0 = (int)blockIdx.x * tile::TM, vec0 = (int)blockIdx.y * tile::TM;
+  tile::Acc<128> acc;
+  acc.clear();
+  tile::mac<128>(acc, tile::opnd(Vp + i0, lda, 0, m - i0, B), tile::opnd(Xp + vec0, ldx, 0, mvec - vec0, B), B, smem);
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const int v = vec0 + tile::Acc<128>::col(b);
+    if (v >= mvec) continue;
+    float* zc = Zr + (long long)v * ldz;
+#pragma unroll
+    for (int a4 = 0; a4 < 2; ++a4) {
+      const int i = i0 + tile::Acc<128>::row(a4 * 4);
+      if (i + 3 < m && ((((uintptr_t)(zc + i)) & 15) == 0)) {
+        float4 z = *reinterpret_cast<float4*>(zc + i);
+        z.x -= acc.v[a4 * 4 + 0][b]; z.y -= acc.v[a4 * 4 + 1][b]; z.z -= acc.v[a4 * 4 + 2][b]; z.w -= acc.v[a4 * 4 + 3][b];
+        *reinterpret_cast<float4*>(zc + i) = z;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (i + q < m) zc[i + q] -= acc.v[a4 * 4 + q][b];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2, int n, float* Z, long long ldz, int mvec,
+              cudaStream_t st) {
+  if (mvec <= 0 || n <= 2) return;
+  const int nsweeps = n - 2;
+  const int ngroups = (nsweeps + B - 1) / B;
+  const int nlev = sb2st_levels(n);
+  Tmp<float> Tq((size_t)ngroups * nlev * B * B, st);
+  k_q2_tfactor<<<dim3(nlev, ngroups), 256, 0, st>>>(V2, ldv2, tau2, ldt2, n, nlev, Tq.p);
+  SCL_CUDA(cudaGetLastError());
+  // vectors per CTA: one CTA per SM and as few rounds as the 88-vector limit allows, balanced
+  const int sms = sm_count();
+  const int rounds = (mvec + sms * 88 - 1) / (sms * 88);
+  int nv = (mvec + sms * rounds - 1) / (sms * rounds);
+  nv = std::max(4, (nv + 3) & ~3);
+  int nvp = nv;
+  if ((nvp & 31) == 0) nvp += 4;   // keeps the transposing shared-memory stores off a single bank
+  const int nslab = (mvec + nv - 1) / nv;
+  const int threads = 16 * (nvp / 4);
+  const size_t smem = ((size_t)128 * nvp + 2 * (size_t)B * nvp + 128 * VS + (size_t)B * VS) * sizeof(float);
+  SCL_REQUIRE(threads <= 384 && smem <= 200 * 1024, "apply_q2: slab does not fit");
+  SCL_CUDA(cudaFuncSetAttribute(k_q2_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  Q2Args a{V2, ldv2, Tq.p, n, nlev, ngroups, Z, ldz, mvec, nv, nvp};
+  k_q2_apply<<<nslab, threads, smem, st>>>(a);
+  SCL_CUDA(cudaGetLastError());
+  count_launches(2);
+}
+
+void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels, float* Z, long long ldz, int mvec,
+              cudaStream_t st) {
+  if (mvec <= 0 || npanels <= 0) return;
+  const long long ldx = ((long long)mvec + 3) & ~3LL;
+  const int max_split = 16;
+  Tmp<float> Xpart((size_t)max_split * B * ldx, st), Xp((size_t)B * ldx, st);
+  const int vt = (mvec + tile::TM - 1) / tile::TM;
+  const int slots = 2 * sm_count();
+  for (int k = npanels - 1; k >= 0; --k) {
+    const int c0 = k * B, r0 = c0 + B, m = n - r0;
+    if (m < 1) continue;
+    const float* Vp = A + r0 + (long long)c0 * lda;
+    int split = std::max(1, std::min(max_split, (4 * slots + vt - 1) / vt));
+    int chunk = ((m + split - 1) / split + tile::KT - 1) / tile::KT * tile::KT;
+    chunk = std::max(chunk, 4 * tile::KT);
+    split = (m + chunk - 1) / chunk;
+    k_q1_x<<<dim3(vt, split), 256, 0, st>>>(Vp, lda, m, Z + r0, ldz, mvec, Xpart.p, ldx, chunk);
+    k_q1_tx<<<(mvec + 127) / 128, 128, 0, st>>>(Xpart.p, split, ldx, mvec, T1 + (size_t)k * B * B, Xp.p);
+    k_q1_z<<<dim3((m + tile::TM - 1) / tile::TM, vt), 256, 0, st>>>(Vp, lda, m, Xp.p, ldx, mvec, Z + r0, ldz);
+  }
+  SCL_CUDA(cudaGetLastError());
+  count_launches(3 * npanels);
+}
+
+}  // namespace scl

@@ -5,6 +5,7 @@
 #include <thread>
 #include "handle.h"
 #include "tmp.cuh"
+#include "twostage.h"
 
 using namespace scl;
 
@@ -675,6 +676,58 @@ int32_t scl_bench_syevd_concurrent(scl_handle* h, int32_t n, int32_t nsolves, in
 int32_t scl_debug_set_eig_api(int32_t v) {
   scl::set_eig_api(v);
   return SCL_OK;
+}
+
+int32_t scl_debug_last_solve(scl_handle* h, double* out) {
+  if (!h || !out || !h->solver) return SCL_ERR_INVALID;
+  for (int i = 0; i < 5; ++i) out[i] = h->solver->tri_two_stage ? h->solver->ts_ms[i] : 0.0;
+  out[5] = h->solver->tri_two_stage ? 1.0 : 0.0;
+  out[6] = (double)h->solver->ts_fallbacks;
+  out[7] = (double)h->solver->tri_fallbacks;
+  return SCL_OK;
+}
+
+int32_t scl_debug_two_stage(scl_handle* h, int32_t n, const float* A, float* AB, float* d, float* e, float* Q2, float* Q,
+                            int32_t* flags) {
+  if (!h || !A || n < 8 || (n & 3)) return SCL_ERR_INVALID;
+  return guard(h, [&] {
+    SCL_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->st;
+    const size_t nn = (size_t)n * n;
+    const int nlev = sb2st_levels(n);
+    const long long ldv2 = (long long)nlev * kBand, ldt2 = nlev;
+    Tmp<float> dA(nn, st), dAB((size_t)n * kLdab, st), T1((size_t)(n / kBand + 2) * kBand * kBand, st), dd(n, st), de(n, st);
+    Tmp<float> V2((size_t)n * ldv2, st), tau2((size_t)n * ldt2, st), Z(nn, st);
+    Tmp<int> fail(1, st);
+    SCL_CUDA(cudaMemcpyAsync(dA.p, A, nn * sizeof(float), cudaMemcpyHostToDevice, st));
+    SCL_CUDA(cudaMemsetAsync(fail.p, 0, sizeof(int), st));
+    SCL_CUDA(cudaMemsetAsync(V2.p, 0, (size_t)n * ldv2 * sizeof(float), st));
+    SCL_CUDA(cudaMemsetAsync(tau2.p, 0, (size_t)n * ldt2 * sizeof(float), st));
+    const int npanels = sy2sb_lower(dA.p, n, n, dAB.p, T1.p, fail.p, st);
+    if (AB) SCL_CUDA(cudaMemcpyAsync(AB, dAB.p, (size_t)n * kLdab * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+    sb2st(dAB.p, n, dd.p, de.p, true, V2.p, ldv2, tau2.p, ldt2, st);
+    if (d) SCL_CUDA(cudaMemcpyAsync(d, dd.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (e) SCL_CUDA(cudaMemcpyAsync(e, de.p, (size_t)(n - 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SCL_CUDA(cudaStreamSynchronize(st));
+    if (Q2 || Q) {
+      std::vector<float> eye(nn, 0.f);
+      for (int i = 0; i < n; ++i) eye[(size_t)i * n + i] = 1.f;
+      SCL_CUDA(cudaMemcpyAsync(Z.p, eye.data(), nn * sizeof(float), cudaMemcpyHostToDevice, st));
+      apply_q2(V2.p, ldv2, tau2.p, ldt2, n, Z.p, n, n, st);
+      if (Q2) SCL_CUDA(cudaMemcpyAsync(Q2, Z.p, nn * sizeof(float), cudaMemcpyDeviceToHost, st));
+      SCL_CUDA(cudaStreamSynchronize(st));
+      if (Q) {
+        apply_q1(dA.p, n, n, T1.p, npanels, Z.p, n, n, st);
+        SCL_CUDA(cudaMemcpyAsync(Q, Z.p, nn * sizeof(float), cudaMemcpyDeviceToHost, st));
+      }
+    }
+    if (flags) {
+      SCL_CUDA(cudaMemcpyAsync(&flags[0], fail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      flags[1] = npanels;
+    }
+    SCL_CUDA(cudaStreamSynchronize(st));
+  });
 }
 
 int32_t scl_debug_set_tuning(int32_t stat_variant, int32_t stat_heavy, int32_t writer) {

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "eigen.h"
 #include "tmp.cuh"
+#include "twostage.h"
 
 namespace scl {
 
@@ -24,6 +25,9 @@ struct Solver::Impl {
   DBuf<float> work;
   DBuf<float> tri_d, tri_e, tri_tau, tri_z, tri_keep, tri_pad;   // own tridiagonal stage: T, reflector scalars, vectors, matrix copy, padded copy
   DBuf<double> tri_w;
+  // two-stage path (twostage.h): band, panel T factors, stage-2 reflectors and their scalars, matrix copy for the fallback
+  DBuf<float> ts_AB, ts_T1, ts_V2, ts_tau2, ts_keep;
+  DBuf<int> ts_fail;
   DBuf<double> dwork;
   DBuf<int> info;
   std::vector<unsigned char> host_work;
@@ -58,8 +62,92 @@ Solver::~Solver() {
   delete impl;
 }
 
+// Two-stage solve (SCL_EIG_API bit 5): dense -> band -> tridiagonal, Float64 tridiagonal stage, Z = Q1 Q2 E.  Same contract as
+// syevd_tri; a panel that cannot be factored (rank-deficient panel) or a failed tridiagonal stage falls back, loudly and
+// counted, to the one-stage path on a kept copy.
+bool Solver::syevd_2stage(float* dA, int n, float* dW, int v0, int v1, cudaStream_t st) {
+  const int m = v1 - v0;
+  const size_t nn = (size_t)n * n;
+  const long long lda = ((long long)n + 3) & ~3LL, ldz = lda;
+  const int nlev = sb2st_levels(n);
+  const long long ldv2 = (long long)nlev * kBand, ldt2 = nlev;
+  cudaEvent_t ev[6];
+  for (auto& e : ev) SCL_CUDA(cudaEventCreate(&e));
+  impl->tri_d.ensure(n); impl->tri_e.ensure(n); impl->tri_w.ensure(n);
+  impl->ts_keep.ensure(nn);
+  impl->ts_AB.ensure((size_t)n * kLdab);
+  impl->ts_T1.ensure((size_t)(n / kBand + 2) * kBand * kBand);
+  impl->ts_fail.ensure(1);
+  SCL_CUDA(cudaMemcpyAsync(impl->ts_keep.p, dA, nn * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SCL_CUDA(cudaMemsetAsync(impl->ts_fail.p, 0, sizeof(int), st));
+  float* Aq = dA;
+  if (lda != n) {
+    impl->tri_pad.ensure((size_t)lda * n);
+    SCL_CUDA(cudaMemsetAsync(impl->tri_pad.p, 0, (size_t)lda * n * sizeof(float), st));
+    SCL_CUDA(cudaMemcpy2DAsync(impl->tri_pad.p, (size_t)lda * sizeof(float), dA, (size_t)n * sizeof(float), (size_t)n * sizeof(float),
+                               (size_t)n, cudaMemcpyDeviceToDevice, st));
+    Aq = impl->tri_pad.p;
+  }
+  if (m) {
+    impl->tri_z.ensure((size_t)m * ldz);
+    impl->ts_V2.ensure((size_t)n * ldv2);
+    impl->ts_tau2.ensure((size_t)n * ldt2);
+    SCL_CUDA(cudaMemsetAsync(impl->ts_V2.p, 0, (size_t)n * ldv2 * sizeof(float), st));
+    SCL_CUDA(cudaMemsetAsync(impl->ts_tau2.p, 0, (size_t)n * ldt2 * sizeof(float), st));
+  }
+  SCL_CUDA(cudaEventRecord(ev[0], st));
+  const int npanels = sy2sb_lower(Aq, n, lda, impl->ts_AB.p, impl->ts_T1.p, impl->ts_fail.p, st);
+  SCL_CUDA(cudaEventRecord(ev[1], st));
+  sb2st(impl->ts_AB.p, n, impl->tri_d.p, impl->tri_e.p, m > 0, impl->ts_V2.p, ldv2, impl->ts_tau2.p, ldt2, st);
+  SCL_CUDA(cudaEventRecord(ev[2], st));
+  TridiagStats ts;
+  bool ok = tridiag_eigen(impl->tri_d.p, impl->tri_e.p, n, impl->tri_w.p, dW, v0, v1, impl->tri_z.p, ldz, st, &ts);
+  SCL_CUDA(cudaEventRecord(ev[3], st));
+  tri_clusters = ts.clusters;
+  tri_clustered = ts.clustered;
+  if (ok && m) {
+    apply_q2(impl->ts_V2.p, ldv2, impl->ts_tau2.p, ldt2, n, impl->tri_z.p, ldz, m, st);
+    SCL_CUDA(cudaEventRecord(ev[4], st));
+    apply_q1(Aq, n, lda, impl->ts_T1.p, npanels, impl->tri_z.p, ldz, m, st);
+    SCL_CUDA(cudaMemcpy2DAsync(dA + (size_t)v0 * n, (size_t)n * sizeof(float), impl->tri_z.p, (size_t)ldz * sizeof(float),
+                               (size_t)n * sizeof(float), (size_t)m, cudaMemcpyDeviceToDevice, st));
+  } else {
+    SCL_CUDA(cudaEventRecord(ev[4], st));
+  }
+  SCL_CUDA(cudaEventRecord(ev[5], st));
+  int fail = 0;
+  SCL_CUDA(cudaMemcpyAsync(&fail, impl->ts_fail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < 5; ++i) {
+    float t = 0;
+    cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+    ts_ms[i] = t;
+  }
+  tri_ms[0] = ts_ms[0] + ts_ms[1];
+  tri_ms[1] = ts_ms[2];
+  tri_ms[2] = ts_ms[3] + ts_ms[4];
+  for (auto& e : ev) cudaEventDestroy(e);
+  tri_own_sytrd = true;
+  tri_two_stage = true;
+  if (fail || !ok) {
+    ++ts_fallbacks;
+    fprintf(stderr, "[scl] two-stage reduction failed (panel flag %d, tridiagonal stage %s); this solve takes the one-stage path\n", fail,
+            ok ? "ok" : "failed");
+    SCL_CUDA(cudaMemcpyAsync(dA, impl->ts_keep.p, nn * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    tri_two_stage = false;
+    return syevd_tri_one_stage(dA, n, dW, v0, v1, st);
+  }
+  return true;
+}
+
 bool Solver::syevd_tri(float* dA, int n, float* dW, int v0, int v1, cudaStream_t st) {
   SCL_REQUIRE(n >= 2 && 0 <= v0 && v0 <= v1 && v1 <= n, "bad eigenvector index range");
+  tri_two_stage = false;
+  if ((eig_api() & 32) && n >= 4 * kBand) return syevd_2stage(dA, n, dW, v0, v1, st);
+  return syevd_tri_one_stage(dA, n, dW, v0, v1, st);
+}
+
+bool Solver::syevd_tri_one_stage(float* dA, int n, float* dW, int v0, int v1, cudaStream_t st) {
   const int m = v1 - v0;
   const size_t nn = (size_t)n * n;
   cudaEvent_t ev[4];

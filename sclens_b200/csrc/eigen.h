@@ -20,6 +20,12 @@ struct Solver {
   // (v0 == v1: values only); the other rows of dA are overwritten with scratch.  Falls back to Ssyevd on a kept copy of
   // the matrix (all vectors) when the twisted factorisation fails; returns true when it did not have to.
   bool syevd_tri(float* dA, int n, float* dW, int v0, int v1, cudaStream_t st);
+  bool syevd_tri_one_stage(float* dA, int n, float* dW, int v0, int v1, cudaStream_t st);
+  // two-stage reduction (sy2sb.cu, sb2st.cu, backtrans.cu) with the same contract; SCL_EIG_API bit 5 routes syevd_tri here
+  bool syevd_2stage(float* dA, int n, float* dW, int v0, int v1, cudaStream_t st);
+  double ts_ms[5] = {0, 0, 0, 0, 0};   // last two-stage solve: dense->band, band->tridiagonal, tridiagonal eigenproblem, Q2, Q1 + copy
+  bool tri_two_stage = false;
+  int ts_fallbacks = 0;
   // milliseconds of the last syevd_tri call: [0] Ssytrd, [1] eigenvalues + eigenvectors of T, [2] Sormtr + copy
   double tri_ms[3] = {0, 0, 0};
   int tri_clusters = 0, tri_clustered = 0, tri_fallbacks = 0;
@@ -39,7 +45,7 @@ bool tridiag_eigen(const float* d32, const float* e32, int n, double* w64, float
 
 // SCL_EIG_API: bit 0 = Xsyevd for the full solves, bit 1 = Ssyevdx (index range) in the search steps, bit 2 = own tridiagonal
 // stage (Ssytrd + tridiag.cu + Sormtr) for every solve, bit 3 = with bit 2: vectors of the index range the search step uses only, bit 4 = with bit 2: own tridiagonalisation
-// (sytrd.cu) instead of cusolverDnSsytrd
+// (sytrd.cu) instead of cusolverDnSsytrd, bit 5 = with bit 2: two-stage reduction (twostage.h) for matrices of order >= 256
 // sytrd.cu: own Householder tridiagonalisation (persistent cooperative kernel), output as ssytrd('L'); false = not handled
 bool sytrd_lower(float* dA, int n, int lda, float* d_d, float* d_e, float* d_tau, cudaStream_t st);
 int eig_api();

@@ -1,0 +1,178 @@
+// Register-tiled FP32 tile engine of the two-stage eigensolver (sy2sb.cu, backtrans.cu): a CTA of 256 threads accumulates
+//   acc(i, j) += sum_k A(i, k) * B(j, k),   i < 128, j < TN (128 or 64)
+// with 8 x (TN/16) outputs per thread, 16-deep k-tiles double-buffered through shared memory and the next tile's global
+// loads held in registers while the current one is multiplied.  Operands are described, not copied: three source
+// layouts cover every product of the reduction (panel times small matrix, symmetric matrix from its lower triangle times
+// panel, rank-2k update, reflector blocks times eigenvector slabs), and anything outside an operand's extents reads as 0,
+// so ragged edges need no special kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace scl {
+namespace tile {
+
+constexpr int TM = 128, KT = 16, NT = 256, PAD = 4;
+
+struct Opnd {
+  const float* p;   // element (i = 0, k = 0)
+  long long ld;
+  int layout;       // 0: p[i + k*ld]   1: p[k + i*ld]   2: symmetric block kept in its lower triangle: i >= k ? p[i + k*ld] : p[k + i*ld]
+  int mn, k;        // extents: i < mn, k < k (everything else is zero)
+};
+
+__host__ __device__ inline Opnd opnd(const float* p, long long ld, int layout, long long mn, long long k) {
+  Opnd o;
+  o.p = p; o.ld = ld; o.layout = layout;
+  o.mn = (int)(mn < 0 ? 0 : (mn > 0x3fffffff ? 0x3fffffff : mn));
+  o.k = (int)(k < 0 ? 0 : (k > 0x3fffffff ? 0x3fffffff : k));
+  return o;
+}
+
+template <int W>   // operand tile width (128 or 64): W * KT / 4 float4 per tile, NT threads
+struct Frag {
+  static constexpr int N = W * KT / 4 / NT;
+  float4 r[N];
+};
+
+template <int W>
+__device__ __forceinline__ void g2r(const Opnd& o, int k0, Frag<W>& f) {
+  const int tid = (int)threadIdx.x;
+  const bool vec = (((uintptr_t)o.p & 15) == 0) && ((o.ld & 3) == 0);
+#pragma unroll
+  for (int q = 0; q < Frag<W>::N; ++q) {
+    const int idx = tid + q * NT;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (o.layout == 1) {
+      const int i = idx / (KT / 4), k = k0 + (idx % (KT / 4)) * 4;
+      if (i < o.mn && k < o.k) {
+        const float* s = o.p + (long long)i * o.ld + k;
+        if (vec && k + 3 < o.k) {
+          v = *reinterpret_cast<const float4*>(s);
+        } else {
+          v.x = s[0];
+          if (k + 1 < o.k) v.y = s[1];
+          if (k + 2 < o.k) v.z = s[2];
+          if (k + 3 < o.k) v.w = s[3];
+        }
+      }
+    } else {
+      const int k = k0 + idx / (W / 4), i = (idx % (W / 4)) * 4;
+      if (k < o.k && i < o.mn) {
+        if (o.layout == 0) {
+          const float* s = o.p + (long long)k * o.ld + i;
+          if (vec && i + 3 < o.mn) {
+            v = *reinterpret_cast<const float4*>(s);
+          } else {
+            v.x = s[0];
+            if (i + 1 < o.mn) v.y = s[1];
+            if (i + 2 < o.mn) v.z = s[2];
+            if (i + 3 < o.mn) v.w = s[3];
+          }
+        } else {
+          float e[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int ii = i + t;
+            e[t] = ii < o.mn ? (ii >= k ? o.p[ii + (long long)k * o.ld] : o.p[k + (long long)ii * o.ld]) : 0.f;
+          }
+          v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+      }
+    }
+    f.r[q] = v;
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void r2s(const Opnd& o, const Frag<W>& f, float* S /* [KT][W + PAD] */) {
+  const int tid = (int)threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < Frag<W>::N; ++q) {
+    const int idx = tid + q * NT;
+    if (o.layout == 1) {
+      const int i = idx / (KT / 4), k = (idx % (KT / 4)) * 4;
+      S[(k + 0) * (W + PAD) + i] = f.r[q].x;
+      S[(k + 1) * (W + PAD) + i] = f.r[q].y;
+      S[(k + 2) * (W + PAD) + i] = f.r[q].z;
+      S[(k + 3) * (W + PAD) + i] = f.r[q].w;
+    } else {
+      const int k = idx / (W / 4), i = (idx % (W / 4)) * 4;
+      *reinterpret_cast<float4*>(&S[k * (W + PAD) + i]) = f.r[q];
+    }
+  }
+}
+
+template <int TN>
+struct Acc {
+  static constexpr int NJ = TN / 16;   // 8 or 4 columns per thread
+  float v[8][NJ];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < NJ; ++b) v[a][b] = 0.f;
+  }
+  // tile coordinates of v[a][b] for this thread
+  static __device__ __forceinline__ int row(int a) { return ((int)threadIdx.x & 15) * 4 + (a & 3) + (a >> 2) * 64; }
+  static __device__ __forceinline__ int col(int b) { return ((int)threadIdx.x >> 4) * 4 + (b & 3) + (b >> 2) * 64; }
+};
+
+template <int TN>
+struct Smem {
+  static constexpr int floats = 2 * KT * (TM + PAD) + 2 * KT * (TN + PAD);
+};
+
+// acc += A(:, 0..klen) * B(:, 0..klen)'   (all 256 threads; smem = Smem<TN>::floats floats, 16-byte aligned)
+template <int TN>
+__device__ __forceinline__ void mac(Acc<TN>& acc, const Opnd& A, const Opnd& B, int klen, float* smem) {
+  if (klen <= 0) return;
+  float* As = smem;
+  float* Bs = smem + 2 * KT * (TM + PAD);
+  const int tx = (int)threadIdx.x & 15, ty = (int)threadIdx.x >> 4;
+  const int nk = (klen + KT - 1) / KT;
+  Frag<TM> fa;
+  Frag<TN> fb;
+  g2r<TM>(A, 0, fa);
+  g2r<TN>(B, 0, fb);
+  __syncthreads();   // the previous user of the buffers is done
+  r2s<TM>(A, fa, As);
+  r2s<TN>(B, fb, Bs);
+  __syncthreads();
+  for (int t = 0; t < nk; ++t) {
+    const int cur = t & 1;
+    if (t + 1 < nk) {
+      g2r<TM>(A, (t + 1) * KT, fa);
+      g2r<TN>(B, (t + 1) * KT, fb);
+    }
+    const float* as = As + cur * KT * (TM + PAD);
+    const float* bs = Bs + cur * KT * (TN + PAD);
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&as[k * (TM + PAD) + tx * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&as[k * (TM + PAD) + 64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[Acc<TN>::NJ];
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(&bs[k * (TN + PAD) + ty * 4]);
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+        if constexpr (TN == 128) {
+          const float4 b1 = *reinterpret_cast<const float4*>(&bs[k * (TN + PAD) + 64 + ty * 4]);
+          bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < Acc<TN>::NJ; ++b) acc.v[a][b] = fmaf(av[a], bv[b], acc.v[a][b]);
+    }
+    if (t + 1 < nk) {
+      r2s<TM>(A, fa, As + (cur ^ 1) * KT * (TM + PAD));
+      r2s<TN>(B, fb, Bs + (cur ^ 1) * KT * (TN + PAD));
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace tile
+}  // namespace scl
