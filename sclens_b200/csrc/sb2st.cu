@@ -9,6 +9,8 @@
 // cooperative kernel (co-residency is what makes the spin-waits safe); the whole band (n x 2 kBand floats, 10 MB at
 // n = 20 000) lives in L2.  The critical path is 2n dependent steps, which is why a step is kept to a handful of barriers.
 #include <algorithm>
+#include <cstdlib>
+#include <vector>
 #include "common.cuh"
 #include "tmp.cuh"
 #include "twostage.h"
@@ -29,7 +31,22 @@ struct SbArgs {
   float* tau2;
   long long ldt2;
   int keep;
+  unsigned long long* prof;   // [grid][8] nanoseconds of thread 0 per section (SCL_TRACE), may be null
 };
+
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define SB_TICK(slot)                         \
+  do {                                        \
+    if (a.prof && tid == 0) {                 \
+      const unsigned long long t_ = now_ns(); \
+      tacc[slot] += t_ - tlast;               \
+      tlast = t_;                             \
+    }                                         \
+  } while (0)
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -71,6 +88,7 @@ __global__ void __launch_bounds__(256, 1) k_sb2st(SbArgs a) {
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n;
   int seen = 0;   // thread 0: last progress value read from the predecessor
+  unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = now_ns();
 
   auto wait_for = [&](int s, int need) {
     if (s > 0 && tid == 0) {
@@ -154,7 +172,9 @@ __global__ void __launch_bounds__(256, 1) k_sb2st(SbArgs a) {
       const float* v = vbuf[cur];
       float* v1 = vbuf[cur ^ 1];
       const float tau = s_tau[cur];
+      SB_TICK(0);
       wait_for(s, k + 2);
+      SB_TICK(1);
       // ---- the block below: rows r1.., columns r0..r0+L-1 (band offset of (i, c): L + i - c)
       {
         const int i = tid & 63;
@@ -164,6 +184,7 @@ __global__ void __launch_bounds__(256, 1) k_sb2st(SbArgs a) {
       }
       if (L1 >= 2) load_diag(r1, L1);
       __syncthreads();
+      SB_TICK(2);
       {  // x = B v, then B -= tau x v'
         const int i = tid >> 2, q = tid & 3;
         float s1 = 0.f;
@@ -180,6 +201,7 @@ __global__ void __launch_bounds__(256, 1) k_sb2st(SbArgs a) {
         for (int c = tid >> 6; c < L; c += 4) Bt[c][i] = fmaf(-xi, v[c], Bt[c][i]);
       }
       __syncthreads();
+      SB_TICK(3);
       if (L1 >= 2) {
         // new reflector from the block's first column
         if (warp == 0) house_warp(Bt[0], L1, v1, &s_tau[cur ^ 1], &s_beta);
@@ -210,15 +232,20 @@ __global__ void __launch_bounds__(256, 1) k_sb2st(SbArgs a) {
         }
       }
       if (L1 < 2) break;
+      SB_TICK(4);
       two_sided(r1, L1, v1, s_tau[cur ^ 1]);
       keep_reflector(s, k, v1, s_tau[cur ^ 1]);
+      SB_TICK(5);
       publish(s, k + 1);
+      SB_TICK(6);
       r0 = r1;
       L = L1;
       cur ^= 1;
     }
     publish(s, kDone);
   }
+  if (a.prof && tid == 0)
+    for (int q = 0; q < 8; ++q) a.prof[(size_t)blockIdx.x * 8 + q] = tacc[q];
 }
 
 __global__ void k_band_to_tridiag(const float* __restrict__ AB, int n, float* __restrict__ d, float* __restrict__ e) {
@@ -243,9 +270,26 @@ void sb2st(float* AB, int n, float* d, float* e, bool keep, float* V2, long long
     SCL_REQUIRE(per_sm >= 1, "sb2st: kernel does not fit on an SM");
     // at most n / (2 kBand) sweeps can be in flight at once (each trails its predecessor by two steps)
     const int grid = std::max(1, std::min(sms, n / (2 * B) + 2));
-    SbArgs args{AB, n, prog.p, V2, ldv2, tau2, ldt2, keep ? 1 : 0};
+    static const bool trace = getenv("SCL_TRACE") != nullptr;
+    Tmp<unsigned long long> prof(trace ? (size_t)grid * 8 : 1, st);
+    SbArgs args{AB, n, prog.p, V2, ldv2, tau2, ldt2, keep ? 1 : 0, trace ? prof.p : nullptr};
     void* params[] = {&args};
     SCL_CUDA(cudaLaunchCooperativeKernel((void*)k_sb2st, dim3(grid), dim3(256), params, 0, st));
+    if (trace) {
+      std::vector<unsigned long long> hp((size_t)grid * 8);
+      SCL_CUDA(cudaMemcpyAsync(hp.data(), prof.p, hp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      SCL_CUDA(cudaStreamSynchronize(st));
+      static const char* name[7] = {"(step 0 / loop overhead)", "wait for predecessor", "load blocks", "right apply", "reflector + left apply + store",
+                                    "two-sided diagonal block", "publish (fence + flag)"};
+      for (int q = 0; q < 7; ++q) {
+        double mn = 1e30, mx = 0, av = 0;
+        for (int g = 0; g < grid; ++g) {
+          const double v = (double)hp[(size_t)g * 8 + q] * 1e-6;
+          mn = std::min(mn, v); mx = std::max(mx, v); av += v / grid;
+        }
+        fprintf(stderr, "[scl] sb2st n=%d grid=%d %-32s ms per CTA: min %8.2f  mean %8.2f  max %8.2f\n", n, grid, name[q], mn, av, mx);
+      }
+    }
   }
   k_band_to_tridiag<<<(n + 255) / 256, 256, 0, st>>>(AB, n, d, e);
   SCL_CUDA(cudaGetLastError());
