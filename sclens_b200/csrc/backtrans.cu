@@ -7,7 +7,8 @@
 // levels ascending inside a group (oracle/two_stage_ref.py: apply_q2 == apply_q2_plain).  Every eigenvector is independent:
 // a CTA owns a slab of vectors, keeps the 127-row window of its slab in shared memory (consecutive levels overlap in 63
 // rows, which never leave the SM), and walks all blocks.
-// Q1 (stage-1 panels): Z[r0:] -= V (T (V' Z[r0:])) panel by panel, last panel first, on the FP32 tile engine.
+// Q1 (stage-1 panels): Z[r0:] -= (V T) (V' Z[r0:]) panel by panel, last panel first, on the FP32 tile engine (V T was stored by
+// stage 1 in the upper triangle of A).
 #include <algorithm>
 #include "common.cuh"
 #include "sgemm_tile.cuh"
@@ -71,45 +72,81 @@ struct Q2Args {
   int mvec, nv, nvp;
 };
 
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 4 : 0;   // src-size 0: the destination is zero-filled, the source is not read
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // blockDim = 16 * (nvp / 4): thread (g = tid & 15, vg = tid >> 4) owns vectors 4 vg .. 4 vg + 3 and, per product, the
-// reflectors 4 g .. 4 g + 3 (first product, T product) or the window rows 8 g .. 8 g + 7 (second product)
+// reflectors 4 g .. 4 g + 3 (first product, T product) or the window rows 8 g .. 8 g + 7 (second product).
+// Everything a block needs from global memory - its reflectors (scattered into the parallelogram), its T factor and the 64
+// window rows that enter - is fetched with cp.async while the previous block is being multiplied (double-buffered V / T, a
+// staging area for the rows); only the first block of a group of sweeps waits for its loads.
 __global__ void __launch_bounds__(384, 1) k_q2_apply(Q2Args a) {
   extern __shared__ __align__(16) float sm[];
   const int nvp = a.nvp;
   float* Zs = sm;                        // [128][nvp]  window rows (slot = window row & 127, see below) x vectors
   float* Xs = Zs + 128 * nvp;            // [64][nvp]
   float* X2s = Xs + B * nvp;             // [64][nvp]
-  float* Vs = X2s + B * nvp;             // [128][VS]   parallelogram: Vs[j + i][j] = v_j[i]
-  float* Tt = Vs + 128 * VS;             // [64][VS]
+  float* Zst = X2s + B * nvp;            // [64][nvp]   rows entering the window at the next level
+  float* Vs0 = Zst + B * nvp;            // [2][128][VS] parallelogram: Vs[j + i][j] = v_j[i]
+  float* Tt0 = Vs0 + 2 * 128 * VS;       // [2][64][VS]
   const int tid = (int)threadIdx.x, nthr = (int)blockDim.x;
   const int g = tid & 15, vg = tid >> 4, v0 = vg * 4;
   const int vec0 = (int)blockIdx.x * a.nv, nvv = min(a.nv, a.mvec - vec0);
   const int n = a.n;
-  for (int e = tid; e < 128 * VS; e += nthr) Vs[e] = 0.f;
+  for (int e = tid; e < 2 * 128 * VS; e += nthr) Vs0[e] = 0.f;
   for (int e = tid; e < 128 * nvp; e += nthr) Zs[e] = 0.f;
   __syncthreads();
+  // reflectors and T of block (G, k) into buffer `buf`
+  auto fetch_vt = [&](int G, int k, int buf) {
+    float* Vs = Vs0 + buf * 128 * VS;
+    float* Tt = Tt0 + buf * B * VS;
+    const int s0 = G * B;
+    for (int e = tid; e < B * B; e += nthr) {
+      const int j = e / B, i = e % B, s = s0 + j;
+      const bool ok = s < n - 2;
+      cp_async4(&Vs[(j + i) * VS + j], ok ? a.V2 + (size_t)s * a.ldv2 + (size_t)k * B + i : a.V2, ok);
+    }
+    const float* tq = a.Tq + ((size_t)G * a.nlev + k) * B * B;
+    for (int e = tid; e < B * B / 4; e += nthr) cp_async16(&Tt[(e / (B / 4)) * VS + (e % (B / 4)) * 4], tq + (size_t)e * 4);
+  };
+  // window rows [w0, w0 + nrow) of the window starting at global row rlo: staging area dst[(w - w0)][v], or the window's own slots
+  auto fetch_rows = [&](int rlo, int w0, int nrow, float* dst, int slot0, bool to_slots) {
+    for (int e = tid; e < nrow * nvp; e += nthr) {
+      const int v = e / nrow, w = e % nrow, r = rlo + w0 + w;
+      const bool ok = v < nvv && r < n;
+      float* d = to_slots ? &Zs[((slot0 + w0 + w) & 127) * nvp + v] : &dst[w * nvp + v];
+      cp_async4(d, ok ? a.Z + (size_t)(vec0 + v) * a.ldz + r : a.Z, ok);
+    }
+  };
+  int blk = 0;
   for (int G = a.ngroups - 1; G >= 0; --G) {
     const int s0 = G * B, base = s0 + 1;   // window row w of level k is global row base + 64 k + w, kept in slot (64 k + w) & 127
-    for (int k = 0;; ++k) {
+    if (base > n - 2) continue;
+    // the group's first block: nothing to overlap with
+    fetch_vt(G, 0, blk & 1);
+    fetch_rows(base, 0, 127, nullptr, 0, true);
+    cp_async_commit();
+    for (int k = 0;; ++k, ++blk) {
       const int rlo = base + B * k;
-      if (rlo > n - 2) break;
       const bool last = rlo + B > n - 2;
-      // ---- loads: new window rows (all 127 at level 0, the upper 64 afterwards), reflectors, T
-      {
-        const int w_first = k == 0 ? 0 : B - 1;
-        const int nrow = 127 - w_first;
-        for (int e = tid; e < nrow * nvp; e += nthr) {
-          const int v = e / nrow, w = w_first + e % nrow, r = rlo + w;
-          if (v < nvp) Zs[((B * k + w) & 127) * nvp + v] = (v < nvv && r < n) ? a.Z[(size_t)(vec0 + v) * a.ldz + r] : 0.f;
-        }
-        for (int e = tid; e < B * B; e += nthr) {
-          const int j = e / B, i = e % B, s = s0 + j;
-          Vs[(j + i) * VS + j] = s < n - 2 ? a.V2[(size_t)s * a.ldv2 + (size_t)k * B + i] : 0.f;
-        }
-        const float* tq = a.Tq + ((size_t)G * a.nlev + k) * B * B;
-        for (int e = tid; e < B * B; e += nthr) Tt[(e / B) * VS + (e % B)] = tq[e];
-      }
+      const float* Vs = Vs0 + (blk & 1) * 128 * VS;
+      const float* Tt = Tt0 + (blk & 1) * B * VS;
+      cp_async_wait_all();
       __syncthreads();
+      if (!last) {
+        fetch_vt(G, k + 1, (blk + 1) & 1);
+        fetch_rows(rlo + B, B - 1, B, Zst, 0, false);
+        cp_async_commit();
+      }
       // ---- X[c][vec] = sum_w V[w][c] Z[w][vec], w in [c, c + 63]
       {
         float acc[4][4];
@@ -199,8 +236,18 @@ __global__ void __launch_bounds__(384, 1) k_q2_apply(Q2Args a) {
           if (v < nvv && r < n) a.Z[(size_t)(vec0 + v) * a.ldz + r] = Zs[((B * k + w) & 127) * nvp + v];
         }
       }
+      if (last) {
+        ++blk;
+        __syncthreads();
+        break;
+      }
+      // ---- the prefetched rows take the slots of the rows that just left: window rows 63..126 of level k + 1
+      cp_async_wait_all();
       __syncthreads();
-      if (last) break;
+      for (int e = tid; e < B * nvp; e += nthr) {
+        const int w = e / nvp, v = e % nvp;
+        Zs[((B * (k + 1) + B - 1 + w) & 127) * nvp + v] = Zst[w * nvp + v];
+      }
     }
   }
 }
@@ -227,38 +274,22 @@ __global__ void __launch_bounds__(256, 2) k_q1_x(const float* __restrict__ Vp, l
   }
 }
 
-// X'[c][vec] = sum_c' T[c][c'] sum_s Xpart[s][c'][vec]   (T row-major, upper triangular); one thread per vector
-__global__ void __launch_bounds__(128) k_q1_tx(const float* __restrict__ Xpart, int nparts, long long ldx, int mvec,
-                                               const float* __restrict__ T, float* __restrict__ Xout) {
-  __shared__ float Ts[B][B + 1];
-  for (int e = (int)threadIdx.x; e < B * B; e += (int)blockDim.x) Ts[e / B][e % B] = T[e];
-  __syncthreads();
-  const int v = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (v >= mvec) return;
-  float x[B];
-#pragma unroll
-  for (int c = 0; c < B; ++c) {
-    float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += Xpart[(size_t)p * B * ldx + (long long)c * ldx + v];
-    x[c] = s;
-  }
-#pragma unroll
-  for (int c = 0; c < B; ++c) {
-    float s = 0.f;
-#pragma unroll
-    for (int cp = c; cp < B; ++cp) s = fmaf(Ts[c][cp], x[cp], s);
-    Xout[(long long)c * ldx + v] = s;
-  }
+__global__ void k_sum_parts32(const float* __restrict__ part, int nparts, size_t stride, size_t n, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(size_t)p * stride + i];
+  out[i] = s;
 }
 
-// Z[vec][r0 + i] -= sum_c V[c][i] X'[c][vec]
-__global__ void __launch_bounds__(256, 2) k_q1_z(const float* __restrict__ Vp, long long lda, int m, const float* __restrict__ Xp,
+// Z[vec][r0 + i] -= sum_c (V T)[i][c] X[c][vec]   (VTt: the panel's V T as sy2sb left it, element (i, c) at VTt[c + i * lda])
+__global__ void __launch_bounds__(256, 2) k_q1_z(const float* __restrict__ VTt, long long lda, int m, const float* __restrict__ Xp,
                                                  long long ldx, int mvec, float* Zr, long long ldz) {
   __shared__ __align__(16) float smem[tile::Smem<128>::floats];
   const int i0 = (int)blockIdx.x * tile::TM, vec0 = (int)blockIdx.y * tile::TM;
   tile::Acc<128> acc;
   acc.clear();
-  tile::mac<128>(acc, tile::opnd(Vp + i0, lda, 0, m - i0, B), tile::opnd(Xp + vec0, ldx, 0, mvec - vec0, B), B, smem);
+  tile::mac<128>(acc, tile::opnd(VTt + (long long)i0 * lda, lda, 1, m - i0, B), tile::opnd(Xp + vec0, ldx, 0, mvec - vec0, B), B, smem);
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
     const int v = vec0 + tile::Acc<128>::col(b);
@@ -300,8 +331,8 @@ void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2
   if ((nvp & 31) == 0) nvp += 4;   // keeps the transposing shared-memory stores off a single bank
   const int nslab = (mvec + nv - 1) / nv;
   const int threads = 16 * (nvp / 4);
-  const size_t smem = ((size_t)128 * nvp + 2 * (size_t)B * nvp + 128 * VS + (size_t)B * VS) * sizeof(float);
-  SCL_REQUIRE(threads <= 384 && smem <= 200 * 1024, "apply_q2: slab does not fit");
+  const size_t smem = ((size_t)128 * nvp + 3 * (size_t)B * nvp + 2 * 128 * VS + 2 * (size_t)B * VS) * sizeof(float);
+  SCL_REQUIRE(threads <= 384 && smem <= 227 * 1024, "apply_q2: slab does not fit");
   SCL_CUDA(cudaFuncSetAttribute(k_q2_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   Q2Args a{V2, ldv2, Tq.p, n, nlev, ngroups, Z, ldz, mvec, nv, nvp};
   k_q2_apply<<<nslab, threads, smem, st>>>(a);
@@ -326,8 +357,9 @@ void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels
     chunk = std::max(chunk, 4 * tile::KT);
     split = (m + chunk - 1) / chunk;
     k_q1_x<<<dim3(vt, split), 256, 0, st>>>(Vp, lda, m, Z + r0, ldz, mvec, Xpart.p, ldx, chunk);
-    k_q1_tx<<<(mvec + 127) / 128, 128, 0, st>>>(Xpart.p, split, ldx, mvec, T1 + (size_t)k * B * B, Xp.p);
-    k_q1_z<<<dim3((m + tile::TM - 1) / tile::TM, vt), 256, 0, st>>>(Vp, lda, m, Xp.p, ldx, mvec, Z + r0, ldz);
+    const size_t nx = (size_t)B * ldx;
+    k_sum_parts32<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(Xpart.p, split, nx, nx, Xp.p);
+    k_q1_z<<<dim3((m + tile::TM - 1) / tile::TM, vt), 256, 0, st>>>(A + c0 + (long long)r0 * lda, lda, m, Xp.p, ldx, mvec, Z + r0, ldz);
   }
   SCL_CUDA(cudaGetLastError());
   count_launches(3 * npanels);

@@ -28,6 +28,7 @@ struct Solver::Impl {
   // two-stage path (twostage.h): band, panel T factors, stage-2 reflectors and their scalars, matrix copy for the fallback
   DBuf<float> ts_AB, ts_T1, ts_V2, ts_tau2, ts_keep;
   DBuf<int> ts_fail;
+  Sy2sbAux ts_aux;
   DBuf<double> dwork;
   DBuf<int> info;
   std::vector<unsigned char> host_work;
@@ -57,6 +58,11 @@ Solver::Solver(cudaStream_t st) : impl(new Impl) {
   impl->info.ensure(1);
 }
 Solver::~Solver() {
+  if (impl->ts_aux.stream) {
+    cudaStreamDestroy(impl->ts_aux.stream);
+    cudaEventDestroy(impl->ts_aux.ready);
+    cudaEventDestroy(impl->ts_aux.done);
+  }
   if (impl->params) cusolverDnDestroyParams(impl->params);
   if (impl->h) cusolverDnDestroy(impl->h);
   delete impl;
@@ -96,7 +102,15 @@ bool Solver::syevd_2stage(float* dA, int n, float* dW, int v0, int v1, cudaStrea
     SCL_CUDA(cudaMemsetAsync(impl->ts_tau2.p, 0, (size_t)n * ldt2 * sizeof(float), st));
   }
   SCL_CUDA(cudaEventRecord(ev[0], st));
-  const int npanels = sy2sb_lower(Aq, n, lda, impl->ts_AB.p, impl->ts_T1.p, impl->ts_fail.p, st);
+  if (!impl->ts_aux.stream) {
+    int lo = 0, hi = 0;
+    SCL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SCL_CUDA(cudaStreamCreateWithPriority(&impl->ts_aux.stream, cudaStreamNonBlocking, hi));
+    SCL_CUDA(cudaEventCreateWithFlags(&impl->ts_aux.ready, cudaEventDisableTiming));
+    SCL_CUDA(cudaEventCreateWithFlags(&impl->ts_aux.done, cudaEventDisableTiming));
+  }
+  static const bool no_ahead = getenv("SCL_NO_LOOKAHEAD") != nullptr;
+  const int npanels = sy2sb_lower(Aq, n, lda, impl->ts_AB.p, impl->ts_T1.p, impl->ts_fail.p, st, no_ahead ? nullptr : &impl->ts_aux);
   SCL_CUDA(cudaEventRecord(ev[1], st));
   sb2st(impl->ts_AB.p, n, impl->tri_d.p, impl->tri_e.p, m > 0, impl->ts_V2.p, ldv2, impl->ts_tau2.p, ldt2, st);
   SCL_CUDA(cudaEventRecord(ev[2], st));

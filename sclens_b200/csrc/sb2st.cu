@@ -60,32 +60,31 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// LAPACK slarfg on x[0..L) (shared memory), by warp 0: v (v[0] = 1, zero-padded to kBand), tau, beta
-__device__ __forceinline__ void house_warp(const float* x, int L, float* v, float* tau, float* beta) {
+// LAPACK slarfg on x[0..64) (shared memory, zero beyond the reflector's length), by every warp for itself: the reflector is
+// v[0] = 1, v[i] = x[i] * sc; returns tau, beta, sc in every lane
+__device__ __forceinline__ void house_all(const float* x, float& tau, float& beta, float& sc) {
   const int lane = (int)threadIdx.x & 31;
-  const float x0 = lane < L ? x[lane] : 0.f, x1 = lane + 32 < L ? x[lane + 32] : 0.f;
+  const float x0 = x[lane], x1 = x[lane + 32];
   const float alpha = __shfl_sync(0xffffffffu, x0, 0);
   float ss = (lane == 0 ? 0.f : x0 * x0) + x1 * x1;
   ss = warp_sum(ss);
-  float t = 0.f, b = alpha, sc = 0.f;
+  tau = 0.f; beta = alpha; sc = 0.f;
   if (ss > 0.f) {
-    b = -copysignf(sqrtf(alpha * alpha + ss), alpha);
-    t = (b - alpha) / b;
-    sc = 1.f / (alpha - b);
-  }
-  v[lane] = lane == 0 ? 1.f : x0 * sc;
-  v[lane + 32] = x1 * sc;
-  if (lane == 0) {
-    *tau = t;
-    *beta = b;
+    beta = -copysignf(sqrtf(alpha * alpha + ss), alpha);
+    tau = (beta - alpha) / beta;
+    sc = 1.f / (alpha - beta);
   }
 }
 
+// Thread (ri = tid / 4, q = tid % 4) keeps its part of a 64 x 64 block in registers: for the passes that sum along a row it
+// owns row ri, columns q + 4j (j < 16); for the pass that sums along a column it owns column ri, rows q + 4j - the four
+// partial sums of a line always sit in adjacent lanes (two shuffles), and the block changes ownership once through shared
+// memory.  Loops have fixed trip counts (ragged blocks at the end of the band are zero-filled), so everything unrolls.
 __global__ void __launch_bounds__(256, 1) k_sb2st(SbArgs a) {
-  __shared__ __align__(16) float Bt[B][LD], Dt[B][LD];   // [column][row]
-  __shared__ float vbuf[2][B], xs[B], ws[B];
-  __shared__ float s_tau[2], s_beta;
-  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ __align__(16) float Bt[B][LD];   // [column][row]; Bt[0] is the column the new reflector is made from
+  __shared__ float ws[B];
+  const int tid = (int)threadIdx.x, lane = tid & 31;
+  const int ri = tid >> 2, q = tid & 3;
   const int n = a.n;
   int seen = 0;   // thread 0: last progress value read from the predecessor
   unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = now_ns();
@@ -96,156 +95,132 @@ __global__ void __launch_bounds__(256, 1) k_sb2st(SbArgs a) {
     }
     __syncthreads();
   };
+  // the barrier orders every thread's band stores before thread 0's release store (cumulativity)
   auto publish = [&](int s, int val) {
-    __threadfence();
     __syncthreads();
     if (tid == 0) st_release(a.prog + s, val);
   };
-  // diagonal block rows/cols r..r+L-1 -> Dt, full symmetric
-  auto load_diag = [&](int r, int L) {
-    const int ii = tid & 63;
-#pragma unroll 4
-    for (int c = tid >> 6; c < L; c += 4) {
-      const int i = c + ii;
-      if (i < L) {
-        const float v = __ldcg(a.AB + (size_t)(r + c) * kLdab + ii);
-        Dt[c][i] = v;
-        Dt[i][c] = v;
-      }
+  // diagonal block rows/cols r..r+Ld-1 from its lower triangle: dq[j] = D[q + 4j][ri]
+  auto load_diag = [&](float (&dq)[16], int r, int Ld) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = q + 4 * j;
+      const int lo = min(ri, c), hi = max(ri, c);
+      dq[j] = hi < Ld ? __ldcg(a.AB + (size_t)(r + lo) * kLdab + (hi - lo)) : 0.f;
     }
   };
-  // D <- H D H with H = I - tau v v', written straight back to the band (lower triangle)
-  auto two_sided = [&](int r, int L, const float* v, float tau) {
-    {  // w = tau D v : thread (i = tid / 4, q = tid % 4) sums c = q, q + 4, ...
-      const int i = tid >> 2, q = tid & 3;
-      float s = 0.f;
-      if (i < L)
-        for (int c = q; c < L; c += 4) s = fmaf(Dt[c][i], v[c], s);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (q == 0) ws[i] = i < L ? tau * s : 0.f;
-    }
+  // D <- H D H, H = I - tau v v' with v[x] = x == 0 ? 1 : Bt[0][x] * sc; lower triangle written straight back to the band
+  auto two_sided = [&](const float (&dq)[16], const float (&vc)[16], float vi, float tau, float sc, int r, int Ld) {
+    float w = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w = fmaf(dq[j], vc[j], w);
+    w += __shfl_xor_sync(0xffffffffu, w, 1);
+    w += __shfl_xor_sync(0xffffffffu, w, 2);
+    if (q == 0) ws[ri] = tau * w;
     __syncthreads();
-    // alpha = w'v, every warp for itself
-    float al = ws[lane] * v[lane] + ws[lane + 32] * v[lane + 32];
+    const float vl0 = lane == 0 ? 1.f : Bt[0][lane] * sc, vl1 = Bt[0][lane + 32] * sc;
+    float al = ws[lane] * vl0 + ws[lane + 32] * vl1;
     al = warp_sum(al);
     const float h = 0.5f * tau * al;
-    const int ii = tid & 63;
-#pragma unroll 4
-    for (int c = tid >> 6; c < L; c += 4) {
-      const int i = c + ii;
-      if (i < L) {
-        const float wi = ws[i] - h * v[i], wc = ws[c] - h * v[c];
-        __stcg(a.AB + (size_t)(r + c) * kLdab + ii, Dt[c][i] - v[i] * wc - wi * v[c]);
-      }
+    const float wi = ws[ri] - h * vi;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = q + 4 * j;
+      const float wc = ws[c] - h * vc[j];
+      if (ri >= c && ri < Ld) __stcg(a.AB + (size_t)(r + c) * kLdab + (ri - c), dq[j] - vi * wc - wi * vc[j]);
     }
   };
-  auto keep_reflector = [&](int s, int k, const float* v, float tau) {
+  auto keep_reflector = [&](int s, int k, float tau, float sc) {
     if (a.keep) {
-      if (tid < B) a.V2[(size_t)s * a.ldv2 + (size_t)k * B + tid] = v[tid];
+      if (tid < B) a.V2[(size_t)s * a.ldv2 + (size_t)k * B + tid] = tid == 0 ? 1.f : Bt[0][tid] * sc;
       if (tid == 0) a.tau2[(size_t)s * a.ldt2 + k] = tau;
     }
   };
 
   for (int s = (int)blockIdx.x; s < n - 2; s += (int)gridDim.x) {
     seen = 0;
-    int cur = 0;
     int r0 = s + 1, L = min(B, n - r0);
+    float vq[16], dq[16];
+    float tau, beta, sc;
     // ---- step 0: the reflector of column s, applied to its diagonal block from both sides
     wait_for(s, 2);
-    if (tid < B) {
-      xs[tid] = tid < L ? __ldcg(a.AB + (size_t)s * kLdab + 1 + tid) : 0.f;
-      vbuf[0][tid] = 0.f;
-      vbuf[1][tid] = 0.f;
-    }
-    load_diag(r0, L);
+    if (tid < B) Bt[0][tid] = tid < L ? __ldcg(a.AB + (size_t)s * kLdab + 1 + tid) : 0.f;
+    load_diag(dq, r0, L);
     __syncthreads();
-    if (warp == 0) house_warp(xs, L, vbuf[cur], &s_tau[cur], &s_beta);
-    __syncthreads();
-    if (tid < L) __stcg(a.AB + (size_t)s * kLdab + 1 + tid, tid == 0 ? s_beta : 0.f);
-    two_sided(r0, L, vbuf[cur], s_tau[cur]);
-    keep_reflector(s, 0, vbuf[cur], s_tau[cur]);
+    house_all(Bt[0], tau, beta, sc);
+    if (tid < L) __stcg(a.AB + (size_t)s * kLdab + 1 + tid, tid == 0 ? beta : 0.f);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) vq[j] = (q + 4 * j) == 0 ? 1.f : Bt[0][q + 4 * j] * sc;
+    two_sided(dq, vq, ri == 0 ? 1.f : Bt[0][ri] * sc, tau, sc, r0, L);
+    keep_reflector(s, 0, tau, sc);
     publish(s, 1);
     for (int k = 1;; ++k) {
       const int r1 = r0 + L, L1 = min(B, n - r1);
       if (L1 < 1) break;
-      const float* v = vbuf[cur];
-      float* v1 = vbuf[cur ^ 1];
-      const float tau = s_tau[cur];
       SB_TICK(0);
       wait_for(s, k + 2);
       SB_TICK(1);
-      // ---- the block below: rows r1.., columns r0..r0+L-1 (band offset of (i, c): L + i - c)
-      {
-        const int i = tid & 63;
-#pragma unroll 4
-        for (int c = tid >> 6; c < L; c += 4)
-          Bt[c][i] = i < L1 ? __ldcg(a.AB + (size_t)(r0 + c) * kLdab + (L - c) + i) : 0.f;
+      // ---- the block below: rows r1.., columns r0..r0+L-1 (band offset of (row i, column c): L + i - c); bq[j] = B[q + 4j][ri]
+      float bq[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c = q + 4 * j;
+        bq[j] = (c < L && ri < L1) ? __ldcg(a.AB + (size_t)(r0 + c) * kLdab + (L - c) + ri) : 0.f;
       }
-      if (L1 >= 2) load_diag(r1, L1);
+      if (L1 >= 2) load_diag(dq, r1, L1);
+      {  // B <- B (I - tau v v')
+        float x = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x = fmaf(bq[j], vq[j], x);
+        x += __shfl_xor_sync(0xffffffffu, x, 1);
+        x += __shfl_xor_sync(0xffffffffu, x, 2);
+        x *= tau;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) Bt[q + 4 * j][ri] = fmaf(-x, vq[j], bq[j]);
+      }
       __syncthreads();
       SB_TICK(2);
-      {  // x = B v, then B -= tau x v'
-        const int i = tid >> 2, q = tid & 3;
-        float s1 = 0.f;
-        for (int c = q; c < L; c += 4) s1 = fmaf(Bt[c][i], v[c], s1);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-        if (q == 0) xs[i] = tau * s1;
-      }
-      __syncthreads();
-      {
-        const int i = tid & 63;
-        const float xi = xs[i];
-#pragma unroll 4
-        for (int c = tid >> 6; c < L; c += 4) Bt[c][i] = fmaf(-xi, v[c], Bt[c][i]);
-      }
-      __syncthreads();
-      SB_TICK(3);
+      // ---- ownership by columns: thread owns column ri, rows q + 4j
+      float bc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bc[j] = Bt[ri][q + 4 * j];
+      float tau1 = 0.f, sc1 = 0.f;
       if (L1 >= 2) {
-        // new reflector from the block's first column
-        if (warp == 0) house_warp(Bt[0], L1, v1, &s_tau[cur ^ 1], &s_beta);
-        __syncthreads();
-        const float tau1 = s_tau[cur ^ 1];
-        {  // columns 1.. : B -= tau1 v1 (v1' B); the four lanes of a column own all of its rows
-          const int c = tid >> 2, q = tid & 3;
-          const bool act = c >= 1 && c < L;
-          float y = 0.f;
-          if (act)
-            for (int i = q; i < L1; i += 4) y = fmaf(v1[i], Bt[c][i], y);
-          y += __shfl_xor_sync(0xffffffffu, y, 1);   // converged: every lane of the warp takes part
-          y += __shfl_xor_sync(0xffffffffu, y, 2);
-          y *= tau1;
-          if (act) {
-            for (int i = q; i < L1; i += 4) Bt[c][i] = fmaf(-y, v1[i], Bt[c][i]);
-          } else if (c == 0) {
-            for (int i = q; i < L1; i += 4) Bt[0][i] = i == 0 ? s_beta : 0.f;
-          }
+        house_all(Bt[0], tau1, beta, sc1);
+        float vr[16], y = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          vr[j] = (q + 4 * j) == 0 ? 1.f : Bt[0][q + 4 * j] * sc1;
+          y = fmaf(vr[j], bc[j], y);
         }
-        __syncthreads();
+        y += __shfl_xor_sync(0xffffffffu, y, 1);
+        y += __shfl_xor_sync(0xffffffffu, y, 2);
+        y *= tau1;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) bc[j] = ri == 0 ? ((q + 4 * j) == 0 ? beta : 0.f) : fmaf(-y, vr[j], bc[j]);
       }
-      {
-        const int i = tid & 63;
-        if (i < L1) {
-#pragma unroll 4
-          for (int c = tid >> 6; c < L; c += 4) __stcg(a.AB + (size_t)(r0 + c) * kLdab + (L - c) + i, Bt[c][i]);
-        }
+      if (ri < L) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (q + 4 * j < L1) __stcg(a.AB + (size_t)(r0 + ri) * kLdab + (L - ri) + q + 4 * j, bc[j]);
       }
+      SB_TICK(3);
       if (L1 < 2) break;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) vq[j] = (q + 4 * j) == 0 ? 1.f : Bt[0][q + 4 * j] * sc1;
+      two_sided(dq, vq, ri == 0 ? 1.f : Bt[0][ri] * sc1, tau1, sc1, r1, L1);
+      keep_reflector(s, k, tau1, sc1);
       SB_TICK(4);
-      two_sided(r1, L1, v1, s_tau[cur ^ 1]);
-      keep_reflector(s, k, v1, s_tau[cur ^ 1]);
-      SB_TICK(5);
       publish(s, k + 1);
-      SB_TICK(6);
+      SB_TICK(5);
       r0 = r1;
       L = L1;
-      cur ^= 1;
+      tau = tau1;
     }
     publish(s, kDone);
   }
   if (a.prof && tid == 0)
-    for (int q = 0; q < 8; ++q) a.prof[(size_t)blockIdx.x * 8 + q] = tacc[q];
+    for (int t = 0; t < 8; ++t) a.prof[(size_t)blockIdx.x * 8 + t] = tacc[t];
 }
 
 __global__ void k_band_to_tridiag(const float* __restrict__ AB, int n, float* __restrict__ d, float* __restrict__ e) {
@@ -279,9 +254,9 @@ void sb2st(float* AB, int n, float* d, float* e, bool keep, float* V2, long long
       std::vector<unsigned long long> hp((size_t)grid * 8);
       SCL_CUDA(cudaMemcpyAsync(hp.data(), prof.p, hp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
       SCL_CUDA(cudaStreamSynchronize(st));
-      static const char* name[7] = {"(step 0 / loop overhead)", "wait for predecessor", "load blocks", "right apply", "reflector + left apply + store",
-                                    "two-sided diagonal block", "publish (fence + flag)"};
-      for (int q = 0; q < 7; ++q) {
+      static const char* name[6] = {"(step 0 / next sweep's start)", "wait for predecessor", "loads + right apply", "reflector + left apply + store",
+                                    "two-sided diagonal block", "publish (barrier + flag)"};
+      for (int q = 0; q < 6; ++q) {
         double mn = 1e30, mx = 0, av = 0;
         for (int g = 0; g < grid; ++g) {
           const double v = (double)hp[(size_t)g * 8 + q] * 1e-6;

@@ -28,7 +28,11 @@ namespace {
 constexpr int B = kBand;
 constexpr int kSlab = 512;   // rows per CTA of the panel dot products
 
-// part[p][c1][c2] = sum over the rows of slab p of X[c1][i] * Y[c2][i]   (Float64 accumulation of Float32 data)
+// part[p][c1][c2] = sum over the rows of slab p of X[c1][i] * Y[c2][i].  F64 = true: every product accumulated in Float64 (the
+// panel Gram matrix, whose Cholesky factor squares the panel's condition number).  F64 = false: Float32 accumulation over 64
+// rows at a time, the 64-row sums added in Float64 (V'V and V'Z, which enter T and W at working precision only; the
+// Float64 pipe of this part is an order of magnitude slower than the Float32 one).
+template <bool F64>
 __global__ void __launch_bounds__(256) k_dot64(const float* __restrict__ X, long long ldx, const float* __restrict__ Y,
                                                long long ldy, int rows, double* __restrict__ part) {
   __shared__ float Xs[B][B + 1], Ys[B][B + 1];
@@ -48,17 +52,41 @@ __global__ void __launch_bounds__(256) k_dot64(const float* __restrict__ X, long
       Ys[c][i] = ok ? Y[(long long)c * ldy + r0 + i] : 0.f;
     }
     __syncthreads();
+    if constexpr (F64) {
 #pragma unroll 4
-    for (int r = 0; r < B; ++r) {
-      double xa[4], yb[4];
+      for (int r = 0; r < B; ++r) {
+        double xa[4], yb[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) xa[a] = (double)Xs[ty + 16 * a][r];
+        for (int a = 0; a < 4; ++a) xa[a] = (double)Xs[ty + 16 * a][r];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) yb[b] = (double)Ys[tx + 16 * b][r];
+        for (int b = 0; b < 4; ++b) yb[b] = (double)Ys[tx + 16 * b][r];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fma(xa[a], yb[b], acc[a][b]);
+      }
+    } else {
+      float fa[4][4];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fma(xa[a], yb[b], acc[a][b]);
+        for (int b = 0; b < 4; ++b) fa[a][b] = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < B; ++r) {
+        float xa[4], yb[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) xa[a] = Xs[ty + 16 * a][r];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) yb[b] = Ys[tx + 16 * b][r];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) fa[a][b] = fmaf(xa[a], yb[b], fa[a][b]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] += (double)fa[a][b];
     }
   }
   double* out = part + (size_t)blockIdx.x * B * B;
@@ -241,7 +269,8 @@ __global__ void __launch_bounds__(256) k_sfactor(const double* __restrict__ part
 // In/Out/Add: kBand vectors of `rows` entries (vector c at + c * ld); Mat: kBand x kBand row-major.  In-place use
 // (Out == In or Out == Add) is safe: a CTA reads exactly the rows it writes and finishes reading first.
 __global__ void __launch_bounds__(256, 2) k_panel_mul(const float* In, long long ldin, const float* __restrict__ Mat, float* Out,
-                                                      long long ldout, int rows, float alpha, const float* Add, long long ldadd) {
+                                                      long long ldout, int rows, float alpha, const float* Add, long long ldadd,
+                                                      int transposed_out) {
   __shared__ __align__(16) float smem[tile::Smem<64>::floats];
   const int i0 = (int)blockIdx.x * tile::TM;
   tile::Acc<64> acc;
@@ -256,7 +285,8 @@ __global__ void __launch_bounds__(256, 2) k_panel_mul(const float* In, long long
       if (i < rows) {
         float v = alpha * acc.v[a][b];
         if (Add) v += Add[(long long)c * ldadd + i];
-        Out[(long long)c * ldout + i] = v;
+        if (transposed_out) Out[(long long)i * ldout + c] = v;
+        else Out[(long long)c * ldout + i] = v;
       }
     }
   }
@@ -310,14 +340,24 @@ __global__ void k_sum_parts(const float* __restrict__ part, int nparts, size_t s
 
 // A22 -= V W' + W V', lower triangle, one 128 x 128 tile per CTA
 __global__ void __launch_bounds__(256, 2) k_syr2k(float* A22, long long lda, int m, const float* __restrict__ V, long long ldv,
-                                                  const float* __restrict__ W, long long ldw) {
+                                                  const float* __restrict__ W, long long ldw, int mode) {
   __shared__ __align__(16) float smem[tile::Smem<128>::floats];
-  // linear tile index -> (I, J), J <= I
+  // mode 0: linear tile index -> (I, J), J <= I.  mode 1: the first tile column only (J = 0).  mode 2: everything else.
   const int t = (int)blockIdx.x;
-  int I = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-  while ((I + 1) * (I + 2) / 2 <= t) ++I;
-  while (I * (I + 1) / 2 > t) --I;
-  const int J = t - I * (I + 1) / 2;
+  int I, J;
+  if (mode == 1) {
+    I = t;
+    J = 0;
+  } else {
+    I = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+    while ((I + 1) * (I + 2) / 2 <= t) ++I;
+    while (I * (I + 1) / 2 > t) --I;
+    J = t - I * (I + 1) / 2;
+    if (mode == 2) {
+      ++I;
+      ++J;
+    }
+  }
   const int i0 = I * tile::TM, j0 = J * tile::TM;
   tile::Acc<128> acc;
   acc.clear();
@@ -453,6 +493,16 @@ __global__ void __launch_bounds__(64) k_tail_panel(float* A, long long lda, int 
     }
     Tout[e] = (float)T[e / B][e % B];
   }
+  __syncthreads();
+  // V T, transposed into the upper triangle of A like every other panel's
+  for (int e = tid; e < B * B; e += 64) {
+    const int i = e / B, c = e % B;
+    if (i < m) {
+      double s = 0;
+      for (int k = 0; k <= c; ++k) s += V[i][k] * T[k][c];
+      A[(c0 + c) + (long long)(r0 + i) * lda] = (float)s;
+    }
+  }
 }
 
 // diagonal blocks of the reduced matrix -> band storage (the sub-diagonal blocks were written by the panel kernels)
@@ -465,7 +515,7 @@ __global__ void k_extract_band(const float* __restrict__ A, long long lda, int n
 
 }  // namespace
 
-int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fail, cudaStream_t st) {
+int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fail, cudaStream_t st, const Sy2sbAux* aux) {
   SCL_REQUIRE((lda & 3) == 0 && ((uintptr_t)A & 15) == 0 && lda >= n, "sy2sb: leading dimension must be a multiple of 4");
   const long long ldy = ((long long)n + 3) & ~3LL;
   const int max_slabs = (n + kSlab - 1) / kSlab + 1;
@@ -483,8 +533,27 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     attr_done = true;
   }
   const int slots = 2 * sm_count();
-  int k = 0;
   long launches = 0;
+  // factorisation of panel k (full-size panels only) on stream s: V in place, T, V T into the upper triangle, R' into the band
+  auto factor = [&](int k, cudaStream_t s) {
+    const int c0 = k * B, r0 = c0 + B, m = n - r0;
+    float* Pp = A + r0 + (long long)c0 * lda;
+    float* Tk = T1 + (size_t)k * B * B;
+    const int nslab = (m + kSlab - 1) / kSlab, ntile = (m + tile::TM - 1) / tile::TM;
+    k_dot64<true><<<nslab, 256, 0, s>>>(Pp, lda, Pp, lda, m, part.p);
+    k_panel_factor<<<1, 256, sm3, s>>>(part.p, nslab, Pp, lda, AB, c0, Mbuf.p, d_fail);
+    if (m > B) {
+      const int nt2 = (m - B + tile::TM - 1) / tile::TM;
+      k_panel_mul<<<nt2, 256, 0, s>>>(Pp + B, lda, Mbuf.p, Pp + B, lda, m - B, 1.f, nullptr, 0, 0);
+    }
+    k_dot64<false><<<nslab, 256, 0, s>>>(Pp, lda, Pp, lda, m, part.p);
+    k_tfactor<<<1, 256, sm2, s>>>(part.p, nslab, Tk);
+    // V T for the back-transformation, transposed into the (otherwise unused) upper triangle of A: (V T)[i][c] at A(c0 + c, r0 + i)
+    k_panel_mul<<<ntile, 256, 0, s>>>(Pp, lda, Tk, A + c0 + (long long)r0 * lda, lda, m, 1.f, nullptr, 0, 1);
+    launches += 6;
+  };
+  int k = 0;
+  bool factored = false;   // panel k was factored ahead (look-ahead) and the main stream already waits for it
   for (;; ++k) {
     const int c0 = k * B, r0 = c0 + B, m = n - r0;
     if (m <= 1) break;
@@ -499,14 +568,8 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     }
     const int nslab = (m + kSlab - 1) / kSlab;
     const int ntile = (m + tile::TM - 1) / tile::TM;
-    k_dot64<<<nslab, 256, 0, st>>>(Pp, lda, Pp, lda, m, part.p);
-    k_panel_factor<<<1, 256, sm3, st>>>(part.p, nslab, Pp, lda, AB, c0, Mbuf.p, d_fail);
-    if (m > B) {
-      const int nt2 = (m - B + tile::TM - 1) / tile::TM;
-      k_panel_mul<<<nt2, 256, 0, st>>>(Pp + B, lda, Mbuf.p, Pp + B, lda, m - B, 1.f, nullptr, 0);
-    }
-    k_dot64<<<nslab, 256, 0, st>>>(Pp, lda, Pp, lda, m, part.p);
-    k_tfactor<<<1, 256, sm2, st>>>(part.p, nslab, Tk);
+    if (!factored) factor(k, st);
+    factored = false;
     // Y = A22 V, split over the contraction so that the grid covers the SMs several times over
     int split = std::max(1, std::min(max_split, (4 * slots + ntile - 1) / ntile));
     int chunk = ((m + split - 1) / split + tile::TM - 1) / tile::TM * tile::TM;
@@ -515,12 +578,28 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     k_symm<<<dim3(ntile, split), 256, 0, st>>>(A22, lda, m, Pp, lda, Ypart.p, ldy, chunk);
     const size_t ny = (size_t)B * ldy;
     k_sum_parts<<<(unsigned)((ny + 255) / 256), 256, 0, st>>>(Ypart.p, split, ny, ny, Y.p);
-    k_panel_mul<<<ntile, 256, 0, st>>>(Y.p, ldy, Tk, Z.p, ldy, m, 1.f, nullptr, 0);
-    k_dot64<<<nslab, 256, 0, st>>>(Pp, lda, Z.p, ldy, m, part.p);
+    k_panel_mul<<<ntile, 256, 0, st>>>(Y.p, ldy, Tk, Z.p, ldy, m, 1.f, nullptr, 0, 0);
+    k_dot64<false><<<nslab, 256, 0, st>>>(Pp, lda, Z.p, ldy, m, part.p);
     k_sfactor<<<1, 256, sm3, st>>>(part.p, nslab, Tk, Sbuf.p);
-    k_panel_mul<<<ntile, 256, 0, st>>>(Pp, lda, Sbuf.p, Z.p, ldy, m, -0.5f, Z.p, ldy);
-    k_syr2k<<<ntile * (ntile + 1) / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy);
-    launches += 12;
+    k_panel_mul<<<ntile, 256, 0, st>>>(Pp, lda, Sbuf.p, Z.p, ldy, m, -0.5f, Z.p, ldy, 0);
+    launches += 7;
+    // look-ahead: the first tile column of the update holds the next panel; once it is done the next panel is factored on the
+    // auxiliary stream (one or a few CTAs per kernel) while the main stream updates the rest of the trailing matrix
+    const bool ahead = aux && aux->stream && ntile >= 4 && m - B >= B;
+    if (ahead) {
+      k_syr2k<<<ntile, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 1);
+      SCL_CUDA(cudaEventRecord(aux->ready, st));
+      SCL_CUDA(cudaStreamWaitEvent(aux->stream, aux->ready, 0));
+      factor(k + 1, aux->stream);
+      SCL_CUDA(cudaEventRecord(aux->done, aux->stream));
+      k_syr2k<<<(ntile - 1) * ntile / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 2);
+      SCL_CUDA(cudaStreamWaitEvent(st, aux->done, 0));
+      factored = true;
+      ++launches;
+    } else {
+      k_syr2k<<<ntile * (ntile + 1) / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 0);
+    }
+    ++launches;
   }
   k_extract_band<<<n, 64, 0, st>>>(A, lda, n, k, AB);
   SCL_CUDA(cudaGetLastError());

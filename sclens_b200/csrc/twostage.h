@@ -23,7 +23,13 @@ struct TwoStageTimes {
 // k kBand .. of A, rows (k+1) kBand .. n, unit lower trapezoidal, stored explicitly), their T factors in T1 [panel][kBand^2]
 // (row-major).  *d_fail (device flag) is raised when a panel could not be factored (rank-deficient panel).
 // Returns the number of panels.
-int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fail, cudaStream_t st);
+// aux (optional): a second stream and two events for the look-ahead - the next panel is factored there while the main stream
+// finishes the trailing update.
+struct Sy2sbAux {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ready = nullptr, done = nullptr;
+};
+int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fail, cudaStream_t st, const Sy2sbAux* aux = nullptr);
 
 // stage 2.  AB as above (destroyed).  d (n), e (n - 1).  With keep = true the reflector of sweep s, chase level k is stored at
 // V2 + s * ldv2 + k * kBand (kBand floats, v[0] = 1) and its tau at tau2 + s * ldt2 + k.

@@ -516,3 +516,99 @@ def test_scores_match_oracle(h):
     np.testing.assert_allclose(m, rob["m_scores"], atol=5e-6)
     np.testing.assert_allclose(sd, rob["sd_scores"], atol=5e-6)
     np.testing.assert_array_equal(sid[:nrob.value], sig)
+
+
+TWO_STAGE = 4 | 8 | 16 | 32
+
+
+@pytest.mark.parametrize("n,case", [(300, "wishart"), (1000, "centred"), (2531, "wishart"), (1536, "wide_range_of_scales")])
+def test_two_stage_solver_matches_float64(h, n, case):
+    """Two-stage reduction (sy2sb.cu dense -> band, sb2st.cu band -> tridiagonal by bulge chasing, backtrans.cu) behind
+    SCL_EIG_API bit 5: eigenvalues, residuals and orthogonality against numpy's Float64 eigh of the same FP32 matrix, with the
+    tolerances of the one-stage path; orders that are not multiples of the 64-column panel, the 128 x 128 update tile or 4
+    (padded copy); all vectors / an index range / values only agree."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n + 300))
+    if case == "centred":
+        A -= A.mean(axis=0)
+    if case == "wide_range_of_scales":
+        A *= np.exp(rng.normal(0, 1.5, size=(n, 1)))
+    G = (A @ A.T / A.shape[1]).astype(np.float32)
+    Lref = np.linalg.eigvalsh(G.astype(np.float64))
+    scale = float(Lref[-1])
+    st = np.zeros(8)
+    try:
+        h.lib.scl_debug_set_eig_api(TWO_STAGE)
+        L, V, out = _tri_solve(h, G, 0, n)
+        h._ck(h.lib.scl_debug_last_solve(h.h, ptr(st, C.c_double)))
+        v0, v1 = 3, n // 2 + 40
+        L2, V2, _ = _tri_solve(h, G, v0, v1)
+        L3, _, _ = _tri_solve(h, G, 0, 0)
+    finally:
+        h.lib.scl_debug_set_eig_api(-1)
+    assert out[5] == 0 and st[5] == 1 and st[6] == 0, ("the two-stage path did not produce the result", out, st)
+    np.testing.assert_allclose(L, Lref, rtol=2e-5, atol=3e-6 * scale)
+    G64 = G.astype(np.float64)
+    assert np.max(np.abs(G64 @ V - V * L[None, :])) < 5e-5 * max(1.0, scale)
+    assert np.max(np.abs(V.T.astype(np.float64) @ V - np.eye(n))) < 5e-5
+    np.testing.assert_array_equal(L2, L)
+    assert np.max(np.abs(np.abs(np.sum(V2 * V[:, v0:v1], axis=0)) - 1.0)) < 1e-5
+    np.testing.assert_array_equal(L3, L)
+
+
+def test_two_stage_solver_rank_deficient_panels_fall_back(h):
+    """A block-diagonal matrix with an exactly zero block has panels that CholeskyQR cannot factor: the solve must notice
+    (panel flag), take the one-stage path on the kept copy, say so in the counters, and still be right."""
+    rng = np.random.default_rng(11)
+    nb = 300
+    A = rng.standard_normal((nb, 500))
+    Bm = (A @ A.T / 500).astype(np.float32)
+    n = 2 * nb + 40
+    G = np.zeros((n, n), np.float32)
+    G[:nb, :nb] = Bm
+    G[nb:2 * nb, nb:2 * nb] = Bm
+    st = np.zeros(8)
+    try:
+        h.lib.scl_debug_set_eig_api(TWO_STAGE)
+        L, V, out = _tri_solve(h, G, 0, n)
+        h._ck(h.lib.scl_debug_last_solve(h.h, ptr(st, C.c_double)))
+    finally:
+        h.lib.scl_debug_set_eig_api(-1)
+    Lref = np.linalg.eigvalsh(G.astype(np.float64))
+    np.testing.assert_allclose(L, Lref, rtol=2e-5, atol=5e-6)
+    assert np.max(np.abs(G.astype(np.float64) @ V - V * L[None, :])) < 5e-5
+    assert np.max(np.abs(V.T.astype(np.float64) @ V - np.eye(n))) < 5e-5
+    assert st[6] >= 1 or st[5] == 1, st
+
+
+@pytest.mark.parametrize("n", [256, 520, 1000])
+def test_two_stage_reduction_stage_by_stage(h, n):
+    """scl_debug_two_stage: the band matrix after stage 1 and the tridiagonal matrix after stage 2 keep the spectrum; the
+    stage-2 transformation applied to the identity is orthogonal and maps band to tridiagonal; Q = Q1 Q2 maps the input to
+    the tridiagonal matrix."""
+    rng = np.random.default_rng(n)
+    X = rng.standard_normal((n, n + 300))
+    X -= X.mean(axis=0)
+    G = np.ascontiguousarray((X @ X.T / X.shape[1]).astype(np.float32))
+    G64 = G.astype(np.float64)
+    wref = np.linalg.eigvalsh(G64)
+    AB = np.zeros((n, 128), np.float32)
+    d, e = np.zeros(n, np.float32), np.zeros(n - 1, np.float32)
+    Q2, Q = np.zeros((n, n), np.float32), np.zeros((n, n), np.float32)
+    flags = (C.c_int32 * 2)()
+    h._ck(h.lib.scl_debug_two_stage(h.h, n, ptr(G, C.c_float), ptr(AB, C.c_float), ptr(d, C.c_float), ptr(e, C.c_float),
+                                    ptr(Q2, C.c_float), ptr(Q, C.c_float), flags))
+    assert flags[0] == 0
+    Bd = np.zeros((n, n))
+    for dg in range(65):
+        Bd[np.arange(dg, n), np.arange(0, n - dg)] = AB[: n - dg, dg]
+    Bd = Bd + np.tril(Bd, -1).T
+    assert np.abs(AB[:, 65:]).max() == 0.0
+    tol = 2e-6 * wref[-1]
+    assert np.abs(np.linalg.eigvalsh(Bd) - wref).max() < tol
+    T = np.diag(d.astype(np.float64)) + np.diag(e.astype(np.float64), 1) + np.diag(e.astype(np.float64), -1)
+    assert np.abs(np.linalg.eigvalsh(T) - wref).max() < tol
+    Q2m, Qm = Q2.T.astype(np.float64), Q.T.astype(np.float64)
+    assert np.abs(Q2m.T @ Q2m - np.eye(n)).max() < 1e-5 and np.abs(Qm.T @ Qm - np.eye(n)).max() < 1e-5
+    assert np.abs(Q2m.T @ Bd @ Q2m - T).max() < 5e-6 * wref[-1]
+    assert np.abs(Qm.T @ G64 @ Qm - T).max() < 5e-6 * wref[-1]
