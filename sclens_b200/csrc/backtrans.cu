@@ -85,7 +85,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // blockDim = 16 * (nvp / 4): thread (g = tid & 15, vg = tid >> 4) owns vectors 4 vg .. 4 vg + 3 and, per product, the
-// reflectors 4 g .. 4 g + 3 (first product, T product) or the window rows 8 g .. 8 g + 7 (second product).
+// reflectors 4 g .. 4 g + 3 (first product, T product) or the window rows g, g + 16, ... (second product).
 // Everything a block needs from global memory - its reflectors (scattered into the parallelogram), its T factor and the 64
 // window rows that enter - is fetched with cp.async while the previous block is being multiplied (double-buffered V / T, a
 // staging area for the rows); only the first block of a group of sweeps waits for its loads.
@@ -193,22 +193,22 @@ __global__ void __launch_bounds__(384, 1) k_q2_apply(Q2Args a) {
           *reinterpret_cast<float4*>(&X2s[(c0 + x) * nvp + v0]) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
       }
       __syncthreads();
-      // ---- Z[w][vec] -= sum_c V[w][c] X2[c][vec], c in [w - 63, w]
+      // ---- Z[w][vec] -= sum_c V[w][c] X2[c][vec]: the thread's eight rows are g, g + 16, ..., so that the lanes of a warp read
+      // consecutive rows of V (stride VS floats: every bank once per 8-lane phase)
       {
-        const int w0 = g * 8;
         float acc[8][4];
 #pragma unroll
         for (int x = 0; x < 8; ++x)
 #pragma unroll
           for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
-        const int clo = max(0, w0 - (B - 1)) & ~3, chi = min(B - 1, w0 + 7);
-        for (int c = clo; c <= chi; c += 4) {
+#pragma unroll 2
+        for (int c = 0; c < B; c += 4) {
           float4 xr[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) xr[j] = *reinterpret_cast<const float4*>(&X2s[(c + j) * nvp + v0]);
 #pragma unroll
           for (int x = 0; x < 8; ++x) {
-            const float4 vr = *reinterpret_cast<const float4*>(&Vs[(w0 + x) * VS + c]);
+            const float4 vr = *reinterpret_cast<const float4*>(&Vs[(g + 16 * x) * VS + c]);
             acc[x][0] = fmaf(vr.x, xr[0].x, acc[x][0]); acc[x][1] = fmaf(vr.x, xr[0].y, acc[x][1]);
             acc[x][2] = fmaf(vr.x, xr[0].z, acc[x][2]); acc[x][3] = fmaf(vr.x, xr[0].w, acc[x][3]);
             acc[x][0] = fmaf(vr.y, xr[1].x, acc[x][0]); acc[x][1] = fmaf(vr.y, xr[1].y, acc[x][1]);
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(384, 1) k_q2_apply(Q2Args a) {
         }
 #pragma unroll
         for (int x = 0; x < 8; ++x) {
-          float4* zp = reinterpret_cast<float4*>(&Zs[((B * k + w0 + x) & 127) * nvp + v0]);
+          float4* zp = reinterpret_cast<float4*>(&Zs[((B * k + g + 16 * x) & 127) * nvp + v0]);
           float4 z = *zp;
           z.x -= acc[x][0]; z.y -= acc[x][1]; z.z -= acc[x][2]; z.w -= acc[x][3];
           *zp = z;
@@ -328,7 +328,7 @@ void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2
   int nv = (mvec + sms * rounds - 1) / (sms * rounds);
   nv = std::max(4, (nv + 3) & ~3);
   int nvp = nv;
-  if ((nvp & 31) == 0) nvp += 4;   // keeps the transposing shared-memory stores off a single bank
+  if ((nvp & 7) == 0) nvp += 4;   // nvp / 4 odd: rows of the window that are one apart sit 4 (mod 8) banks apart
   const int nslab = (mvec + nv - 1) / nv;
   const int threads = 16 * (nvp / 4);
   const size_t smem = ((size_t)128 * nvp + 3 * (size_t)B * nvp + 2 * 128 * VS + 2 * (size_t)B * VS) * sizeof(float);
