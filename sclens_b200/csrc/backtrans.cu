@@ -21,7 +21,7 @@ namespace {
 constexpr int B = kBand;
 constexpr int VS = 68;   // shared-memory stride of the reflector block and of T
 
-// T factor (stored transposed: Tt[c'][c] = T[c][c']) of every (group, level) block of stage-2 reflectors
+// T factor (row-major, upper triangular) of every (group, level) block of stage-2 reflectors
 __global__ void __launch_bounds__(256) k_q2_tfactor(const float* __restrict__ V2, long long ldv2, const float* __restrict__ tau2,
                                                     long long ldt2, int n, int nlev, float* __restrict__ Tq) {
   const int k = (int)blockIdx.x, G = (int)blockIdx.y, s0 = G * B;
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) k_q2_tfactor(const float* __restrict__ V2
     __syncthreads();
   }
   float* out = Tq + ((size_t)G * nlev + k) * B * B;
-  for (int e = tid; e < B * B; e += 256) out[e] = (e % B) <= (e / B) ? T[e % B][e / B] : 0.f;   // out[c'][c] = T[c][c'], upper triangular
+  for (int e = tid; e < B * B; e += 256) out[e] = (e / B) <= (e % B) ? T[e / B][e % B] : 0.f;   // out[c][c'] = T[c][c'], upper triangular
 }
 
 struct Q2Args {
@@ -84,12 +84,50 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// blockDim = 16 * (nvp / 4): thread (g = tid & 15, vg = tid >> 4) owns vectors 4 vg .. 4 vg + 3 and, per product, the
-// reflectors 4 g .. 4 g + 3 (first product, T product) or the window rows g, g + 16, ... (second product).
+// Tensor-core products in error-compensated TF32 (mma.sync m16n8k8): x = hi + lo with hi = tf32(x), lo = tf32(x - hi), and
+// a b ~ a_lo b_hi + a_hi b_lo + a_hi b_hi accumulated in FP32 - FP32-level accuracy (relative 2^-21) with FP32 range, so the
+// reflectors and eigenvectors need no scaling.  The three products of a block have ~230 000 scalar FMAs per CTA; as MMAs
+// they are ~2 700 instructions.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// d (16 x 8 tiles j < NJ) += A (16 x 8, fragment from a0..a3) * B_j (8 x 8): pb = &B[k = t][n = g] of tile 0, tiles 8 columns apart,
+// rows k and k + 4 at pb and pb4
+constexpr int kMaxNJ = 6;
+__device__ __forceinline__ void mma_row(float (&acc)[kMaxNJ][4], int nj, float a0, float a1, float a2, float a3, const float* pb,
+                                        const float* pb4) {
+  uint32_t ahi[4], alo[4];
+  split_tf32(a0, ahi[0], alo[0]);
+  split_tf32(a1, ahi[1], alo[1]);
+  split_tf32(a2, ahi[2], alo[2]);
+  split_tf32(a3, ahi[3], alo[3]);
+#pragma unroll
+  for (int j = 0; j < kMaxNJ; ++j) {
+    if (j < nj) {
+      uint32_t bhi[2], blo[2];
+      split_tf32(pb[8 * j], bhi[0], blo[0]);
+      split_tf32(pb4[8 * j], bhi[1], blo[1]);
+      mma_tf32(acc[j], alo, bhi);
+      mma_tf32(acc[j], ahi, blo);
+      mma_tf32(acc[j], ahi, bhi);
+    }
+  }
+}
+
+// 256 threads.  Warp w works on reflector rows / window rows given by (w & 3) and on the half (w >> 2) of the CTA's vectors
+// (8-vector tiles; nvp = 8 (mod 16), which also keeps the B fragments - 4 rows x 8 vectors per load - on 32 different banks).
 // Everything a block needs from global memory - its reflectors (scattered into the parallelogram), its T factor and the 64
 // window rows that enter - is fetched with cp.async while the previous block is being multiplied (double-buffered V / T, a
 // staging area for the rows); only the first block of a group of sweeps waits for its loads.
-__global__ void __launch_bounds__(384, 1) k_q2_apply(Q2Args a) {
+__global__ void __launch_bounds__(256, 1) k_q2_apply(Q2Args a) {
   extern __shared__ __align__(16) float sm[];
   const int nvp = a.nvp;
   float* Zs = sm;                        // [128][nvp]  window rows (slot = window row & 127, see below) x vectors
@@ -99,7 +137,10 @@ __global__ void __launch_bounds__(384, 1) k_q2_apply(Q2Args a) {
   float* Vs0 = Zst + B * nvp;            // [2][128][VS] parallelogram: Vs[j + i][j] = v_j[i]
   float* Tt0 = Vs0 + 2 * 128 * VS;       // [2][64][VS]
   const int tid = (int)threadIdx.x, nthr = (int)blockDim.x;
-  const int g = tid & 15, vg = tid >> 4, v0 = vg * 4;
+  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int ntile = nvp / 8, nhalf = (ntile + 1) / 2;
+  const int nbase = (warp >> 2) * nhalf, nj = (warp >> 2) ? ntile - nhalf : nhalf;   // this warp's vector tiles
+  const int vb = 8 * nbase;
   const int vec0 = (int)blockIdx.x * a.nv, nvv = min(a.nv, a.mvec - vec0);
   const int n = a.n;
   for (int e = tid; e < 2 * 128 * VS; e += nthr) Vs0[e] = 0.f;
@@ -116,7 +157,7 @@ __global__ void __launch_bounds__(384, 1) k_q2_apply(Q2Args a) {
       cp_async4(&Vs[(j + i) * VS + j], ok ? a.V2 + (size_t)s * a.ldv2 + (size_t)k * B + i : a.V2, ok);
     }
     const float* tq = a.Tq + ((size_t)G * a.nlev + k) * B * B;
-    for (int e = tid; e < B * B / 4; e += nthr) cp_async16(&Tt[(e / (B / 4)) * VS + (e % (B / 4)) * 4], tq + (size_t)e * 4);
+    for (int e = tid; e < B * B / 4; e += nthr) cp_async16(&Tt[(e / (B / 4)) * VS + (e % (B / 4)) * 4], tq + (size_t)e * 4);   // Tt[c][c']
   };
   // window rows [w0, w0 + nrow) of the window starting at global row rlo: staging area dst[(w - w0)][v], or the window's own slots
   auto fetch_rows = [&](int rlo, int w0, int nrow, float* dst, int slot0, bool to_slots) {
@@ -147,85 +188,72 @@ __global__ void __launch_bounds__(384, 1) k_q2_apply(Q2Args a) {
         fetch_rows(rlo + B, B - 1, B, Zst, 0, false);
         cp_async_commit();
       }
-      // ---- X[c][vec] = sum_w V[w][c] Z[w][vec], w in [c, c + 63]
+      // ---- X[c][vec] = sum_w V[w][c] Z[w][vec]: 16 reflectors c0.. per warp, window rows c0 .. c0 + 79 (w in [c, c + 63])
       {
-        float acc[4][4];
+        float acc[kMaxNJ][4];
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
-        const int c0 = g * 4;
-#pragma unroll 4
-        for (int w = c0; w < c0 + 67; ++w) {
-          const float4 vr = *reinterpret_cast<const float4*>(&Vs[w * VS + c0]);
-          const float4 z = *reinterpret_cast<const float4*>(&Zs[((B * k + w) & 127) * nvp + v0]);
-          const float vv[4] = {vr.x, vr.y, vr.z, vr.w}, zz[4] = {z.x, z.y, z.z, z.w};
-#pragma unroll
-          for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(vv[x], zz[y], acc[x][y]);
+        for (int j = 0; j < kMaxNJ; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        const int c0 = 16 * (warp & 3);
+#pragma unroll 2
+        for (int ks = 0; ks < 10; ++ks) {
+          const int w0 = c0 + 8 * ks;
+          const float* va = &Vs[(w0 + t) * VS + c0 + g];   // A[m = c][k = w] = V[w][c]
+          const float* zb = &Zs[((B * k + w0 + t) & 127) * nvp + vb + g];
+          const float* zb4 = &Zs[((B * k + w0 + t + 4) & 127) * nvp + vb + g];
+          mma_row(acc, nj, va[0], va[8], va[4 * VS], va[4 * VS + 8], zb, zb4);
         }
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
-          *reinterpret_cast<float4*>(&Xs[(c0 + x) * nvp + v0]) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+        for (int j = 0; j < kMaxNJ; ++j)
+          if (j < nj) {
+            *reinterpret_cast<float2*>(&Xs[(c0 + g) * nvp + vb + 8 * j + 2 * t]) = make_float2(acc[j][0], acc[j][1]);
+            *reinterpret_cast<float2*>(&Xs[(c0 + g + 8) * nvp + vb + 8 * j + 2 * t]) = make_float2(acc[j][2], acc[j][3]);
+          }
       }
       __syncthreads();
       // ---- X2[c][vec] = sum_{c' >= c} T[c][c'] X[c'][vec]
       {
-        float acc[4][4];
+        float acc[kMaxNJ][4];
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
-        const int c0 = g * 4;
-#pragma unroll 4
-        for (int cp = c0; cp < B; ++cp) {
-          const float4 tr = *reinterpret_cast<const float4*>(&Tt[cp * VS + c0]);
-          const float4 x4 = *reinterpret_cast<const float4*>(&Xs[cp * nvp + v0]);
-          const float tt[4] = {tr.x, tr.y, tr.z, tr.w}, xx[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-          for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(tt[x], xx[y], acc[x][y]);
+        for (int j = 0; j < kMaxNJ; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        const int c0 = 16 * (warp & 3);
+        for (int k0 = c0; k0 < B; k0 += 8) {
+          const float* ta = &Tt[(c0 + g) * VS + k0 + t];   // A[m = c][k = c'] = T[c][c']
+          const float* xb = &Xs[(k0 + t) * nvp + vb + g];
+          mma_row(acc, nj, ta[0], ta[8 * VS], ta[4], ta[8 * VS + 4], xb, xb + 4 * nvp);
         }
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
-          *reinterpret_cast<float4*>(&X2s[(c0 + x) * nvp + v0]) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+        for (int j = 0; j < kMaxNJ; ++j)
+          if (j < nj) {
+            *reinterpret_cast<float2*>(&X2s[(c0 + g) * nvp + vb + 8 * j + 2 * t]) = make_float2(acc[j][0], acc[j][1]);
+            *reinterpret_cast<float2*>(&X2s[(c0 + g + 8) * nvp + vb + 8 * j + 2 * t]) = make_float2(acc[j][2], acc[j][3]);
+          }
       }
       __syncthreads();
-      // ---- Z[w][vec] -= sum_c V[w][c] X2[c][vec]: the thread's eight rows are g, g + 16, ..., so that the lanes of a warp read
-      // consecutive rows of V (stride VS floats: every bank once per 8-lane phase)
-      {
-        float acc[8][4];
+      // ---- Z[w][vec] -= sum_c V[w][c] X2[c][vec]: window rows 16 mt .. 16 mt + 15 need c in [16 mt - 63, 16 mt + 15]; a warp takes the
+      // row tiles p and p + 4 (2 + 8, 4 + 6, ... = 10 steps of 8 reflectors each way)
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int mt = (warp & 3) + 4 * half, w0 = 16 * mt;
+        float acc[kMaxNJ][4];
 #pragma unroll
-        for (int x = 0; x < 8; ++x)
+        for (int j = 0; j < kMaxNJ; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        const int clo = max(0, w0 - (B - 1)) & ~7, chi = min(B - 1, w0 + 15);
+        for (int c = clo; c <= chi; c += 8) {
+          const float* va = &Vs[(w0 + g) * VS + c + t];   // A[m = w][k = c] = V[w][c]
+          const float* xb = &X2s[(c + t) * nvp + vb + g];
+          mma_row(acc, nj, va[0], va[8 * VS], va[4], va[8 * VS + 4], xb, xb + 4 * nvp);
+        }
 #pragma unroll
-          for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
-#pragma unroll 2
-        for (int c = 0; c < B; c += 4) {
-          float4 xr[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) xr[j] = *reinterpret_cast<const float4*>(&X2s[(c + j) * nvp + v0]);
-#pragma unroll
-          for (int x = 0; x < 8; ++x) {
-            const float4 vr = *reinterpret_cast<const float4*>(&Vs[(g + 16 * x) * VS + c]);
-            acc[x][0] = fmaf(vr.x, xr[0].x, acc[x][0]); acc[x][1] = fmaf(vr.x, xr[0].y, acc[x][1]);
-            acc[x][2] = fmaf(vr.x, xr[0].z, acc[x][2]); acc[x][3] = fmaf(vr.x, xr[0].w, acc[x][3]);
-            acc[x][0] = fmaf(vr.y, xr[1].x, acc[x][0]); acc[x][1] = fmaf(vr.y, xr[1].y, acc[x][1]);
-            acc[x][2] = fmaf(vr.y, xr[1].z, acc[x][2]); acc[x][3] = fmaf(vr.y, xr[1].w, acc[x][3]);
-            acc[x][0] = fmaf(vr.z, xr[2].x, acc[x][0]); acc[x][1] = fmaf(vr.z, xr[2].y, acc[x][1]);
-            acc[x][2] = fmaf(vr.z, xr[2].z, acc[x][2]); acc[x][3] = fmaf(vr.z, xr[2].w, acc[x][3]);
-            acc[x][0] = fmaf(vr.w, xr[3].x, acc[x][0]); acc[x][1] = fmaf(vr.w, xr[3].y, acc[x][1]);
-            acc[x][2] = fmaf(vr.w, xr[3].z, acc[x][2]); acc[x][3] = fmaf(vr.w, xr[3].w, acc[x][3]);
+        for (int j = 0; j < kMaxNJ; ++j)
+          if (j < nj) {
+            float2* z0 = reinterpret_cast<float2*>(&Zs[((B * k + w0 + g) & 127) * nvp + vb + 8 * j + 2 * t]);
+            float2* z1 = reinterpret_cast<float2*>(&Zs[((B * k + w0 + g + 8) & 127) * nvp + vb + 8 * j + 2 * t]);
+            float2 u = *z0, v2 = *z1;
+            u.x -= acc[j][0]; u.y -= acc[j][1];
+            v2.x -= acc[j][2]; v2.y -= acc[j][3];
+            *z0 = u;
+            *z1 = v2;
           }
-        }
-#pragma unroll
-        for (int x = 0; x < 8; ++x) {
-          float4* zp = reinterpret_cast<float4*>(&Zs[((B * k + g + 16 * x) & 127) * nvp + v0]);
-          float4 z = *zp;
-          z.x -= acc[x][0]; z.y -= acc[x][1]; z.z -= acc[x][2]; z.w -= acc[x][3];
-          *zp = z;
-        }
       }
       __syncthreads();
       // ---- rows leaving the window go back to global memory (everything at the group's last level)
@@ -322,17 +350,21 @@ void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2
   Tmp<float> Tq((size_t)ngroups * nlev * B * B, st);
   k_q2_tfactor<<<dim3(nlev, ngroups), 256, 0, st>>>(V2, ldv2, tau2, ldt2, n, nlev, Tq.p);
   SCL_CUDA(cudaGetLastError());
-  // vectors per CTA: one CTA per SM and as few rounds as the 88-vector limit allows, balanced
+  // vectors per CTA: one CTA per SM and as few rounds as the 88-vector limit allows, balanced; padded to nvp = 8 (mod 16)
   const int sms = sm_count();
   const int rounds = (mvec + sms * 88 - 1) / (sms * 88);
   int nv = (mvec + sms * rounds - 1) / (sms * rounds);
-  nv = std::max(4, (nv + 3) & ~3);
+  nv = std::max(8, (nv + 7) & ~7);
   int nvp = nv;
-  if ((nvp & 7) == 0) nvp += 4;   // nvp / 4 odd: rows of the window that are one apart sit 4 (mod 8) banks apart
+  if ((nvp & 15) == 0) nvp += 8;
+  if (nvp > 88) {   // 96 vectors would not fit: split once more
+    nv = 88;
+    nvp = 88;
+  }
   const int nslab = (mvec + nv - 1) / nv;
-  const int threads = 16 * (nvp / 4);
+  const int threads = 256;
   const size_t smem = ((size_t)128 * nvp + 3 * (size_t)B * nvp + 2 * 128 * VS + 2 * (size_t)B * VS) * sizeof(float);
-  SCL_REQUIRE(threads <= 384 && smem <= 227 * 1024, "apply_q2: slab does not fit");
+  SCL_REQUIRE(nvp / 8 <= 2 * kMaxNJ && smem <= 227 * 1024, "apply_q2: slab does not fit");
   SCL_CUDA(cudaFuncSetAttribute(k_q2_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   Q2Args a{V2, ldv2, Tq.p, n, nlev, ngroups, Z, ldz, mvec, nv, nvp};
   k_q2_apply<<<nslab, threads, smem, st>>>(a);
