@@ -88,10 +88,22 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // a b ~ a_lo b_hi + a_hi b_lo + a_hi b_hi accumulated in FP32 - FP32-level accuracy (relative 2^-21) with FP32 range, so the
 // reflectors and eigenvectors need no scaling.  The three products of a block have ~230 000 scalar FMAs per CTA; as MMAs
 // they are ~2 700 instructions.
+// round to nearest (ties away) on the 13 bits the tensor core ignores: two integer operations per rounding instead of the
+// dozen instructions cvt.rna.tf32.f32 expands to here (measured: the conversions were 60 % of the kernel's instructions);
+// the operands are finite and far from overflow
+__device__ __forceinline__ uint32_t rn_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = rn_tf32(x);
+  lo = rn_tf32(x - __uint_as_float(hi));
+}
+// The tensor core adds with truncation: a chain of n MMAs on one accumulator loses ~n * 3e-8 of the sum, one-sided (measured:
+// eigenvectors came back 8e-6 short after ten blocks).  Every k-step is therefore accumulated from zero (the two small
+// cross terms first) and added to the running sum with a rounded FP32 add.
+__device__ __forceinline__ void mma_tf32_zero(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.f));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
@@ -115,9 +127,11 @@ __device__ __forceinline__ void mma_row(float (&acc)[kMaxNJ][4], int nj, float a
       uint32_t bhi[2], blo[2];
       split_tf32(pb[8 * j], bhi[0], blo[0]);
       split_tf32(pb4[8 * j], bhi[1], blo[1]);
-      mma_tf32(acc[j], alo, bhi);
-      mma_tf32(acc[j], ahi, blo);
-      mma_tf32(acc[j], ahi, bhi);
+      float d[4];
+      mma_tf32_zero(d, alo, bhi);
+      mma_tf32(d, ahi, blo);
+      mma_tf32(d, ahi, bhi);
+      acc[j][0] += d[0]; acc[j][1] += d[1]; acc[j][2] += d[2]; acc[j][3] += d[3];
     }
   }
 }
@@ -151,21 +165,25 @@ __global__ void __launch_bounds__(256, 1) k_q2_apply(Q2Args a) {
     float* Vs = Vs0 + buf * 128 * VS;
     float* Tt = Tt0 + buf * B * VS;
     const int s0 = G * B;
-    for (int e = tid; e < B * B; e += nthr) {
-      const int j = e / B, i = e % B, s = s0 + j;
+    for (int j = warp; j < B; j += 8) {
+      const int s = s0 + j;
       const bool ok = s < n - 2;
-      cp_async4(&Vs[(j + i) * VS + j], ok ? a.V2 + (size_t)s * a.ldv2 + (size_t)k * B + i : a.V2, ok);
+      const float* src = ok ? a.V2 + (size_t)s * a.ldv2 + (size_t)k * B : a.V2;
+      cp_async4(&Vs[(j + lane) * VS + j], ok ? src + lane : src, ok);
+      cp_async4(&Vs[(j + lane + 32) * VS + j], ok ? src + lane + 32 : src, ok);
     }
     const float* tq = a.Tq + ((size_t)G * a.nlev + k) * B * B;
     for (int e = tid; e < B * B / 4; e += nthr) cp_async16(&Tt[(e / (B / 4)) * VS + (e % (B / 4)) * 4], tq + (size_t)e * 4);   // Tt[c][c']
   };
   // window rows [w0, w0 + nrow) of the window starting at global row rlo: staging area dst[(w - w0)][v], or the window's own slots
   auto fetch_rows = [&](int rlo, int w0, int nrow, float* dst, int slot0, bool to_slots) {
-    for (int e = tid; e < nrow * nvp; e += nthr) {
-      const int v = e / nrow, w = e % nrow, r = rlo + w0 + w;
-      const bool ok = v < nvv && r < n;
-      float* d = to_slots ? &Zs[((slot0 + w0 + w) & 127) * nvp + v] : &dst[w * nvp + v];
-      cp_async4(d, ok ? a.Z + (size_t)(vec0 + v) * a.ldz + r : a.Z, ok);
+    for (int v = warp; v < nvp; v += 8) {
+      const float* src = a.Z + (size_t)(vec0 + min(v, nvv - 1)) * a.ldz + rlo + w0;
+      for (int w = lane; w < nrow; w += 32) {
+        const bool ok = v < nvv && rlo + w0 + w < n;
+        float* d = to_slots ? &Zs[((slot0 + w0 + w) & 127) * nvp + v] : &dst[w * nvp + v];
+        cp_async4(d, ok ? src + w : a.Z, ok);
+      }
     }
   };
   int blk = 0;
@@ -259,9 +277,10 @@ __global__ void __launch_bounds__(256, 1) k_q2_apply(Q2Args a) {
       // ---- rows leaving the window go back to global memory (everything at the group's last level)
       {
         const int nrow = last ? 127 : B;
-        for (int e = tid; e < nrow * nvp; e += nthr) {
-          const int v = e / nrow, w = e % nrow, r = rlo + w;
-          if (v < nvv && r < n) a.Z[(size_t)(vec0 + v) * a.ldz + r] = Zs[((B * k + w) & 127) * nvp + v];
+        for (int v = warp; v < nvv; v += 8) {
+          float* dst = a.Z + (size_t)(vec0 + v) * a.ldz + rlo;
+          for (int w = lane; w < nrow; w += 32)
+            if (rlo + w < n) dst[w] = Zs[((B * k + w) & 127) * nvp + v];
         }
       }
       if (last) {
@@ -272,9 +291,10 @@ __global__ void __launch_bounds__(256, 1) k_q2_apply(Q2Args a) {
       // ---- the prefetched rows take the slots of the rows that just left: window rows 63..126 of level k + 1
       cp_async_wait_all();
       __syncthreads();
-      for (int e = tid; e < B * nvp; e += nthr) {
-        const int w = e / nvp, v = e % nvp;
-        Zs[((B * (k + 1) + B - 1 + w) & 127) * nvp + v] = Zst[w * nvp + v];
+      for (int w = warp; w < B; w += 8) {
+        float* d = &Zs[((B * (k + 1) + B - 1 + w) & 127) * nvp];
+        const float* sr = &Zst[w * nvp];
+        for (int v = lane; v < nvp; v += 32) d[v] = sr[v];
       }
     }
   }
