@@ -10,6 +10,7 @@
 // Q1 (stage-1 panels): Z[r0:] -= (V T) (V' Z[r0:]) panel by panel, last panel first, on the FP32 tile engine (V T was stored by
 // stage 1 in the upper triangle of A).
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "sgemm_tile.cuh"
 #include "tmp.cuh"
@@ -100,13 +101,13 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 // eigenvectors came back 8e-6 short after ten blocks).  Every k-step is therefore accumulated from zero (the two small
 // cross terms first) and added to the running sum with a rounded FP32 add.
 __device__ __forceinline__ void mma_tf32_zero(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
       : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.f));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
@@ -300,6 +301,336 @@ __global__ void __launch_bounds__(256, 1) k_q2_apply(Q2Args a) {
   }
 }
 
+// ------------------------------------------------------------------------------------- Q2, register-stationary variant
+// The window of a slab never leaves the register file.  A warp owns 16 eigenvectors and keeps their 128-row window as the
+// accumulator fragments of sixteen m16n8 tiles (vectors = the M dimension, window rows = N).  With vectors on M, the C/D
+// fragment of a tile (thread (g, t): rows g and g + 8, columns 2t and 2t + 1) IS an A fragment of the next product once the
+// contraction index is read as k = t <-> column 2t, k = t + 4 <-> column 2t + 1, and the same permutation is applied to the
+// rows of the B operand when it is fetched.  So  X' = Z' V  ->  X2' = X' T'  ->  Z' -= X2' V'  chain through registers:
+// no shared-memory window, no CTA-wide barrier, and the only operands that come from shared memory are the reflector block
+// and its T factor.  Those are the same for every warp and every vector, so a pre-pass (k_q2_images) writes them once, already
+// split into TF32 (hi, lo) pairs and already in the shared-memory layout, and one elected thread streams one 72 KB image per
+// block through a three-stage cp.async.bulk ring (mbarrier full / empty pairs); warps never wait for each other except
+// through that ring.  Layout of an image: four planes of 64 rows x 72 floats - hi and lo parts of P[c][u] = V[w = u + 8 (c / 8)][c]
+// (72 entries per reflector c: the nine 8-row steps that meet the 8-reflector tile of c), hi and lo parts of T[c][c'].  The
+// B operand of an MMA is a pair of consecutive registers, so a fragment fetched as one 8-byte load from a plane (two
+// consecutive rows of one reflector: the first product and the T product) needs no register moves; the last product reads
+// one row of two consecutive reflectors with 4-byte loads.  Bit 3 of u is flipped by bit 2 of c, which keeps both patterns
+// free of bank conflicts (the last eight entries of a row are not swizzled: a 2-way conflict in one step of nine).
+// Accumulation: the tensor core adds with truncation, so the leading term a_hi b_hi of every step starts from a zero
+// accumulator and is added to the running sum with a rounded FP32 add; the two cross terms, 2^-11 of it, are chained in
+// tensor-core accumulators of their own (their truncation is 2^-35 of the result), which also keeps the dependent chains short.
+constexpr int kImgRow = 72;                     // floats per plane row
+constexpr int kPlane = B * kImgRow;             // 4608 floats per plane
+constexpr int kBlkFloats = 4 * kPlane;          // P hi, P lo, T hi, T lo: 73 728 bytes
+constexpr int kBlkBytes = kBlkFloats * 4;
+constexpr int kStages = 3;
+static_assert(B == 64, "the register-stationary kernel is written for a half bandwidth of 64");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "Q2_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra Q2_DONE;\n\t"
+      "bra Q2_WAIT;\n\t"
+      "Q2_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __host__ __forceinline__ int q2_swz(int c) { return ((c >> 2) & 1) << 3; }
+
+// Pre-pass: T factor of block (G, k) as in k_q2_tfactor, then the block's two images at its place in processing order
+// (groups descending, levels ascending: block index (q - G)(q - G + 1) / 2 + k with q = the last group).
+__global__ void __launch_bounds__(256) k_q2_images(const float* __restrict__ V2, long long ldv2, const float* __restrict__ tau2,
+                                                   long long ldt2, int n, int q, float* __restrict__ Img) {
+  const int k = (int)blockIdx.x, G = (int)blockIdx.y, s0 = G * B;
+  if (s0 + 1 + B * k > n - 2) return;
+  __shared__ float Vc[B][B + 1], T[B][B + 1];
+  __shared__ float tau[B];
+  const int tid = (int)threadIdx.x;
+  for (int e = tid; e < B * B; e += 256) {
+    const int j = e / B, i = e % B, s = s0 + j;
+    Vc[j][i] = s < n - 2 ? V2[(size_t)s * ldv2 + (size_t)k * B + i] : 0.f;
+    if (j <= i) T[j][i] = 0.f;
+  }
+  if (tid < B) tau[tid] = s0 + tid < n - 2 ? tau2[(size_t)(s0 + tid) * ldt2 + k] : 0.f;
+  __syncthreads();
+  for (int e = tid; e < B * B; e += 256) {
+    const int a = e / B, b = e % B;
+    if (a < b) {
+      const int sh = b - a;
+      float s = 0.f;
+      for (int i = 0; i + sh < B; ++i) s = fmaf(Vc[a][i + sh], Vc[b][i], s);
+      T[b][a] = s;
+    }
+  }
+  __syncthreads();
+  for (int j = 0; j < B; ++j) {
+    if (tid < j) {
+      float s = 0.f;
+      for (int qq = tid; qq < j; ++qq) s = fmaf(T[tid][qq], T[j][qq], s);
+      T[tid][j] = -tau[j] * s;
+    } else if (tid == j) {
+      T[j][j] = tau[j];
+    }
+    __syncthreads();
+  }
+  float* img = Img + ((size_t)(q - G) * (q - G + 1) / 2 + k) * kBlkFloats;
+  for (int e = tid; e < B * kImgRow; e += 256) {
+    const int c = e / kImgRow, u = e % kImgRow;
+    const int i = u + 8 * (c >> 3) - c - 1;   // window row w = u + 8 (c / 8) is entry w - c - 1 of reflector c
+    const float x = (i >= 0 && i < B) ? Vc[c][i] : 0.f;
+    const int up = u < 64 ? (u ^ q2_swz(c)) : u;
+    uint32_t hi, lo;
+    split_tf32(x, hi, lo);
+    img[c * kImgRow + up] = __uint_as_float(hi);
+    img[kPlane + c * kImgRow + up] = __uint_as_float(lo);
+    const float tv = (u < B && c <= u) ? T[c][u] : 0.f;
+    split_tf32(tv, hi, lo);
+    img[2 * kPlane + c * kImgRow + u] = __uint_as_float(hi);
+    img[3 * kPlane + c * kImgRow + u] = __uint_as_float(lo);
+  }
+}
+
+struct Q2RsArgs {
+  const float* Img;
+  float* Z;
+  long long ldz;
+  int n, mvec, q, tiles, base, extra;   // CTA b owns base + (b < extra) 16-vector tiles
+};
+
+__device__ __forceinline__ void split_frag(const float (&r)[4], uint32_t (&ah)[4], uint32_t (&al)[4]) {
+  split_tf32(r[0], ah[0], al[0]);   // (g, k = t)      <- column 2t
+  split_tf32(r[2], ah[1], al[1]);   // (g + 8, k = t)
+  split_tf32(r[1], ah[2], al[2]);   // (g, k = t + 4)  <- column 2t + 1
+  split_tf32(r[3], ah[3], al[3]);
+}
+__device__ __forceinline__ void ld_b2(uint32_t (&b)[2], const float* p) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  b[0] = __float_as_uint(v.x);
+  b[1] = __float_as_uint(v.y);
+}
+// acc += a_hi b_hi from a zero accumulator; cross (+)= a_lo b_hi + a_hi b_lo
+template <bool kFirst>
+__device__ __forceinline__ void mma_step(float (&acc)[4], float (&cross)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                         const uint32_t (&bh)[2], const uint32_t (&bl)[2], float sign) {
+  float d[4];
+  mma_tf32_zero(d, ah, bh);
+  if (kFirst) mma_tf32_zero(cross, al, bh);
+  else mma_tf32(cross, al, bh);
+  mma_tf32(cross, ah, bl);
+  acc[0] = fmaf(sign, d[0], acc[0]); acc[1] = fmaf(sign, d[1], acc[1]); acc[2] = fmaf(sign, d[2], acc[2]); acc[3] = fmaf(sign, d[3], acc[3]);
+}
+__device__ __forceinline__ void ld_rows(float (&r)[4], const float* za, const float* zb, bool oka, bool okb, int row, int n) {
+  float2 u = make_float2(0.f, 0.f), v = u;
+  if (row + 1 < n) {
+    if (oka) u = *reinterpret_cast<const float2*>(za + row);
+    if (okb) v = *reinterpret_cast<const float2*>(zb + row);
+  } else if (row < n) {
+    if (oka) u.x = za[row];
+    if (okb) v.x = zb[row];
+  }
+  r[0] = u.x; r[1] = u.y; r[2] = v.x; r[3] = v.y;
+}
+__device__ __forceinline__ void st_rows(const float (&r)[4], float* za, float* zb, bool oka, bool okb, int row, int n) {
+  if (row + 1 < n) {
+    if (oka) *reinterpret_cast<float2*>(za + row) = make_float2(r[0], r[1]);
+    if (okb) *reinterpret_cast<float2*>(zb + row) = make_float2(r[2], r[3]);
+  } else if (row < n) {
+    if (oka) za[row] = r[0];
+    if (okb) zb[row] = r[2];
+  }
+}
+
+template <int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1) k_q2_apply_rs(Q2RsArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + kStages * kBlkFloats);
+  uint64_t* empty = full + kStages;
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int cta = (int)blockIdx.x;
+  const int ntile = a.base + (cta < a.extra ? 1 : 0);
+  const int tile0 = cta * a.base + min(cta, a.extra);
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], (uint32_t)ntile);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp >= ntile) return;
+  const int q = a.q, n = a.n;
+  const int nblk = (q + 1) * (q + 2) / 2;
+  if (tid == 0) {
+    for (int b = 0; b < 2 && b < nblk; ++b) {
+      mbar_arrive_expect_tx(&full[b], kBlkBytes);
+      bulk_g2s(sm + b * kBlkFloats, a.Img + (size_t)b * kBlkFloats, kBlkBytes, &full[b]);
+    }
+  }
+  const int va = (tile0 + warp) * 16 + g, vb = va + 8;
+  const bool oka = va < a.mvec, okb = vb < a.mvec;
+  float* za = a.Z + (size_t)(oka ? va : 0) * a.ldz;
+  float* zb = a.Z + (size_t)(okb ? vb : 0) * a.ldz;
+  // thread-constant offsets (floats) into a plane, see the layout above: even / odd 8-row steps, the unswizzled last step
+  const int gb = (g >> 2) & 1, tb = (t >> 1) & 1;
+  const int offA = g * kImgRow + 2 * t, offAe = offA + 8 * gb, offAo = offA - 8 * gb;
+  const int offB = 2 * t * kImgRow + g, offBe = offB + 8 * tb, offBo = offB - 8 * tb;
+  float z[16][4];
+  int b = 0;
+  for (int G = q; G >= 0; --G) {
+    const int nl = q - G + 1;
+    int R0 = B * G;   // the window of level k holds rows R0 .. R0 + 127 (reflector c of the block acts on window rows c + 1 .. c + 64)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ld_rows(z[i], za, zb, oka, okb, R0 + 8 * i + 2 * t, n);
+    for (int k = 0; k < nl; ++k, ++b, R0 += B) {
+      const int s = b % kStages;
+      if (tid == 0 && b + 2 < nblk) {   // refill the stage block b - 1 used, once every warp has released it
+        const int s2 = (b + 2) % kStages;
+        if (b >= 1) mbar_wait(&empty[s2], (uint32_t)(((b - 1) / kStages) & 1));
+        mbar_arrive_expect_tx(&full[s2], kBlkBytes);
+        bulk_g2s(sm + s2 * kBlkFloats, a.Img + (size_t)(b + 2) * kBlkFloats, kBlkBytes, &full[s2]);
+      }
+      __syncwarp();
+      const bool more = k + 1 < nl;
+      if (more) {   // the 64 rows that enter the window after this block: into L2 now, into registers when their slots are free
+        const int v = (tile0 + warp) * 16 + (lane >> 1);
+        const int r = R0 + 128 + ((lane & 1) ? 63 : 0);
+        if (v < a.mvec && r < n) {
+          const float* pz = a.Z + (size_t)v * a.ldz + r;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pz));
+          if (!(lane & 1) && r + 32 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(pz + 32));
+        }
+      }
+      mbar_wait(&full[s], (uint32_t)((b / kStages) & 1));
+      const float* Ph = sm + s * kBlkFloats;   // planes: Ph, Ph + kPlane (lo), Th = Ph + 2 kPlane, Th + kPlane (lo)
+      const float* Th = Ph + 2 * kPlane;
+      // ---- X'[vec][c] = sum_w Z'[vec][w] V[w][c]: tile j of X' (reflectors 8j ..) meets the row tiles j .. j + 8
+      float x[8][4], xc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        uint32_t ah[4], al[4];
+        split_frag(z[i], ah, al);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int d = i - j;
+          if (d >= 0 && d <= 8) {
+            const float* p = Ph + 8 * j * kImgRow + 8 * d + (d == 8 ? offA : ((d & 1) ? offAo : offAe));
+            uint32_t bh[2], bl[2];
+            ld_b2(bh, p);
+            ld_b2(bl, p + kPlane);
+            if (d == 0) mma_step<true>(x[j], xc[j], ah, al, bh, bl, 1.f);
+            else mma_step<false>(x[j], xc[j], ah, al, bh, bl, 1.f);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        x[j][0] += xc[j][0]; x[j][1] += xc[j][1]; x[j][2] += xc[j][2]; x[j][3] += xc[j][3];
+      }
+      // ---- X2'[vec][c] = sum_{c' >= c} X'[vec][c'] T[c][c']   (a fifth of the work: plain three-term chains from zero)
+      float x2[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x2[j][0] = x2[j][1] = x2[j][2] = x2[j][3] = 0.f;
+#pragma unroll
+      for (int jk = 0; jk < 8; ++jk) {
+        uint32_t ah[4], al[4];
+        split_frag(x[jk], ah, al);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j <= jk) {
+            const float* p = Th + (8 * j + g) * kImgRow + 8 * jk + 2 * t;
+            uint32_t bh[2], bl[2];
+            ld_b2(bh, p);
+            ld_b2(bl, p + kPlane);
+            float dd[4];
+            mma_tf32_zero(dd, al, bh);
+            mma_tf32(dd, ah, bl);
+            mma_tf32(dd, ah, bh);
+            x2[j][0] += dd[0]; x2[j][1] += dd[1]; x2[j][2] += dd[2]; x2[j][3] += dd[3];
+          }
+        }
+      }
+      // ---- Z'[vec][w] -= sum_c X2'[vec][c] V[w][c]: row tile i meets the reflector tiles i - 8 .. i
+      {
+        uint32_t x2h[8][4], x2l[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_frag(x2[j], x2h[j], x2l[j]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float zc[4];
+#pragma unroll
+          for (int jc = 0; jc < 8; ++jc) {
+            const int d = i - jc;
+            if (d >= 0 && d <= 8) {
+              const float* p = Ph + 8 * jc * kImgRow + 8 * d + (d == 8 ? offB : ((d & 1) ? offBo : offBe));
+              uint32_t bh[2], bl[2];
+              bh[0] = __float_as_uint(p[0]);
+              bh[1] = __float_as_uint(p[kImgRow]);
+              bl[0] = __float_as_uint(p[kPlane]);
+              bl[1] = __float_as_uint(p[kPlane + kImgRow]);
+              if (jc == (i > 8 ? i - 8 : 0)) mma_step<true>(z[i], zc, x2h[jc], x2l[jc], bh, bl, -1.f);
+              else mma_step<false>(z[i], zc, x2h[jc], x2l[jc], bh, bl, -1.f);
+            }
+          }
+          z[i][0] -= zc[0]; z[i][1] -= zc[1]; z[i][2] -= zc[2]; z[i][3] -= zc[3];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      // ---- the first 64 rows leave the window (all 128 at the group's last level); the prefetched rows enter
+#pragma unroll
+      for (int i = 0; i < 8; ++i) st_rows(z[i], za, zb, oka, okb, R0 + 8 * i + 2 * t, n);
+      if (more) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) z[i][e] = z[i + 8][e];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ld_rows(z[i + 8], za, zb, oka, okb, R0 + 128 + 8 * i + 2 * t, n);   // first used a quarter block later
+      } else {
+#pragma unroll
+        for (int i = 8; i < 16; ++i) st_rows(z[i], za, zb, oka, okb, R0 + 8 * i + 2 * t, n);
+      }
+    }
+  }
+}
+
+// unit length again: the tensor core adds with truncation, so every block update comes back a few 1e-8 short, which shortens a
+// vector by ~1e-7 n / 64 over the whole of Q2 (measured 4e-6 at n = 2531) while turning it by far less
+__global__ void __launch_bounds__(256) k_unit_vectors(float* __restrict__ Z, long long ldz, int n, int mvec) {
+  const int v = (int)blockIdx.x * 8 + ((int)threadIdx.x >> 5), lane = (int)threadIdx.x & 31;
+  if (v >= mvec) return;
+  float* z = Z + (size_t)v * ldz;
+  double s = 0.0;
+  for (int i = lane; i < n; i += 32) s += (double)z[i] * (double)z[i];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (!(s > 0.0)) return;
+  const float f = (float)(1.0 / sqrt(s));
+  for (int i = lane; i < n; i += 32) z[i] *= f;
+}
+
 // ---------------------------------------------------------------------------------------------------------------- Q1
 // Xpart[s][c][vec] = sum over rows i of chunk s of V[c][i] * Z[vec][r0 + i]
 __global__ void __launch_bounds__(256, 2) k_q1_x(const float* __restrict__ Vp, long long lda, int m, const float* __restrict__ Zr,
@@ -367,6 +698,34 @@ void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2
   const int nsweeps = n - 2;
   const int ngroups = (nsweeps + B - 1) / B;
   const int nlev = sb2st_levels(n);
+  // SCL_Q2_VARIANT=0: the shared-memory window kernel (k_q2_apply); default: the register-stationary kernel
+  static const int variant = [] { const char* e = getenv("SCL_Q2_VARIANT"); return e ? atoi(e) : 1; }();
+  if (variant != 0 && n >= 3) {
+    const int q = (n - 3) / B;   // last group; group G has q - G + 1 levels
+    const size_t nblk = (size_t)(q + 1) * (q + 2) / 2;
+    Tmp<float> Img(nblk * kBlkFloats, st);
+    k_q2_images<<<dim3(nlev, ngroups), 256, 0, st>>>(V2, ldv2, tau2, ldt2, n, q, Img.p);
+    SCL_CUDA(cudaGetLastError());
+    // 16-vector tiles, one warp each; at most 12 warps per CTA (registers are granted to a CTA in units of four warps: 255 per
+    // thread up to 8 warps, 168 up to 12), as few waves as that allows
+    const int tiles = (mvec + 15) / 16, sms = sm_count();
+    const int waves = (tiles + sms * 12 - 1) / (sms * 12);
+    const int grid = std::min(tiles, sms * waves);
+    const int base = tiles / grid, extra = tiles % grid;
+    const int warps = base + (extra ? 1 : 0);
+    const size_t smem = (size_t)kStages * kBlkBytes + 2 * kStages * sizeof(uint64_t);
+    Q2RsArgs a{Img.p, Z, ldz, n, mvec, q, tiles, base, extra};
+    if (warps <= 8) {
+      SCL_CUDA(cudaFuncSetAttribute(k_q2_apply_rs<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_q2_apply_rs<8><<<grid, warps * 32, smem, st>>>(a);
+    } else {
+      SCL_CUDA(cudaFuncSetAttribute(k_q2_apply_rs<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_q2_apply_rs<12><<<grid, warps * 32, smem, st>>>(a);
+    }
+    SCL_CUDA(cudaGetLastError());
+    count_launches(2);
+    return;
+  }
   Tmp<float> Tq((size_t)ngroups * nlev * B * B, st);
   k_q2_tfactor<<<dim3(nlev, ngroups), 256, 0, st>>>(V2, ldv2, tau2, ldt2, n, nlev, Tq.p);
   SCL_CUDA(cudaGetLastError());
@@ -390,6 +749,13 @@ void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2
   k_q2_apply<<<nslab, threads, smem, st>>>(a);
   SCL_CUDA(cudaGetLastError());
   count_launches(2);
+}
+
+void unit_vectors(float* Z, long long ldz, int n, int mvec, cudaStream_t st) {
+  if (mvec <= 0) return;
+  k_unit_vectors<<<(mvec + 7) / 8, 256, 0, st>>>(Z, ldz, n, mvec);
+  SCL_CUDA(cudaGetLastError());
+  count_launches(1);
 }
 
 void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels, float* Z, long long ldz, int mvec,

@@ -123,6 +123,7 @@ bool Solver::syevd_2stage(float* dA, int n, float* dW, int v0, int v1, cudaStrea
     apply_q2(impl->ts_V2.p, ldv2, impl->ts_tau2.p, ldt2, n, impl->tri_z.p, ldz, m, st);
     SCL_CUDA(cudaEventRecord(ev[4], st));
     apply_q1(Aq, n, lda, impl->ts_T1.p, npanels, impl->tri_z.p, ldz, m, st);
+    unit_vectors(impl->tri_z.p, ldz, n, m, st);
     SCL_CUDA(cudaMemcpy2DAsync(dA + (size_t)v0 * n, (size_t)n * sizeof(float), impl->tri_z.p, (size_t)ldz * sizeof(float),
                                (size_t)n * sizeof(float), (size_t)m, cudaMemcpyDeviceToDevice, st));
   } else {

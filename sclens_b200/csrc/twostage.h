@@ -44,4 +44,7 @@ void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2
 void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels, float* Z, long long ldz, int mvec,
               cudaStream_t st);
 
+// every vector scaled to unit length (after the back-transformation: the tensor-core products of apply_q2 lose ~1e-7 n / 64)
+void unit_vectors(float* Z, long long ldz, int n, int mvec, cudaStream_t st);
+
 }  // namespace scl
