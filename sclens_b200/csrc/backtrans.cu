@@ -89,29 +89,11 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // a b ~ a_lo b_hi + a_hi b_lo + a_hi b_hi accumulated in FP32 - FP32-level accuracy (relative 2^-21) with FP32 range, so the
 // reflectors and eigenvectors need no scaling.  The three products of a block have ~230 000 scalar FMAs per CTA; as MMAs
 // they are ~2 700 instructions.
-// round to nearest (ties away) on the 13 bits the tensor core ignores: two integer operations per rounding instead of the
-// dozen instructions cvt.rna.tf32.f32 expands to here (measured: the conversions were 60 % of the kernel's instructions);
-// the operands are finite and far from overflow
-__device__ __forceinline__ uint32_t rn_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = rn_tf32(x);
-  lo = rn_tf32(x - __uint_as_float(hi));
-}
-// The tensor core adds with truncation: a chain of n MMAs on one accumulator loses ~n * 3e-8 of the sum, one-sided (measured:
-// eigenvectors came back 8e-6 short after ten blocks).  Every k-step is therefore accumulated from zero (the two small
-// cross terms first) and added to the running sum with a rounded FP32 add.
-__device__ __forceinline__ void mma_tf32_zero(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.f));
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
+// (split_tf32 / mma_tf32 / mma_tf32_zero: sgemm_tile.cuh; the rounding is two integer operations per value instead of the
+// dozen instructions cvt.rna.tf32.f32 expands to - the conversions were 60 % of this kernel's instructions)
+using tile::mma_tf32;
+using tile::mma_tf32_zero;
+using tile::split_tf32;
 // d (16 x 8 tiles j < NJ) += A (16 x 8, fragment from a0..a3) * B_j (8 x 8): pb = &B[k = t][n = g] of tile 0, tiles 8 columns apart,
 // rows k and k + 4 at pb and pb4
 constexpr int kMaxNJ = 6;
@@ -690,6 +672,58 @@ __global__ void __launch_bounds__(256, 2) k_q1_z(const float* __restrict__ VTt, 
   }
 }
 
+// ---- the same two products on the tensor-core tile engine (error-compensated TF32, sgemm_tile.cuh)
+__global__ void __launch_bounds__(256, 2) k_q1_x_tc(const float* __restrict__ Vp, long long lda, int m, const float* __restrict__ Zr,
+                                                    long long ldz, int mvec, float* __restrict__ Xpart, long long ldx, int chunk) {
+  __shared__ __align__(16) float smem[tile::SmemT<64>::floats];
+  const int vec0 = (int)blockIdx.x * tile::TM;
+  const int ka = (int)blockIdx.y * chunk, kl = min(m, ka + chunk) - ka;
+  tile::AccT<64> acc;
+  acc.clear();
+  tile::mac_tc<64>(acc, tile::opnd(Zr + (long long)vec0 * ldz + ka, ldz, 1, mvec - vec0, kl), tile::opnd(Vp + ka, lda, 1, B, kl), kl, smem);
+  float* out = Xpart + (size_t)blockIdx.y * B * ldx;
+#pragma unroll
+  for (int nt = 0; nt < tile::AccT<64>::NTL; ++nt)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int v = vec0 + tile::AccT<64>::row(mt, e), c = tile::AccT<64>::col(nt, e);
+        if (v < mvec) out[(long long)c * ldx + v] = acc.v[mt][nt][e];
+      }
+}
+
+// Z[vec][r0 + i] -= sum_c X[c][vec] (V T)[i][c]: vectors on the rows of the tile, matrix rows on its columns, so that a thread's
+// two adjacent outputs are adjacent in memory
+__global__ void __launch_bounds__(256, 2) k_q1_z_tc(const float* __restrict__ VTt, long long lda, int m, const float* __restrict__ Xp,
+                                                    long long ldx, int mvec, float* Zr, long long ldz) {
+  __shared__ __align__(16) float smem[tile::SmemT<128>::floats];
+  const int i0 = (int)blockIdx.x * tile::TM, vec0 = (int)blockIdx.y * tile::TM;
+  tile::AccT<128> acc;
+  acc.clear();
+  tile::mac_tc<128>(acc, tile::opnd(Xp + vec0, ldx, 0, mvec - vec0, B), tile::opnd(VTt + (long long)i0 * lda, lda, 1, m - i0, B), B, smem);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int v = vec0 + tile::AccT<128>::row(mt, 2 * h);
+      if (v >= mvec) continue;
+      float* zc = Zr + (long long)v * ldz;
+#pragma unroll
+      for (int nt = 0; nt < tile::AccT<128>::NTL; ++nt) {
+        const int i = i0 + tile::AccT<128>::col(nt, 0);
+        if (i + 1 < m) {
+          float2 z = *reinterpret_cast<float2*>(zc + i);
+          z.x -= acc.v[mt][nt][2 * h];
+          z.y -= acc.v[mt][nt][2 * h + 1];
+          *reinterpret_cast<float2*>(zc + i) = z;
+        } else if (i < m) {
+          zc[i] -= acc.v[mt][nt][2 * h];
+        }
+      }
+    }
+}
+
 }  // namespace
 
 void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2, int n, float* Z, long long ldz, int mvec,
@@ -774,10 +808,16 @@ void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels
     int chunk = ((m + split - 1) / split + tile::KT - 1) / tile::KT * tile::KT;
     chunk = std::max(chunk, 4 * tile::KT);
     split = (m + chunk - 1) / chunk;
-    k_q1_x<<<dim3(vt, split), 256, 0, st>>>(Vp, lda, m, Z + r0, ldz, mvec, Xpart.p, ldx, chunk);
     const size_t nx = (size_t)B * ldx;
-    k_sum_parts32<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(Xpart.p, split, nx, nx, Xp.p);
-    k_q1_z<<<dim3((m + tile::TM - 1) / tile::TM, vt), 256, 0, st>>>(A + c0 + (long long)r0 * lda, lda, m, Xp.p, ldx, mvec, Z + r0, ldz);
+    if (tile_engine_tc()) {
+      k_q1_x_tc<<<dim3(vt, split), 256, 0, st>>>(Vp, lda, m, Z + r0, ldz, mvec, Xpart.p, ldx, chunk);
+      k_sum_parts32<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(Xpart.p, split, nx, nx, Xp.p);
+      k_q1_z_tc<<<dim3((m + tile::TM - 1) / tile::TM, vt), 256, 0, st>>>(A + c0 + (long long)r0 * lda, lda, m, Xp.p, ldx, mvec, Z + r0, ldz);
+    } else {
+      k_q1_x<<<dim3(vt, split), 256, 0, st>>>(Vp, lda, m, Z + r0, ldz, mvec, Xpart.p, ldx, chunk);
+      k_sum_parts32<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(Xpart.p, split, nx, nx, Xp.p);
+      k_q1_z<<<dim3((m + tile::TM - 1) / tile::TM, vt), 256, 0, st>>>(A + c0 + (long long)r0 * lda, lda, m, Xp.p, ldx, mvec, Z + r0, ldz);
+    }
   }
   SCL_CUDA(cudaGetLastError());
   count_launches(3 * npanels);

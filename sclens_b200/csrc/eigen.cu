@@ -41,12 +41,14 @@ struct Solver::Impl {
 // an index range instead of a full solve (474 ms in the same first look); also opt-in until parity-tested.
 static std::atomic<int> g_eig_api_override{-1};
 int eig_api() {
-  // default 28: the own tridiagonal stage for every solve (bit 2) with index-range vectors in the search steps (bit 3) on
-  // the own tridiagonalisation (bit 4).  Measured at n = 20 000 (profiles/r2_eig_study2.json, r2_eig_study3_20000.json):
-  // Ssyevd with all vectors 3.65 s on the 68k x 20k data Gram matrix (2.69 s on a synthetic Wishart matrix); Ssytrd + own
-  // stage + Sormtr 2.85 s; own sytrd (1.98 s against 2.13 s for Ssytrd) + own stage + Sormtr 2.42 s, 2.25 s for the
-  // smallest half, 2.03 s for values only.  SCL_EIG_API=0 is the plain library solve (the call the reference makes).
-  static const int v = [] { const char* e = getenv("SCL_EIG_API"); return e ? atoi(e) : 28; }();
+  // default 60: the own tridiagonal stage for every solve (bit 2) with index-range vectors in the search steps (bit 3) behind
+  // the two-stage reduction (bit 5: dense -> band -> tridiagonal, twostage.h); bit 4 = the own one-stage tridiagonalisation,
+  // which a solve falls back to when a panel of the two-stage reduction cannot be factored and which serves orders below
+  // 4 kBand.  Measured at n = 20 000 (all vectors / smallest half / values only): two-stage 1.71 / 1.29 / 0.62 s; one-stage own
+  // sytrd + own stage + Sormtr 2.42 / 2.25 / 2.03 s; Ssytrd + own stage + Sormtr 2.85 s; Ssyevd 3.65 s on the 68k x 20k data
+  // Gram matrix (2.69 s on a synthetic Wishart matrix).  SCL_EIG_API=28 is the one-stage path, 0 the plain library solve (the
+  // call the reference makes).
+  static const int v = [] { const char* e = getenv("SCL_EIG_API"); return e ? atoi(e) : 60; }();
   const int o = g_eig_api_override.load(std::memory_order_relaxed);
   return o >= 0 ? o : v;
 }

@@ -84,21 +84,21 @@ __device__ __forceinline__ void g2r(const Opnd& o, int k0, Frag<W>& f) {
   }
 }
 
-template <int W>
-__device__ __forceinline__ void r2s(const Opnd& o, const Frag<W>& f, float* S /* [KT][W + PAD] */) {
+template <int W, int P = PAD>
+__device__ __forceinline__ void r2s(const Opnd& o, const Frag<W>& f, float* S /* [KT][W + P] */) {
   const int tid = (int)threadIdx.x;
 #pragma unroll
   for (int q = 0; q < Frag<W>::N; ++q) {
     const int idx = tid + q * NT;
     if (o.layout == 1) {
       const int i = idx / (KT / 4), k = (idx % (KT / 4)) * 4;
-      S[(k + 0) * (W + PAD) + i] = f.r[q].x;
-      S[(k + 1) * (W + PAD) + i] = f.r[q].y;
-      S[(k + 2) * (W + PAD) + i] = f.r[q].z;
-      S[(k + 3) * (W + PAD) + i] = f.r[q].w;
+      S[(k + 0) * (W + P) + i] = f.r[q].x;
+      S[(k + 1) * (W + P) + i] = f.r[q].y;
+      S[(k + 2) * (W + P) + i] = f.r[q].z;
+      S[(k + 3) * (W + P) + i] = f.r[q].w;
     } else {
       const int k = idx / (W / 4), i = (idx % (W / 4)) * 4;
-      *reinterpret_cast<float4*>(&S[k * (W + PAD) + i]) = f.r[q];
+      *reinterpret_cast<float4*>(&S[k * (W + P) + i]) = f.r[q];
     }
   }
 }
@@ -169,6 +169,114 @@ __device__ __forceinline__ void mac(Acc<TN>& acc, const Opnd& A, const Opnd& B, 
     if (t + 1 < nk) {
       r2s<TM>(A, fa, As + (cur ^ 1) * KT * (TM + PAD));
       r2s<TN>(B, fb, Bs + (cur ^ 1) * KT * (TN + PAD));
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core variant of the same engine: mma.sync m16n8k8 in error-compensated TF32.  x = hi + lo with hi = tf32(x),
+// lo = tf32(x - hi);  a b ~ a_lo b_hi + a_hi b_lo + a_hi b_hi, the three products of a k-step accumulated from a ZERO
+// accumulator and added to the running FP32 sum with a rounded add (the tensor core itself adds with truncation: a long
+// chain on one accumulator drifts by ~3e-8 per MMA, one-sided).  FP32-level accuracy (2^-21 per product) and FP32 range,
+// so no operand needs scaling.  Same operand descriptions, same pipeline; 8 warps as 4 (rows) x 2 (columns), a warp owns
+// 32 x TN/2 outputs as 2 x TN/16 accumulator fragments.  Shared-memory rows are padded to a stride of 8 (mod 32) floats, which
+// makes every fragment load (4 k-rows x 8 consecutive columns) conflict-free.
+__device__ __forceinline__ uint32_t rn_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = rn_tf32(x);
+  lo = rn_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32_zero(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.f));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+constexpr int PADT = 8;
+
+template <int TN>
+struct AccT {
+  static constexpr int NTL = TN / 16;   // 8-column fragments per warp
+  float v[2][NTL][4];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < NTL; ++b) v[a][b][0] = v[a][b][1] = v[a][b][2] = v[a][b][3] = 0.f;
+  }
+  // tile coordinates of v[mt][nt][e] for this thread: rows g and g + 8 of the fragment (e >> 1), columns 2t and 2t + 1 (e & 1)
+  static __device__ __forceinline__ int row(int mt, int e) {
+    return (((int)threadIdx.x >> 5) & 3) * 32 + mt * 16 + (((int)threadIdx.x & 31) >> 2) + 8 * (e >> 1);
+  }
+  static __device__ __forceinline__ int col(int nt, int e) {
+    return ((int)threadIdx.x >> 7) * (TN / 2) + nt * 8 + 2 * ((int)threadIdx.x & 3) + (e & 1);
+  }
+};
+
+template <int TN>
+struct SmemT {
+  static constexpr int floats = 2 * KT * (TM + PADT) + 2 * KT * (TN + PADT);
+};
+
+template <int TN>
+__device__ __forceinline__ void mac_tc(AccT<TN>& acc, const Opnd& A, const Opnd& Bo, int klen, float* smem) {
+  if (klen <= 0) return;
+  constexpr int LDA = TM + PADT, LDB = TN + PADT, NTL = TN / 16;
+  float* As = smem;
+  float* Bs = smem + 2 * KT * LDA;
+  const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int m0 = (warp & 3) * 32 + g, n0 = (warp >> 2) * (TN / 2) + g;
+  const int nk = (klen + KT - 1) / KT;
+  Frag<TM> fa;
+  Frag<TN> fb;
+  g2r<TM>(A, 0, fa);
+  g2r<TN>(Bo, 0, fb);
+  __syncthreads();   // the previous user of the buffers is done
+  r2s<TM, PADT>(A, fa, As);
+  r2s<TN, PADT>(Bo, fb, Bs);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) {
+      g2r<TM>(A, (kt + 1) * KT, fa);
+      g2r<TN>(Bo, (kt + 1) * KT, fb);
+    }
+#pragma unroll
+    for (int ks = 0; ks < KT / 8; ++ks) {
+      const float* as = As + cur * KT * LDA + (8 * ks + t) * LDA + m0;
+      const float* bs = Bs + cur * KT * LDB + (8 * ks + t) * LDB + n0;
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        split_tf32(as[mt * 16], ah[mt][0], al[mt][0]);
+        split_tf32(as[mt * 16 + 8], ah[mt][1], al[mt][1]);
+        split_tf32(as[4 * LDA + mt * 16], ah[mt][2], al[mt][2]);
+        split_tf32(as[4 * LDA + mt * 16 + 8], ah[mt][3], al[mt][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        uint32_t bh[2], bl[2];
+        split_tf32(bs[nt * 8], bh[0], bl[0]);
+        split_tf32(bs[4 * LDB + nt * 8], bh[1], bl[1]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          float d[4];
+          mma_tf32_zero(d, al[mt], bh);
+          mma_tf32(d, ah[mt], bl);
+          mma_tf32(d, ah[mt], bh);
+          acc.v[mt][nt][0] += d[0]; acc.v[mt][nt][1] += d[1]; acc.v[mt][nt][2] += d[2]; acc.v[mt][nt][3] += d[3];
+        }
+      }
+    }
+    if (kt + 1 < nk) {
+      r2s<TM, PADT>(A, fa, As + (cur ^ 1) * KT * LDA);
+      r2s<TN, PADT>(Bo, fb, Bs + (cur ^ 1) * KT * LDB);
     }
     __syncthreads();
   }

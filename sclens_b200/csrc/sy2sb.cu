@@ -330,6 +330,43 @@ __global__ void __launch_bounds__(256, 2) k_symm(const float* __restrict__ A22, 
   }
 }
 
+// k_symm on the tensor-core tile engine
+__global__ void __launch_bounds__(256, 2) k_symm_tc(const float* __restrict__ A22, long long lda, int m, const float* __restrict__ V,
+                                                    long long ldv, float* __restrict__ Ypart, long long ldy, int chunk) {
+  __shared__ __align__(16) float smem[tile::SmemT<64>::floats];
+  const int i0 = (int)blockIdx.x * tile::TM;
+  const int ka = (int)blockIdx.y * chunk, kb = min(m, ka + chunk);
+  tile::AccT<64> acc;
+  acc.clear();
+  const int mi = m - i0;
+  {
+    const int k1 = min(kb, i0);
+    if (k1 > ka)
+      tile::mac_tc<64>(acc, tile::opnd(A22 + i0 + (long long)ka * lda, lda, 0, mi, k1 - ka), tile::opnd(V + ka, ldv, 1, B, k1 - ka),
+                       k1 - ka, smem);
+  }
+  if (ka <= i0 && i0 < kb) {
+    const int kl = min(tile::TM, mi);
+    tile::mac_tc<64>(acc, tile::opnd(A22 + i0 + (long long)i0 * lda, lda, 2, mi, kl), tile::opnd(V + i0, ldv, 1, B, kl), kl, smem);
+  }
+  {
+    const int k3 = max(ka, i0 + tile::TM);
+    if (kb > k3)
+      tile::mac_tc<64>(acc, tile::opnd(A22 + k3 + (long long)i0 * lda, lda, 1, mi, kb - k3), tile::opnd(V + k3, ldv, 1, B, kb - k3),
+                       kb - k3, smem);
+  }
+  float* out = Ypart + (size_t)blockIdx.y * B * ldy;
+#pragma unroll
+  for (int nt = 0; nt < tile::AccT<64>::NTL; ++nt)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i0 + tile::AccT<64>::row(mt, e), c = tile::AccT<64>::col(nt, e);
+        if (i < m) out[(long long)c * ldy + i] = acc.v[mt][nt][e];
+      }
+}
+
 __global__ void k_sum_parts(const float* __restrict__ part, int nparts, size_t stride, size_t n, float* __restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -382,6 +419,54 @@ __global__ void __launch_bounds__(256, 2) k_syr2k(float* A22, long long lda, int
       }
     }
   }
+}
+
+// k_syr2k on the tensor-core tile engine: the tile is formed transposed (columns j of the trailing matrix on the rows of the
+// accumulator, rows i on its columns), so a thread's two adjacent outputs are adjacent in memory
+__global__ void __launch_bounds__(256, 2) k_syr2k_tc(float* A22, long long lda, int m, const float* __restrict__ V, long long ldv,
+                                                     const float* __restrict__ W, long long ldw, int mode) {
+  __shared__ __align__(16) float smem[tile::SmemT<128>::floats];
+  const int t = (int)blockIdx.x;
+  int I, J;
+  if (mode == 1) {
+    I = t;
+    J = 0;
+  } else {
+    I = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+    while ((I + 1) * (I + 2) / 2 <= t) ++I;
+    while (I * (I + 1) / 2 > t) --I;
+    J = t - I * (I + 1) / 2;
+    if (mode == 2) {
+      ++I;
+      ++J;
+    }
+  }
+  const int i0 = I * tile::TM, j0 = J * tile::TM;
+  tile::AccT<128> acc;
+  acc.clear();
+  tile::mac_tc<128>(acc, tile::opnd(W + j0, ldw, 0, m - j0, B), tile::opnd(V + i0, ldv, 0, m - i0, B), B, smem);
+  tile::mac_tc<128>(acc, tile::opnd(V + j0, ldv, 0, m - j0, B), tile::opnd(W + i0, ldw, 0, m - i0, B), B, smem);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = j0 + tile::AccT<128>::row(mt, 2 * h);
+      if (j >= m) continue;
+      float* col = A22 + (long long)j * lda;
+#pragma unroll
+      for (int nt = 0; nt < tile::AccT<128>::NTL; ++nt) {
+        const int i = i0 + tile::AccT<128>::col(nt, 0);
+        if (i + 1 < m && i >= j) {
+          float2 c = *reinterpret_cast<float2*>(col + i);
+          c.x -= acc.v[mt][nt][2 * h];
+          c.y -= acc.v[mt][nt][2 * h + 1];
+          *reinterpret_cast<float2*>(col + i) = c;
+        } else {
+          if (i < m && i >= j) col[i] -= acc.v[mt][nt][2 * h];
+          if (i + 1 < m && i + 1 >= j) col[i + 1] -= acc.v[mt][nt][2 * h + 1];
+        }
+      }
+    }
 }
 
 // the last, short panel (2 <= m < kBand rows): plain Householder QR of the m x kBand block, the two-sided update of the m x m
@@ -533,6 +618,7 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     attr_done = true;
   }
   const int slots = 2 * sm_count();
+  const bool tc = tile_engine_tc();
   long launches = 0;
   // factorisation of panel k (full-size panels only) on stream s: V in place, T, V T into the upper triangle, R' into the band
   auto factor = [&](int k, cudaStream_t s) {
@@ -575,7 +661,8 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     int chunk = ((m + split - 1) / split + tile::TM - 1) / tile::TM * tile::TM;
     chunk = std::max(chunk, 2 * tile::TM);
     split = (m + chunk - 1) / chunk;
-    k_symm<<<dim3(ntile, split), 256, 0, st>>>(A22, lda, m, Pp, lda, Ypart.p, ldy, chunk);
+    if (tc) k_symm_tc<<<dim3(ntile, split), 256, 0, st>>>(A22, lda, m, Pp, lda, Ypart.p, ldy, chunk);
+    else k_symm<<<dim3(ntile, split), 256, 0, st>>>(A22, lda, m, Pp, lda, Ypart.p, ldy, chunk);
     const size_t ny = (size_t)B * ldy;
     k_sum_parts<<<(unsigned)((ny + 255) / 256), 256, 0, st>>>(Ypart.p, split, ny, ny, Y.p);
     k_panel_mul<<<ntile, 256, 0, st>>>(Y.p, ldy, Tk, Z.p, ldy, m, 1.f, nullptr, 0, 0);
@@ -587,17 +674,20 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     // auxiliary stream (one or a few CTAs per kernel) while the main stream updates the rest of the trailing matrix
     const bool ahead = aux && aux->stream && ntile >= 4 && m - B >= B;
     if (ahead) {
-      k_syr2k<<<ntile, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 1);
+      if (tc) k_syr2k_tc<<<ntile, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 1);
+      else k_syr2k<<<ntile, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 1);
       SCL_CUDA(cudaEventRecord(aux->ready, st));
       SCL_CUDA(cudaStreamWaitEvent(aux->stream, aux->ready, 0));
       factor(k + 1, aux->stream);
       SCL_CUDA(cudaEventRecord(aux->done, aux->stream));
-      k_syr2k<<<(ntile - 1) * ntile / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 2);
+      if (tc) k_syr2k_tc<<<(ntile - 1) * ntile / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 2);
+      else k_syr2k<<<(ntile - 1) * ntile / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 2);
       SCL_CUDA(cudaStreamWaitEvent(st, aux->done, 0));
       factored = true;
       ++launches;
     } else {
-      k_syr2k<<<ntile * (ntile + 1) / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 0);
+      if (tc) k_syr2k_tc<<<ntile * (ntile + 1) / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 0);
+      else k_syr2k<<<ntile * (ntile + 1) / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 0);
     }
     ++launches;
   }

@@ -7,6 +7,7 @@
 // The algebra is restated on the CPU in oracle/two_stage_ref.py (tests/test_two_stage_cpu.py).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace scl {
@@ -43,6 +44,13 @@ void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2
 // Z <- Q1 Z with the panels left in A by sy2sb_lower
 void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels, float* Z, long long ldz, int mvec,
               cudaStream_t st);
+
+// which tile engine runs the matrix-matrix products of stage 1 and of the Q1 back-transformation: the tensor-core engine
+// (error-compensated TF32, default) or the FP32 FMA engine (SCL_TILE_ENGINE=0); both in sgemm_tile.cuh
+inline bool tile_engine_tc() {
+  static const bool v = [] { const char* e = getenv("SCL_TILE_ENGINE"); return e ? atoi(e) != 0 : true; }();
+  return v;
+}
 
 // every vector scaled to unit length (after the back-transformation: the tensor-core products of apply_q2 lose ~1e-7 n / 64)
 void unit_vectors(float* Z, long long ldz, int n, int mvec, cudaStream_t st);

@@ -536,7 +536,8 @@ def test_two_stage_solver_matches_float64(h, n, case):
     G = (A @ A.T / A.shape[1]).astype(np.float32)
     Lref = np.linalg.eigvalsh(G.astype(np.float64))
     scale = float(Lref[-1])
-    st = np.zeros(8)
+    st, st0 = np.zeros(8), np.zeros(8)
+    h.lib.scl_debug_last_solve(h.h, ptr(st0, C.c_double))   # fallback counters are cumulative per handle
     try:
         h.lib.scl_debug_set_eig_api(TWO_STAGE)
         L, V, out = _tri_solve(h, G, 0, n)
@@ -546,7 +547,7 @@ def test_two_stage_solver_matches_float64(h, n, case):
         L3, _, _ = _tri_solve(h, G, 0, 0)
     finally:
         h.lib.scl_debug_set_eig_api(-1)
-    assert out[5] == 0 and st[5] == 1 and st[6] == 0, ("the two-stage path did not produce the result", out, st)
+    assert out[5] == 0 and st[5] == 1 and st[6] == st0[6], ("the two-stage path did not produce the result", out, st, st0)
     np.testing.assert_allclose(L, Lref, rtol=2e-5, atol=3e-6 * scale)
     G64 = G.astype(np.float64)
     assert np.max(np.abs(G64 @ V - V * L[None, :])) < 5e-5 * max(1.0, scale)
