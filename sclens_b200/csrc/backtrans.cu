@@ -9,6 +9,7 @@
 // rows, which never leave the SM), and walks all blocks.
 // Q1 (stage-1 panels): Z[r0:] -= (V T) (V' Z[r0:]) panel by panel, last panel first, on the FP32 tile engine (V T was stored by
 // stage 1 in the upper triangle of A).
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <cstdlib>
 #include "common.cuh"
@@ -598,6 +599,292 @@ __global__ void __launch_bounds__(MAXW * 32, 1) k_q2_apply_rs(Q2RsArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------- Q2, register-stationary variant in split binary16
+// Measured on B200 (scripts/mma_rate.cu): the warp-level tensor path issues one mma.sync per 8 cycles and sub-partition for
+// m16n8k8 TF32 and for m16n8k16 FP16 alike, so a binary16 step contracts twice as many terms in the same time.  Same kernel as
+// above with x = hi + lo / 2048, hi = half(x), lo = half((x - hi) 2048): 22 significant bits like the TF32 pair; the factor keeps
+// lo out of the subnormal range, and values below 6e-5 (eigenvector entries never need more) keep an absolute error of 1.5e-11.
+// Everything that is multiplied is O(1) or smaller: eigenvector entries, reflectors (|v| <= 1), T (|tau| <= 2), X, X2.
+// A 16-row step of the window is two accumulator tiles: registers (tile i | tile i + 1) are the A fragment as they stand
+// (natural k order).  B fragments come from the image by ldmatrix: plain for the first product and for T (pairs along the
+// window rows of one reflector), transposed for the last product (pairs along the reflectors of one window row); one
+// ldmatrix.x4 fetches the hi and lo fragments of a step.  Image of a block: binary16 planes P hi, P lo (64 rows of 88: 8
+// zeros, the 72 entries of the nine steps, 8 zeros - the zeros serve the half steps that stick out of the band), T hi, T lo
+// (64 rows of 72); row pitches of 176 and 144 bytes spread the eight 16-byte rows of an ldmatrix over all banks.
+constexpr int kPRowH = 88, kTRowH = 72;
+constexpr int kPPlaneH = B * kPRowH, kTPlaneH = B * kTRowH;        // halves per plane
+constexpr int kBlkHalves = 2 * kPPlaneH + 2 * kTPlaneH;            // 20 480 halves = 40 960 bytes
+constexpr int kBlkBytesH = kBlkHalves * 2;
+constexpr int kStagesH = 4;
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+
+__global__ void __launch_bounds__(256) k_q2_images_h(const float* __restrict__ V2, long long ldv2, const float* __restrict__ tau2,
+                                                     long long ldt2, int n, int q, __half* __restrict__ Img) {
+  const int k = (int)blockIdx.x, G = (int)blockIdx.y, s0 = G * B;
+  if (s0 + 1 + B * k > n - 2) return;
+  __shared__ float Vc[B][B + 1], T[B][B + 1];
+  __shared__ float tau[B];
+  const int tid = (int)threadIdx.x;
+  for (int e = tid; e < B * B; e += 256) {
+    const int j = e / B, i = e % B, s = s0 + j;
+    Vc[j][i] = s < n - 2 ? V2[(size_t)s * ldv2 + (size_t)k * B + i] : 0.f;
+    if (j <= i) T[j][i] = 0.f;
+  }
+  if (tid < B) tau[tid] = s0 + tid < n - 2 ? tau2[(size_t)(s0 + tid) * ldt2 + k] : 0.f;
+  __syncthreads();
+  for (int e = tid; e < B * B; e += 256) {
+    const int a = e / B, b = e % B;
+    if (a < b) {
+      const int sh = b - a;
+      float s = 0.f;
+      for (int i = 0; i + sh < B; ++i) s = fmaf(Vc[a][i + sh], Vc[b][i], s);
+      T[b][a] = s;
+    }
+  }
+  __syncthreads();
+  for (int j = 0; j < B; ++j) {
+    if (tid < j) {
+      float s = 0.f;
+      for (int qq = tid; qq < j; ++qq) s = fmaf(T[tid][qq], T[j][qq], s);
+      T[tid][j] = -tau[j] * s;
+    } else if (tid == j) {
+      T[j][j] = tau[j];
+    }
+    __syncthreads();
+  }
+  __half* img = Img + ((size_t)(q - G) * (q - G + 1) / 2 + k) * kBlkHalves;
+  for (int e = tid; e < B * kPRowH; e += 256) {
+    const int c = e / kPRowH, up = e % kPRowH;
+    const int i = up - 8 - (c & 7) - 1;   // entry up holds window row 8 (c / 8) + up - 8 = entry i of reflector c
+    const float x = (i >= 0 && i < B) ? Vc[c][i] : 0.f;
+    const __half hi = __float2half_rn(x);
+    img[e] = hi;
+    img[kPPlaneH + e] = __float2half_rn((x - __half2float(hi)) * kLoScale);
+  }
+  for (int e = tid; e < B * kTRowH; e += 256) {
+    const int c = e / kTRowH, u = e % kTRowH;
+    const float x = (u < B && c <= u) ? T[c][u] : 0.f;
+    const __half hi = __float2half_rn(x);
+    img[2 * kPPlaneH + e] = hi;
+    img[2 * kPPlaneH + kTPlaneH + e] = __float2half_rn((x - __half2float(hi)) * kLoScale);
+  }
+}
+
+struct Q2HArgs {
+  const __half* Img;
+  float* Z;
+  long long ldz;
+  int n, mvec, q, tiles, base, extra;
+};
+
+__device__ __forceinline__ void mma_f16_zero(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.f));
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <bool kTrans>
+__device__ __forceinline__ void ldsm4(uint32_t (&bh)[2], uint32_t (&bl)[2], uint32_t addr) {
+  if (kTrans)
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(bh[0]), "=r"(bh[1]), "=r"(bl[0]), "=r"(bl[1]) : "r"(addr));
+  else
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(bh[0]), "=r"(bh[1]), "=r"(bl[0]), "=r"(bl[1]) : "r"(addr));
+}
+// one accumulator tile (rows g | g + 8, columns 2t, 2t + 1) as the two half-fragments (hi, lo) of a 16-deep A operand
+__device__ __forceinline__ void pack_hl(const float (&r)[4], uint32_t (&h)[2], uint32_t (&l)[2]) {
+  const __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn((r[0] - f0.x) * kLoScale, (r[1] - f0.y) * kLoScale);
+  const __half2 l1 = __floats2half2_rn((r[2] - f1.x) * kLoScale, (r[3] - f1.y) * kLoScale);
+  h[0] = *reinterpret_cast<const uint32_t*>(&h0);
+  h[1] = *reinterpret_cast<const uint32_t*>(&h1);
+  l[0] = *reinterpret_cast<const uint32_t*>(&l0);
+  l[1] = *reinterpret_cast<const uint32_t*>(&l1);
+}
+// acc += sign * a_hi b_hi from a zero accumulator; cross (+)= a_lo b_hi + a_hi b_lo (both carry the factor 2048)
+template <bool kFirst>
+__device__ __forceinline__ void mma_step_h(float (&acc)[4], float (&cross)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           const uint32_t (&bh)[2], const uint32_t (&bl)[2], float sign) {
+  float d[4];
+  mma_f16_zero(d, ah, bh);
+  if (kFirst) mma_f16_zero(cross, al, bh);
+  else mma_f16(cross, al, bh);
+  mma_f16(cross, ah, bl);
+  acc[0] = fmaf(sign, d[0], acc[0]); acc[1] = fmaf(sign, d[1], acc[1]); acc[2] = fmaf(sign, d[2], acc[2]); acc[3] = fmaf(sign, d[3], acc[3]);
+}
+
+template <int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1) k_q2_apply_h(Q2HArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  __half* smh = reinterpret_cast<__half*>(sm);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smh + kStagesH * kBlkHalves);
+  uint64_t* empty = full + kStagesH;
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int cta = (int)blockIdx.x;
+  const int ntile = a.base + (cta < a.extra ? 1 : 0);
+  const int tile0 = cta * a.base + min(cta, a.extra);
+  if (tid == 0) {
+    for (int s = 0; s < kStagesH; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], (uint32_t)ntile);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp >= ntile) return;
+  const int q = a.q, n = a.n;
+  const int nblk = (q + 1) * (q + 2) / 2;
+  if (tid == 0) {
+    for (int b = 0; b < kStagesH - 1 && b < nblk; ++b) {
+      mbar_arrive_expect_tx(&full[b], kBlkBytesH);
+      bulk_g2s(smh + b * kBlkHalves, a.Img + (size_t)b * kBlkHalves, kBlkBytesH, &full[b]);
+    }
+  }
+  const int va = (tile0 + warp) * 16 + g, vb = va + 8;
+  const bool oka = va < a.mvec, okb = vb < a.mvec;
+  float* za = a.Z + (size_t)(oka ? va : 0) * a.ldz;
+  float* zb = a.Z + (size_t)(okb ? vb : 0) * a.ldz;
+  // ldmatrix row addresses of this lane (bytes, relative to a stage): matrix m = lane / 8 (0, 1: hi plane, 2, 3: lo plane; odd:
+  // the second half of the 16-deep step), row r = lane % 8
+  const int lm = lane >> 3, lr = lane & 7;
+  const uint32_t offP = 2u * (uint32_t)((lm >> 1) * kPPlaneH + lr * kPRowH + (lm & 1) * 8);                        // first product
+  const uint32_t offT = 2u * (uint32_t)(2 * kPPlaneH + (lm >> 1) * kTPlaneH + lr * kTRowH + (lm & 1) * 8);          // T product
+  const uint32_t offU = 2u * (uint32_t)((lm >> 1) * kPPlaneH + ((lm & 1) * 8 + lr) * kPRowH - (lm & 1) * 8);        // last product
+  const uint32_t sm0 = smem_u32(smh);
+  float z[16][4];
+  int b = 0;
+  for (int G = q; G >= 0; --G) {
+    const int nl = q - G + 1;
+    int R0 = B * G;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ld_rows(z[i], za, zb, oka, okb, R0 + 8 * i + 2 * t, n);
+    for (int k = 0; k < nl; ++k, ++b, R0 += B) {
+      const int s = b % kStagesH;
+      if (tid == 0 && b + kStagesH - 1 < nblk) {   // refill the stage block b - 1 used, once every warp has released it
+        const int s2 = (b + kStagesH - 1) % kStagesH;
+        if (b >= 1) mbar_wait(&empty[s2], (uint32_t)(((b - 1) / kStagesH) & 1));
+        mbar_arrive_expect_tx(&full[s2], kBlkBytesH);
+        bulk_g2s(smh + s2 * kBlkHalves, a.Img + (size_t)(b + kStagesH - 1) * kBlkHalves, kBlkBytesH, &full[s2]);
+      }
+      __syncwarp();
+      const bool more = k + 1 < nl;
+      if (more) {
+        const int v = (tile0 + warp) * 16 + (lane >> 1);
+        const int r = R0 + 128 + ((lane & 1) ? 63 : 0);
+        if (v < a.mvec && r < n) {
+          const float* pz = a.Z + (size_t)v * a.ldz + r;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pz));
+          if (!(lane & 1) && r + 32 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(pz + 32));
+        }
+      }
+      mbar_wait(&full[s], (uint32_t)((b / kStagesH) & 1));
+      const uint32_t st0 = sm0 + (uint32_t)s * kBlkBytesH;
+      // ---- X'[vec][c] = sum_w Z'[vec][w] V[w][c]: the 16 rows of tiles (i, i + 1) meet the reflector tiles j = i - 2 s, s = 0 .. 4
+      float x[8][4], xc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0.f;
+      {
+        uint32_t ph[2], pl[2];
+        pack_hl(z[0], ph, pl);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          uint32_t qh[2] = {0u, 0u}, ql[2] = {0u, 0u};
+          if (i + 1 < 16) pack_hl(z[i + 1], qh, ql);
+          const uint32_t ah[4] = {ph[0], ph[1], qh[0], qh[1]}, al[4] = {pl[0], pl[1], ql[0], ql[1]};
+#pragma unroll
+          for (int sq = 0; sq < 5; ++sq) {
+            const int j = i - 2 * sq;
+            if (j >= 0 && j <= 7) {
+              uint32_t bh[2], bl[2];
+              ldsm4<false>(bh, bl, st0 + offP + 2u * (uint32_t)(8 * j * kPRowH + 8 + 16 * sq));
+              if (sq == 0) mma_step_h<true>(x[j], xc[j], ah, al, bh, bl, 1.f);
+              else mma_step_h<false>(x[j], xc[j], ah, al, bh, bl, 1.f);
+            }
+          }
+          ph[0] = qh[0]; ph[1] = qh[1]; pl[0] = ql[0]; pl[1] = ql[1];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        x[j][0] = fmaf(xc[j][0], kLoInv, x[j][0]); x[j][1] = fmaf(xc[j][1], kLoInv, x[j][1]);
+        x[j][2] = fmaf(xc[j][2], kLoInv, x[j][2]); x[j][3] = fmaf(xc[j][3], kLoInv, x[j][3]);
+      }
+      // ---- X2'[vec][c] = sum_{c' >= c} X'[vec][c'] T[c][c']: 16 columns c' per step
+      float x2[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x2[j][0] = x2[j][1] = x2[j][2] = x2[j][3] = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        uint32_t h0[2], l0[2], h1[2], l1[2];
+        pack_hl(x[2 * kb], h0, l0);
+        pack_hl(x[2 * kb + 1], h1, l1);
+        const uint32_t ah[4] = {h0[0], h0[1], h1[0], h1[1]}, al[4] = {l0[0], l0[1], l1[0], l1[1]};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j <= 2 * kb + 1) {
+            uint32_t bh[2], bl[2];
+            ldsm4<false>(bh, bl, st0 + offT + 2u * (uint32_t)(8 * j * kTRowH + 16 * kb));
+            float dm[4], dc[4];
+            mma_f16_zero(dm, ah, bh);
+            mma_f16_zero(dc, al, bh);
+            mma_f16(dc, ah, bl);
+            x2[j][0] += fmaf(dc[0], kLoInv, dm[0]); x2[j][1] += fmaf(dc[1], kLoInv, dm[1]);
+            x2[j][2] += fmaf(dc[2], kLoInv, dm[2]); x2[j][3] += fmaf(dc[3], kLoInv, dm[3]);
+          }
+        }
+      }
+      // ---- Z'[vec][w] -= sum_c X2'[vec][c] V[w][c]: row tile i meets the 16-reflector steps kb with 0 <= i - 2 kb <= 9
+      {
+        uint32_t x2h[8][2], x2l[8][2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pack_hl(x2[j], x2h[j], x2l[j]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float zc[4];
+          bool first = true;
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            const int d = i - 2 * kb;
+            if (d >= 0 && d <= 9) {
+              const uint32_t ah[4] = {x2h[2 * kb][0], x2h[2 * kb][1], x2h[2 * kb + 1][0], x2h[2 * kb + 1][1]};
+              const uint32_t al[4] = {x2l[2 * kb][0], x2l[2 * kb][1], x2l[2 * kb + 1][0], x2l[2 * kb + 1][1]};
+              uint32_t bh[2], bl[2];
+              ldsm4<true>(bh, bl, st0 + offU + 2u * (uint32_t)(16 * kb * kPRowH + 8 + 8 * d));
+              if (first) mma_step_h<true>(z[i], zc, ah, al, bh, bl, -1.f);
+              else mma_step_h<false>(z[i], zc, ah, al, bh, bl, -1.f);
+              first = false;
+            }
+          }
+          z[i][0] = fmaf(zc[0], -kLoInv, z[i][0]); z[i][1] = fmaf(zc[1], -kLoInv, z[i][1]);
+          z[i][2] = fmaf(zc[2], -kLoInv, z[i][2]); z[i][3] = fmaf(zc[3], -kLoInv, z[i][3]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) st_rows(z[i], za, zb, oka, okb, R0 + 8 * i + 2 * t, n);
+      if (more) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) z[i][e] = z[i + 8][e];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ld_rows(z[i + 8], za, zb, oka, okb, R0 + 128 + 8 * i + 2 * t, n);
+      } else {
+#pragma unroll
+        for (int i = 8; i < 16; ++i) st_rows(z[i], za, zb, oka, okb, R0 + 8 * i + 2 * t, n);
+      }
+    }
+  }
+}
+
 // unit length again: the tensor core adds with truncation, so every block update comes back a few 1e-8 short, which shortens a
 // vector by ~1e-7 n / 64 over the whole of Q2 (measured 4e-6 at n = 2531) while turning it by far less
 __global__ void __launch_bounds__(256) k_unit_vectors(float* __restrict__ Z, long long ldz, int n, int mvec) {
@@ -732,8 +1019,34 @@ void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2
   const int nsweeps = n - 2;
   const int ngroups = (nsweeps + B - 1) / B;
   const int nlev = sb2st_levels(n);
-  // SCL_Q2_VARIANT=0: the shared-memory window kernel (k_q2_apply); default: the register-stationary kernel
-  static const int variant = [] { const char* e = getenv("SCL_Q2_VARIANT"); return e ? atoi(e) : 1; }();
+  // SCL_Q2_VARIANT=0: the shared-memory window kernel (k_q2_apply); 1: the register-stationary kernel in three-term TF32;
+  // default 2: the register-stationary kernel in split binary16 (253 / 440 ms for the smallest half / all vectors at n = 20 000
+  // against 380 / 558 ms for 1 and 818 / 1627 ms for 0)
+  static const int variant = [] { const char* e = getenv("SCL_Q2_VARIANT"); return e ? atoi(e) : 2; }();
+  if (variant == 2 && n >= 3) {
+    const int q = (n - 3) / B;
+    const size_t nblk = (size_t)(q + 1) * (q + 2) / 2;
+    Tmp<__half> Img(nblk * kBlkHalves, st);
+    k_q2_images_h<<<dim3(nlev, ngroups), 256, 0, st>>>(V2, ldv2, tau2, ldt2, n, q, Img.p);
+    SCL_CUDA(cudaGetLastError());
+    const int tiles = (mvec + 15) / 16, sms = sm_count();
+    const int waves = (tiles + sms * 12 - 1) / (sms * 12);
+    const int grid = std::min(tiles, sms * waves);
+    const int base = tiles / grid, extra = tiles % grid;
+    const int warps = base + (extra ? 1 : 0);
+    const size_t smem = (size_t)kStagesH * kBlkBytesH + 2 * kStagesH * sizeof(uint64_t);
+    Q2HArgs a{Img.p, Z, ldz, n, mvec, q, tiles, base, extra};
+    if (warps <= 8) {
+      SCL_CUDA(cudaFuncSetAttribute(k_q2_apply_h<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_q2_apply_h<8><<<grid, warps * 32, smem, st>>>(a);
+    } else {
+      SCL_CUDA(cudaFuncSetAttribute(k_q2_apply_h<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_q2_apply_h<12><<<grid, warps * 32, smem, st>>>(a);
+    }
+    SCL_CUDA(cudaGetLastError());
+    count_launches(2);
+    return;
+  }
   if (variant != 0 && n >= 3) {
     const int q = (n - 3) / B;   // last group; group G has q - G + 1 levels
     const size_t nblk = (size_t)(q + 1) * (q + 2) / 2;
