@@ -960,14 +960,15 @@ __global__ void __launch_bounds__(256, 2) k_q1_z(const float* __restrict__ VTt, 
 }
 
 // ---- the same two products on the tensor-core tile engine (error-compensated TF32, sgemm_tile.cuh)
+template <int ENG>
 __global__ void __launch_bounds__(256, 2) k_q1_x_tc(const float* __restrict__ Vp, long long lda, int m, const float* __restrict__ Zr,
                                                     long long ldz, int mvec, float* __restrict__ Xpart, long long ldx, int chunk) {
-  __shared__ __align__(16) float smem[tile::SmemT<64>::floats];
+  __shared__ __align__(16) unsigned char smem[tile::SmemE<ENG, 64>::bytes];
   const int vec0 = (int)blockIdx.x * tile::TM;
   const int ka = (int)blockIdx.y * chunk, kl = min(m, ka + chunk) - ka;
   tile::AccT<64> acc;
   acc.clear();
-  tile::mac_tc<64>(acc, tile::opnd(Zr + (long long)vec0 * ldz + ka, ldz, 1, mvec - vec0, kl), tile::opnd(Vp + ka, lda, 1, B, kl), kl, smem);
+  tile::mac_e<ENG, 64, 1, 1>(acc, tile::opnd(Zr + (long long)vec0 * ldz + ka, ldz, 1, mvec - vec0, kl), tile::opnd(Vp + ka, lda, 1, B, kl), kl, smem);
   float* out = Xpart + (size_t)blockIdx.y * B * ldx;
 #pragma unroll
   for (int nt = 0; nt < tile::AccT<64>::NTL; ++nt)
@@ -982,13 +983,14 @@ __global__ void __launch_bounds__(256, 2) k_q1_x_tc(const float* __restrict__ Vp
 
 // Z[vec][r0 + i] -= sum_c X[c][vec] (V T)[i][c]: vectors on the rows of the tile, matrix rows on its columns, so that a thread's
 // two adjacent outputs are adjacent in memory
+template <int ENG>
 __global__ void __launch_bounds__(256, 2) k_q1_z_tc(const float* __restrict__ VTt, long long lda, int m, const float* __restrict__ Xp,
                                                     long long ldx, int mvec, float* Zr, long long ldz) {
-  __shared__ __align__(16) float smem[tile::SmemT<128>::floats];
+  __shared__ __align__(16) unsigned char smem[tile::SmemE<ENG, 128>::bytes];
   const int i0 = (int)blockIdx.x * tile::TM, vec0 = (int)blockIdx.y * tile::TM;
   tile::AccT<128> acc;
   acc.clear();
-  tile::mac_tc<128>(acc, tile::opnd(Xp + vec0, ldx, 0, mvec - vec0, B), tile::opnd(VTt + (long long)i0 * lda, lda, 1, m - i0, B), B, smem);
+  tile::mac_e<ENG, 128, 0, 1>(acc, tile::opnd(Xp + vec0, ldx, 0, mvec - vec0, B), tile::opnd(VTt + (long long)i0 * lda, lda, 1, m - i0, B), B, smem);
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -1113,6 +1115,7 @@ void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels
   Tmp<float> Xpart((size_t)max_split * B * ldx, st), Xp((size_t)B * ldx, st);
   const int vt = (mvec + tile::TM - 1) / tile::TM;
   const int slots = 2 * sm_count();
+  const int eng = tile_engine_q1();
   for (int k = npanels - 1; k >= 0; --k) {
     const int c0 = k * B, r0 = c0 + B, m = n - r0;
     if (m < 1) continue;
@@ -1122,10 +1125,14 @@ void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels
     chunk = std::max(chunk, 4 * tile::KT);
     split = (m + chunk - 1) / chunk;
     const size_t nx = (size_t)B * ldx;
-    if (tile_engine_tc()) {
-      k_q1_x_tc<<<dim3(vt, split), 256, 0, st>>>(Vp, lda, m, Z + r0, ldz, mvec, Xpart.p, ldx, chunk);
+    if (eng == 2) {   // eigenvector slabs, reflector panels and their products are O(1): split binary16
+      k_q1_x_tc<2><<<dim3(vt, split), 256, 0, st>>>(Vp, lda, m, Z + r0, ldz, mvec, Xpart.p, ldx, chunk);
       k_sum_parts32<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(Xpart.p, split, nx, nx, Xp.p);
-      k_q1_z_tc<<<dim3((m + tile::TM - 1) / tile::TM, vt), 256, 0, st>>>(A + c0 + (long long)r0 * lda, lda, m, Xp.p, ldx, mvec, Z + r0, ldz);
+      k_q1_z_tc<2><<<dim3((m + tile::TM - 1) / tile::TM, vt), 256, 0, st>>>(A + c0 + (long long)r0 * lda, lda, m, Xp.p, ldx, mvec, Z + r0, ldz);
+    } else if (eng == 1) {
+      k_q1_x_tc<1><<<dim3(vt, split), 256, 0, st>>>(Vp, lda, m, Z + r0, ldz, mvec, Xpart.p, ldx, chunk);
+      k_sum_parts32<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(Xpart.p, split, nx, nx, Xp.p);
+      k_q1_z_tc<1><<<dim3((m + tile::TM - 1) / tile::TM, vt), 256, 0, st>>>(A + c0 + (long long)r0 * lda, lda, m, Xp.p, ldx, mvec, Z + r0, ldz);
     } else {
       k_q1_x<<<dim3(vt, split), 256, 0, st>>>(Vp, lda, m, Z + r0, ldz, mvec, Xpart.p, ldx, chunk);
       k_sum_parts32<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(Xpart.p, split, nx, nx, Xp.p);

@@ -6,6 +6,7 @@
 // panel, rank-2k update, reflector blocks times eigenvector slabs), and anything outside an operand's extents reads as 0,
 // so ragged edges need no special kernels.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -280,6 +281,145 @@ __device__ __forceinline__ void mac_tc(AccT<TN>& acc, const Opnd& A, const Opnd&
     }
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Split-binary16 variant (mma.sync m16n8k16): x = hi + lo / 2048 with hi = half(x), lo = half((x - hi) 2048) - the same 22
+// significant bits as the TF32 pair at twice the contraction depth per instruction (scripts/mma_rate.cu: both issue once per
+// 8 cycles and sub-partition on B200).  For operands that are O(1) or smaller in magnitude (eigenvector slabs, reflector
+// panels and their T products; anything above 65504 would overflow).  The conversion happens once per element, on the way
+// into shared memory (hi and lo planes); fragments are fetched with ldmatrix - plain from a tile stored [row][k]
+// (kind 1: the operand is k-contiguous in global memory), transposed from a tile stored [k][row] (kind 0: row-contiguous,
+// or the mirrored diagonal block).  Row pitches of 48 and 272 (144) bytes keep the eight rows of an ldmatrix on distinct banks.
+// Same accumulator layout (AccT), same pipeline.
+constexpr int KPH = 24;   // halves per row of a [row][k] tile (16 + 8 pad)
+
+template <int TN>
+struct SmemH {
+  static constexpr int plane_a = TM * KPH, plane_b = TN * KPH;   // the larger of the two storage kinds
+  static constexpr int halves = 2 * 2 * (plane_a + plane_b);     // two stages, hi + lo
+};
+
+__device__ __forceinline__ void cvt_hl4(const float4& v, uint2& h, uint2& l) {
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn((v.x - f0.x) * 2048.f, (v.y - f0.y) * 2048.f);
+  const __half2 l1 = __floats2half2_rn((v.z - f1.x) * 2048.f, (v.w - f1.y) * 2048.f);
+  h.x = *reinterpret_cast<const uint32_t*>(&h0); h.y = *reinterpret_cast<const uint32_t*>(&h1);
+  l.x = *reinterpret_cast<const uint32_t*>(&l0); l.y = *reinterpret_cast<const uint32_t*>(&l1);
+}
+
+// KIND 1: o.layout == 1, tile stored [W][KPH];  KIND 0: o.layout 0 or 2, tile stored [KT][W + 8]
+template <int W, int KIND>
+__device__ __forceinline__ void r2s_h(const Frag<W>& f, __half* Sh, __half* Sl) {
+  const int tid = (int)threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < Frag<W>::N; ++q) {
+    const int idx = tid + q * NT;
+    uint2 h, l;
+    cvt_hl4(f.r[q], h, l);
+    int off;
+    if (KIND == 1) off = (idx / (KT / 4)) * KPH + (idx % (KT / 4)) * 4;
+    else off = (idx / (W / 4)) * (W + 8) + (idx % (W / 4)) * 4;
+    *reinterpret_cast<uint2*>(Sh + off) = h;
+    *reinterpret_cast<uint2*>(Sl + off) = l;
+  }
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_f16_zero(float (&d)[4], const uint32_t (&a)[4], const uint32_t* b) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.f));
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t* b) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// acc += A(:, 0..klen) * B(:, 0..klen)';  KA / KB: storage kind of the operand (1 for layout 1, 0 for layouts 0 and 2);
+// smem: SmemH<TN>::halves halves, 16-byte aligned
+template <int TN, int KA, int KB>
+__device__ __forceinline__ void mac_h(AccT<TN>& acc, const Opnd& A, const Opnd& Bo, int klen, __half* smem) {
+  if (klen <= 0) return;
+  constexpr int NTL = TN / 16;
+  constexpr int PA = SmemH<TN>::plane_a, PB = SmemH<TN>::plane_b, STG = 2 * (PA + PB);   // a stage: A hi, A lo, B hi, B lo
+  const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5;
+  const int mi = lane >> 3, lr = lane & 7;
+  const int m0 = (warp & 3) * 32, n0 = (warp >> 2) * (TN / 2);
+  // lane offsets (halves) of the ldmatrix rows.  A: registers a0..a3 = (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15),
+  // (rows 8-15, k 8-15).  B: (hi: k 0-7, k 8-15), (lo: k 0-7, k 8-15) of one 8-column fragment.
+  const int offa = KA == 1 ? (m0 + (mi & 1) * 8 + lr) * KPH + (mi >> 1) * 8 : ((mi >> 1) * 8 + lr) * (TM + 8) + m0 + (mi & 1) * 8;
+  const int offb = (mi >> 1) * PB + (KB == 1 ? (n0 + lr) * KPH + (mi & 1) * 8 : ((mi & 1) * 8 + lr) * (TN + 8) + n0);
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
+  const int nk = (klen + KT - 1) / KT;
+  Frag<TM> fa;
+  Frag<TN> fb;
+  g2r<TM>(A, 0, fa);
+  g2r<TN>(Bo, 0, fb);
+  __syncthreads();   // the previous user of the buffers is done
+  r2s_h<TM, KA>(fa, smem, smem + PA);
+  r2s_h<TN, KB>(fb, smem + 2 * PA, smem + 2 * PA + PB);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) {
+      g2r<TM>(A, (kt + 1) * KT, fa);
+      g2r<TN>(Bo, (kt + 1) * KT, fb);
+    }
+    const uint32_t sa = s0 + 2u * (uint32_t)(cur * STG + offa), sb = s0 + 2u * (uint32_t)(cur * STG + 2 * PA + offb);
+    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const uint32_t d = 2u * (uint32_t)(KA == 1 ? mt * 16 * KPH : mt * 16);
+      if (KA == 1) {
+        ldsm_x4(ah[mt], sa + d);
+        ldsm_x4(al[mt], sa + d + 2u * PA);
+      } else {
+        ldsm_x4_t(ah[mt], sa + d);
+        ldsm_x4_t(al[mt], sa + d + 2u * PA);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) {
+      uint32_t b[4];   // hi b0, hi b1, lo b0, lo b1
+      if (KB == 1) ldsm_x4(b, sb + 2u * (uint32_t)(nt * 8 * KPH));
+      else ldsm_x4_t(b, sb + 2u * (uint32_t)(nt * 8));
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        float dm[4], dc[4];
+        mma_f16_zero(dm, ah[mt], b);
+        mma_f16_zero(dc, al[mt], b);
+        mma_f16(dc, ah[mt], b + 2);
+        acc.v[mt][nt][0] += fmaf(dc[0], 1.f / 2048.f, dm[0]); acc.v[mt][nt][1] += fmaf(dc[1], 1.f / 2048.f, dm[1]);
+        acc.v[mt][nt][2] += fmaf(dc[2], 1.f / 2048.f, dm[2]); acc.v[mt][nt][3] += fmaf(dc[3], 1.f / 2048.f, dm[3]);
+      }
+    }
+    if (kt + 1 < nk) {
+      __half* nx = smem + (cur ^ 1) * STG;
+      r2s_h<TM, KA>(fa, nx, nx + PA);
+      r2s_h<TN, KB>(fb, nx + 2 * PA, nx + 2 * PA + PB);
+    }
+    __syncthreads();
+  }
+}
+
+// engine selector for kernels that are compiled for both tensor-core engines: ENG 1 = three-term TF32, 2 = split binary16
+template <int ENG, int TN>
+struct SmemE {
+  static constexpr int bytes = ENG == 2 ? SmemH<TN>::halves * 2 : SmemT<TN>::floats * 4;
+};
+template <int ENG, int TN, int KA, int KB>
+__device__ __forceinline__ void mac_e(AccT<TN>& acc, const Opnd& A, const Opnd& Bo, int klen, void* smem) {
+  if constexpr (ENG == 2) mac_h<TN, KA, KB>(acc, A, Bo, klen, reinterpret_cast<__half*>(smem));
+  else mac_tc<TN>(acc, A, Bo, klen, reinterpret_cast<float*>(smem));
 }
 
 }  // namespace tile

@@ -618,7 +618,7 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     attr_done = true;
   }
   const int slots = 2 * sm_count();
-  const bool tc = tile_engine_tc();
+  const bool tc = tile_engine_s1() != 0;
   long launches = 0;
   // factorisation of panel k (full-size panels only) on stream s: V in place, T, V T into the upper triangle, R' into the band
   auto factor = [&](int k, cudaStream_t s) {

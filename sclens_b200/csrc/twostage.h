@@ -45,10 +45,15 @@ void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2
 void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels, float* Z, long long ldz, int mvec,
               cudaStream_t st);
 
-// which tile engine runs the matrix-matrix products of stage 1 and of the Q1 back-transformation: the tensor-core engine
-// (error-compensated TF32, default) or the FP32 FMA engine (SCL_TILE_ENGINE=0); both in sgemm_tile.cuh
-inline bool tile_engine_tc() {
-  static const bool v = [] { const char* e = getenv("SCL_TILE_ENGINE"); return e ? atoi(e) != 0 : true; }();
+// which tile engine (sgemm_tile.cuh) runs the matrix-matrix products: 0 = FP32 FMA, 1 = tensor cores in three-term TF32,
+// 2 = tensor cores in split binary16 (operands must be O(1): fine for the back-transformation, whose operands are eigenvector
+// slabs and reflector panels).  SCL_TILE_ENGINE sets stage 1 (default 1), SCL_TILE_ENGINE_Q1 the Q1 back-transformation (default 2).
+inline int tile_engine_s1() {
+  static const int v = [] { const char* e = getenv("SCL_TILE_ENGINE"); return e ? atoi(e) : 1; }();
+  return v;
+}
+inline int tile_engine_q1() {
+  static const int v = [] { const char* e = getenv("SCL_TILE_ENGINE_Q1"); return e ? atoi(e) : 2; }();
   return v;
 }
 
