@@ -28,6 +28,7 @@ Under torchrun (N>1) every rank owns one GPU; ranks cooperate on ONE sclens() pa
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -542,8 +543,29 @@ def main():
                           "achieved": stats_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": stats_gbs / hbm_peak,
                           "calls": int(prof.stats_calls), "alg_bytes": "40 nnz per normalisation (4 nnz + 3 x 8 nnz + 12 nnz patch pass)",
                           "avg_ms_per_call": prof.stats_ms / max(1, prof.stats_calls)}}
+    # the eigensolves: own two-stage solver (dense -> band -> tridiagonal -> Float64 tridiagonal stage -> Q2, Q1) since round 2;
+    # cuSOLVER runs only when a solve falls back (counted).  Stage totals come from the solver's own CUDA events.
+    eig = np.zeros(8)
+    h.lib.scl_debug_eig_stage_totals(h.h, eig.ctypes.data_as(C.POINTER(C.c_double)))
+    n_eig = min(N, M)
+    q_blk = (n_eig - 3) // 64
+    nblk = (q_blk + 1) * (q_blk + 2) // 2
+    q2_exec = eig[6] / 16.0 * nblk * 300 * 4096.0        # 300 m16n8k16 MMAs per 16 vectors and reflector block
+    q2_peak = 148 * 4 * 4096 / 8.0 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12   # one mma.sync per 8 cycles and sub-partition
+    roofline["eigensolver"] = {
+        "solver": "own two-stage reduction (sy2sb.cu, sb2st.cu, tridiag.cu, backtrans.cu); cuSOLVER only on fallback",
+        "solves": int(eig[5]), "fallbacks_to_one_stage": int(eig[7]), "eigenvector_columns_back_transformed": int(eig[6]),
+        "ms_by_stage": {"dense_to_band": eig[0], "band_to_tridiagonal": eig[1], "tridiagonal_eigenproblem_f64": eig[2],
+                        "back_transformation_q2": eig[3], "back_transformation_q1": eig[4]},
+        "q2_kernel": {"kernel": "k_q2_apply_h (register-stationary block reflectors, split binary16 on mma.sync m16n8k16)",
+                      "bound": "tensor (warp-level path)", "achieved": rate(q2_exec, eig[3], 1e12), "peak": q2_peak,
+                      "unit": "TFLOP/s executed", "frac": rate(q2_exec, eig[3], 1e12) / q2_peak if q2_peak else None,
+                      "peak_source": "scripts/mma_rate.cu measured on B200: 8 cycles per mma.sync per sub-partition, at sm_max_mhz",
+                      "alg_flops": 2.0 * n_eig * n_eig * eig[6],
+                      "note": "executed = 3 MMAs per step (hi hi, lo hi, hi lo) x the compact-WY block form; algorithmic = 2 n^2 per vector"}}
     stage_ms = {"gram_gemm": prof.gram_gemm_ms, "other_gemm": prof.other_gemm_ms, "densify": prof.densify_ms,
-                "stats": prof.stats_ms, "sparse": prof.sparse_ms, "syevd_library": prof.syevd_ms,
+                "stats": prof.stats_ms, "sparse": prof.sparse_ms, "eigensolves": prof.syevd_ms, "syevd_library": prof.syevd_ms,
+                "syevd_library_note": "historical key: since round 2 these are the own eigensolver's kernels (see roofline.eigensolver)",
                 "syevd_calls": int(prof.syevd_calls), "refine_f64": prof.refine_ms, "small": prof.small_ms,
                 "nccl_collectives": prof.comm_ms, "nccl_payload_bytes": prof.comm_bytes, "total": ms}
     phase = {"signal_normalise_gram": si.t_gram_ms, "signal_syevd": si.t_syevd_ms, "null_matrix": si.t_null_ms,
@@ -558,7 +580,7 @@ def main():
     line = {"metric": "sclens_cells_per_s", "value": value, "unit": "cells/s", "n_gpus": world, "steps": steps,
             "steps_requested": args.steps, "warmup": warm_done, "warmup_requested": args.warmup,
             "warmup_seconds": warm_s, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (Gram), f32 syevd, f64 statistics",
+            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (Gram), f32 eigensolver (split-f16 / three-term tf32 tensor-core products, f64 tridiagonal stage), f64 statistics",
             "data": "synthetic", "config": config, "clocks": clk, "gpu_launches": int(launches),
             "roofline": roofline, "stage_ms_over_timed_region": stage_ms, "phase_ms": phase, "phase_ms_last_step": phase,
             "gemm_tflops": {"other_gemm_2mnk": rate(prof.other_gemm_flops, prof.other_gemm_ms, 1e12)},

@@ -307,6 +307,9 @@ SCL_API int32_t scl_debug_set_eig_api(int32_t v);
  * the two-stage path produced the result; out[6] = number of two-stage solves of this handle that fell back to one stage;
  * out[7] = number of own-path solves that fell back to cusolverDnSsyevd. */
 SCL_API int32_t scl_debug_last_solve(scl_handle* h, double out[8]);
+/* Totals over the handle's two-stage solves since scl_reset_profile, milliseconds: out[0..4] = the five stages as above; out[5] =
+ * number of two-stage solves; out[6] = eigenvector columns back-transformed; out[7] = solves that fell back to one stage. */
+SCL_API int32_t scl_debug_eig_stage_totals(scl_handle* h, double out[8]);
 /* The stages of the two-stage reduction one by one on a host matrix A (n x n, symmetric, n a multiple of 4), for the stage-wise
  * parity tests: AB (n x 128, band storage AB[j*128 + (i-j)]) after dense -> band; d (n), e (n-1) after band -> tridiagonal;
  * Q2 (n x n, column v at Q2 + v*n) = the stage-2 transformation applied to the identity; Q (same layout) = Q1 Q2.  Any output

@@ -123,6 +123,7 @@ int32_t scl_get_profile(scl_handle* h, scl_profile* out) {
 int32_t scl_reset_profile(scl_handle* h) {
   if (!h) return SCL_ERR_INVALID;
   h->prof.reset();
+  if (h->solver) for (double& v : h->solver->ts_total) v = 0.0;
   return SCL_OK;
 }
 
@@ -684,6 +685,13 @@ int32_t scl_debug_last_solve(scl_handle* h, double* out) {
   out[5] = h->solver->tri_two_stage ? 1.0 : 0.0;
   out[6] = (double)h->solver->ts_fallbacks;
   out[7] = (double)h->solver->tri_fallbacks;
+  return SCL_OK;
+}
+
+int32_t scl_debug_eig_stage_totals(scl_handle* h, double* out) {
+  if (!h || !out || !h->solver) return SCL_ERR_INVALID;
+  for (int i = 0; i < 7; ++i) out[i] = h->solver->ts_total[i];
+  out[7] = (double)h->solver->ts_fallbacks;
   return SCL_OK;
 }
 

@@ -140,6 +140,11 @@ bool Solver::syevd_2stage(float* dA, int n, float* dW, int v0, int v1, cudaStrea
     cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
     ts_ms[i] = t;
   }
+  if (!fail && ok) {
+    for (int i = 0; i < 5; ++i) ts_total[i] += ts_ms[i];
+    ts_total[5] += 1.0;
+    ts_total[6] += (double)m;
+  }
   tri_ms[0] = ts_ms[0] + ts_ms[1];
   tri_ms[1] = ts_ms[2];
   tri_ms[2] = ts_ms[3] + ts_ms[4];

@@ -25,6 +25,8 @@ struct Solver {
   bool syevd_2stage(float* dA, int n, float* dW, int v0, int v1, cudaStream_t st);
   double ts_ms[5] = {0, 0, 0, 0, 0};   // last two-stage solve: dense->band, band->tridiagonal, tridiagonal eigenproblem, Q2, Q1 + copy
   bool tri_two_stage = false;
+  // totals over the two-stage solves since the last reset: the five stages above, [5] solves, [6] eigenvector columns back-transformed
+  double ts_total[7] = {0, 0, 0, 0, 0, 0, 0};
   int ts_fallbacks = 0;
   // milliseconds of the last syevd_tri call: [0] Ssytrd, [1] eigenvalues + eigenvectors of T, [2] Sormtr + copy
   double tri_ms[3] = {0, 0, 0};
