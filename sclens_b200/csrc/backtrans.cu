@@ -1013,6 +1013,135 @@ __global__ void __launch_bounds__(256, 2) k_q1_z_tc(const float* __restrict__ VT
     }
 }
 
+// ---------------------------------------------------------------------------------------- Q1 on the tcgen05 GEMM
+// Eight panels at a time: H_a H_a+1 ... H_a+7 Z = Z - (VT)_blk X with X_j = V_j' Z - sum_{l > j} (V_j' V_l T_l) X_l, j descending.
+// Y = V_blk' Z (512 x vectors, contraction over the rows) and Z -= (VT)_blk X (contraction over the 512 reflectors) are two
+// large products on gemm_umma.cu in split binary16 (hi hi + hi lo + lo hi, FP32 accumulation in TMEM); the couplings come from
+// the Gram matrix V_blk' V_blk (one more product) and the recursion runs per vector in the 512-dimensional space.  Operands are
+// converted once per block; powers of two keep their low-order parts in binary16's normal range.
+constexpr int kQ1Panels = 8;
+constexpr float kScV = 1024.f, kScVT = 64.f, kScZ = 1024.f, kScX = 256.f;
+
+// V of the block's panels as (hi, lo) binary16, reflector-major [ncols][ldk] over the rows r0 .. n; zero above a panel's first row
+__global__ void __launch_bounds__(256) k_q1_conv_v(const float* __restrict__ A, long long lda, int n, int c0, int r0, long long ldk,
+                                                   __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int c = (int)blockIdx.y;
+  const int rj = c0 + (c / B) * B + B;   // first row of the panel that holds column c
+  const float* col = A + (long long)(c0 + c) * lda;
+  for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < ldk; k += (long long)gridDim.x * 256) {
+    const long long i = r0 + k;
+    const float x = (i < n && i >= rj) ? col[i] * kScV : 0.f;
+    const __half h = __float2half_rn(x);
+    hi[(long long)c * ldk + k] = h;
+    lo[(long long)c * ldk + k] = __float2half_rn(x - __half2float(h));
+  }
+}
+// (V T) of the block's panels, row-major [m][ldo]: element (i, c) sits at A[(c0 + c) + i lda] for i >= the panel's first row
+__global__ void __launch_bounds__(256) k_q1_conv_vt(const float* __restrict__ A, long long lda, int n, int c0, int ncols, int r0,
+                                                    long long ldo, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const long long i = r0 + (long long)blockIdx.x;
+  if (i >= n) return;
+  const float* row = A + i * lda + c0;
+  for (int c = (int)threadIdx.x; c < ldo; c += 256) {
+    const int rj = c0 + (c / B) * B + B;
+    const float x = (c < ncols && i >= rj) ? row[c] * kScVT : 0.f;
+    const __half h = __float2half_rn(x);
+    hi[(long long)blockIdx.x * ldo + c] = h;
+    lo[(long long)blockIdx.x * ldo + c] = __float2half_rn(x - __half2float(h));
+  }
+}
+// St[j][l][c'][c] = sum_d G[64 j + c][64 l + d] T_l[d][c']   (l > j)
+__global__ void __launch_bounds__(256) k_q1_couplings(const float* __restrict__ G, int ldg, const float* __restrict__ T1, int np,
+                                                      float* __restrict__ St) {
+  const int l = (int)blockIdx.x, j = (int)blockIdx.y;
+  if (l <= j || l >= np) return;
+  __shared__ float Gs[B][B + 1], Ts[B][B + 1];
+  for (int e = (int)threadIdx.x; e < B * B; e += 256) {
+    Gs[e / B][e % B] = G[(long long)(B * j + e / B) * ldg + B * l + e % B];
+    Ts[e / B][e % B] = T1[(size_t)l * B * B + e];
+  }
+  __syncthreads();
+  float* out = St + ((size_t)j * np + l) * B * B;
+  for (int e = (int)threadIdx.x; e < B * B; e += 256) {
+    const int cp = e / B, c = e % B;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < B; ++d) acc = fmaf(Gs[c][d], Ts[d][cp], acc);
+    out[cp * B + c] = acc;
+  }
+}
+// X_j = Y_j - sum_{l > j} S_jl X_l, j = np - 2 .. 0, in place on Y [np 64][ldy]; one thread per vector
+__global__ void __launch_bounds__(128) k_q1_recursion(float* __restrict__ Y, long long ldy, int mvec, int np, const float* __restrict__ St) {
+  extern __shared__ __align__(16) float Ss[];   // [np - 1 - j][c'][c]
+  const int v = (int)blockIdx.x * 128 + (int)threadIdx.x;
+  for (int j = np - 2; j >= 0; --j) {
+    const int nl = np - 1 - j;
+    __syncthreads();
+    for (int e = (int)threadIdx.x; e < nl * B * B / 4; e += 128)
+      reinterpret_cast<float4*>(Ss)[e] = reinterpret_cast<const float4*>(St + ((size_t)j * np + j + 1) * B * B)[e];
+    __syncthreads();
+    if (v < mvec) {
+      float acc[B];
+#pragma unroll
+      for (int c = 0; c < B; ++c) acc[c] = Y[(long long)(B * j + c) * ldy + v];
+      for (int l = 0; l < nl; ++l) {
+        const float* Yl = Y + (long long)(B * (j + 1 + l)) * ldy + v;
+        const float* Sl = Ss + (size_t)l * B * B;
+        for (int cp = 0; cp < B; ++cp) {
+          const float xl = Yl[(long long)cp * ldy];
+#pragma unroll
+          for (int c4 = 0; c4 < B / 4; ++c4) {
+            const float4 sv = *reinterpret_cast<const float4*>(Sl + cp * B + 4 * c4);
+            acc[4 * c4 + 0] = fmaf(-sv.x, xl, acc[4 * c4 + 0]);
+            acc[4 * c4 + 1] = fmaf(-sv.y, xl, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(-sv.z, xl, acc[4 * c4 + 2]);
+            acc[4 * c4 + 3] = fmaf(-sv.w, xl, acc[4 * c4 + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < B; ++c) Y[(long long)(B * j + c) * ldy + v] = acc[c];
+    }
+  }
+}
+// X [ncols][ldy] (FP32) -> (hi, lo) binary16, vector-major [mvec][ldo]
+__global__ void __launch_bounds__(256) k_q1_conv_x(const float* __restrict__ X, long long ldy, int mvec, int ncols, long long ldo,
+                                                   __half* __restrict__ hi, __half* __restrict__ lo) {
+  __shared__ float tl[32][33];
+  const int v0 = (int)blockIdx.x * 32, c0 = (int)blockIdx.y * 32;
+  const int tx = (int)threadIdx.x & 31, ty = (int)threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, v = v0 + tx;
+    tl[r][tx] = (c < ncols && v < mvec) ? X[(long long)c * ldy + v] * kScX : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int v = v0 + r, c = c0 + tx;
+    if (v < mvec && c < ldo) {
+      const float x = tl[tx][r];
+      const __half h = __float2half_rn(x);
+      hi[(long long)v * ldo + c] = h;
+      lo[(long long)v * ldo + c] = __float2half_rn(x - __half2float(h));
+    }
+  }
+}
+// Z[v][r0 + k] += U[v][k]
+__global__ void __launch_bounds__(256) k_q1_add(float* __restrict__ Z, long long ldz, int r0, const float* __restrict__ U, long long ldu,
+                                                int m) {
+  float* z = Z + (long long)blockIdx.y * ldz + r0;
+  const float* u = U + (long long)blockIdx.y * ldu;
+  for (int k = ((int)blockIdx.x * 256 + (int)threadIdx.x) * 4; k < m; k += (int)gridDim.x * 1024) {
+    if (k + 3 < m) {
+      float4 a = *reinterpret_cast<float4*>(z + k);
+      const float4 b = *reinterpret_cast<const float4*>(u + k);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      *reinterpret_cast<float4*>(z + k) = a;
+    } else {
+      for (int q = k; q < m; ++q) z[q] += u[q];
+    }
+  }
+}
+
 }  // namespace
 
 void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2, int n, float* Z, long long ldz, int mvec,
@@ -1107,9 +1236,70 @@ void unit_vectors(float* Z, long long ldz, int n, int mvec, cudaStream_t st) {
   count_launches(1);
 }
 
+static void apply_q1_umma(const float* A, int n, long long lda, const float* T1, int npanels, float* Z, long long ldz, int mvec,
+                          cudaStream_t st) {
+  const int nblocks = (npanels + kQ1Panels - 1) / kQ1Panels;
+  const long long ldk_max = (((long long)n + 7) & ~7LL), ldo = kQ1Panels * B;
+  const long long ldy = ((long long)mvec + 7) & ~7LL;
+  Tmp<__half> vh((size_t)ldo * ldk_max, st), vl((size_t)ldo * ldk_max, st), th((size_t)ldk_max * ldo, st), tl((size_t)ldk_max * ldo, st);
+  Tmp<__half> zh((size_t)mvec * ldk_max, st), zl((size_t)mvec * ldk_max, st), xh((size_t)mvec * ldo, st), xl((size_t)mvec * ldo, st);
+  Tmp<float> Y((size_t)ldo * ldy, st), G((size_t)ldo * ldo, st), St((size_t)kQ1Panels * kQ1Panels * B * B, st), U((size_t)mvec * ldk_max, st);
+  const size_t rec_smem = (size_t)(kQ1Panels - 1) * B * B * sizeof(float);
+  SCL_CUDA(cudaFuncSetAttribute(k_q1_recursion, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem));
+  long launches = 0;
+  static const int q1_chunk = [] { const char* e = getenv("SCL_Q1_CHUNK_KB"); return e ? atoi(e) : 4; }();
+  for (int b = nblocks - 1; b >= 0; --b) {
+    const int a = b * kQ1Panels, np = std::min(kQ1Panels, npanels - a);
+    const int c0 = a * B, r0 = c0 + B, m = n - r0, ncols = np * B;
+    if (m < 1) continue;
+    const long long ldk = ((long long)m + 7) & ~7LL;
+    k_q1_conv_v<<<dim3((unsigned)std::min<long long>((ldk + 255) / 256, 64), ncols), 256, 0, st>>>(A, lda, n, c0, r0, ldk, vh.p, vl.p);
+    k_q1_conv_vt<<<m, 256, 0, st>>>(A, lda, n, c0, ncols, r0, ldo, th.p, tl.p);
+    strided_split_f32_to_f16(Z + r0, mvec, m, ldz, ldk, zh.p, zl.p, st, kScZ);
+    GemmArgs g;
+    // Y = V' Z
+    g.A.hi = vh.p; g.A.lo = vl.p; g.A.rows = ncols; g.A.K = m; g.A.ld = ldk;
+    g.B.hi = zh.p; g.B.lo = zl.p; g.B.rows = mvec; g.B.K = m; g.B.ld = ldk;
+    g.alpha = 1.f / (kScV * kScZ);
+    g.chunk_kb = q1_chunk;   // short tensor-core chains: the accumulator truncates, 3e-8 per MMA of a chain, one-sided
+    g.epi = Epilogue::Store;
+    g.C = Y.p; g.ldc = ldy;
+    gemm_umma(g, st);
+    if (np > 1) {
+      GemmArgs s2;
+      s2.A.hi = vh.p; s2.A.lo = vl.p; s2.A.rows = ncols; s2.A.K = m; s2.A.ld = ldk;
+      s2.B = s2.A;
+      s2.syrk = true;
+      s2.alpha = 1.f / (kScV * kScV);
+      s2.C = G.p; s2.ldc = ldo;
+      gemm_umma(s2, st);
+      k_q1_couplings<<<dim3(np, np), 256, 0, st>>>(G.p, (int)ldo, T1 + (size_t)a * B * B, np, St.p);
+      k_q1_recursion<<<(mvec + 127) / 128, 128, rec_smem, st>>>(Y.p, ldy, mvec, np, St.p);
+      launches += 3;
+    }
+    k_q1_conv_x<<<dim3((mvec + 31) / 32, (unsigned)(ldo / 32)), 256, 0, st>>>(Y.p, ldy, mvec, ncols, ldo, xh.p, xl.p);
+    // U = - X' (VT)'
+    GemmArgs u;
+    u.A.hi = xh.p; u.A.lo = xl.p; u.A.rows = mvec; u.A.K = ncols; u.A.ld = ldo;
+    u.B.hi = th.p; u.B.lo = tl.p; u.B.rows = m; u.B.K = ncols; u.B.ld = ldo;
+    u.alpha = -1.f / (kScX * kScVT);
+    u.chunk_kb = q1_chunk;
+    u.C = U.p; u.ldc = ldk;
+    gemm_umma(u, st);
+    k_q1_add<<<dim3((unsigned)std::min((m + 1023) / 1024, 64), mvec), 256, 0, st>>>(Z, ldz, r0, U.p, ldk, m);
+    launches += 7;
+  }
+  SCL_CUDA(cudaGetLastError());
+  count_launches((int)launches);
+}
+
 void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels, float* Z, long long ldz, int mvec,
               cudaStream_t st) {
   if (mvec <= 0 || npanels <= 0) return;
+  if (tile_engine_q1() == 3) {
+    apply_q1_umma(A, n, lda, T1, npanels, Z, ldz, mvec, st);
+    return;
+  }
   const long long ldx = ((long long)mvec + 3) & ~3LL;
   const int max_split = 16;
   Tmp<float> Xpart((size_t)max_split * B * ldx, st), Xp((size_t)B * ldx, st);

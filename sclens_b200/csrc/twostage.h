@@ -45,15 +45,17 @@ void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2
 void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels, float* Z, long long ldz, int mvec,
               cudaStream_t st);
 
-// which tile engine (sgemm_tile.cuh) runs the matrix-matrix products: 0 = FP32 FMA, 1 = tensor cores in three-term TF32,
-// 2 = tensor cores in split binary16 (operands must be O(1): fine for the back-transformation, whose operands are eigenvector
-// slabs and reflector panels).  SCL_TILE_ENGINE sets stage 1 (default 1), SCL_TILE_ENGINE_Q1 the Q1 back-transformation (default 2).
+// which engine runs the matrix-matrix products.  Tile engines of sgemm_tile.cuh: 0 = FP32 FMA, 1 = tensor cores in three-term
+// TF32 (mma.sync), 2 = tensor cores in split binary16 (mma.sync; operands must be O(1)).  3 (Q1 only): eight panels at a time on
+// the tcgen05 GEMM of gemm_umma.cu in split binary16 (backtrans.cu, apply_q1_umma).  SCL_TILE_ENGINE sets stage 1 (default 1:
+// its operands are not bounded a priori), SCL_TILE_ENGINE_Q1 the Q1 back-transformation (default 3; measured at n = 20 000,
+// smallest half / all vectors: 83 / 130 ms against 192 / 366 ms for 2, 251 / 474 ms for 1, 252 / 487 ms for 0).
 inline int tile_engine_s1() {
   static const int v = [] { const char* e = getenv("SCL_TILE_ENGINE"); return e ? atoi(e) : 1; }();
   return v;
 }
 inline int tile_engine_q1() {
-  static const int v = [] { const char* e = getenv("SCL_TILE_ENGINE_Q1"); return e ? atoi(e) : 2; }();
+  static const int v = [] { const char* e = getenv("SCL_TILE_ENGINE_Q1"); return e ? atoi(e) : 3; }();
   return v;
 }
 
