@@ -310,6 +310,11 @@ SCL_API int32_t scl_debug_last_solve(scl_handle* h, double out[8]);
 /* Totals over the handle's two-stage solves since scl_reset_profile, milliseconds: out[0..4] = the five stages as above; out[5] =
  * number of two-stage solves; out[6] = eigenvector columns back-transformed; out[7] = solves that fell back to one stage. */
 SCL_API int32_t scl_debug_eig_stage_totals(scl_handle* h, double out[8]);
+/* Kernel variants of the two-stage solver, for the parity tests (process-wide; a negative value restores the environment /
+ * default): q2_variant 0 shared-memory window, 1 register-stationary three-term TF32, 2 register-stationary split binary16
+ * (SCL_Q2_VARIANT); stage1_engine 0 FP32 FMA, 1 three-term TF32 mma.sync (SCL_TILE_ENGINE); q1_engine 0 FP32 FMA, 1 TF32 mma.sync,
+ * 2 split-binary16 mma.sync, 3 eight-panel block reflectors on the tcgen05 GEMM (SCL_TILE_ENGINE_Q1). */
+SCL_API int32_t scl_debug_set_two_stage(int32_t q2_variant, int32_t stage1_engine, int32_t q1_engine);
 /* The stages of the two-stage reduction one by one on a host matrix A (n x n, symmetric, n a multiple of 4), for the stage-wise
  * parity tests: AB (n x 128, band storage AB[j*128 + (i-j)]) after dense -> band; d (n), e (n-1) after band -> tridiagonal;
  * Q2 (n x n, column v at Q2 + v*n) = the stage-2 transformation applied to the identity; Q (same layout) = Q1 Q2.  Any output

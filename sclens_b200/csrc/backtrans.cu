@@ -18,6 +18,9 @@
 #include "twostage.h"
 
 namespace scl {
+
+std::atomic<int> g_two_stage_override[3] = {{-1}, {-1}, {-1}};
+
 namespace {
 
 constexpr int B = kBand;
@@ -1153,7 +1156,7 @@ void apply_q2(const float* V2, long long ldv2, const float* tau2, long long ldt2
   // SCL_Q2_VARIANT=0: the shared-memory window kernel (k_q2_apply); 1: the register-stationary kernel in three-term TF32;
   // default 2: the register-stationary kernel in split binary16 (253 / 440 ms for the smallest half / all vectors at n = 20 000
   // against 380 / 558 ms for 1 and 818 / 1627 ms for 0)
-  static const int variant = [] { const char* e = getenv("SCL_Q2_VARIANT"); return e ? atoi(e) : 2; }();
+  const int variant = q2_variant();
   if (variant == 2 && n >= 3) {
     const int q = (n - 3) / B;
     const size_t nblk = (size_t)(q + 1) * (q + 2) / 2;

@@ -688,6 +688,13 @@ int32_t scl_debug_last_solve(scl_handle* h, double* out) {
   return SCL_OK;
 }
 
+int32_t scl_debug_set_two_stage(int32_t q2_variant, int32_t stage1_engine, int32_t q1_engine) {
+  scl::g_two_stage_override[0].store(q2_variant, std::memory_order_relaxed);
+  scl::g_two_stage_override[1].store(stage1_engine, std::memory_order_relaxed);
+  scl::g_two_stage_override[2].store(q1_engine, std::memory_order_relaxed);
+  return SCL_OK;
+}
+
 int32_t scl_debug_eig_stage_totals(scl_handle* h, double* out) {
   if (!h || !out || !h->solver) return SCL_ERR_INVALID;
   for (int i = 0; i < 7; ++i) out[i] = h->solver->ts_total[i];

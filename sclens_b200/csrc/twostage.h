@@ -7,6 +7,7 @@
 // The algebra is restated on the CPU in oracle/two_stage_ref.py (tests/test_two_stage_cpu.py).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdlib>
 #include "common.cuh"
 
@@ -50,14 +51,17 @@ void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels
 // the tcgen05 GEMM of gemm_umma.cu in split binary16 (backtrans.cu, apply_q1_umma).  SCL_TILE_ENGINE sets stage 1 (default 1:
 // its operands are not bounded a priori), SCL_TILE_ENGINE_Q1 the Q1 back-transformation (default 3; measured at n = 20 000,
 // smallest half / all vectors: 83 / 130 ms against 192 / 366 ms for 2, 251 / 474 ms for 1, 252 / 487 ms for 0).
-inline int tile_engine_s1() {
-  static const int v = [] { const char* e = getenv("SCL_TILE_ENGINE"); return e ? atoi(e) : 1; }();
-  return v;
+// run-time overrides for the parity tests (scl_debug_set_two_stage): [0] Q2 variant, [1] stage-1 engine, [2] Q1 engine; < 0 = unset
+extern std::atomic<int> g_two_stage_override[3];
+inline int two_stage_choice(int which, const char* env, int dflt) {
+  const int o = g_two_stage_override[which].load(std::memory_order_relaxed);
+  if (o >= 0) return o;
+  const char* e = getenv(env);
+  return e ? atoi(e) : dflt;
 }
-inline int tile_engine_q1() {
-  static const int v = [] { const char* e = getenv("SCL_TILE_ENGINE_Q1"); return e ? atoi(e) : 3; }();
-  return v;
-}
+inline int q2_variant() { return two_stage_choice(0, "SCL_Q2_VARIANT", 2); }
+inline int tile_engine_s1() { return two_stage_choice(1, "SCL_TILE_ENGINE", 1); }
+inline int tile_engine_q1() { return two_stage_choice(2, "SCL_TILE_ENGINE_Q1", 3); }
 
 // every vector scaled to unit length (after the back-transformation: the tensor-core products of apply_q2 lose ~1e-7 n / 64)
 void unit_vectors(float* Z, long long ldz, int n, int mvec, cudaStream_t st);

@@ -557,6 +557,34 @@ def test_two_stage_solver_matches_float64(h, n, case):
     np.testing.assert_array_equal(L3, L)
 
 
+@pytest.mark.parametrize("q2,s1,q1", [(0, 0, 0), (1, 1, 1), (2, 1, 2), (2, 0, 3)])
+def test_two_stage_kernel_variants_agree(h, q2, s1, q1):
+    """Every selectable kernel variant of the two-stage solver (scl_debug_set_two_stage: stage-2 back-transformation in FP32 from a
+    shared-memory window / register-stationary three-term TF32 / split binary16; tile engines FP32 FMA / TF32 / split binary16 /
+    tcgen05 block reflectors) meets the tolerances of the default path on one matrix whose order is not a multiple of anything."""
+    n = 1203
+    rng = np.random.default_rng(77)
+    A = rng.standard_normal((n, n + 500))
+    A -= A.mean(axis=0)
+    G = (A @ A.T / A.shape[1]).astype(np.float32)
+    Lref = np.linalg.eigvalsh(G.astype(np.float64))
+    scale = float(Lref[-1])
+    st = np.zeros(8)
+    try:
+        h.lib.scl_debug_set_eig_api(TWO_STAGE)
+        h.lib.scl_debug_set_two_stage(q2, s1, q1)
+        L, V, out = _tri_solve(h, G, 0, n)
+        h._ck(h.lib.scl_debug_last_solve(h.h, ptr(st, C.c_double)))
+    finally:
+        h.lib.scl_debug_set_two_stage(-1, -1, -1)
+        h.lib.scl_debug_set_eig_api(-1)
+    assert out[5] == 0 and st[5] == 1, ("the two-stage path did not produce the result", out, st)
+    np.testing.assert_allclose(L, Lref, rtol=2e-5, atol=3e-6 * scale)
+    G64 = G.astype(np.float64)
+    assert np.max(np.abs(G64 @ V - V * L[None, :])) < 5e-5 * max(1.0, scale)
+    assert np.max(np.abs(V.T.astype(np.float64) @ V - np.eye(n))) < 5e-5
+
+
 def test_two_stage_solver_rank_deficient_panels_fall_back(h):
     """A block-diagonal matrix with an exactly zero block has panels that CholeskyQR cannot factor: the solve must notice
     (panel flag), take the one-stage path on the kept copy, say so in the counters, and still be right."""
