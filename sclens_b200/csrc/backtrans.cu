@@ -1130,17 +1130,19 @@ __global__ void __launch_bounds__(256) k_q1_conv_x(const float* __restrict__ X, 
 }
 // Z[v][r0 + k] += U[v][k]
 __global__ void __launch_bounds__(256) k_q1_add(float* __restrict__ Z, long long ldz, int r0, const float* __restrict__ U, long long ldu,
-                                                int m) {
-  float* z = Z + (long long)blockIdx.y * ldz + r0;
-  const float* u = U + (long long)blockIdx.y * ldu;
-  for (int k = ((int)blockIdx.x * 256 + (int)threadIdx.x) * 4; k < m; k += (int)gridDim.x * 1024) {
-    if (k + 3 < m) {
-      float4 a = *reinterpret_cast<float4*>(z + k);
-      const float4 b = *reinterpret_cast<const float4*>(u + k);
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-      *reinterpret_cast<float4*>(z + k) = a;
-    } else {
-      for (int q = k; q < m; ++q) z[q] += u[q];
+                                                int m, int mvec) {
+  for (int v = (int)blockIdx.y; v < mvec; v += (int)gridDim.y) {
+    float* z = Z + (long long)v * ldz + r0;
+    const float* u = U + (long long)v * ldu;
+    for (int k = ((int)blockIdx.x * 256 + (int)threadIdx.x) * 4; k < m; k += (int)gridDim.x * 1024) {
+      if (k + 3 < m) {
+        float4 a = *reinterpret_cast<float4*>(z + k);
+        const float4 b = *reinterpret_cast<const float4*>(u + k);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        *reinterpret_cast<float4*>(z + k) = a;
+      } else {
+        for (int q = k; q < m; ++q) z[q] += u[q];
+      }
     }
   }
 }
@@ -1289,7 +1291,7 @@ static void apply_q1_umma(const float* A, int n, long long lda, const float* T1,
     u.chunk_kb = q1_chunk;
     u.C = U.p; u.ldc = ldk;
     gemm_umma(u, st);
-    k_q1_add<<<dim3((unsigned)std::min((m + 1023) / 1024, 64), mvec), 256, 0, st>>>(Z, ldz, r0, U.p, ldk, m);
+    k_q1_add<<<dim3((unsigned)std::min((m + 1023) / 1024, 64), (unsigned)std::min(mvec, 65535)), 256, 0, st>>>(Z, ldz, r0, U.p, ldk, m, mvec);
     launches += 7;
   }
   SCL_CUDA(cudaGetLastError());
@@ -1299,7 +1301,7 @@ static void apply_q1_umma(const float* A, int n, long long lda, const float* T1,
 void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels, float* Z, long long ldz, int mvec,
               cudaStream_t st) {
   if (mvec <= 0 || npanels <= 0) return;
-  if (tile_engine_q1() == 3) {
+  if (tile_engine_q1() == 3 && mvec >= 64) {   // a handful of vectors is not worth the block machinery: panel by panel below
     apply_q1_umma(A, n, lda, T1, npanels, Z, ldz, mvec, st);
     return;
   }
@@ -1308,7 +1310,7 @@ void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels
   Tmp<float> Xpart((size_t)max_split * B * ldx, st), Xp((size_t)B * ldx, st);
   const int vt = (mvec + tile::TM - 1) / tile::TM;
   const int slots = 2 * sm_count();
-  const int eng = tile_engine_q1();
+  const int eng = std::min(2, tile_engine_q1());
   for (int k = npanels - 1; k >= 0; --k) {
     const int c0 = k * B, r0 = c0 + B, m = n - r0;
     if (m < 1) continue;

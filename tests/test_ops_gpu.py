@@ -585,6 +585,25 @@ def test_two_stage_kernel_variants_agree(h, q2, s1, q1):
     assert np.max(np.abs(V.T.astype(np.float64) @ V - np.eye(n))) < 5e-5
 
 
+@pytest.mark.parametrize("v0,v1", [(100, 110), (0, 1), (650, 700)])
+def test_two_stage_few_vectors(h, v0, v1):
+    """An index range of a few eigenvectors (one 16-vector tile of the stage-2 kernel, the panel-by-panel stage-1
+    back-transformation instead of the block reflectors) gives the vectors of the full solve."""
+    n = 700
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((n, n + 200))
+    G = (A @ A.T / A.shape[1]).astype(np.float32)
+    try:
+        h.lib.scl_debug_set_eig_api(TWO_STAGE)
+        L, V, out = _tri_solve(h, G, 0, n)
+        L2, V2, out2 = _tri_solve(h, G, v0, v1)
+    finally:
+        h.lib.scl_debug_set_eig_api(-1)
+    assert out[5] == 0 and out2[5] == 0
+    np.testing.assert_array_equal(L2, L)
+    assert np.max(np.abs(np.abs(np.sum(V2 * V[:, v0:v1], axis=0)) - 1.0)) < 1e-5
+
+
 def test_two_stage_solver_rank_deficient_panels_fall_back(h):
     """A block-diagonal matrix with an exactly zero block has panels that CholeskyQR cannot factor: the solve must notice
     (panel flag), take the one-stage path on the kept copy, say so in the counters, and still be right."""
