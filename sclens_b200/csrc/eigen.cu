@@ -112,7 +112,8 @@ bool Solver::syevd_2stage(float* dA, int n, float* dW, int v0, int v1, cudaStrea
     SCL_CUDA(cudaEventCreateWithFlags(&impl->ts_aux.done, cudaEventDisableTiming));
   }
   static const bool no_ahead = getenv("SCL_NO_LOOKAHEAD") != nullptr;
-  const int npanels = sy2sb_lower(Aq, n, lda, impl->ts_AB.p, impl->ts_T1.p, impl->ts_fail.p, st, no_ahead ? nullptr : &impl->ts_aux);
+  const bool half_ok = tile_engine_s1() == 2 && half_range_ok(Aq, n, lda, st);
+  const int npanels = sy2sb_lower(Aq, n, lda, impl->ts_AB.p, impl->ts_T1.p, impl->ts_fail.p, st, no_ahead ? nullptr : &impl->ts_aux, half_ok);
   SCL_CUDA(cudaEventRecord(ev[1], st));
   sb2st(impl->ts_AB.p, n, impl->tri_d.p, impl->tri_e.p, m > 0, impl->ts_V2.p, ldv2, impl->ts_tau2.p, ldt2, st);
   SCL_CUDA(cudaEventRecord(ev[2], st));

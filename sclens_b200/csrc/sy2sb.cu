@@ -330,10 +330,11 @@ __global__ void __launch_bounds__(256, 2) k_symm(const float* __restrict__ A22, 
   }
 }
 
-// k_symm on the tensor-core tile engine
+// k_symm on the tensor-core tile engines (ENG 1: three-term TF32, 2: split binary16)
+template <int ENG>
 __global__ void __launch_bounds__(256, 2) k_symm_tc(const float* __restrict__ A22, long long lda, int m, const float* __restrict__ V,
                                                     long long ldv, float* __restrict__ Ypart, long long ldy, int chunk) {
-  __shared__ __align__(16) float smem[tile::SmemT<64>::floats];
+  __shared__ __align__(16) unsigned char smem[tile::SmemE<ENG, 64>::bytes];
   const int i0 = (int)blockIdx.x * tile::TM;
   const int ka = (int)blockIdx.y * chunk, kb = min(m, ka + chunk);
   tile::AccT<64> acc;
@@ -342,17 +343,17 @@ __global__ void __launch_bounds__(256, 2) k_symm_tc(const float* __restrict__ A2
   {
     const int k1 = min(kb, i0);
     if (k1 > ka)
-      tile::mac_tc<64>(acc, tile::opnd(A22 + i0 + (long long)ka * lda, lda, 0, mi, k1 - ka), tile::opnd(V + ka, ldv, 1, B, k1 - ka),
+      tile::mac_e<ENG, 64, 0, 1>(acc, tile::opnd(A22 + i0 + (long long)ka * lda, lda, 0, mi, k1 - ka), tile::opnd(V + ka, ldv, 1, B, k1 - ka),
                        k1 - ka, smem);
   }
   if (ka <= i0 && i0 < kb) {
     const int kl = min(tile::TM, mi);
-    tile::mac_tc<64>(acc, tile::opnd(A22 + i0 + (long long)i0 * lda, lda, 2, mi, kl), tile::opnd(V + i0, ldv, 1, B, kl), kl, smem);
+    tile::mac_e<ENG, 64, 0, 1>(acc, tile::opnd(A22 + i0 + (long long)i0 * lda, lda, 2, mi, kl), tile::opnd(V + i0, ldv, 1, B, kl), kl, smem);
   }
   {
     const int k3 = max(ka, i0 + tile::TM);
     if (kb > k3)
-      tile::mac_tc<64>(acc, tile::opnd(A22 + k3 + (long long)i0 * lda, lda, 1, mi, kb - k3), tile::opnd(V + k3, ldv, 1, B, kb - k3),
+      tile::mac_e<ENG, 64, 1, 1>(acc, tile::opnd(A22 + k3 + (long long)i0 * lda, lda, 1, mi, kb - k3), tile::opnd(V + k3, ldv, 1, B, kb - k3),
                        kb - k3, smem);
   }
   float* out = Ypart + (size_t)blockIdx.y * B * ldy;
@@ -423,9 +424,10 @@ __global__ void __launch_bounds__(256, 2) k_syr2k(float* A22, long long lda, int
 
 // k_syr2k on the tensor-core tile engine: the tile is formed transposed (columns j of the trailing matrix on the rows of the
 // accumulator, rows i on its columns), so a thread's two adjacent outputs are adjacent in memory
+template <int ENG>
 __global__ void __launch_bounds__(256, 2) k_syr2k_tc(float* A22, long long lda, int m, const float* __restrict__ V, long long ldv,
                                                      const float* __restrict__ W, long long ldw, int mode) {
-  __shared__ __align__(16) float smem[tile::SmemT<128>::floats];
+  __shared__ __align__(16) unsigned char smem[tile::SmemE<ENG, 128>::bytes];
   const int t = (int)blockIdx.x;
   int I, J;
   if (mode == 1) {
@@ -444,8 +446,8 @@ __global__ void __launch_bounds__(256, 2) k_syr2k_tc(float* A22, long long lda, 
   const int i0 = I * tile::TM, j0 = J * tile::TM;
   tile::AccT<128> acc;
   acc.clear();
-  tile::mac_tc<128>(acc, tile::opnd(W + j0, ldw, 0, m - j0, B), tile::opnd(V + i0, ldv, 0, m - i0, B), B, smem);
-  tile::mac_tc<128>(acc, tile::opnd(V + j0, ldv, 0, m - j0, B), tile::opnd(W + i0, ldw, 0, m - i0, B), B, smem);
+  tile::mac_e<ENG, 128, 0, 0>(acc, tile::opnd(W + j0, ldw, 0, m - j0, B), tile::opnd(V + i0, ldv, 0, m - i0, B), B, smem);
+  tile::mac_e<ENG, 128, 0, 0>(acc, tile::opnd(V + j0, ldv, 0, m - j0, B), tile::opnd(W + i0, ldw, 0, m - i0, B), B, smem);
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -600,7 +602,41 @@ __global__ void k_extract_band(const float* __restrict__ A, long long lda, int n
 
 }  // namespace
 
-int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fail, cudaStream_t st, const Sy2sbAux* aux) {
+namespace {
+__global__ void __launch_bounds__(256) k_frob2(const float* __restrict__ A, int n, long long lda, double* __restrict__ out) {
+  double s = 0.0;
+  for (int c = (int)blockIdx.x; c < n; c += (int)gridDim.x) {
+    const float* col = A + (long long)c * lda;
+    for (int i = (int)threadIdx.x; i < n; i += 256) s += (double)col[i] * (double)col[i];
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    atomicAdd(out, t);
+  }
+}
+}  // namespace
+
+// May stage 1 multiply in split binary16?  Every quantity it forms is bounded by a small multiple of the Frobenius norm (an
+// invariant of the reduction), so the norm must stay clear of binary16's overflow; and the absolute floor of the split
+// (1.5e-11 per entry) must stay below FP32 rounding of the matrix as a whole.  One pass over the matrix and one synchronisation.
+bool half_range_ok(const float* A, int n, long long lda, cudaStream_t st) {
+  Tmp<double> acc(1, st);
+  SCL_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double), st));
+  k_frob2<<<std::min(n, 4 * sm_count()), 256, 0, st>>>(A, n, lda, acc.p);
+  double f2 = 0.0;
+  SCL_CUDA(cudaMemcpyAsync(&f2, acc.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCL_CUDA(cudaStreamSynchronize(st));
+  count_launches(1);
+  const double f = std::sqrt(f2);
+  return std::isfinite(f) && f <= 1024.0 && f >= (double)n / 8192.0;
+}
+
+int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fail, cudaStream_t st, const Sy2sbAux* aux, bool half_ok) {
   SCL_REQUIRE((lda & 3) == 0 && ((uintptr_t)A & 15) == 0 && lda >= n, "sy2sb: leading dimension must be a multiple of 4");
   const long long ldy = ((long long)n + 3) & ~3LL;
   const int max_slabs = (n + kSlab - 1) / kSlab + 1;
@@ -618,7 +654,8 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     attr_done = true;
   }
   const int slots = 2 * sm_count();
-  const bool tc = tile_engine_s1() != 0;
+  const int eng = (tile_engine_s1() == 2 && !half_ok) ? 1 : tile_engine_s1();   // split binary16 only for a matrix within its range
+  const bool tc = eng != 0;
   long launches = 0;
   // factorisation of panel k (full-size panels only) on stream s: V in place, T, V T into the upper triangle, R' into the band
   auto factor = [&](int k, cudaStream_t s) {
@@ -661,7 +698,8 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     int chunk = ((m + split - 1) / split + tile::TM - 1) / tile::TM * tile::TM;
     chunk = std::max(chunk, 2 * tile::TM);
     split = (m + chunk - 1) / chunk;
-    if (tc) k_symm_tc<<<dim3(ntile, split), 256, 0, st>>>(A22, lda, m, Pp, lda, Ypart.p, ldy, chunk);
+    if (eng == 2) k_symm_tc<2><<<dim3(ntile, split), 256, 0, st>>>(A22, lda, m, Pp, lda, Ypart.p, ldy, chunk);
+    else if (tc) k_symm_tc<1><<<dim3(ntile, split), 256, 0, st>>>(A22, lda, m, Pp, lda, Ypart.p, ldy, chunk);
     else k_symm<<<dim3(ntile, split), 256, 0, st>>>(A22, lda, m, Pp, lda, Ypart.p, ldy, chunk);
     const size_t ny = (size_t)B * ldy;
     k_sum_parts<<<(unsigned)((ny + 255) / 256), 256, 0, st>>>(Ypart.p, split, ny, ny, Y.p);
@@ -674,19 +712,22 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     // auxiliary stream (one or a few CTAs per kernel) while the main stream updates the rest of the trailing matrix
     const bool ahead = aux && aux->stream && ntile >= 4 && m - B >= B;
     if (ahead) {
-      if (tc) k_syr2k_tc<<<ntile, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 1);
+      if (eng == 2) k_syr2k_tc<2><<<ntile, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 1);
+      else if (tc) k_syr2k_tc<1><<<ntile, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 1);
       else k_syr2k<<<ntile, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 1);
       SCL_CUDA(cudaEventRecord(aux->ready, st));
       SCL_CUDA(cudaStreamWaitEvent(aux->stream, aux->ready, 0));
       factor(k + 1, aux->stream);
       SCL_CUDA(cudaEventRecord(aux->done, aux->stream));
-      if (tc) k_syr2k_tc<<<(ntile - 1) * ntile / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 2);
+      if (eng == 2) k_syr2k_tc<2><<<(ntile - 1) * ntile / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 2);
+      else if (tc) k_syr2k_tc<1><<<(ntile - 1) * ntile / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 2);
       else k_syr2k<<<(ntile - 1) * ntile / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 2);
       SCL_CUDA(cudaStreamWaitEvent(st, aux->done, 0));
       factored = true;
       ++launches;
     } else {
-      if (tc) k_syr2k_tc<<<ntile * (ntile + 1) / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 0);
+      if (eng == 2) k_syr2k_tc<2><<<ntile * (ntile + 1) / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 0);
+      else if (tc) k_syr2k_tc<1><<<ntile * (ntile + 1) / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 0);
       else k_syr2k<<<ntile * (ntile + 1) / 2, 256, 0, st>>>(A22, lda, m, Pp, lda, Z.p, ldy, 0);
     }
     ++launches;

@@ -31,7 +31,10 @@ struct Sy2sbAux {
   cudaStream_t stream = nullptr;
   cudaEvent_t ready = nullptr, done = nullptr;
 };
-int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fail, cudaStream_t st, const Sy2sbAux* aux = nullptr);
+// half_ok: the matrix passed half_range_ok, so the products of the trailing update may run in split binary16 (engine 2)
+int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fail, cudaStream_t st, const Sy2sbAux* aux = nullptr,
+                bool half_ok = false);
+bool half_range_ok(const float* A, int n, long long lda, cudaStream_t st);
 
 // stage 2.  AB as above (destroyed).  d (n), e (n - 1).  With keep = true the reflector of sweep s, chase level k is stored at
 // V2 + s * ldv2 + k * kBand (kBand floats, v[0] = 1) and its tau at tau2 + s * ldt2 + k.
@@ -48,8 +51,8 @@ void apply_q1(const float* A, int n, long long lda, const float* T1, int npanels
 
 // which engine runs the matrix-matrix products.  Tile engines of sgemm_tile.cuh: 0 = FP32 FMA, 1 = tensor cores in three-term
 // TF32 (mma.sync), 2 = tensor cores in split binary16 (mma.sync; operands must be O(1)).  3 (Q1 only): eight panels at a time on
-// the tcgen05 GEMM of gemm_umma.cu in split binary16 (backtrans.cu, apply_q1_umma).  SCL_TILE_ENGINE sets stage 1 (default 1:
-// its operands are not bounded a priori), SCL_TILE_ENGINE_Q1 the Q1 back-transformation (default 3; measured at n = 20 000,
+// the tcgen05 GEMM of gemm_umma.cu in split binary16 (backtrans.cu, apply_q1_umma).  SCL_TILE_ENGINE sets stage 1 (default 2, which
+// applies only to a matrix whose Frobenius norm passes half_range_ok - otherwise 1 runs; 304 vs 369 ms at n = 20 000), SCL_TILE_ENGINE_Q1 the Q1 back-transformation (default 3; measured at n = 20 000,
 // smallest half / all vectors: 83 / 130 ms against 192 / 366 ms for 2, 251 / 474 ms for 1, 252 / 487 ms for 0).
 // run-time overrides for the parity tests (scl_debug_set_two_stage): [0] Q2 variant, [1] stage-1 engine, [2] Q1 engine; < 0 = unset
 extern std::atomic<int> g_two_stage_override[3];
@@ -60,7 +63,7 @@ inline int two_stage_choice(int which, const char* env, int dflt) {
   return e ? atoi(e) : dflt;
 }
 inline int q2_variant() { return two_stage_choice(0, "SCL_Q2_VARIANT", 2); }
-inline int tile_engine_s1() { return two_stage_choice(1, "SCL_TILE_ENGINE", 1); }
+inline int tile_engine_s1() { return two_stage_choice(1, "SCL_TILE_ENGINE", 2); }
 inline int tile_engine_q1() { return two_stage_choice(2, "SCL_TILE_ENGINE_Q1", 3); }
 
 // every vector scaled to unit length (after the back-transformation: the tensor-core products of apply_q2 lose ~1e-7 n / 64)

@@ -557,7 +557,7 @@ def test_two_stage_solver_matches_float64(h, n, case):
     np.testing.assert_array_equal(L3, L)
 
 
-@pytest.mark.parametrize("q2,s1,q1", [(0, 0, 0), (1, 1, 1), (2, 1, 2), (2, 0, 3)])
+@pytest.mark.parametrize("q2,s1,q1", [(0, 0, 0), (1, 1, 1), (2, 1, 2), (2, 0, 3), (2, 2, 3)])
 def test_two_stage_kernel_variants_agree(h, q2, s1, q1):
     """Every selectable kernel variant of the two-stage solver (scl_debug_set_two_stage: stage-2 back-transformation in FP32 from a
     shared-memory window / register-stationary three-term TF32 / split binary16; tile engines FP32 FMA / TF32 / split binary16 /
