@@ -26,7 +26,12 @@ namespace scl {
 namespace {
 
 constexpr int B = kBand;
-constexpr int kSlab = 512;   // rows per CTA of the panel dot products
+// rows per CTA of the panel dot products (SCL_S1_SLAB; a multiple of 64): fewer rows = more CTAs on these short kernels, which
+// sit on the critical path of every panel, against more partial matrices for the single-CTA kernels that sum them
+static int slab_rows() {
+  static const int v = [] { const char* e = getenv("SCL_S1_SLAB"); const int s = e ? atoi(e) : 256; return std::max(64, s / 64 * 64); }();
+  return v;
+}
 
 // part[p][c1][c2] = sum over the rows of slab p of X[c1][i] * Y[c2][i].  F64 = true: every product accumulated in Float64 (the
 // panel Gram matrix, whose Cholesky factor squares the panel's condition number).  F64 = false: Float32 accumulation over 64
@@ -34,38 +39,52 @@ constexpr int kSlab = 512;   // rows per CTA of the panel dot products
 // Float64 pipe of this part is an order of magnitude slower than the Float32 one).
 template <bool F64>
 __global__ void __launch_bounds__(256) k_dot64(const float* __restrict__ X, long long ldx, const float* __restrict__ Y,
-                                               long long ldy, int rows, double* __restrict__ part) {
-  __shared__ float Xs[B][B + 1], Ys[B][B + 1];
+                                               long long ldy, int rows, int slab, double* __restrict__ part) {
+  // F64: 32-row chunks converted to Float64 once, on the way into shared memory (a conversion per use was 16 per element
+  // and cost more than the multiply-adds); FP32: 64-row chunks
+  constexpr int RC = F64 ? 32 : B;
+  __shared__ __align__(16) unsigned char raw[2 * B * 33 * 8];
   const int tid = (int)threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int base = (int)blockIdx.x * kSlab, end = min(rows, base + kSlab);
+  const int base = (int)blockIdx.x * slab, end = min(rows, base + slab);
   double acc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-  for (int r0 = base; r0 < end; r0 += B) {
-    __syncthreads();
-    for (int e = tid; e < B * B; e += 256) {
-      const int c = e / B, i = e % B;
-      const bool ok = r0 + i < end;
-      Xs[c][i] = ok ? X[(long long)c * ldx + r0 + i] : 0.f;
-      Ys[c][i] = ok ? Y[(long long)c * ldy + r0 + i] : 0.f;
-    }
+  for (int r0 = base; r0 < end; r0 += RC) {
     __syncthreads();
     if constexpr (F64) {
+      double (*Xd)[33] = reinterpret_cast<double (*)[33]>(raw);
+      double (*Yd)[33] = Xd + B;
+      for (int e = tid; e < B * RC; e += 256) {
+        const int c = e / RC, i = e % RC;
+        const bool ok = r0 + i < end;
+        Xd[c][i] = ok ? (double)X[(long long)c * ldx + r0 + i] : 0.0;
+        Yd[c][i] = ok ? (double)Y[(long long)c * ldy + r0 + i] : 0.0;
+      }
+      __syncthreads();
 #pragma unroll 4
-      for (int r = 0; r < B; ++r) {
+      for (int r = 0; r < RC; ++r) {
         double xa[4], yb[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) xa[a] = (double)Xs[ty + 16 * a][r];
+        for (int a = 0; a < 4; ++a) xa[a] = Xd[ty + 16 * a][r];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) yb[b] = (double)Ys[tx + 16 * b][r];
+        for (int b = 0; b < 4; ++b) yb[b] = Yd[tx + 16 * b][r];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
           for (int b = 0; b < 4; ++b) acc[a][b] = fma(xa[a], yb[b], acc[a][b]);
       }
     } else {
+      float (*Xs)[B + 1] = reinterpret_cast<float (*)[B + 1]>(raw);
+      float (*Ys)[B + 1] = Xs + B;
+      for (int e = tid; e < B * B; e += 256) {
+        const int c = e / B, i = e % B;
+        const bool ok = r0 + i < end;
+        Xs[c][i] = ok ? X[(long long)c * ldx + r0 + i] : 0.f;
+        Ys[c][i] = ok ? Y[(long long)c * ldy + r0 + i] : 0.f;
+      }
+      __syncthreads();
       float fa[4][4];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
@@ -639,6 +658,7 @@ bool half_range_ok(const float* A, int n, long long lda, cudaStream_t st) {
 int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fail, cudaStream_t st, const Sy2sbAux* aux, bool half_ok) {
   SCL_REQUIRE((lda & 3) == 0 && ((uintptr_t)A & 15) == 0 && lda >= n, "sy2sb: leading dimension must be a multiple of 4");
   const long long ldy = ((long long)n + 3) & ~3LL;
+  const int kSlab = slab_rows();
   const int max_slabs = (n + kSlab - 1) / kSlab + 1;
   const int max_split = 16;
   Tmp<double> part((size_t)max_slabs * B * B, st);
@@ -663,13 +683,13 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     float* Pp = A + r0 + (long long)c0 * lda;
     float* Tk = T1 + (size_t)k * B * B;
     const int nslab = (m + kSlab - 1) / kSlab, ntile = (m + tile::TM - 1) / tile::TM;
-    k_dot64<true><<<nslab, 256, 0, s>>>(Pp, lda, Pp, lda, m, part.p);
+    k_dot64<true><<<nslab, 256, 0, s>>>(Pp, lda, Pp, lda, m, kSlab, part.p);
     k_panel_factor<<<1, 256, sm3, s>>>(part.p, nslab, Pp, lda, AB, c0, Mbuf.p, d_fail);
     if (m > B) {
       const int nt2 = (m - B + tile::TM - 1) / tile::TM;
       k_panel_mul<<<nt2, 256, 0, s>>>(Pp + B, lda, Mbuf.p, Pp + B, lda, m - B, 1.f, nullptr, 0, 0);
     }
-    k_dot64<false><<<nslab, 256, 0, s>>>(Pp, lda, Pp, lda, m, part.p);
+    k_dot64<false><<<nslab, 256, 0, s>>>(Pp, lda, Pp, lda, m, kSlab, part.p);
     k_tfactor<<<1, 256, sm2, s>>>(part.p, nslab, Tk);
     // V T for the back-transformation, transposed into the (otherwise unused) upper triangle of A: (V T)[i][c] at A(c0 + c, r0 + i)
     k_panel_mul<<<ntile, 256, 0, s>>>(Pp, lda, Tk, A + c0 + (long long)r0 * lda, lda, m, 1.f, nullptr, 0, 1);
@@ -704,7 +724,7 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     const size_t ny = (size_t)B * ldy;
     k_sum_parts<<<(unsigned)((ny + 255) / 256), 256, 0, st>>>(Ypart.p, split, ny, ny, Y.p);
     k_panel_mul<<<ntile, 256, 0, st>>>(Y.p, ldy, Tk, Z.p, ldy, m, 1.f, nullptr, 0, 0);
-    k_dot64<false><<<nslab, 256, 0, st>>>(Pp, lda, Z.p, ldy, m, part.p);
+    k_dot64<false><<<nslab, 256, 0, st>>>(Pp, lda, Z.p, ldy, m, kSlab, part.p);
     k_sfactor<<<1, 256, sm3, st>>>(part.p, nslab, Tk, Sbuf.p);
     k_panel_mul<<<ntile, 256, 0, st>>>(Pp, lda, Sbuf.p, Z.p, ldy, m, -0.5f, Z.p, ldy, 0);
     launches += 7;
