@@ -115,6 +115,20 @@ __global__ void __launch_bounds__(256) k_dot64(const float* __restrict__ X, long
     for (int b = 0; b < 4; ++b) out[(ty + 16 * a) * B + tx + 16 * b] = acc[a][b];
 }
 
+// out[e] = sum over the slabs p (in order) of part[p][e]: sixteen CTAs instead of the single CTA of the small-matrix kernel that
+// consumes the sum (which otherwise spends most of its time reading nslab x 32 KB)
+__global__ void __launch_bounds__(256) k_sum_dparts(const double* __restrict__ part, int nslab, double* __restrict__ out) {
+  const int e = (int)blockIdx.x * 256 + (int)threadIdx.x;
+  double s0 = 0.0, s1 = 0.0;
+  int p = 0;
+  for (; p + 1 < nslab; p += 2) {
+    s0 += part[(size_t)p * B * B + e];
+    s1 += part[(size_t)(p + 1) * B * B + e];
+  }
+  if (p < nslab) s0 += part[(size_t)p * B * B + e];
+  out[e] = s0 + s1;
+}
+
 typedef double (*Mat65)[B + 1];
 
 __device__ void sum_parts(const double* part, int nslab, Mat65 G) {
@@ -661,7 +675,7 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
   const int kSlab = slab_rows();
   const int max_slabs = (n + kSlab - 1) / kSlab + 1;
   const int max_split = 16;
-  Tmp<double> part((size_t)max_slabs * B * B, st);
+  Tmp<double> part((size_t)max_slabs * B * B, st), psum((size_t)B * B, st);
   Tmp<float> Mbuf(B * B, st), Sbuf(B * B, st), Ypart((size_t)max_split * B * ldy, st), Y((size_t)B * ldy, st), Z((size_t)B * ldy, st);
   SCL_CUDA(cudaMemsetAsync(AB, 0, (size_t)n * kLdab * sizeof(float), st));
   const size_t sm3 = 3 * B * (B + 1) * sizeof(double), sm2 = 2 * B * (B + 1) * sizeof(double), sm4 = 4 * B * (B + 1) * sizeof(double);
@@ -684,16 +698,18 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     float* Tk = T1 + (size_t)k * B * B;
     const int nslab = (m + kSlab - 1) / kSlab, ntile = (m + tile::TM - 1) / tile::TM;
     k_dot64<true><<<nslab, 256, 0, s>>>(Pp, lda, Pp, lda, m, kSlab, part.p);
-    k_panel_factor<<<1, 256, sm3, s>>>(part.p, nslab, Pp, lda, AB, c0, Mbuf.p, d_fail);
+    k_sum_dparts<<<B * B / 256, 256, 0, s>>>(part.p, nslab, psum.p);
+    k_panel_factor<<<1, 256, sm3, s>>>(psum.p, 1, Pp, lda, AB, c0, Mbuf.p, d_fail);
     if (m > B) {
       const int nt2 = (m - B + tile::TM - 1) / tile::TM;
       k_panel_mul<<<nt2, 256, 0, s>>>(Pp + B, lda, Mbuf.p, Pp + B, lda, m - B, 1.f, nullptr, 0, 0);
     }
     k_dot64<false><<<nslab, 256, 0, s>>>(Pp, lda, Pp, lda, m, kSlab, part.p);
-    k_tfactor<<<1, 256, sm2, s>>>(part.p, nslab, Tk);
+    k_sum_dparts<<<B * B / 256, 256, 0, s>>>(part.p, nslab, psum.p);
+    k_tfactor<<<1, 256, sm2, s>>>(psum.p, 1, Tk);
     // V T for the back-transformation, transposed into the (otherwise unused) upper triangle of A: (V T)[i][c] at A(c0 + c, r0 + i)
     k_panel_mul<<<ntile, 256, 0, s>>>(Pp, lda, Tk, A + c0 + (long long)r0 * lda, lda, m, 1.f, nullptr, 0, 1);
-    launches += 6;
+    launches += 8;
   };
   int k = 0;
   bool factored = false;   // panel k was factored ahead (look-ahead) and the main stream already waits for it
@@ -725,9 +741,10 @@ int sy2sb_lower(float* A, int n, long long lda, float* AB, float* T1, int* d_fai
     k_sum_parts<<<(unsigned)((ny + 255) / 256), 256, 0, st>>>(Ypart.p, split, ny, ny, Y.p);
     k_panel_mul<<<ntile, 256, 0, st>>>(Y.p, ldy, Tk, Z.p, ldy, m, 1.f, nullptr, 0, 0);
     k_dot64<false><<<nslab, 256, 0, st>>>(Pp, lda, Z.p, ldy, m, kSlab, part.p);
-    k_sfactor<<<1, 256, sm3, st>>>(part.p, nslab, Tk, Sbuf.p);
+    k_sum_dparts<<<B * B / 256, 256, 0, st>>>(part.p, nslab, psum.p);
+    k_sfactor<<<1, 256, sm3, st>>>(psum.p, 1, Tk, Sbuf.p);
     k_panel_mul<<<ntile, 256, 0, st>>>(Pp, lda, Sbuf.p, Z.p, ldy, m, -0.5f, Z.p, ldy, 0);
-    launches += 7;
+    launches += 8;
     // look-ahead: the first tile column of the update holds the next panel; once it is done the next panel is factored on the
     // auxiliary stream (one or a few CTAs per kernel) while the main stream updates the rest of the trailing matrix
     const bool ahead = aux && aux->stream && ntile >= 4 && m - B >= B;
