@@ -221,11 +221,12 @@ SCL_API int32_t scl_op_gemm_tn(scl_handle* h, int32_t m, int32_t n, int64_t K, i
                        float alpha, int32_t c_colmajor, float* C);
 /* _get_eigen (:375-382): cuSOLVER syevd('V','U'), ascending. V may be NULL (values only). */
 SCL_API int32_t scl_op_syevd(scl_handle* h, int32_t n, const float* A, float* L, float* V, double* ms);
-/* The same solve with the library's tridiagonal stage replaced by this library's own (tridiag.cu): cusolverDnSsytrd ->
- * Float64 Sturm multisection + twisted factorisation -> cusolverDnSormtr.  L: all n eigenvalues ascending; V: the
- * eigenvectors with ascending 0-based indices [v0, v1) as columns (n x (v1 - v0) column-major; v0 == v1: values only, V
- * may be NULL).  out (may be NULL): [ms Ssytrd, ms tridiagonal stage, ms Sormtr, eigenvalue clusters, eigenvalues in
- * clusters, 1 if the solve fell back to Ssyevd]. */
+/* The same solve on this library's own eigensolver, the path scl_run_* use (default: the two-stage solver - dense -> band ->
+ * tridiagonal, Float64 Sturm multisection + twisted factorisation, back-transformations Q2 and Q1, no library call; orders below
+ * 256 or a panel that cannot be factored: own one-stage tridiagonalisation + cusolverDnSormtr; SCL_EIG_API selects).  L: all n
+ * eigenvalues ascending; V: the eigenvectors with ascending 0-based indices [v0, v1) as the columns of an n x (v1 - v0) column-major
+ * array (vector v at V + (v - v0) n; v0 == v1: values only, V may be NULL).  out (may be NULL): out[0..2] = milliseconds of [reduction to tridiagonal form, tridiagonal eigenproblem, back-transformation + copy], out[3..5] =
+ * [eigenvalue clusters re-solved by inverse iteration, eigenvalues in such clusters, 1 if the solve fell back to Ssyevd]. */
 SCL_API int32_t scl_op_syevd_tri(scl_handle* h, int32_t n, const float* A, int32_t v0, int32_t v1, float* L, float* V, double out[6]);
 /* _mp_calculation + _tw + mp_check (:424-487) on host doubles. out: [lambda_c,b_plus,b_minus,
  * ks_static, n_Lmp, mp_iters, pass, n_signal]. */
