@@ -312,6 +312,9 @@ def make_counts_csc_gpu(N, M, seed, device, gene_block=64):
 
 
 def main():
+    # stdout carries ONE JSON line: NCCL's version banner (printed to stdout at NCCL_DEBUG=VERSION) would precede it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None, help="timed passes requested (default 2; fewer are timed when they do not fit the budget)")
