@@ -311,10 +311,25 @@ def make_counts_csc_gpu(N, M, seed, device, gene_block=64):
     return X
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str):
+    """the one JSON line, on the process's original stdout"""
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(line, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 def main():
-    # stdout carries ONE JSON line: NCCL's version banner (printed to stdout at NCCL_DEBUG=VERSION) would precede it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries ONE JSON line.  Native libraries write there too (NCCL prints its version banner to stdout at
+    # NCCL_DEBUG=VERSION and =WARN), so file descriptor 1 points at stderr for the whole run and the line goes to the saved one.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None, help="timed passes requested (default 2; fewer are timed when they do not fit the budget)")
@@ -352,7 +367,7 @@ def main():
         ref_budget = float(os.environ.get("SCLENS_REF_BUDGET_S", "420"))
         total, cores, sample, detail = reference_arm(X, args.workload, NOMINAL_SEARCH_STEPS[args.workload], args.n_perturb, ref_budget)
         v = N / total
-        print(json.dumps({"impl": "reference", "metric": "sclens_cells_per_s", "value": v, "unit": "cells/s",
+        emit(json.dumps({"impl": "reference", "metric": "sclens_cells_per_s", "value": v, "unit": "cells/s",
                           "n_gpus": args.gpus, "steps": 1, "steps_requested": args.steps, "warmup": 0,
                           "warmup_requested": args.warmup, "ms_per_step": total * 1e3,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -601,7 +616,7 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {type(exc).__name__}: {exc}"[:300]}
     line["wall_s_at_line"] = time.perf_counter() - T_START
-    print(json.dumps(line))
+    emit(json.dumps(line))
     h.close()
     if world > 1:
         dist.destroy_process_group()
