@@ -7,7 +7,8 @@ implement, so the scheme can be checked on a CPU (tests/test_two_stage_cpu.py) b
            (Ballard et al., "Reconstructing Householder vectors from TSQR": LU of Q1 - S), T from V'V, two-sided update
            A22 -= V W' + W V'
   stage 2  band -> tridiagonal by bulge chasing (Householder, column by column), reflectors kept
-  back     Z = Q1 Q2 E: Q2 applied in blocks of g sweeps x one chase level (the order proven below), Q1 panel by panel
+  back     Z = Q1 Q2 E: Q2 applied in blocks of g sweeps x one chase level (the order proven below), Q1 panel by panel or p
+           panels at a time as one block reflector (apply_q1_blocked: the recursion of backtrans.cu::apply_q1_umma)
 
 The reference's solver is `eigen(Symmetric(...))` / CUSOLVER syevd (src/scLENS.jl:375-387); this file has no counterpart
 there - it documents the replacement's arithmetic.
@@ -195,6 +196,35 @@ def apply_q1(refl1, Z):
     Z = Z.copy()
     for r0, V, T in reversed(refl1):
         Z[r0:] -= V @ (T @ (V.T @ Z[r0:]))
+    return Z
+
+
+def apply_q1_blocked(refl1, Z, p=8):
+    """Z <- Q1 Z with p consecutive panels applied as ONE block reflector, as backtrans.cu::apply_q1_umma does on the tcgen05 GEMM:
+    H_a H_a+1 ... H_a+p-1 Z = Z - sum_j (V_j T_j) X_j with X_j = V_j' Z - sum_{l > j} (V_j' V_l T_l) X_l, j descending.  The large
+    products are Y = V_blk' Z and Z -= (VT)_blk X; the couplings S_jl = (V_blk' V_blk)_jl T_l come from the Gram matrix of the block.
+    Panels are padded with zeros above their first row so the block shares the row range of its first panel."""
+    Z = Z.copy()
+    n = Z.shape[0]
+    for a in range((len(refl1) - 1) // p * p, -1, -p):
+        blk = refl1[a:a + p]
+        r0 = blk[0][0]
+        w = blk[0][1].shape[1]
+        Vb = np.zeros((n - r0, w * len(blk)), dtype=Z.dtype)
+        VTb = np.zeros_like(Vb)
+        for j, (rj, V, T) in enumerate(blk):
+            Vb[rj - r0:, w * j:w * j + V.shape[1]] = V
+            VTb[rj - r0:, w * j:w * j + V.shape[1]] = V @ T
+        Y = Vb.T @ Z[r0:]
+        G = Vb.T @ Vb
+        X = Y.copy()
+        for j in range(len(blk) - 2, -1, -1):
+            for l in range(j + 1, len(blk)):
+                Tl = np.zeros((w, w), dtype=Z.dtype)
+                Tl[:blk[l][2].shape[0], :blk[l][2].shape[1]] = blk[l][2]
+                S = G[w * j:w * j + w, w * l:w * l + w] @ Tl
+                X[w * j:w * j + w] -= S @ X[w * l:w * l + w]
+        Z[r0:] -= VTb @ X
     return Z
 
 

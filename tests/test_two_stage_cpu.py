@@ -40,3 +40,15 @@ def test_panel_reconstruction_is_a_householder_qr():
     R = H.T @ P
     assert np.abs(R[8:]).max() < 1e-10 * np.abs(P).max() and np.abs(R[:8] - Rp).max() < 1e-10 * np.abs(P).max()
     assert np.abs(np.tril(V[:8], -1) + np.eye(8) - V[:8]).max() == 0.0
+
+
+@pytest.mark.parametrize("n,b,p", [(100, 8, 4), (131, 8, 8), (70, 4, 3)])
+def test_q1_block_reflectors_equal_panel_by_panel(n, b, p):
+    """The recursion behind the tcgen05 stage-1 back-transformation (p panels as one block reflector, couplings from the Gram matrix
+    of the block) gives what the panels give one by one - including a last, short panel and a first block with fewer panels."""
+    rng = np.random.default_rng(n + p)
+    X = rng.standard_normal((n, 2 * n))
+    A = X @ X.T / (2 * n)
+    _, r1 = ts.sy2sb(A, b)
+    Z = rng.standard_normal((n, 17))
+    assert np.abs(ts.apply_q1_blocked(r1, Z, p) - ts.apply_q1(r1, Z)).max() < 1e-12
